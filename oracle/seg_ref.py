@@ -1,0 +1,227 @@
+"""Segmented float64 restatement of the reference's in-batch ranking losses (NumPy).
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Same semantics as dense_ref.py /
+the reference (closed forms in SURVEY.md section 8a), but evaluated group by
+group in float64, so it is the truth for loss and gradient at any batch size
+and never builds a (B,B) tensor.  Integer outputs (pair counts per row, per
+primary group and in total; row-major pair lists) are exact.
+
+Citations: PW:n = /root/reference/rec_now/rec_block/pairwise_loss_from_batch.py:n,
+LW:n = /root/reference/rec_now/rec_block/listwise_loss_from_batch.py:n.
+
+The fused weight menu mirrored here (and in include/recnow_b200.h):
+    label_func "step":  C = y_i > y_j,              W = None      (PW:188-190, the default)
+    label_func "diff":  W = (y_i - y_j) * [y_i > y_j] [* rw_pos_i] [* rw_neg_j],  C = W > 0   (PW:192-193)
+    label_func "step" with row weights:  W = [y_i > y_j] [* rw_pos_i] [* rw_neg_j], C = W > 0
+i.e. what a reference user writes as label_pair_to_weight_func(Y, Yt, sample_weight=w).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+F32 = np.float32
+
+
+@dataclass
+class PairSpec:
+    factor: float = 1.0                 # bpr_loss_func factor            PW:118-119
+    reduce_mean: bool = True            # bpr_loss_func reduce_mean       PW:125-126
+    only_wrong: bool = False            # only_use_wrong_order_pair       PW:197-203
+    power: float = 0.0                  # click_occurance_power           PW:282-291
+    label_func: str = "step"            # "step" | "diff"
+    rw_pos: Optional[np.ndarray] = None  # per-sample weight applied on the positive (row) side
+    rw_neg: Optional[np.ndarray] = None  # per-sample weight applied on the negative (column) side
+
+
+def canonical_keys(groups) -> tuple[np.ndarray, np.ndarray]:
+    """Composite-key canonicalisation: value equality per key (PW:33-35), -0.0 == +0.0,
+    NaN/+-inf match nothing.  Returns (int64 keys [K,B], row_ok bool[B])."""
+    cols = groups if isinstance(groups, (list, tuple)) else [groups]
+    out, ok = [], None
+    for g in cols:
+        g = np.asarray(g).reshape(-1)
+        fin = np.ones(g.size, bool)
+        if g.dtype.kind == "f":
+            fin = np.isfinite(g)
+            gz = np.where(fin, g, 0) + g.dtype.type(0)          # -0.0 -> +0.0
+            k = gz.astype(np.float64).view(np.int64) if g.dtype != np.float64 else gz.view(np.int64)
+        else:
+            k = g.astype(np.int64)
+        out.append(np.ascontiguousarray(k))
+        ok = fin if ok is None else (ok & fin)
+    return np.stack(out), ok
+
+
+def _group_members(keys: np.ndarray, row_ok: np.ndarray):
+    """Lists of member rows (ascending) per composite group, groups in first-occurrence order."""
+    rows = np.flatnonzero(row_ok)
+    if rows.size == 0:
+        return []
+    sub = keys[:, rows]
+    order = np.lexsort(tuple(sub[k] for k in range(sub.shape[0] - 1, -1, -1)) )  # stable -> rows ascending
+    ks = sub[:, order]
+    brk = np.flatnonzero(np.any(ks[:, 1:] != ks[:, :-1], axis=0)) + 1
+    segs = np.split(rows[order], brk)
+    segs.sort(key=lambda m: m[0])
+    return segs
+
+
+def _softplus_neg(x):
+    """sigmoid-CE with label 1 = softplus(-x), TF stable form (PW:120-121), float64."""
+    return np.maximum(x, 0.0) - x + np.log1p(np.exp(-np.abs(x)))
+
+
+def _sigma_neg(x):
+    """sigma(-x) = -d softplus(-x)/dx, overflow-safe."""
+    e = np.exp(-np.abs(x))
+    return np.where(x >= 0, e / (1.0 + e), 1.0 / (1.0 + e))
+
+
+def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
+             want_pairs: bool = False, chunk_elems: int = 1 << 22):
+    """float64 truth for pairwise_loss (PW:228-279) with pairloss_func = bpr_loss_func.
+
+    Returns dict: loss, grad[B], grad_abs[B] (A_i of SURVEY 8d), n_pair, row_pairs[B] (pairs with the
+    row on the positive side), prim_count{primary key -> c_h}, and if want_pairs: pos_idx, neg_idx, w
+    (row-major order, as PW:217 defines it).
+    """
+    s32 = np.asarray(outputs, F32).reshape(-1)
+    y32 = np.asarray(labels, F32).reshape(-1)
+    b = s32.size
+    keys, ok = canonical_keys(groups)
+    if mask is not None:
+        ok = ok & np.asarray(mask, bool).reshape(-1)                         # PW:154-172
+    rwp = None if spec.rw_pos is None else np.asarray(spec.rw_pos, F32).reshape(-1)
+    rwn = None if spec.rw_neg is None else np.asarray(spec.rw_neg, F32).reshape(-1)
+    has_w = spec.label_func == "diff" or rwp is not None or rwn is not None
+    segs = _group_members(keys, ok)
+
+    row_pairs = np.zeros(b, np.int64)
+    # pass 1: exact counts (needed for c_h before any weight can be formed, PW:288-289)
+    per_seg = []
+    for m in segs:
+        if m.size < 2:
+            continue
+        per_seg.append(m)
+    prim_count: dict[int, int] = {}
+
+    def pair_block(mi, m):
+        """cond (bool) and float32 weight matrix (or None) for positive rows mi x negative rows m."""
+        yi, yj = y32[mi][:, None], y32[m][None, :]
+        gt = yi > yj
+        if not has_w:
+            cond, w = gt, None                                               # PW:188-190
+        else:
+            if spec.label_func == "diff":
+                w = ((yi - yj).astype(F32) * gt.astype(F32)).astype(F32)
+            else:
+                w = gt.astype(F32)
+            if rwp is not None:
+                w = (w * rwp[mi][:, None]).astype(F32)
+            if rwn is not None:
+                w = (w * rwn[m][None, :]).astype(F32)
+            cond = w > 0                                                     # PW:193
+        cond = cond & (mi[:, None] != m[None, :])                            # PW:36 (identity removed)
+        if spec.only_wrong:
+            cond = cond & (s32[mi][:, None] < s32[m][None, :])               # PW:200-202
+        return cond, w
+
+    def chunks(m):
+        step = max(1, chunk_elems // m.size)
+        for a in range(0, m.size, step):
+            yield m[a:a + step]
+
+    for m in per_seg:
+        for mi in chunks(m):
+            cond, _ = pair_block(mi, m)
+            row_pairs[mi] += cond.sum(axis=1)
+    n = int(row_pairs.sum())
+    prim = keys[0]
+    if n:
+        nz = np.flatnonzero(row_pairs)
+        for k, c in zip(prim[nz].tolist(), row_pairs[nz].tolist()):
+            prim_count[k] = prim_count.get(k, 0) + c
+
+    loss = 0.0
+    grad = np.zeros(b, np.float64)
+    gabs = np.zeros(b, np.float64)
+    out_pos, out_neg, out_w = [], [], []
+    f = float(spec.factor)
+    for m in per_seg:
+        for mi in chunks(m):
+            cond, w = pair_block(mi, m)
+            if not cond.any():
+                continue
+            x = (s32[mi][:, None] - s32[m][None, :]).astype(F32)             # PW:117 (float32 subtract)
+            if spec.factor != 1.0:
+                x = (x * F32(spec.factor)).astype(F32)                        # PW:118-119
+            x = x.astype(np.float64)
+            wt = np.ones_like(x) if w is None else w.astype(np.float64)
+            if spec.power != 0.0:                                            # PW:285-290
+                c = np.array([prim_count.get(k, 1) for k in prim[mi].tolist()], np.float64)
+                wt = wt * np.power(c, float(spec.power))[:, None]
+            wt = np.where(cond, wt, 0.0)
+            loss += float((wt * _softplus_neg(x)).sum())
+            d = wt * _sigma_neg(x) * f
+            grad[mi] -= d.sum(axis=1)
+            np.add.at(grad, m, d.sum(axis=0))
+            gabs[mi] += np.abs(d).sum(axis=1)
+            np.add.at(gabs, m, np.abs(d).sum(axis=0))
+            if want_pairs:
+                ii, jj = np.nonzero(cond)
+                out_pos.append(mi[ii]); out_neg.append(m[jj]); out_w.append(wt[ii, jj])
+    denom = float(F32(F32(n) + F32(1e-10))) if spec.reduce_mean else 1.0     # PW:125-126, PW:13
+    res = dict(loss=loss / denom, grad=grad / denom, grad_abs=gabs / denom, n_pair=n,
+               row_pairs=row_pairs, prim_count=prim_count)
+    if want_pairs:
+        if out_pos:
+            p, q, w = np.concatenate(out_pos), np.concatenate(out_neg), np.concatenate(out_w)
+            o = np.lexsort((q, p))                                           # row-major: i asc, then j asc
+            res.update(pos_idx=p[o].astype(np.int64), neg_idx=q[o].astype(np.int64), w=w[o])
+        else:
+            res.update(pos_idx=np.zeros(0, np.int64), neg_idx=np.zeros(0, np.int64), w=np.zeros(0))
+    return res
+
+
+def listwise(group_ids, labels, logits, weights=None, pos_neg_th=0.5):
+    """float64 truth for to_listwise_sample + listwise_loss_via_softmax_cross_entropy_with_logits with the
+    default masking (do_mask_logits=True, th >= 0): closed form of SURVEY 8a (LW:109-148, LW:166-172).
+
+    `weights`: optional per-VALID-list weights in first-occurrence order (LW:168-169).
+    Returns dict(loss, grad[B], n_valid, n_group, list_loss[V], list_first_row[V], list_size[V]).
+    """
+    s32 = np.asarray(logits, F32).reshape(-1)
+    y32 = np.asarray(labels, F32).reshape(-1)
+    keys, ok = canonical_keys(group_ids)
+    # tf.unique puts every row in some list; a NaN/inf id equals nothing, i.e. is a singleton list, and a
+    # singleton is never valid (needs a positive AND a negative) -> dropping those rows gives the same result
+    segs = _group_members(keys, ok)
+    th = F32(pos_neg_th)
+    losses, firsts, sizes, members = [], [], [], []
+    for m in segs:
+        ym = y32[m]
+        if not (np.any(ym > th) and np.any((ym - th).astype(F32) < 0)):      # LW:135-137
+            continue
+        z = s32[m].astype(np.float64)
+        p = (ym / np.sum(ym, dtype=F32)).astype(F32).astype(np.float64)      # LW:144 (float32 normalise)
+        zs = z - z.max()
+        lse = np.log(np.exp(zs).sum())
+        losses.append(float((p * (lse - zs)).sum()))
+        firsts.append(int(m[0])); sizes.append(int(m.size)); members.append((m, p, zs, lse))
+    v = len(losses)
+    grad = np.zeros(s32.size, np.float64)
+    ll = np.asarray(losses, np.float64)
+    w = np.ones(v) if weights is None else np.asarray(weights, np.float64).reshape(-1)
+    if v:
+        lw = ll * w
+        loss = float(lw.mean())
+        for r, (m, p, zs, lse) in enumerate(members):
+            sm = np.exp(zs - lse)
+            grad[m] = (w[r] / v) * (sm * p.sum() - p)
+    else:
+        lw, loss = ll, 0.0                                                   # LW:172 nan_to_zero
+    return dict(loss=loss, grad=grad, n_valid=v, n_group=len(segs) + int((~ok).sum()), list_loss=lw,
+                list_first_row=np.asarray(firsts, np.int64), list_size=np.asarray(sizes, np.int64))
