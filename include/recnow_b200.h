@@ -1,0 +1,155 @@
+/*
+ * recnow_b200.h — C ABI of librecnow_b200.so: the B200 (sm_100a) implementation of rec_now's in-batch
+ * ranking-loss hot path.  This header is the drop-in boundary: plain C, plain pointers and sizes, no
+ * TensorFlow / torch / C++ types.  A TensorFlow custom op (rec_now_b200/tf_ops/recnow_tf_ops.cc), the torch
+ * front end (rec_now_b200/rec_block/*.py via ctypes) and the tests all bind exactly these symbols.
+ *
+ * Reference interfaces replaced (all under /root/reference/rec_now/rec_block/):
+ *   pairwise_loss_from_batch.py:228-279  pairwise_loss(...)            -> rn_pairwise_fwd_bwd
+ *   pairwise_loss_from_batch.py:96-127   bpr_loss_func(...)            -> fused into rn_pairwise_fwd_bwd
+ *   pairwise_loss_from_batch.py:130-151  occurance_power_weight(...)   -> rn_occurrence_power_weight
+ *   pairwise_loss_from_batch.py:43-74, 206-217  generate_pair_mask + boolean_mask pair extraction
+ *                                                                      -> rn_pair_indices_count / _fill
+ *   listwise_loss_from_batch.py:89-148   to_listwise_sample(...)       -> rn_listwise_fwd_bwd (segmented),
+ *                                                                         rn_listwise_dense (compat layout)
+ *   listwise_loss_from_batch.py:151-173  listwise_loss_via_softmax_cross_entropy_with_logits
+ *                                                                      -> rn_listwise_fwd_bwd
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
+ *     including the scratch arena (size from rn_*_scratch_bytes).  The library never allocates, never
+ *     synchronises the stream (except the _host count read-backs, which say so) and keeps no state between
+ *     calls: calls on different streams with different scratch arenas are independent.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph capturable.
+ *   - Return value: RN_OK or an RN_ERR_* code; rn_strerror() names it.  No exceptions, no abort().
+ *   - Device pointers must be 16-byte aligned (RN_ERR_ALIGN otherwise).
+ *   - Group keys are canonical int64 (equality of the int64 == equality in the reference's sense).  Float
+ *     group ids (what the reference uses, pairwise_loss_from_batch.py:33-35) are canonicalised by
+ *     rn_canon_keys_f32/_f64: value equality, -0.0 == +0.0, NaN/+-inf match nothing (row_ok = 0).
+ */
+#ifndef RECNOW_B200_H_
+#define RECNOW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_VERSION 100 /* 0.1.0 */
+
+enum {
+  RN_OK = 0,
+  RN_ERR_ARG = 1,          /* NULL / negative / inconsistent argument */
+  RN_ERR_ALIGN = 2,        /* device pointer not 16-byte aligned */
+  RN_ERR_SCRATCH = 3,      /* scratch arena too small */
+  RN_ERR_LAUNCH = 4,       /* CUDA launch / runtime error (cudaGetLastError) */
+  RN_ERR_UNSUPPORTED = 5,  /* valid request outside the fused menu */
+  RN_ERR_NO_DEVICE = 6,    /* no sm_100 device / wrong architecture */
+  RN_ERR_INTERNAL = 7      /* device-side consistency check failed (see rn_last_device_error) */
+};
+
+/* label_pair_to_weight_func menu (pairwise_loss_from_batch.py:175-194).
+ *   STEP: C = y_i > y_j, W = 1            (the default, label_pair_to_weight_func=None)
+ *   DIFF: W = (y_i - y_j)*[y_i > y_j]     (label-gain weights)
+ * Optional per-sample factors rw_pos (row/positive side) and rw_neg (column/negative side) multiply W;
+ * whenever any weight is present the reference's rule C = (W > 0) applies (a non-positive or NaN factor
+ * removes the pairs it touches).  Anything else goes through rn_pair_indices_* + the caller's own code. */
+enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1 };
+
+typedef struct rn_pairwise_args {
+  int64_t B;               /* rows in the batch */
+  int32_t K;               /* number of group-key columns (>= 1); keys AND together (PW:68-73) */
+  int32_t label_func;      /* RN_LABEL_* */
+  const int64_t* keys;     /* [K][B], key k of row i at keys[k*B + i]; keys[0] is the primary key (PW:286) */
+  const float* logits;     /* [B] outputs */
+  const float* labels;     /* [B] */
+  const uint8_t* row_ok;   /* NULL or [B]; 0 = row forms no pair (sample mask PW:154-172 AND finite key) */
+  const float* rw_pos;     /* NULL or [B] */
+  const float* rw_neg;     /* NULL or [B] */
+  float factor;            /* bpr_loss_func factor (PW:118-119) */
+  float power;             /* click_occurance_power (PW:282-291); 0 disables */
+  int32_t only_wrong;      /* only_use_wrong_order_pair (PW:197-203) */
+  int32_t reduce_mean;     /* bpr_loss_func reduce_mean (PW:125-126) */
+  /* Work partition for the multi-GPU "global in-batch" mode: this call scores tiles
+   * [part_rank, part_count) of the pair space over the SAME (all-gathered) rows; loss and dlogits are then
+   * partial sums to be added across ranks, n_pair / row_pairs are already global.  Single GPU: 0, 1. */
+  int32_t part_rank;
+  int32_t part_count;
+  /* outputs */
+  float* loss;             /* [1]  sum_P w*l / (float(n)+1e-10)   (or the plain sum if !reduce_mean) */
+  float* n_pair_f32;       /* [1]  float32(n) as PW:276 returns it */
+  int64_t* n_pair;         /* [1]  exact n */
+  float* dlogits;          /* [B]  d loss / d logits */
+  int64_t* row_pairs;      /* NULL or [B]: number of kept pairs with row i on the positive side */
+} rn_pairwise_args;
+
+typedef struct rn_listwise_args {
+  int64_t B;
+  const int64_t* keys;     /* [B] canonical group ids */
+  const uint8_t* row_ok;   /* NULL or [B]; 0 = id was NaN/inf (a singleton list, never valid) */
+  const float* labels;     /* [B] */
+  const float* logits;     /* [B] */
+  const float* list_w;     /* NULL or [>= V]: per VALID list weights, first-occurrence order (LW:168-169) */
+  float pos_neg_th;        /* LW:89 default 0.5; must be >= 0 for the segmented form */
+  int32_t do_reduce;       /* LW:170-172 */
+  /* outputs */
+  float* loss;             /* [1] mean over valid lists, 0 if none (only written if do_reduce) */
+  float* list_loss;        /* NULL or [B]: per-valid-list losses, first-occurrence order (first V entries) */
+  int32_t* n_valid;        /* [1] V */
+  int32_t* n_group;        /* [1] G (number of distinct ids) */
+  float* dlogits;          /* [B] d mean-loss / d logits (d sum of list_loss if !do_reduce) */
+} rn_listwise_args;
+
+int rn_version(void);
+const char* rn_strerror(int code);
+
+/* Float group ids -> canonical int64 keys; row_ok[i] = 0 where the id is NaN/+-inf.  If and_into != 0 the
+ * flag is ANDed into the existing row_ok (used to merge the sample mask and several key columns). */
+int rn_canon_keys_f32(const float* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into, void* stream);
+int rn_canon_keys_f64(const double* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into, void* stream);
+
+/* ---- pairwise --------------------------------------------------------------------------------------- */
+size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K);
+int rn_pairwise_fwd_bwd(const rn_pairwise_args* args, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Pair materialisation in the reference's row-major order (i ascending, then j ascending; PW:217).
+ * Two phases because P is data dependent: _count enqueues the segmentation + counting, then synchronises
+ * the stream once to return P on the host; _fill writes pos_idx/neg_idx (int32) and, if w != NULL, the
+ * pair weight (without the occurrence factor).  label_cond = 0 lists every same-group ordered pair i != j
+ * (the candidates an arbitrary label_pair_to_weight_func is then evaluated on). */
+size_t rn_pair_indices_scratch_bytes(int64_t B, int32_t K);
+int rn_pair_indices_count(const rn_pairwise_args* args, int32_t label_cond, void* scratch, size_t scratch_bytes,
+                          int64_t* n_pairs_host, void* stream);
+int rn_pair_indices_fill(const rn_pairwise_args* args, int32_t label_cond, void* scratch, size_t scratch_bytes,
+                         int32_t* pos_idx, int32_t* neg_idx, float* w, int64_t capacity, void* stream);
+
+/* occurance_power_weight (PW:130-151): out[i] = count(ids == ids[i]) ^ power, float32. */
+size_t rn_occurrence_scratch_bytes(int64_t N);
+int rn_occurrence_power_weight(const int64_t* ids, int64_t N, float power, float* out,
+                               void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- listwise --------------------------------------------------------------------------------------- */
+size_t rn_listwise_scratch_bytes(int64_t B);
+int rn_listwise_fwd_bwd(const rn_listwise_args* args, void* scratch, size_t scratch_bytes, void* stream);
+/* Compat layout of to_listwise_sample (LW:142-145): after rn_listwise_fwd_bwd on the same scratch, fill the
+ * (V,B) dense_mask / dense_labels / dense_logits the reference returns.  V rows = *n_valid (read it first). */
+int rn_listwise_dense(const rn_listwise_args* args, void* scratch, size_t scratch_bytes, int64_t V,
+                      uint8_t* dense_mask, float* dense_labels, float* dense_logits,
+                      int32_t do_mask_logits, float value_of_masked_logit, void* stream);
+
+/* ---- measurement helpers ---------------------------------------------------------------------------- */
+/* Issues iters*3 MUFU ops (ex2, lg2, rcp) per thread on a full grid; used by bench.py to MEASURE the SFU
+ * peak the pair kernel is normalised against.  mufu_ops_out_host receives the op count issued. */
+int rn_bench_mufu(int32_t iters, float* sink, int64_t* mufu_ops_out_host, void* stream);
+/* Device-side status word of the last call that used `scratch` (0 = ok); reads it back (synchronises). */
+int rn_last_device_error(void* scratch, int32_t* err_host, void* stream);
+/* Stage timing breakdown helper: number of kernel launches the last-built pipeline enqueues per call. */
+int rn_pairwise_launch_count(int64_t B, int32_t K);
+int rn_listwise_launch_count(int64_t B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECNOW_B200_H_ */

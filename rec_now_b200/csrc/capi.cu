@@ -1,0 +1,84 @@
+// Small C-ABI entry points: version, error strings, float-id canonicalisation, SFU peak probe.
+#include "common.cuh"
+
+namespace rn {
+
+template <typename F, typename I>
+__global__ void __launch_bounds__(256) k_canon(const F* __restrict__ ids, int64_t B, int64_t* __restrict__ out,
+                                               uint8_t* __restrict__ ok, int and_into) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  F v = ids[i];
+  bool fin = (v - v) == (F)0;          // false for NaN and +-inf
+  v = fin ? v + (F)0 : (F)0;           // -0.0 -> +0.0
+  double dv = (double)v;               // float32 ids widen exactly; equality is preserved
+  out[i] = __double_as_longlong(dv);
+  if (ok) ok[i] = and_into ? (uint8_t)(ok[i] && fin) : (uint8_t)fin;
+}
+
+__global__ void __launch_bounds__(256) k_mufu(int iters, float* sink) {
+  float a = 0.5f + 1e-3f * threadIdx.x, b = 1.5f, c = 0.25f, d = 0.75f;
+  for (int i = 0; i < iters; ++i) {
+    // four independent ex2 -> lg2 -> rcp chains: 12 MUFU per iteration, values stay in (0.4, 2.5)
+    a = mufu_rcp(mufu_lg2(mufu_ex2(a) + 1.0f) + 0.5f);
+    b = mufu_rcp(mufu_lg2(mufu_ex2(b) + 1.0f) + 0.5f);
+    c = mufu_rcp(mufu_lg2(mufu_ex2(c) + 1.0f) + 0.5f);
+    d = mufu_rcp(mufu_lg2(mufu_ex2(d) + 1.0f) + 0.5f);
+  }
+  if (a + b + c + d == -1.f) sink[0] = a;      // never true; keeps the chains alive
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" int rn_version(void) { return RN_VERSION; }
+
+extern "C" const char* rn_strerror(int code) {
+  switch (code) {
+    case RN_OK: return "ok";
+    case RN_ERR_ARG: return "invalid argument";
+    case RN_ERR_ALIGN: return "device pointer not 16-byte aligned";
+    case RN_ERR_SCRATCH: return "scratch arena too small";
+    case RN_ERR_LAUNCH: return "CUDA launch/runtime error";
+    case RN_ERR_UNSUPPORTED: return "request outside the fused menu";
+    case RN_ERR_NO_DEVICE: return "no sm_100 device";
+    case RN_ERR_INTERNAL: return "device-side consistency check failed";
+  }
+  return "unknown error";
+}
+
+extern "C" int rn_canon_keys_f32(const float* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into,
+                                 void* stream) {
+  if (!ids || !keys_out || B <= 0) return RN_ERR_ARG;
+  k_canon<float, int><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, B, keys_out, row_ok, and_into);
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+extern "C" int rn_canon_keys_f64(const double* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into,
+                                 void* stream) {
+  if (!ids || !keys_out || B <= 0) return RN_ERR_ARG;
+  k_canon<double, int><<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ids, B, keys_out, row_ok, and_into);
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+extern "C" int rn_bench_mufu(int32_t iters, float* sink, int64_t* mufu_ops_out_host, void* stream) {
+  if (iters <= 0 || !sink) return RN_ERR_ARG;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8;
+  k_mufu<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, sink);
+  if (mufu_ops_out_host) *mufu_ops_out_host = (int64_t)blocks * 256 * 12 * (int64_t)iters;
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+extern "C" int rn_last_device_error(void* scratch, int32_t* err_host, void* stream) {
+  if (!scratch || !err_host) return RN_ERR_ARG;
+  // the control block sits at offset 0 of every arena layout
+  Ctl h;
+  if (cudaMemcpyAsync(&h, scratch, sizeof(Ctl), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return RN_ERR_LAUNCH;
+  if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return RN_ERR_LAUNCH;
+  *err_host = (int32_t)h.err;
+  return RN_OK;
+}

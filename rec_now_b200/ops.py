@@ -1,0 +1,102 @@
+"""Thin torch-tensor wrappers over the C ABI (torch is only the allocator / stream provider here).
+
+Every function requires CUDA tensors and enqueues on torch's current stream; nothing synchronises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import ListwiseArgs, PairwiseArgs, check, lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rec_now_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    return t.detach().reshape(-1).to(torch.float32).contiguous()
+
+
+def canon_keys(groups, row_ok: Optional[torch.Tensor] = None):
+    """Group id tensor(s) -> (int64 keys [K,B], row_ok uint8[B] or None).
+
+    Float ids (what the reference passes, pairwise_loss_from_batch.py:33-35) are canonicalised on the device:
+    value equality, -0.0 == +0.0, NaN/inf match nothing.  Integer ids are used as they are.
+    """
+    cols = list(groups) if isinstance(groups, (list, tuple)) else [groups]
+    _need_cuda(*cols)
+    b = cols[0].numel()
+    dev = cols[0].device
+    keys = torch.empty((len(cols), b), dtype=torch.int64, device=dev)
+    ok = None if row_ok is None else row_ok.detach().reshape(-1).to(torch.uint8).contiguous().clone()
+    for k, g in enumerate(cols):
+        g = g.detach().reshape(-1)
+        if g.numel() != b:
+            raise ValueError("all group key tensors must hold the same number of elements")
+        if g.dtype in (torch.float32, torch.float64, torch.float16, torch.bfloat16):
+            if g.dtype in (torch.float16, torch.bfloat16):
+                g = g.to(torch.float32)
+            g = g.contiguous()
+            and_into = 1
+            if ok is None:
+                ok = torch.empty(b, dtype=torch.uint8, device=dev)
+                and_into = 0
+            fn = lib().rn_canon_keys_f32 if g.dtype == torch.float32 else lib().rn_canon_keys_f64
+            check(fn(g.data_ptr(), b, keys[k].data_ptr(), ok.data_ptr(), and_into, _stream()), "rn_canon_keys")
+        else:
+            keys[k].copy_(g.to(torch.int64))
+    return keys, ok
+
+
+def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
+                     factor=1.0, power=0.0, only_wrong=False, reduce_mean=True, part=(0, 1),
+                     want_row_pairs=False):
+    """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors."""
+    _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
+    s, y = _f32(logits), _f32(labels)
+    b = s.numel()
+    keys = keys.reshape(-1, b).contiguous()
+    kk = keys.shape[0]
+    dev = s.device
+    rwp, rwn = _f32(rw_pos), _f32(rw_neg)
+    ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    out = torch.empty(2, dtype=torch.float32, device=dev)          # loss, n_pair_f32
+    n_pair = torch.empty(1, dtype=torch.int64, device=dev)
+    dlogits = torch.empty(b, dtype=torch.float32, device=dev)
+    row_pairs = torch.empty(b, dtype=torch.int64, device=dev) if want_row_pairs else None
+    nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a = PairwiseArgs(
+        B=b, K=kk, label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
+        keys=keys.data_ptr(), logits=s.data_ptr(), labels=y.data_ptr(),
+        row_ok=_ptr(ok), rw_pos=_ptr(rwp), rw_neg=_ptr(rwn),
+        factor=float(factor), power=float(power), only_wrong=int(bool(only_wrong)),
+        reduce_mean=int(bool(reduce_mean)), part_rank=int(part[0]), part_count=int(part[1]),
+        loss=out.data_ptr(), n_pair_f32=out.data_ptr() + 4, n_pair=n_pair.data_ptr(),
+        dlogits=dlogits.data_ptr(), row_pairs=_ptr(row_pairs))
+    with torch.cuda.device(dev):
+        check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, _stream()), "rn_pairwise_fwd_bwd")
+    return dict(loss=out[0], n_pair_f32=out[1], n_pair=n_pair[0], dlogits=dlogits, row_pairs=row_pairs,
+                _scratch=scratch)
+
+
+def device_error(scratch: torch.Tensor) -> int:
+    err = C.c_int32(0)
+    check(lib().rn_last_device_error(scratch.data_ptr(), C.byref(err), _stream()), "rn_last_device_error")
+    return err.value

@@ -1,0 +1,119 @@
+"""GPU parity: rn_pairwise_fwd_bwd (through the C ABI) vs the float64 segmented oracle.
+
+Bars (BASELINE.json north_star): pair counts bit-exact, fp32 loss and gradient within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from oracle import generators as G
+from oracle import seg_ref as S
+from tests.util import check_pairwise, dev, run_pairwise
+
+pytestmark = pytest.mark.gpu
+
+
+def col(v, dt=np.float32):
+    return np.asarray([v], dtype=dt).T
+
+
+def test_reference_known_answers():
+    """tests/rec_block/test_pairwise_loss_from_batch.py:33-74 of the reference, float32 ids."""
+    g, s, y = col([1, 1, 2, 2, 2]), col([0, 1, 2, 3, 4]), col([1.1, 0, 0, 1, 1])
+    out = run_pairwise(s, y, g, S.PairSpec(power=-0.5))
+    assert int(out["n_pair"].item()) == 3
+    assert abs(float(out["loss"].item()) - 0.5415076) < 1e-5
+    out = run_pairwise(s, y, g, S.PairSpec(power=-0.5, rw_pos=np.ones(5, np.float32)))
+    assert abs(float(out["loss"].item()) - 0.5415076) < 1e-5
+    out = run_pairwise(s, y, g, S.PairSpec(power=-0.5), mask=[True, True, False, False, False])
+    assert int(out["n_pair"].item()) == 1
+    assert abs(float(out["loss"].item()) - 1.3132617) < 1e-5
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_cfg1(seed):
+    d = G.cfg1(seed)
+    for ids in (d["g"], d["g_f32"]):
+        out = run_pairwise(d["s"], d["y"], ids)
+        check_pairwise(out, S.pairwise(d["s"], d["y"], ids), ctx=f"cfg1 seed{seed}")
+
+
+SPECS = {
+    "default": dict(),
+    "power": dict(power=-0.5),
+    "power1": dict(power=1.0),
+    "factor": dict(factor=2.5),
+    "sum": dict(reduce_mean=False),
+    "wrong": dict(only_wrong=True),
+    "wrong_power": dict(only_wrong=True, power=-1.0),
+    "diff": dict(label_func="diff"),
+    "diff_rwp_power": dict(label_func="diff", rw_pos="w", power=-0.5),
+    "rwp": dict(rw_pos="w"),
+    "rwn": dict(rw_neg="w"),
+    "diff_rwn_wrong": dict(label_func="diff", rw_neg="w", rw_pos="w2", only_wrong=True, power=0.5),
+}
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+@pytest.mark.parametrize("graded", [False, True])
+def test_options_small(name, graded):
+    rng = np.random.default_rng(hash(name) % 1000 + graded)
+    b = 3000
+    gidx = G.zipf_groups(rng, b, 97)
+    s = rng.standard_normal(b).astype(np.float32) * 2
+    y = (rng.integers(0, 5, b) if graded else (rng.random(b) < 0.3)).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, b).astype(np.float32)
+    w2 = rng.uniform(0.1, 2.0, b).astype(np.float32)
+    w[rng.integers(0, b, 40)] = 0.0           # non-positive factors remove pairs (W > 0 rule)
+    w2[rng.integers(0, b, 10)] = -1.0
+    kw = {k: (w if v == "w" else w2 if v == "w2" else v) for k, v in SPECS[name].items()}
+    spec = S.PairSpec(**kw)
+    mask = rng.random(b) < 0.9 if name in ("power", "diff") else None
+    ids = (gidx.astype(np.int64) * 7919 + 13)
+    out = run_pairwise(s, y, ids, spec, mask=mask)
+    check_pairwise(out, S.pairwise(s, y, ids, spec, mask=mask), ctx=name)
+
+
+def test_multi_key_and_float_ids():
+    rng = np.random.default_rng(5)
+    b = 2048
+    k0 = rng.integers(0, 30, b).astype(np.float32)
+    k1 = rng.integers(0, 3, b).astype(np.float64) - 1.0     # contains -1, 0, 1
+    k0[rng.integers(0, b, 20)] = np.nan
+    k0[rng.integers(0, b, 20)] = np.inf
+    k1[k1 == 0] = np.where(rng.random((k1 == 0).sum()) < 0.5, 0.0, -0.0)
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(0, 3, b).astype(np.float32)
+    spec = S.PairSpec(power=-0.5)
+    out = run_pairwise(s, y, [k0, k1], spec)
+    check_pairwise(out, S.pairwise(s, y, [k0, k1], spec), ctx="multikey")
+
+
+def test_degenerate():
+    # no pair at all -> loss 0, zero gradient, not NaN (PW:13, PW:126)
+    s = np.arange(8, dtype=np.float32)
+    out = run_pairwise(s, np.ones(8, np.float32), np.arange(8, dtype=np.int64))
+    assert int(out["n_pair"].item()) == 0 and float(out["loss"].item()) == 0.0
+    assert not out["dlogits"].cpu().numpy().any()
+    # one row
+    out = run_pairwise(s[:1], np.ones(1, np.float32), np.zeros(1, np.int64))
+    assert int(out["n_pair"].item()) == 0
+    # one big group, all distinct labels: n = B(B-1)/2; extreme logits stay finite
+    b = 777
+    rng = np.random.default_rng(1)
+    s = (rng.standard_normal(b) * 40).astype(np.float32)
+    y = rng.permutation(b).astype(np.float32)
+    ids = np.zeros(b, np.int64)
+    out = run_pairwise(s, y, ids)
+    assert int(out["n_pair"].item()) == b * (b - 1) // 2
+    check_pairwise(out, S.pairwise(s, y, ids), ctx="one-group")
+    # NaN labels pair with nothing
+    y2 = y.copy(); y2[::7] = np.nan
+    out = run_pairwise(s, y2, ids)
+    check_pairwise(out, S.pairwise(s, y2, ids), ctx="nan-labels")
+
+
+def test_cfg2():
+    d = G.cfg2(0)
+    out = run_pairwise(d["s"], d["y"], d["g"])
+    r = check_pairwise(out, S.pairwise(d["s"], d["y"], d["g"]), ctx="cfg2")
+    print("cfg2 parity", r, "n_pair", int(out["n_pair"].item()))
