@@ -36,7 +36,9 @@ def _col(v):
 def unique_with_counts(x):
     """tf.unique_with_counts: (values in first-occurrence order, idx, counts)."""
     x = np.asarray(x).reshape(-1)
-    vals, first, inv, cnt = np.unique(x, return_index=True, return_inverse=True, return_counts=True)
+    # tf.unique hashes with operator==: NaN != NaN, so every NaN is its own value
+    kw = dict(equal_nan=False) if x.dtype.kind == "f" else {}
+    vals, first, inv, cnt = np.unique(x, return_index=True, return_inverse=True, return_counts=True, **kw)
     order = np.argsort(first, kind="stable")           # sorted-unique -> first-occurrence rank
     rank = np.empty_like(order)
     rank[order] = np.arange(order.size)

@@ -167,6 +167,11 @@ struct SegInputs {
 // (keyA,valA) if plan.npass is even else (keyB,valB) -- consumers recompute the plan from ctl.
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, cudaStream_t st);
 int seg_launch_count(const Layout& L);
+// Group bounds of the sorted batch: astart[p] = first sorted position of p's group, gend[astart] = one past
+// its last position, perm[p] = original row; up to 4 float columns are gathered into sorted order.  One launch.
+struct GatherCols { const float* src[4]; float* dst[4]; };
+cudaError_t seg_bounds(const Layout& L, void* scratch, int use_label, u32* astart, u32* gend, u32* perm,
+                       const GatherCols& gc, cudaStream_t st);
 
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 

@@ -193,6 +193,67 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(int pass, int64_t B,
   }
 }
 
+// ---- group bounds (used by the listwise path and by pair materialisation) ----------------------------
+__global__ void __launch_bounds__(1024) k_bounds(u32 B, int gbits, int use_label, const u64* keyA, const u64* keyB,
+                                                 const u32* valA, const u32* valB, u32* __restrict__ astart,
+                                                 u32* __restrict__ gend, u32* __restrict__ perm, GatherCols gc,
+                                                 Ctl* ctl) {
+  const Plan pl = make_plan(ctl->lab_or, ctl->lab_nor, gbits, use_label != 0);
+  const u64* __restrict__ key = (pl.npass & 1) ? keyB : keyA;
+  const u32* __restrict__ val = (pl.npass & 1) ? valB : valA;
+  __shared__ u32 wmax[32];
+  __shared__ u32 carry;
+  const u32 t0 = blockIdx.x * 1024u, p = t0 + threadIdx.x, ln = lane_id(), w = threadIdx.x >> 5;
+  const bool in = p < B;
+  const u32 gid = in ? (u32)(key[p] >> 32) : 0u;
+  const u32 gprev = (in && p > 0) ? (u32)(key[p - 1] >> 32) : ~gid;
+  const u32 gnext = (in && p + 1 < B) ? (u32)(key[p + 1] >> 32) : ~gid;
+  if (w == 0) {
+    // warp-cooperative 32-ary lower bound of the group id at the tile start over [0, t0]
+    const u32 g0 = (u32)(key[t0] >> 32);
+    u32 lo = 0, hi = t0;                 // answer in [lo, hi]; key[hi] has gid == g0
+    while (hi - lo > 0) {
+      const u32 span = hi - lo, step = (span + 30) / 31;     // lane 31 always probes hi
+      const u32 q = lo + min(ln * step, span);
+      const bool ge = (u32)(key[q] >> 32) >= g0;
+      const u32 bal = __ballot_sync(0xFFFFFFFFu, ge);
+      const u32 f = __ffs(bal) - 1;      // first probe that is >= g0 (exists: lane hitting hi or beyond)
+      const u32 nhi = lo + min(f * step, span);
+      const u32 nlo = f ? lo + min((f - 1) * step, span) + 1 : lo;
+      hi = nhi; lo = min(nlo, nhi);
+    }
+    if (ln == 0) carry = lo;
+  }
+  u32 x = (in && gid != gprev) ? p + 1 : 0u;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, x, o); if (ln >= (u32)o) x = max(x, t); }
+  if (ln == 31) wmax[w] = x;
+  __syncthreads();
+  u32 c = 0;
+  for (u32 k = 0; k < w; ++k) c = max(c, wmax[k]);
+  x = max(x, c);
+  if (in) {
+    const u32 a = x ? x - 1 : carry;
+    astart[p] = a;
+    if (gid != gnext) gend[a] = p + 1;
+    const u32 row = val[p];
+    perm[p] = row;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (gc.src[k]) gc.dst[k][p] = gc.src[k][row];
+  }
+}
+
+cudaError_t seg_bounds(const Layout& L, void* scratch, int use_label, u32* astart, u32* gend, u32* perm,
+                       const GatherCols& gc, cudaStream_t st) {
+  char* base = static_cast<char*>(scratch);
+  k_bounds<<<(unsigned)((L.B + 1023) / 1024), 1024, 0, st>>>((u32)L.B, L.gbits, use_label, at<u64>(base, L.keyA),
+                                                            at<u64>(base, L.keyB), at<u32>(base, L.valA),
+                                                            at<u32>(base, L.valB), astart, gend, perm, gc,
+                                                            at<Ctl>(base, L.ctl));
+  return cudaGetLastError();
+}
+
 int seg_launch_count(const Layout& L) { return 3 + max_label_passes() + group_passes(L.gbits); }
 
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, cudaStream_t st) {

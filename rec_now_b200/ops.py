@@ -100,3 +100,101 @@ def device_error(scratch: torch.Tensor) -> int:
     err = C.c_int32(0)
     check(lib().rn_last_device_error(scratch.data_ptr(), C.byref(err), _stream()), "rn_last_device_error")
     return err.value
+
+
+def _pair_args(s, y, keys, ok, rwp, rwn, label_func, only_wrong, factor=1.0, power=0.0, reduce_mean=True):
+    b = s.numel()
+    return PairwiseArgs(
+        B=b, K=keys.shape[0], label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
+        keys=keys.data_ptr(), logits=s.data_ptr(), labels=y.data_ptr(),
+        row_ok=_ptr(ok), rw_pos=_ptr(rwp), rw_neg=_ptr(rwn), factor=float(factor), power=float(power),
+        only_wrong=int(bool(only_wrong)), reduce_mean=int(bool(reduce_mean)), part_rank=0, part_count=1,
+        loss=None, n_pair_f32=None, n_pair=None, dlogits=None, row_pairs=None)
+
+
+def pair_indices(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
+                 only_wrong=False, label_cond=True, want_weights=False):
+    """rn_pair_indices_count + _fill: (pos_idx int32[P], neg_idx int32[P], w f32[P] or None) in the reference's
+    row-major pair order (PW:217).  Synchronises once (P is data dependent).  label_cond=False lists every
+    same-group ordered pair i != j."""
+    _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
+    s, y = _f32(logits), _f32(labels)
+    b = s.numel()
+    keys = keys.reshape(-1, b).contiguous()
+    dev = s.device
+    rwp, rwn = _f32(rw_pos), _f32(rw_neg)
+    ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    nbytes = lib().rn_pair_indices_scratch_bytes(b, keys.shape[0])
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a = _pair_args(s, y, keys, ok, rwp, rwn, label_func, only_wrong)
+    n = C.c_int64(0)
+    with torch.cuda.device(dev):
+        check(lib().rn_pair_indices_count(C.byref(a), int(bool(label_cond)), scratch.data_ptr(), nbytes,
+                                          C.byref(n), _stream()), "rn_pair_indices_count")
+        p = n.value
+        pos = torch.empty(p, dtype=torch.int32, device=dev)
+        neg = torch.empty(p, dtype=torch.int32, device=dev)
+        w = torch.empty(p, dtype=torch.float32, device=dev) if want_weights else None
+        check(lib().rn_pair_indices_fill(C.byref(a), int(bool(label_cond)), scratch.data_ptr(), nbytes,
+                                         pos.data_ptr(), neg.data_ptr(), _ptr(w), p, _stream()),
+              "rn_pair_indices_fill")
+    return pos, neg, w
+
+
+def occurrence_power_weight(ids: torch.Tensor, power: float) -> torch.Tensor:
+    """rn_occurrence_power_weight on canonical int64 ids."""
+    _need_cuda(ids)
+    ids = ids.reshape(-1).to(torch.int64).contiguous()
+    n = ids.numel()
+    out = torch.empty(n, dtype=torch.float32, device=ids.device)
+    if n == 0:
+        return out
+    nbytes = lib().rn_occurrence_scratch_bytes(n)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=ids.device)
+    with torch.cuda.device(ids.device):
+        check(lib().rn_occurrence_power_weight(ids.data_ptr(), n, float(power), out.data_ptr(),
+                                               scratch.data_ptr(), nbytes, _stream()), "rn_occurrence_power_weight")
+    return out
+
+
+def listwise_fwd_bwd(keys, labels, logits, row_ok=None, list_w=None, pos_neg_th=0.5, do_reduce=True,
+                     want_list_loss=False):
+    """rn_listwise_fwd_bwd.  keys: canonical int64 [B].  Returns dict of device tensors (+ the scratch arena
+    and args needed by listwise_dense)."""
+    _need_cuda(keys, labels, logits, row_ok, list_w)
+    s, y = _f32(logits), _f32(labels)
+    b = s.numel()
+    keys = keys.reshape(-1).to(torch.int64).contiguous()
+    dev = s.device
+    ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    lw = _f32(list_w)
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+    counts = torch.empty(8, dtype=torch.int32, device=dev)          # [0] n_valid, [4] n_group (16 B apart)
+    dlogits = torch.empty(b, dtype=torch.float32, device=dev)
+    list_loss = torch.empty(b, dtype=torch.float32, device=dev) if (want_list_loss or not do_reduce) else None
+    nbytes = lib().rn_listwise_scratch_bytes(b)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    a = ListwiseArgs(B=b, keys=keys.data_ptr(), row_ok=_ptr(ok), labels=y.data_ptr(), logits=s.data_ptr(),
+                     list_w=_ptr(lw), pos_neg_th=float(pos_neg_th), do_reduce=int(bool(do_reduce)),
+                     loss=loss.data_ptr(), list_loss=_ptr(list_loss), n_valid=counts.data_ptr(),
+                     n_group=counts.data_ptr() + 16, dlogits=dlogits.data_ptr())
+    with torch.cuda.device(dev):
+        check(lib().rn_listwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, _stream()), "rn_listwise_fwd_bwd")
+    return dict(loss=loss[0], n_valid=counts[0], n_group=counts[4], dlogits=dlogits, list_loss=list_loss,
+                _scratch=scratch, _args=a, _keep=(keys, ok, lw, y, s))
+
+
+def listwise_dense(fwd: dict, n_valid: int, do_mask_logits=True, value_of_masked_logit=-1e9):
+    """rn_listwise_dense: the (V,B) dense_mask / dense_labels / dense_logits of to_listwise_sample (LW:142-145)."""
+    a = fwd["_args"]
+    b = int(a.B)
+    dev = fwd["dlogits"].device
+    dm = torch.empty((n_valid, b), dtype=torch.bool, device=dev)
+    dl = torch.empty((n_valid, b), dtype=torch.float32, device=dev)
+    dz = torch.empty((n_valid, b), dtype=torch.float32, device=dev)
+    scratch = fwd["_scratch"]
+    with torch.cuda.device(dev):
+        check(lib().rn_listwise_dense(C.byref(a), scratch.data_ptr(), scratch.numel(), n_valid, dm.data_ptr(),
+                                      dl.data_ptr(), dz.data_ptr(), int(bool(do_mask_logits)),
+                                      float(value_of_masked_logit), _stream()), "rn_listwise_dense")
+    return dm, dl, dz

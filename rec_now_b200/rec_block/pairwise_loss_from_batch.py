@@ -1,0 +1,229 @@
+"""Drop-in for rec_now/rec_block/pairwise_loss_from_batch.py of the reference, on torch CUDA tensors.
+
+Same public names, positional order, defaults and return arity as the reference
+(/root/reference/rec_now/rec_block/pairwise_loss_from_batch.py, cited below as PW:n); the dense (B,B)
+TensorFlow graph is replaced by librecnow_b200.so (segmentation + fused pair kernels, sm_100a).
+
+Dispatch of ``pairwise_loss`` (PW:228-279):
+  * fused path  -- ``pairloss_func`` is ``bpr_loss_func`` or a ``functools.partial`` of it, and
+    ``label_pair_to_weight_func`` is None or a :class:`FusedPairWeight`: one C-ABI call computes loss, n_pair
+    and d loss / d outputs; autograd just scales the saved gradient.
+  * general path -- any other callable (e.g. the wrapper the reference's own test uses, tests/rec_block/
+    test_pairwise_loss_from_batch.py:38-39): pairs are materialised on the GPU in the reference's row-major
+    order (rn_pair_indices_*), the caller's functions run on the gathered pair vectors, torch autograd does the
+    rest.  An arbitrary ``label_pair_to_weight_func`` must be elementwise in its two label arguments (the
+    documented contract, PW:180-182); tensor kwargs shaped (B,1)/(B,) follow the positive side, (1,B) the
+    negative side.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Callable, Optional
+
+import torch
+
+from .. import ops
+
+SMALL_POSIVITE_FLOAT = 1.0E-10      # (sic) PW:13
+
+
+# --------------------------------------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------------------------------------
+def _as_cuda(x, dtype=None) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("rec_now_b200 needs CUDA tensors (there is no CPU fallback)")
+        return x if dtype is None else x.to(dtype)
+    return torch.as_tensor(x, dtype=dtype, device="cuda")
+
+
+def _generate_pair_mask(sample_group_idx_var, only_upper_band=False):
+    """PW:16-40 (dense compat helper)."""
+    g = _as_cuda(sample_group_idx_var).reshape(-1, 1)
+    n = g.numel()
+    same = ((g - g.t()) == 0.0).to(torch.float32)
+    m = (same - torch.eye(n, device=g.device)).to(torch.bool)
+    if only_upper_band:
+        m = torch.triu(m, 0) & torch.tril(m, 1)          # band_part(., 0, 1)
+    return m
+
+
+def generate_pair_mask(group_tensor_or_list, only_upper_band=False):
+    """PW:43-74.  Dense (B,B) bool mask -- compat helper; pairwise_loss itself never builds it."""
+    if not isinstance(group_tensor_or_list, list):
+        group_tensor_or_list = [group_tensor_or_list]
+    pair_mask = None
+    for group in group_tensor_or_list:
+        one = _generate_pair_mask(group, only_upper_band)
+        pair_mask = one if pair_mask is None else torch.logical_and(pair_mask, one)
+    return pair_mask
+
+
+def vec_to_matrix_pair(vec):
+    """PW:77-93 (dense compat helper): mat[i,j] = v_i, mat_T[i,j] = v_j."""
+    v = _as_cuda(vec).reshape(-1, 1)
+    mat = v.expand(-1, v.numel())
+    return mat, mat.t()
+
+
+def bpr_loss_func(outputs_pos, outputs_neg, weights=None, factor=1.0, reduce_mean=True):
+    """PW:96-127 on explicit pair vectors (used by the general path and by user wrappers)."""
+    logits = outputs_pos - outputs_neg
+    if factor != 1.0:
+        logits = logits * factor
+    # sigmoid_cross_entropy_with_logits(labels=1): max(x,0) - x + log1p(exp(-|x|))
+    losses = torch.clamp(logits, min=0) - logits + torch.log1p(torch.exp(-torch.abs(logits)))
+    if weights is not None:
+        losses = losses * weights
+    loss = torch.sum(losses)
+    if reduce_mean:
+        loss = loss / (float(losses.numel()) + SMALL_POSIVITE_FLOAT)
+    return loss
+
+
+def occurance_power_weight(group_id, power=0.0):
+    """PW:130-151: count(group_id == group_id[i]) ** power, float32."""
+    g = _as_cuda(group_id)
+    keys, ok = ops.canon_keys(g)
+    k0 = keys[0]
+    if ok is not None:
+        # NaN/inf ids equal nothing (each is its own group): give them distinct keys in the NaN-payload range,
+        # which no canonical finite key can take
+        uniq = torch.arange(k0.numel(), device=k0.device, dtype=torch.int64) + 0x7FF8000000000000
+        k0 = torch.where(ok.bool(), k0, uniq)
+    return ops.occurrence_power_weight(k0, float(power)).reshape(g.shape)
+
+
+class FusedPairWeight:
+    """A ``label_pair_to_weight_func`` the fused kernel understands.
+
+    ``W[i,j] = phi(y_i, y_j) * kwargs[pos_kw][i] * kwargs[neg_kw][j]`` with ``phi`` = ``[y_i > y_j]`` ("step")
+    or ``(y_i - y_j) * [y_i > y_j]`` ("diff").  It is also a plain callable with the reference's contract
+    (label_matrix, label_matrix_transpose, **kwargs) -> weights, so the same object works with the reference.
+    """
+
+    def __init__(self, label_func: str = "step", pos_kw: Optional[str] = None, neg_kw: Optional[str] = None):
+        if label_func not in ("step", "diff"):
+            raise ValueError("label_func must be 'step' or 'diff'")
+        self.label_func, self.pos_kw, self.neg_kw = label_func, pos_kw, neg_kw
+
+    def __call__(self, label_matrix, label_matrix_transpose, **kwargs):
+        gt = (label_matrix > label_matrix_transpose).to(torch.float32)
+        w = (label_matrix - label_matrix_transpose) * gt if self.label_func == "diff" else gt
+        if self.pos_kw is not None:
+            w = w * kwargs[self.pos_kw].reshape(-1, 1)
+        if self.neg_kw is not None:
+            w = w * kwargs[self.neg_kw].reshape(1, -1)
+        return w
+
+
+#: cfg3 of BASELINE.json: W = (y_i - y_j) * [y_i > y_j] * sample_weight_i
+label_gain_times_sample_weight = FusedPairWeight("diff", pos_kw="sample_weight")
+
+
+class _FusedPairwiseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor, reduce_mean,
+                only_wrong, power):
+        out = ops.pairwise_fwd_bwd(outputs, labels, keys, row_ok=row_ok, rw_pos=rw_pos, rw_neg=rw_neg,
+                                   label_func=label_func, factor=factor, power=power, only_wrong=only_wrong,
+                                   reduce_mean=reduce_mean)
+        ctx.save_for_backward(out["dlogits"])
+        ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
+        n_pair = out["n_pair_f32"]
+        ctx.mark_non_differentiable(n_pair)
+        return out["loss"], n_pair
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_n):
+        (dlogits,) = ctx.saved_tensors
+        g = (g_loss * dlogits).reshape(ctx.out_shape).to(ctx.out_dtype)
+        return (g,) + (None,) * 10
+
+
+def _match_bpr(pairloss_func) -> Optional[tuple]:
+    """(factor, reduce_mean) if pairloss_func is bpr_loss_func or a keyword-only partial of it."""
+    if pairloss_func is bpr_loss_func:
+        return 1.0, True
+    if isinstance(pairloss_func, functools.partial) and pairloss_func.func is bpr_loss_func and not pairloss_func.args:
+        kw = dict(pairloss_func.keywords)
+        if set(kw) <= {"factor", "reduce_mean"}:
+            return float(kw.get("factor", 1.0)), bool(kw.get("reduce_mean", True))
+    return None
+
+
+def _gather_kwargs(kwargs: dict, b: int, pos: torch.Tensor, neg: torch.Tensor) -> dict:
+    out = {}
+    for k, v in kwargs.items():
+        if isinstance(v, torch.Tensor) and v.numel() == b and b > 1:
+            out[k] = v.reshape(-1)[neg] if (v.dim() == 2 and v.shape[0] == 1) else v.reshape(-1)[pos]
+        else:
+            out[k] = v
+    return out
+
+
+def pairwise_loss(outputs, labels, groups,
+                  pairloss_func=bpr_loss_func,
+                  only_use_wrong_order_pair=False,
+                  return_num_pair=False,
+                  click_occurance_power=0.0,
+                  mask=None,
+                  label_pair_to_weight_func=None,
+                  **kwargs
+                  ):
+    """PW:228-279.  Same arguments and return values as the reference."""
+    outputs = _as_cuda(outputs)
+    labels = _as_cuda(labels)
+    group_list = [_as_cuda(g) for g in groups] if isinstance(groups, list) else [_as_cuda(groups)]
+    b = outputs.numel()
+    mask_t = None if mask is None else _as_cuda(mask).reshape(-1).to(torch.bool)
+    keys, row_ok = ops.canon_keys(group_list, mask_t)
+    fused_w = label_pair_to_weight_func if isinstance(label_pair_to_weight_func, FusedPairWeight) else None
+    rw_pos = rw_neg = None
+    label_func = "step"
+    if fused_w is not None:
+        label_func = fused_w.label_func
+        rw_pos = None if fused_w.pos_kw is None else _as_cuda(kwargs[fused_w.pos_kw])
+        rw_neg = None if fused_w.neg_kw is None else _as_cuda(kwargs[fused_w.neg_kw])
+        if fused_w.label_func == "step" and rw_pos is None and rw_neg is None:
+            # W = [y_i > y_j], C = W > 0: identical to the default; keep the weight-free kernel
+            fused_w = None
+    bpr = _match_bpr(pairloss_func)
+    power = float(click_occurance_power)
+
+    if bpr is not None and (label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight)):
+        factor, reduce_mean = bpr
+        loss, n_pair = _FusedPairwiseLoss.apply(outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor,
+                                                reduce_mean, bool(only_use_wrong_order_pair), power)
+        return (loss, n_pair) if return_num_pair else loss
+
+    # ---- general path: materialised pairs + the caller's callables ------------------------------------
+    flat_out = outputs.reshape(-1)
+    if label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight):
+        want_w = isinstance(label_pair_to_weight_func, FusedPairWeight)
+        pos, neg, w = ops.pair_indices(outputs, labels, keys, row_ok=row_ok, rw_pos=rw_pos, rw_neg=rw_neg,
+                                       label_func=label_func, only_wrong=only_use_wrong_order_pair,
+                                       label_cond=True, want_weights=want_w)
+        pos, neg = pos.long(), neg.long()
+        weights = w
+    else:
+        pos, neg, _ = ops.pair_indices(outputs, labels, keys, row_ok=row_ok, label_cond=False)
+        pos, neg = pos.long(), neg.long()
+        flat_y = labels.reshape(-1).to(torch.float32)
+        wmat = label_pair_to_weight_func(flat_y[pos], flat_y[neg], **_gather_kwargs(kwargs, b, pos, neg))  # PW:192
+        keep = wmat > 0                                                                                   # PW:193
+        if only_use_wrong_order_pair:
+            keep = keep & (flat_out.detach()[pos] < flat_out.detach()[neg])                               # PW:200-202
+        pos, neg, weights = pos[keep], neg[keep], wmat[keep].to(torch.float32)
+    if power != 0.0:                                                                                      # PW:285-290
+        occ = ops.occurrence_power_weight(keys[0][pos], power) if pos.numel() else torch.empty(0, device=outputs.device)
+        weights = occ if weights is None else weights * occ
+    if weights is not None:
+        weights = weights.detach()                                                                        # PW:270
+    outputs_pos, outputs_neg = flat_out[pos], flat_out[neg]                                               # PW:272-273
+    loss = pairloss_func(outputs_pos, outputs_neg, weights)                                               # PW:274
+    if return_num_pair:
+        return loss, torch.tensor(float(pos.numel()), dtype=torch.float32, device=outputs.device)          # PW:276
+    return loss
