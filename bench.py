@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- in-batch pairwise ranking loss, forward + backward, on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): in-batch pairwise loss fwd+bwd throughput at B = 65536 rows per GPU, reported as
+pairs/s (kept ordered pairs scored per second; `value`) and samples/s (`samples_per_s`).
+  N = 1 : cfg3  -- 65536 rows, 4096 Zipf groups, graded labels 0-4, W_ij = (y_i-y_j)[y_i>y_j] w_i,
+          click_occurance_power = -0.5  (the largest single-GPU configuration of BASELINE.json).
+  N > 1 : cfg5  -- global in-batch mode, 65536 rows per GPU all-gathered over NVLink, same options
+          (weak scaling: per-GPU rows fixed; pairs grow with the global batch).
+A "step" is one full pass of the hot path over one batch: segmentation + pair kernel + finalisation
+(+ all-gather / reduce-scatter for N > 1), producing loss, n_pair and d loss / d logits.
+
+`value` is timed with inputs resident in HBM; `e2e` goes through the public drop-in API
+(rec_now_b200.rec_block.pairwise_loss_from_batch.pairwise_loss + backward) with pinned HOST buffers, H2D and
+D2H copies inside the timed region.  `--impl reference` times the reference's dense (B,B) algorithm on the host
+cores (torch-CPU op-for-op restatement from oracle/torch_dense.py -- TensorFlow is not in this image) on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS_PER_GPU = 65536
+NOMINAL_MUFU_PER_S = 148 * 16 * 1.965e9          # 148 SMs x 16 SFU lanes x max SM clock
+MUFU_PER_PAIR = 3                                # ex2 + lg2 + rcp  (algorithmic work per kept pair)
+HBM_BYTES_PER_SAMPLE = 24                        # g 8 + s 4 + y 4 + w 4 read, dlogits 4 written (cfg3)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs in a thread during warm-up + timed region
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting"}
+
+    def __init__(self, index: int):
+        self.samples, self.mask, self.sm_max, self._stop = [], 0, None, threading.Event()
+        self.timed = [None, None]
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._run, daemon=True)
+            self.t.start()
+        except Exception as e:          # NVML missing: report that, do not fake numbers
+            self.nv = None
+            self.err = repr(e)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, r))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": self.err}
+        self._stop.set()
+        self.t.join(timeout=1)
+        t0, t1 = self.timed
+        inside = [s for s in self.samples if t0 is not None and t0 <= s[0] <= t1] or self.samples[-5:]
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = [n for b, n in self.REASONS.items() if mask & b]
+        return {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
+                "sm_max_mhz": float(self.sm_max), "reasons": reasons, "samples": len(inside)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------
+def make_workload(world: int):
+    from oracle import generators as G        # generators only (pure numpy); nothing of the oracle is timed here
+    d = G.cfg3(0) if world == 1 else G.cfg5(world, 0)
+    name = ("cfg3: pairwise B=65536, 4096 Zipf groups, graded labels 0-4, W=(yi-yj)[yi>yj]*w_i, power=-0.5"
+            if world == 1 else
+            f"cfg5: global in-batch pairwise, {ROWS_PER_GPU} rows/GPU x {world} GPUs, {4096 * world} Zipf groups, "
+            "graded labels, W=(yi-yj)[yi>yj]*w_i, power=-0.5")
+    return d, name
+
+
+# ----------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: dense (B,B) algorithm on the host cores
+# ----------------------------------------------------------------------------------------------------------
+def cpu_dense_step_fn(d, rows):
+    import torch
+    from oracle import torch_dense as T
+    s = torch.tensor(d["s"][:rows]); y = torch.tensor(d["y"][:rows])
+    g = torch.tensor(d["g"][:rows]).to(torch.float64)       # float ids, as the reference requires (PW:35)
+    w = torch.tensor(d["w"][:rows]).reshape(-1, 1)
+    wf = lambda a, b, sample_weight: (a - b) * (a > b).to(torch.float32) * sample_weight
+
+    def step():
+        loss, n, grad = T.pairwise_fwd_bwd(s, y, g, power=-0.5, weight_func=wf, sample_weight=w)
+        return loss, n
+    return step
+
+
+def pick_cpu_rows(d, budget_s, steps):
+    """Largest power-of-two sample whose (steps) dense fwd+bwd passes fit the time budget (cost ~ rows^2)."""
+    step = cpu_dense_step_fn(d, 1024)
+    step()
+    t = time.perf_counter(); step(); t1k = time.perf_counter() - t
+    rows = 1024
+    while rows < 8192 and t1k * ((2 * rows) / 1024) ** 2 * steps <= budget_s:
+        rows *= 2
+    return rows
+
+
+def run_cpu_dense(d, steps, warmup, budget_s):
+    import torch
+    rows = pick_cpu_rows(d, budget_s, steps + warmup)
+    step = cpu_dense_step_fn(d, rows)
+    for _ in range(warmup):
+        step()
+    t = time.perf_counter()
+    n = 0
+    for _ in range(steps):
+        _, n = step()
+    dt = time.perf_counter() - t
+    return dict(rows=rows, n_pair=n, sec_per_step=dt / steps, pairs_per_s=n * steps / dt,
+                samples_per_s=rows * steps / dt, cores=torch.get_num_threads())
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, name = make_workload(max(1, args.gpus))
+    r = run_cpu_dense(d, args.steps, args.warmup, budget_s=150.0)
+    sample = (f"first {r['rows']} rows of the workload batch, dense (B,B) fwd+bwd (the reference algorithm needs "
+              f">= 36*B^2 bytes: B=65536 is infeasible), {r['n_pair']} pairs/step")
+    line = {
+        "impl": "reference", "metric": "pairwise_loss_fwd_bwd_pairs_per_s", "value": r["pairs_per_s"],
+        "unit": "pairs/s", "samples_per_s": r["samples_per_s"], "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded Zipf groups)",
+        "config": {"workload": name, "device": "host CPU", "implementation":
+                   "op-for-op torch-CPU float32 restatement of the reference's dense TF graph (TensorFlow absent)"},
+        "cpu_baseline": {"value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": r["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    from rec_now_b200 import _lib, global_mode, ops
+    from rec_now_b200.rec_block import pairwise_loss_from_batch as PW
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != max(1, args.gpus):
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    K, W = args.steps, max(3, args.warmup)
+
+    d, name = make_workload(world)
+    lo, hi = rank * ROWS_PER_GPU, (rank + 1) * ROWS_PER_GPU
+    host = {k: np.ascontiguousarray(d[k][lo:hi]) for k in ("g", "s", "y", "w")}
+    s, y, w = (torch.tensor(host[k], device=dev) for k in ("s", "y", "w"))
+    keys = torch.tensor(host["g"], device=dev).reshape(1, -1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def step():
+        if world == 1:
+            return ops.pairwise_fwd_bwd(s, y, keys, rw_pos=w, label_func="diff", power=-0.5)
+        return global_mode.global_pairwise_fwd_bwd(s, y, keys, rw_pos=w, label_func="diff", power=-0.5)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- clock ramp + measured SFU peak (same run, same clocks) ---------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    sink = torch.zeros(4, dtype=torch.float32, device=dev)
+    nops = C.c_int64(0)
+    t_end = time.perf_counter() + 0.4
+    while time.perf_counter() < t_end:
+        lib.rn_bench_mufu(2000, sink.data_ptr(), C.byref(nops), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 0.0
+    for _ in range(5):
+        e0.record()
+        lib.rn_bench_mufu(4000, sink.data_ptr(), C.byref(nops), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        e1.record(); torch.cuda.synchronize()
+        best = max(best, nops.value / (e0.elapsed_time(e1) * 1e-3))
+    mufu_peak = best
+
+    # ---- warm-up, then the timed region (per-step events, L2 flushed between steps) --------------------
+    for _ in range(W):
+        out = step()
+    barrier()
+    lib.rn_profile_enable(K)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    if sampler:
+        sampler.timed[0] = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xFF)
+        evs[k][0].record()
+        out = step()
+        evs[k][1].record()
+    barrier()
+    if sampler:
+        sampler.timed[1] = time.perf_counter()
+    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    ms = (C.c_float * K)(); nget = C.c_int32(0)
+    lib.rn_profile_collect(ms, K, C.byref(nget))
+    lib.rn_profile_disable()
+    pair_ms = float(np.mean(list(ms)[:nget.value])) if nget.value else float("nan")
+    n_pair = int(out["n_pair"].item())
+    err = ops.device_error(out["_scratch"]) if world == 1 else 0
+
+    # ---- e2e through the public API: pinned host buffers, H2D + loss.backward() + D2H every step -------
+    pin = {k: torch.tensor(host[k]).pin_memory() for k in ("g", "s", "y", "w")}
+    dbuf = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}
+    h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
+    h_grad = torch.empty(ROWS_PER_GPU, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for k in dbuf:
+            dbuf[k].copy_(pin[k], non_blocking=True)
+        logits = dbuf["s"].requires_grad_(True)
+        if world == 1:
+            loss = PW.pairwise_loss(logits, dbuf["y"], dbuf["g"], click_occurance_power=-0.5,
+                                    label_pair_to_weight_func=PW.label_gain_times_sample_weight,
+                                    sample_weight=dbuf["w"])
+        else:
+            loss = global_mode.global_pairwise_loss(logits, dbuf["y"], dbuf["g"], click_occurance_power=-0.5,
+                                                    label_pair_to_weight_func=PW.label_gain_times_sample_weight,
+                                                    sample_weight=dbuf["w"])
+        loss.backward()
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+        h_grad.copy_(logits.grad, non_blocking=True)
+        logits.grad = None
+        dbuf["s"].requires_grad_(False)
+
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        e2e_step()
+    b.record()
+    barrier()
+    e2e_ms = a.elapsed_time(b)
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = h_loss.numel() * 4 + h_grad.numel() * 4
+
+    # ---- max over ranks ------------------------------------------------------------------------------
+    times = torch.tensor([t_ms, e2e_ms, pair_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    t_ms, e2e_ms, pair_ms = (float(x) for x in times.tolist())
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        clocks = sampler.summary()
+        value = n_pair * K / (t_ms * 1e-3)
+        rows_total = ROWS_PER_GPU * world
+        # roofline of the dominant kernel (k_pair): SFU-bound -- 3 MUFU per kept pair; this rank scored 1/world
+        # of the pairs per launch
+        pairs_per_launch = n_pair / world
+        achieved = MUFU_PER_PAIR * pairs_per_launch / (pair_ms * 1e-3)
+        line = {
+            "metric": "pairwise_loss_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s",
+            "samples_per_s": rows_total * K / (t_ms * 1e-3), "n_pair_per_step": n_pair,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded Zipf groups)",
+            "config": {"workload": name, "rows_per_gpu": ROWS_PER_GPU, "seed": 0,
+                       "l2": "flushed between timed steps (256 MiB write); inputs ~1.6 MB/GPU",
+                       "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks",
+                       "multi_gpu": None if world == 1 else "all-gather rows (NCCL) -> replicated segmentation -> "
+                                    "even tile split -> reduce-scatter grads + all-reduce loss"},
+            "roofline": {"bound": "sfu", "kernel": "k_pair", "achieved": achieved / 1e9, "peak": mufu_peak / 1e9,
+                         "unit": "GMUFU/s", "frac": achieved / mufu_peak,
+                         "peak_source": "measured in this run (rn_bench_mufu ex2/lg2/rcp chains)",
+                         "nominal_peak": NOMINAL_MUFU_PER_S / 1e9, "frac_of_nominal": achieved / NOMINAL_MUFU_PER_S,
+                         "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / (t_ms / K),
+                         "algorithmic_mufu_per_pair": MUFU_PER_PAIR, "pairs_per_launch": pairs_per_launch,
+                         "traffic": None,
+                         "hbm_view": {"bound": "hbm", "achieved": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9,
+                                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peak_src,
+                                      "frac": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
+            "e2e": {"value": n_pair * K / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms / K,
+                    "samples_per_s": rows_total * K / (e2e_ms * 1e-3),
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "rec_block.pairwise_loss_from_batch.pairwise_loss + backward" if world == 1
+                           else "global_mode.global_pairwise_loss + backward"},
+            "gpu_launches": int(lib.rn_pairwise_launch_count(rows_total, 1)) * K,
+            "clocks": clocks, "device_error": err,
+        }
+        if world == 1 and not args.no_cpu:
+            r = run_cpu_dense(d, steps=3, warmup=1, budget_s=25.0)
+            line["cpu_baseline"] = {
+                "value": r["pairs_per_s"], "unit": "pairs/s", "cores": r["cores"], "kind": "port",
+                "samples_per_s": r["samples_per_s"],
+                "sample": f"first {r['rows']} rows of the cfg3 batch through the dense (B,B) torch-CPU restatement of "
+                          f"the reference (fwd+bwd, {r['n_pair']} pairs/step, {r['sec_per_step']:.2f} s/step); the "
+                          "full B=65536 needs >= 155 GB of dense temporaries"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

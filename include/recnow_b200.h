@@ -143,6 +143,13 @@ int rn_listwise_dense(const rn_listwise_args* args, void* scratch, size_t scratc
 /* Issues iters*3 MUFU ops (ex2, lg2, rcp) per thread on a full grid; used by bench.py to MEASURE the SFU
  * peak the pair kernel is normalised against.  mufu_ops_out_host receives the op count issued. */
 int rn_bench_mufu(int32_t iters, float* sink, int64_t* mufu_ops_out_host, void* stream);
+/* Per-kernel timing of the dominant (pair) kernel, for the roofline line of bench.py: while enabled, every
+ * rn_pairwise_fwd_bwd call brackets its pair-kernel launch with a cudaEvent pair on `stream` (up to max_calls
+ * calls).  rn_profile_collect synchronises those events and returns the elapsed milliseconds per call.
+ * Measurement aid only (process-global, not thread-safe, not for use under graph capture). */
+int rn_profile_enable(int32_t max_calls);
+int rn_profile_collect(float* ms_out_host, int32_t capacity, int32_t* n_out_host);
+int rn_profile_disable(void);
 /* Device-side status word of the last call that used `scratch` (0 = ok); reads it back (synchronises). */
 int rn_last_device_error(void* scratch, int32_t* err_host, void* stream);
 /* Stage timing breakdown helper: number of kernel launches the last-built pipeline enqueues per call. */

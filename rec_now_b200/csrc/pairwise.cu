@@ -352,6 +352,34 @@ static cudaError_t dispatch_pair(int mode, const PairParams& P, const Layout& L,
 
 using namespace rn;
 
+// ---- pair-kernel timing (measurement aid, see recnow_b200.h) ------------------------------------------
+static struct { bool on = false; int cap = 0; int n = 0; cudaEvent_t* ev = nullptr; } g_prof;
+
+extern "C" int rn_profile_disable(void) {
+  if (g_prof.ev) { for (int i = 0; i < 2 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]); delete[] g_prof.ev; }
+  g_prof.ev = nullptr; g_prof.on = false; g_prof.cap = g_prof.n = 0;
+  return RN_OK;
+}
+extern "C" int rn_profile_enable(int32_t max_calls) {
+  rn_profile_disable();
+  if (max_calls <= 0 || max_calls > (1 << 20)) return RN_ERR_ARG;
+  g_prof.ev = new cudaEvent_t[2 * max_calls];
+  for (int i = 0; i < 2 * max_calls; ++i)
+    if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return RN_ERR_LAUNCH;
+  g_prof.cap = max_calls; g_prof.n = 0; g_prof.on = true;
+  return RN_OK;
+}
+extern "C" int rn_profile_collect(float* ms_out_host, int32_t capacity, int32_t* n_out_host) {
+  if (!ms_out_host || !n_out_host) return RN_ERR_ARG;
+  int n = g_prof.n < capacity ? g_prof.n : capacity;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(g_prof.ev[2 * i + 1]) != cudaSuccess) return RN_ERR_LAUNCH;
+    if (cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) != cudaSuccess) return RN_ERR_LAUNCH;
+  }
+  *n_out_host = n; g_prof.n = 0;
+  return RN_OK;
+}
+
 extern "C" size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K) {
   if (B <= 0 || K <= 0) return 0;
   return make_layout(B, K).total;
@@ -404,7 +432,10 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
+  const bool prof = g_prof.on && g_prof.n < g_prof.cap;
+  if (prof) cudaEventRecord(g_prof.ev[2 * g_prof.n], st);
   if (dispatch_pair(mode, P, L, base, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  if (prof) { cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st); ++g_prof.n; }
   const u32* slotp = (a->K > 1) ? at<u32>(base, L.slot1) : at<u32>(base, L.slot);
   const u32 g256 = (u32)((a->B + 255) / 256);
   k_fin_counts<<<g256, 256, 0, st>>>(P, at<u32>(base, L.valA), at<u32>(base, L.valB), at<uint2>(base, L.aj),

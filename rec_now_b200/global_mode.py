@@ -1,0 +1,112 @@
+"""Multi-GPU "global in-batch" pairwise loss (BASELINE.json north_star item 4).
+
+Semantics: ``pairwise_loss`` evaluated on the concatenation of all ranks' rows (rank order = row order).  The
+reference has no multi-GPU mode; this is the data-parallel extension the north star defines.
+
+One process per GPU.  Per step and rank:
+  1. all-gather the compact rows (group key(s) int64, logit f32, label f32 [, weight f32]) over NCCL/NVLink;
+  2. every rank segments the SAME global rows (replicated, deterministic) -> pair counts n and c_h are
+     globally consistent without communication;
+  3. the pair space (32x32 micro-tile work units of the sorted batch) is split evenly across ranks
+     (rn_pairwise_args.part_rank/part_count); each rank scores its share and accumulates partial
+     d loss / d logits for ALL global rows, already scaled by the global 1/n and occurrence weights;
+  4. reduce-scatter(sum) returns every rank the gradient of its own rows; the scalar loss is all-reduced.
+The even tile split (instead of "positive side is local") keeps the ranks balanced for any row placement,
+e.g. a loader that shards by user.
+
+``only_use_wrong_order_pair`` / negative-side weights make the pair set depend on scores / weights, i.e. the
+counts would need an extra all-reduce between counting and weighting: not supported here (RN_ERR_UNSUPPORTED).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def _all_gather_cols(cols, group):
+    """all-gather each 1-D column; returns the global columns (rank-major concatenation)."""
+    world = dist.get_world_size(group)
+    outs = []
+    for c in cols:
+        if c is None:
+            outs.append(None)
+            continue
+        c = c.contiguous()
+        out = torch.empty(world * c.numel(), dtype=c.dtype, device=c.device)
+        dist.all_gather_into_tensor(out, c, group=group)
+        outs.append(out)
+    return outs
+
+
+def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: torch.Tensor,
+                            rw_pos: Optional[torch.Tensor] = None, row_ok: Optional[torch.Tensor] = None,
+                            label_func: str = "step", factor: float = 1.0, power: float = 0.0,
+                            reduce_mean: bool = True, group=None, _compute: Optional[Callable] = None):
+    """Global in-batch pairwise loss, forward + backward, for this rank's rows.
+
+    logits/labels/rw_pos/row_ok: [B_loc]; keys: canonical int64 [K, B_loc].  Every rank must pass the same
+    B_loc.  Returns dict(loss (global, identical on all ranks), n_pair (global, exact), dlogits [B_loc]).
+    ``_compute`` replaces the CUDA call (tests of the collective plumbing on CPU/gloo only).
+    """
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b_loc = logits.numel()
+    keys = keys.reshape(-1, b_loc)
+    kk = keys.shape[0]
+    cols = [keys[k] for k in range(kk)] + [logits.reshape(-1).to(torch.float32), labels.reshape(-1).to(torch.float32),
+                                           None if rw_pos is None else rw_pos.reshape(-1).to(torch.float32),
+                                           None if row_ok is None else row_ok.reshape(-1).to(torch.uint8)]
+    g = _all_gather_cols(cols, group)
+    gkeys = torch.stack(g[:kk]) if kk > 1 else g[0].reshape(1, -1)
+    gs, gy, gw, gok = g[kk], g[kk + 1], g[kk + 2], g[kk + 3]
+    if _compute is None:
+        from . import ops
+        _compute = ops.pairwise_fwd_bwd
+    out = _compute(gs, gy, gkeys, row_ok=gok, rw_pos=gw, label_func=label_func, factor=factor, power=power,
+                   reduce_mean=reduce_mean, part=(rank, world))
+    dloc = torch.empty(b_loc, dtype=torch.float32, device=logits.device)
+    dist.reduce_scatter_tensor(dloc, out["dlogits"], op=dist.ReduceOp.SUM, group=group)
+    loss = out["loss"].reshape(1).clone()
+    dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+    return dict(loss=loss[0], n_pair=out["n_pair"], dlogits=dloc)
+
+
+class _GlobalPairwiseLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, outputs, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
+        out = global_pairwise_fwd_bwd(outputs.detach(), labels, keys, rw_pos, row_ok, label_func, factor, power,
+                                      reduce_mean, group)
+        ctx.save_for_backward(out["dlogits"])
+        ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
+        n = out["n_pair"].to(torch.float32)
+        ctx.mark_non_differentiable(n)
+        return out["loss"], n
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_n):
+        (d,) = ctx.saved_tensors
+        return ((g_loss * d).reshape(ctx.out_shape).to(ctx.out_dtype),) + (None,) * 9
+
+
+def global_pairwise_loss(outputs, labels, groups, click_occurance_power=0.0, mask=None, factor=1.0,
+                         reduce_mean=True, label_pair_to_weight_func=None, return_num_pair=False, group=None,
+                         **kwargs):
+    """pairwise_loss over the union of all ranks' batches (BPR loss, fused weight menu).  Differentiable
+    w.r.t. ``outputs``; the returned loss is the GLOBAL loss, so gradients are those of the global objective
+    (no further averaging across ranks is needed for the logits)."""
+    from . import ops
+    from .rec_block.pairwise_loss_from_batch import FusedPairWeight, _as_cuda
+    outputs, labels = _as_cuda(outputs), _as_cuda(labels)
+    gl = [_as_cuda(g) for g in groups] if isinstance(groups, list) else [_as_cuda(groups)]
+    keys, row_ok = ops.canon_keys(gl, None if mask is None else _as_cuda(mask).reshape(-1).to(torch.bool))
+    label_func, rw_pos = "step", None
+    if label_pair_to_weight_func is not None:
+        if not isinstance(label_pair_to_weight_func, FusedPairWeight) or label_pair_to_weight_func.neg_kw is not None:
+            raise NotImplementedError("global mode supports FusedPairWeight with a positive-side weight only")
+        label_func = label_pair_to_weight_func.label_func
+        if label_pair_to_weight_func.pos_kw is not None:
+            rw_pos = _as_cuda(kwargs[label_pair_to_weight_func.pos_kw])
+    loss, n = _GlobalPairwiseLoss.apply(outputs, labels, keys, rw_pos, row_ok, label_func, float(factor),
+                                        float(click_occurance_power), bool(reduce_mean), group)
+    return (loss, n) if return_num_pair else loss
