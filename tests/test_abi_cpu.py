@@ -1,0 +1,98 @@
+"""No-GPU checks of the C-ABI boundary: the library loads, exports every symbol include/recnow_b200.h declares,
+and the host-only entry points (sizes, error strings, argument validation) behave.  No compute is launched."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from rec_now_b200 import _lib
+    return _lib.lib()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "recnow_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_exports_match_header(lib):
+    from rec_now_b200 import _lib
+    declared = header_functions()
+    assert declared, "no functions parsed from the header"
+    assert sorted(_lib.EXPORTS) == declared
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in recnow_b200.h but not exported"
+
+
+def test_version_and_errors(lib):
+    assert lib.rn_version() == 100
+    assert lib.rn_strerror(0) == b"ok"
+    for code in range(1, 8):
+        assert lib.rn_strerror(code) not in (b"ok", b"unknown error")
+    assert lib.rn_strerror(99) == b"unknown error"
+
+
+def test_scratch_sizes(lib):
+    assert lib.rn_pairwise_scratch_bytes(0, 1) == 0
+    assert lib.rn_pairwise_scratch_bytes(10, 0) == 0
+    a, b = lib.rn_pairwise_scratch_bytes(65536, 1), lib.rn_pairwise_scratch_bytes(8 * 65536, 1)
+    assert 0 < a < b
+    assert a < 64 << 20                     # the arena is O(B): ~10 MB at B = 65536
+    assert lib.rn_listwise_scratch_bytes(65536) > 0
+    assert lib.rn_pair_indices_scratch_bytes(65536, 2) > 0
+    assert lib.rn_occurrence_scratch_bytes(1000) > 0
+    assert lib.rn_pairwise_launch_count(65536, 1) > 0
+    assert lib.rn_listwise_launch_count(65536) > 0
+
+
+def test_argument_validation_without_gpu(lib):
+    from rec_now_b200._lib import ListwiseArgs, PairwiseArgs
+    # NULL args / missing pointers are rejected before any CUDA call
+    assert lib.rn_pairwise_fwd_bwd(None, None, 0, None) == 1
+    a = PairwiseArgs(B=16, K=1)
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), None, 0, None) == 1            # RN_ERR_ARG (NULL pointers)
+    buf = (C.c_char * 4096)()
+    base = (C.addressof(buf) + 15) & ~15
+    a = PairwiseArgs(B=16, K=1, keys=base, logits=base, labels=base, loss=base, n_pair_f32=base, n_pair=base,
+                     dlogits=base + 4, part_rank=0, part_count=1)
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), base, 4096, None) == 2         # RN_ERR_ALIGN (dlogits)
+    a.dlogits = base
+    a.label_func = 7
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), base, 4096, None) == 5         # RN_ERR_UNSUPPORTED
+    a.label_func = 0
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), base, 16, None) == 3           # RN_ERR_SCRATCH
+    a.part_count = 2
+    a.only_wrong = 1
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), base, 4096, None) == 5         # partial + score-dependent filter
+    la = ListwiseArgs(B=4, keys=base, labels=base, logits=base, n_valid=base, n_group=base, dlogits=base,
+                      loss=base, do_reduce=1, pos_neg_th=-1.0)
+    assert lib.rn_listwise_fwd_bwd(C.byref(la), base, 4096, None) == 5        # th < 0 outside the segmented form
+    assert lib.rn_occurrence_power_weight(None, 4, 1.0, None, None, 0, None) == 1
+
+
+def test_no_cpu_fallback():
+    import torch
+    from rec_now_b200 import ops
+    t = torch.zeros(4)
+    with pytest.raises(RuntimeError):
+        ops.pairwise_fwd_bwd(t, t, t.long().reshape(1, -1))
+    with pytest.raises(RuntimeError):
+        ops.canon_keys(t)
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "rec_now_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)

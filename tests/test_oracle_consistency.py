@@ -1,0 +1,87 @@
+"""The two oracles against each other (no GPU): the op-for-op dense float32 restatement and the segmented
+float64 one must agree on masks / counts / pair order exactly and on loss / gradient to float32 accuracy."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import dense_ref as D
+from oracle import generators as G
+from oracle import seg_ref as S
+
+
+def _dense_weight_func(spec, w_pos, w_neg):
+    if spec.label_func == "step" and w_pos is None and w_neg is None:
+        return None
+
+    def f(a, b):
+        w = ((a - b) * (a > b)).astype(np.float32) if spec.label_func == "diff" else (a > b).astype(np.float32)
+        if w_pos is not None:
+            w = (w * w_pos[:, None]).astype(np.float32)
+        if w_neg is not None:
+            w = (w * w_neg[None, :]).astype(np.float32)
+        return w
+    return f
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(0, 10 ** 6), st.integers(1, 120), st.integers(1, 12), st.booleans(), st.booleans(),
+       st.sampled_from([0.0, -0.5, 1.0, 2.0]), st.sampled_from(["step", "diff"]), st.integers(0, 3))
+def test_dense_vs_segmented(seed, b, ng, wrong, use_mask, power, label_func, wmode):
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    s = (rng.standard_normal(b) * 3).astype(np.float32)
+    y = rng.integers(0, 4, b).astype(np.float32)
+    wp = rng.uniform(-0.2, 1.5, b).astype(np.float32) if wmode & 1 else None
+    wn = rng.uniform(-0.2, 1.5, b).astype(np.float32) if wmode & 2 else None
+    mask = (rng.random(b) < 0.8) if use_mask else None
+    spec = S.PairSpec(factor=1.7, only_wrong=wrong, power=power, label_func=label_func, rw_pos=wp, rw_neg=wn)
+    r = S.pairwise(s, y, g, spec, mask=mask, want_pairs=True)
+    d = D.pairwise_full(s, y, g, factor=1.7, only_use_wrong_order_pair=wrong, click_occurance_power=power,
+                        mask=mask, label_pair_to_weight_func=_dense_weight_func(spec, wp, wn))
+    assert r["n_pair"] == d["n_pair"]
+    assert np.array_equal(r["pos_idx"], d["pos_idx"]) and np.array_equal(r["neg_idx"], d["neg_idx"])
+    assert np.array_equal(np.bincount(d["pos_idx"], minlength=b), r["row_pairs"])
+    assert abs(r["loss"] - float(d["loss"])) <= 3e-6 * max(1.0, abs(r["loss"]))
+    assert np.abs(r["grad"] - d["grad"]).max() <= 3e-6 * max(1.0, np.abs(r["grad"]).max())
+
+
+def test_multi_key_and_nonfinite_ids():
+    rng = np.random.default_rng(4)
+    b = 200
+    k0 = rng.integers(0, 6, b).astype(np.float32)
+    k1 = rng.integers(0, 3, b).astype(np.float32)
+    k0[[3, 50]] = np.nan
+    k1[[7]] = np.inf
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(0, 3, b).astype(np.float32)
+    r = S.pairwise(s, y, [k0, k1], S.PairSpec(power=-1.0), want_pairs=True)
+    d = D.pairwise_full(s, y, [k0, k1], click_occurance_power=-1.0)
+    assert r["n_pair"] == d["n_pair"] and np.array_equal(r["pos_idx"], d["pos_idx"])
+    assert abs(r["loss"] - float(d["loss"])) < 1e-6
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 10 ** 6), st.integers(1, 150), st.integers(1, 20))
+def test_listwise_dense_vs_segmented(seed, b, ng):
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    y = ((rng.random(b) < 0.4) * rng.integers(1, 3, b)).astype(np.float32)
+    s = (rng.standard_normal(b) * 2).astype(np.float32)
+    d = D.listwise_full(g, y, s)
+    r = S.listwise(g, y, s)
+    assert d["n_valid"] == r["n_valid"]
+    assert abs(float(d["loss"]) - r["loss"]) <= 3e-6 * max(1.0, abs(r["loss"]))
+    assert np.abs(d["grad"] - r["grad"]).max() <= 3e-6
+    if r["n_valid"]:
+        assert np.allclose(d["list_loss"], r["list_loss"], rtol=1e-5, atol=1e-6)
+
+
+def test_generators_shapes_and_estimates():
+    d = G.cfg2(0)
+    assert d["g"].shape == (16384,) and d["y"].max() == 1.0
+    r = S.pairwise(d["s"], d["y"], d["g"])
+    assert 1.2e6 < r["n_pair"] < 1.8e6              # SURVEY 8d estimate: n ~ 1.48 M
+    d4 = G.cfg4(0)
+    assert d4["g"].shape == (65536,) and 1500 < d4["n_lists"] < 2600
+    d5 = G.cfg5(2, rows_per_rank=1024, groups_per_rank=64)
+    assert d5["g"].shape == (2048,)

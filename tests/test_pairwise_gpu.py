@@ -117,3 +117,24 @@ def test_cfg2():
     out = run_pairwise(d["s"], d["y"], d["g"])
     r = check_pairwise(out, S.pairwise(d["s"], d["y"], d["g"]), ctx="cfg2")
     print("cfg2 parity", r, "n_pair", int(out["n_pair"].item()))
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_partition_partials_sum_to_full(parts):
+    """Multi-GPU work split (part_rank/part_count): partial loss / gradients add up to the single-call result,
+    counts are global in every part."""
+    d = G.cfg2(1)
+    rng = np.random.default_rng(0)
+    y = rng.integers(0, 5, d["s"].size).astype(np.float32)
+    spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=rng.uniform(0.5, 1.5, y.size).astype(np.float32))
+    full = run_pairwise(d["s"], y, d["g"], spec)
+    loss, grad = 0.0, 0.0
+    for r in range(parts):
+        out = run_pairwise(d["s"], y, d["g"], spec, part=(r, parts))
+        assert int(out["n_pair"].item()) == int(full["n_pair"].item())
+        loss += float(out["loss"].item())
+        grad = grad + out["dlogits"].double()
+    assert abs(loss - float(full["loss"].item())) <= 2e-6 * abs(loss)
+    ref = S.pairwise(d["s"], y, d["g"], spec)
+    err = np.abs(grad.cpu().numpy() - ref["grad"])
+    assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all()
