@@ -152,6 +152,9 @@ int rn_profile_collect(float* ms_out_host, int32_t capacity, int32_t* n_out_host
 int rn_profile_disable(void);
 /* Device-side status word of the last call that used `scratch` (0 = ok); reads it back (synchronises). */
 int rn_last_device_error(void* scratch, int32_t* err_host, void* stream);
+/* Phase timestamps (%globaltimer, ns) of the last call that used `scratch`, written by CTA 0 of the
+ * segmentation kernel (slots 0-19) and the pair kernel (20-23); reads them back (synchronises). */
+int rn_debug_timestamps(void* scratch, uint64_t* ts_host, int32_t capacity, void* stream);
 /* Stage timing breakdown helper: number of kernel launches the last-built pipeline enqueues per call. */
 int rn_pairwise_launch_count(int64_t B, int32_t K);
 int rn_listwise_launch_count(int64_t B);

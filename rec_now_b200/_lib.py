@@ -23,7 +23,7 @@ EXPORTS = [
     "rn_pair_indices_scratch_bytes", "rn_pair_indices_count", "rn_pair_indices_fill",
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
-    "rn_bench_mufu", "rn_profile_enable", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_pairwise_launch_count", "rn_listwise_launch_count",
+    "rn_bench_mufu", "rn_profile_enable", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
 ]
 
 
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.rn_profile_enable.argtypes = [i32]
     L.rn_profile_collect.argtypes = [C.POINTER(f32), i32, C.POINTER(i32)]
     L.rn_last_device_error.argtypes = [vp, C.POINTER(i32), vp]
+    L.rn_debug_timestamps.argtypes = [vp, C.POINTER(C.c_uint64), i32, vp]
     L.rn_pairwise_launch_count.argtypes = [i64, i32]
     L.rn_listwise_launch_count.argtypes = [i64]
     _lib = L

@@ -1,4 +1,4 @@
-// Shared device helpers, scratch layout and internal launcher declarations.  sm_100a only.
+// Shared device helpers, scratch layout and launch plumbing.  sm_100a only.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,69 +9,68 @@ namespace rn {
 typedef unsigned int u32;
 typedef unsigned long long u64;
 
-constexpr int kRadixBits = 8;                 // digit width of one LSD pass
+constexpr int kRadixBits = 9;                 // digit width of one LSD pass (512 bins = one per thread)
 constexpr int kBins = 1 << kRadixBits;
-constexpr int kMaxPass = 8;                   // <= 4 label passes + <= 4 group passes
-constexpr int kSortThreads = 256;             // 8 warps
-constexpr int kSortIpt = 8;                   // items per thread -> 2048-row tiles
-constexpr int kSortTile = kSortThreads * kSortIpt;
+constexpr int kMaxPass = 7;                   // ceil((28 group bits + 32 label bits) / 9)
+constexpr int kSegThreads = 512;              // threads per CTA of the segmentation kernel (one CTA per SM)
+constexpr int kSegWarps = kSegThreads / 32;
+constexpr int kIB = 64;                       // rows per I-block of the pair kernel (two per lane)
 constexpr u32 kEmpty = 0xFFFFFFFFu;
 
 // Device-side control block (zero-initialised by k_init at the start of every call).
 struct Ctl {
-  u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits -> varying bit range
-  u32 tickets[kMaxPass];        // tile tickets of the sort passes (look-back needs in-order start)
-  u32 heads_done;               // last-block detection in k_heads
+  u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range
+  u32 bar;                      // grid barrier arrivals, segmentation kernel
+  u32 bar2;                     // grid barrier arrivals, pair kernel
   u32 k2_ticket;                // dynamic work-unit ticket of the pair kernel
-  u32 fin_done;                 // last-block detection in the final kernels
+  u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars)
   u32 n_units, unit_c;          // work list: number of units, J-blocks per unit
   u32 n_groups;                 // distinct groups (listwise)
   u32 n_valid;                  // valid lists (listwise)
-  u32 err;                      // device-side error flag (0 ok)
+  u32 err;                      // device-side error flags (0 ok; 1 barrier timeout, 2 pair capacity)
   u64 n_pair;                   // exact kept-pair count
   u64 n_tiles;                  // total 32x32 micro-tiles in the work list
   double loss_sum;              // sum_p wocc * lossrow[p]   (log2 units)
+  u64 ts[24];                   // phase timestamps (%globaltimer, ns) written by CTA 0: measurement aid
+  u64 dbg[8];                   // pair-kernel debug tallies (RN_PAIR_DEBUG=1): see k_pair
 };
 
-struct Plan { int npass; int shift[kMaxPass]; int nbits[kMaxPass]; };
+// Sort plan.  Compact sort key = (gid << labbits) | ((enc_label >> labshift) & mask): only the varying bit
+// range of the order-preserving label encoding is kept (binary / graded labels need 7-9 bits), then the key's
+// gbits + labbits bits are split evenly over the fewest 9-bit passes.  Recomputed (cheaply) from the control
+// block by every kernel that needs it.
+struct Plan { int npass, labshift, labbits; int shift[kMaxPass]; int nbits[kMaxPass]; };
 
-// Sort plan: label digits over the varying bit range of the order-preserving label encoding, then group
-// digits over gbits bits starting at bit 32.  Recomputed (cheaply) by every kernel that needs it.
 __host__ __device__ inline Plan make_plan(u32 lab_or, u32 lab_nor, int gbits, bool use_label) {
-  Plan p; p.npass = 0;
-  u32 vary = use_label ? (lab_or & lab_nor) : 0u;
+  Plan p; p.npass = 0; p.labshift = 0; p.labbits = 0;
+  const u32 vary = use_label ? (lab_or & lab_nor) : 0u;
   if (vary) {
     int lo = 0; while (!((vary >> lo) & 1u)) ++lo;
     int hi = 31; while (!((vary >> hi) & 1u)) --hi;
-    for (int s = lo; s <= hi; s += kRadixBits) {
-      int nb = hi - s + 1; if (nb > kRadixBits) nb = kRadixBits;
-      p.shift[p.npass] = s; p.nbits[p.npass] = nb; ++p.npass;
-    }
+    p.labshift = lo; p.labbits = hi - lo + 1;
   }
-  // spread the group bits evenly over the fewest passes
-  int ngp = (gbits + kRadixBits - 1) / kRadixBits;
-  int s = 32, left = gbits;
-  for (int k = 0; k < ngp; ++k) {
-    int nb = (left + (ngp - k) - 1) / (ngp - k);
+  const int total = gbits + p.labbits;
+  const int np = (total + kRadixBits - 1) / kRadixBits;
+  int s = 0, left = total;
+  for (int k = 0; k < np; ++k) {
+    const int nb = (left + (np - k) - 1) / (np - k);
     p.shift[p.npass] = s; p.nbits[p.npass] = nb; ++p.npass; s += nb; left -= nb;
   }
   return p;
 }
 
 inline int bit_width_u64(uint64_t v) { int n = 0; while (v) { ++n; v >>= 1; } return n; }
-inline int max_label_passes() { return (32 + kRadixBits - 1) / kRadixBits; }
-inline int group_passes(int gbits) { return (gbits + kRadixBits - 1) / kRadixBits; }
 
 // ---- scratch arena layout (host side) ---------------------------------------------------------------
 struct Layout {
-  int64_t B; int K; int gbits; u32 cap; u32 ntiles; u32 nblk;
+  int64_t B; int K; int gbits; int ipt; u32 cap; u32 tile; u32 ntiles; u32 nib;
   size_t zero_begin, zero_end, ones_begin, ones_end, total;
   // zero-initialised region
-  size_t ctl, hist, status, cprim, gacc, lossrow, cnt, gstat;
+  size_t ctl, hist, cprim;
   // 0xFF-initialised region
-  size_t table, first, table1;
+  size_t table, table1;
   // plain
-  size_t slot, slot1, keyA, keyB, valA, valB, aj, ss, sy, swp, swn, blk, ustart, misc;
+  size_t slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, blk, ustart, misc, gstat;
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -81,24 +80,20 @@ inline Layout make_layout(int64_t B, int K) {
   L.gbits = B > 1 ? bit_width_u64((uint64_t)(B - 1)) : 1;
   u32 cap = 1024; while ((int64_t)cap < 2 * B) cap <<= 1;
   L.cap = cap;
-  L.ntiles = (u32)((B + kSortTile - 1) / kSortTile);
-  L.nblk = (u32)((B + 31) / 32);
+  L.ipt = (B <= 148 * 1024) ? 2 : 8;                 // sort tile = 1024 rows (<= 148 tiles) or 4096 rows
+  L.tile = (u32)(kSegThreads * L.ipt);
+  L.ntiles = (u32)((B + L.tile - 1) / L.tile);
+  L.nib = (u32)((B + kIB - 1) / kIB);
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   L.zero_begin = o;
   L.ctl = take(sizeof(Ctl));
   L.hist = take(sizeof(u32) * kMaxPass * kBins);
-  L.status = take(sizeof(u32) * (size_t)kMaxPass * L.ntiles * kBins);
-  L.cprim = take(sizeof(u64) * cap);
-  L.gacc = take(sizeof(float) * B);
-  L.lossrow = take(sizeof(float) * B);
-  L.cnt = take(sizeof(u32) * B);
-  L.gstat = take(sizeof(float) * 8 * B);   // listwise per-group statistics / misc per-row accumulators
+  L.cprim = take(sizeof(u64) * B);
   L.zero_end = o;
   L.ones_begin = o;
   L.table = take(sizeof(u32) * cap);
-  L.first = take(sizeof(u32) * cap);
-  L.table1 = take(sizeof(u32) * cap);
+  L.table1 = K > 1 ? take(sizeof(u32) * cap) : L.table;
   L.ones_end = o;
   L.slot = take(sizeof(u32) * B);
   L.slot1 = take(sizeof(u32) * B);
@@ -106,14 +101,19 @@ inline Layout make_layout(int64_t B, int K) {
   L.keyB = take(sizeof(u64) * B);
   L.valA = take(sizeof(u32) * B);
   L.valB = take(sizeof(u32) * B);
+  L.tilehist = take(sizeof(u32) * 3 * (size_t)L.ntiles * kBins);
   L.aj = take(sizeof(uint2) * B);
   L.ss = take(sizeof(float) * B);
   L.sy = take(sizeof(float) * B);
   L.swp = take(sizeof(float) * B);
   L.swn = take(sizeof(float) * B);
-  L.blk = take(sizeof(uint2) * L.nblk);
-  L.ustart = take(sizeof(u32) * (L.nblk + 1));
+  L.gacc = take(sizeof(float) * B);
+  L.lossrow = take(sizeof(float) * B);
+  L.cnt = take(sizeof(u32) * B);
+  L.blk = take(sizeof(uint2) * L.nib);
+  L.ustart = take(sizeof(u32) * (L.nib + 1));
   L.misc = take(sizeof(u64) * (B + 1));
+  L.gstat = take(sizeof(float) * 8 * B);   // listwise per-list records
   L.total = o;
   return L;
 }
@@ -127,6 +127,38 @@ __device__ __forceinline__ u32 lanemask_lt() { u32 m; asm("mov.u32 %0, %%lanemas
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ u32 ld_relaxed(const u32* p) {
+  u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ u32 ld_acquire(const u32* p) {
+  u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  `epoch` is a per-thread running
+// arrival target (starts at 0; the counter is zeroed by k_init).  The fences publish this CTA's writes and
+// invalidate its L1 so that plain loads after the barrier see other CTAs' data.  A bounded spin turns a
+// scheduling failure into ctl->err instead of a hung GPU.
+__device__ __forceinline__ void grid_sync(u32* bar, u32& epoch, u32* err) {
+  epoch += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    u32 spins = 0;
+    while (ld_acquire(bar) < epoch) {
+      if (++spins > (1u << 26)) { atomicOr(err, 1u); break; }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ u64 globaltimer() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// phase timestamp i (CTA 0, thread 0 only)
+__device__ __forceinline__ void stamp(Ctl* ctl, int i) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ts[i] = globaltimer();
+}
 
 // order-preserving float -> u32 (after -0.0 -> +0.0): a < b  <=>  enc(a) < enc(b) for non-NaN a, b
 __device__ __forceinline__ u32 enc_label(float y) {
@@ -156,22 +188,12 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
   return v;
 }
 
-// ---- internal launchers (segment.cu) ----------------------------------------------------------------
-struct SegInputs {
-  int64_t B; int K;
-  const int64_t* keys; const float* labels; const uint8_t* row_ok;
-  bool use_label;        // sort by (group, label, row) instead of (group, row)
-  bool nan_label_is_trash;
-};
-// Enqueues init + hash grouping + radix sort.  Afterwards the sorted (key, row) arrays are in
-// (keyA,valA) if plan.npass is even else (keyB,valB) -- consumers recompute the plan from ctl.
-cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, cudaStream_t st);
-int seg_launch_count(const Layout& L);
-// Group bounds of the sorted batch: astart[p] = first sorted position of p's group, gend[astart] = one past
-// its last position, perm[p] = original row; up to 4 float columns are gathered into sorted order.  One launch.
-struct GatherCols { const float* src[4]; float* dst[4]; };
-cudaError_t seg_bounds(const Layout& L, void* scratch, int use_label, u32* astart, u32* gend, u32* perm,
-                       const GatherCols& gc, cudaStream_t st);
+// ---- host plumbing (segment.cu) ---------------------------------------------------------------------
+// Zero / 0xFF-fill the initialised regions of the arena (one ordinary launch; it also resets the barriers).
+cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st);
+int device_sm_count();
+// Cooperative launch of `kernel` with `grid` CTAs of `threads` threads (grid must not exceed the co-resident limit).
+cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st);
 
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 

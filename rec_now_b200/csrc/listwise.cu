@@ -5,7 +5,7 @@
 // After K1 (sort by (first-occurrence id, row)) a list is a contiguous run of sorted positions and the runs
 // appear in first-occurrence order, so valid-list ranks (the row order of the reference's dense outputs) are
 // an exclusive scan over run heads.  HBM-bound: 20 algorithmic bytes per sample.
-#include "common.cuh"
+#include "segment.cuh"
 
 namespace rn {
 
@@ -162,7 +162,8 @@ extern "C" size_t rn_listwise_scratch_bytes(int64_t B) { return B > 0 ? make_lay
 extern "C" int rn_listwise_launch_count(int64_t B) {
   if (B <= 0) return 0;
   const Layout L = make_layout(B, 1);
-  return 3 + group_passes(L.gbits) + 4;
+  (void)L;
+  return 2 + 3;    // k_init, k_seg<BoundsTail>, k_lw_group, k_lw_rank, k_lw_grad
 }
 
 static int validate_listwise(const rn_listwise_args* a) {
@@ -184,7 +185,6 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
   SegInputs in{a->B, 1, a->keys, nullptr, a->row_ok, false, false};
-  if (seg_run(L, scratch, in, st) != cudaSuccess) return RN_ERR_LAUNCH;
   u32* astart = at<u32>(base, L.aj);
   u32* gend = at<u32>(base, L.cnt);
   u32* perm = at<u32>(base, L.misc);
@@ -192,7 +192,8 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   float* sy = at<float>(base, L.sy);
   float* rec = at<float>(base, L.gstat);
   GatherCols gc{{a->logits, a->labels, nullptr, nullptr}, {ss, sy, nullptr, nullptr}};
-  if (seg_bounds(L, scratch, 0, astart, gend, perm, gc, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  BoundsTail T{astart, gend, perm, gc};
+  if (seg_run(L, scratch, in, T, st) != cudaSuccess) return RN_ERR_LAUNCH;
   LwParams P{(u32)a->B, L.gbits, a->list_w, a->pos_neg_th, a->do_reduce, a->loss, a->list_loss, a->n_valid,
              a->n_group, a->dlogits};
   Ctl* ctl = at<Ctl>(base, L.ctl);

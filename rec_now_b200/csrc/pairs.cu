@@ -6,7 +6,7 @@
 // test_pairwise_loss_from_batch.py:38-45).  The batch is sorted by (group, row), so a row's candidates are
 // one contiguous run whose rows are already ascending: count per row, exclusive scan in ORIGINAL row order,
 // fill -> pairs come out by i ascending then j ascending, exactly PW:217's order.
-#include "common.cuh"
+#include "segment.cuh"
 
 namespace rn {
 
@@ -96,9 +96,6 @@ __global__ void __launch_bounds__(1024) k_scan_rows(u32 B, const u32* __restrict
 }
 
 // ---- occurance_power_weight -------------------------------------------------------------------------
-__device__ __forceinline__ u32 ld_relaxed_u32(const u32* p) {
-  u32 v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
 __global__ void __launch_bounds__(256) k_occ_insert(const int64_t* __restrict__ ids, u32 N, u32* table, u32* count,
                                                     u32* __restrict__ slot, u32 capmask) {
   const u32 i = blockIdx.x * 256u + threadIdx.x;
@@ -106,7 +103,7 @@ __global__ void __launch_bounds__(256) k_occ_insert(const int64_t* __restrict__ 
   const int64_t key = ids[i];
   u32 s = (u32)mix64(0x9E3779B97F4A7C15ull ^ (u64)key) & capmask;
   for (;;) {
-    u32 cur = ld_relaxed_u32(table + s);
+    u32 cur = ld_relaxed(table + s);
     if (cur == kEmpty) { u32 prev = atomicCAS(table + s, kEmpty, i); cur = (prev == kEmpty) ? i : prev; }
     if (cur == i || ids[cur] == key) break;
     s = (s + 1) & capmask;
@@ -156,11 +153,11 @@ extern "C" int rn_pair_indices_count(const rn_pairwise_args* a, int32_t label_co
   char* base = static_cast<char*>(scratch);
   // NaN labels: with the label condition they pair with nothing (trash); as raw candidates they stay
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, false, label_cond != 0};
-  if (seg_run(L, scratch, in, st) != cudaSuccess) return RN_ERR_LAUNCH;
   GatherCols gc{{a->logits, a->labels, a->rw_pos, a->rw_neg},
                 {at<float>(base, L.ss), at<float>(base, L.sy), at<float>(base, L.swp), at<float>(base, L.swn)}};
   u32* perm = at<u32>(base, L.slot1);       // slot1 is free here (K > 1 primary slots are not needed)
-  if (seg_bounds(L, scratch, 0, at<u32>(base, L.aj), at<u32>(base, L.cnt), perm, gc, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  BoundsTail T{at<u32>(base, L.aj), at<u32>(base, L.cnt), perm, gc};
+  if (seg_run(L, scratch, in, T, st) != cudaSuccess) return RN_ERR_LAUNCH;
   const PiParams P = pi_params(a, label_cond);
   const u32 gw = (u32)((a->B * 32 + 255) / 256);
   k_pi<false><<<gw, 256, 0, st>>>(P, at<u32>(base, L.aj), at<u32>(base, L.cnt), perm, at<float>(base, L.ss),

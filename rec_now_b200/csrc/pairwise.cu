@@ -1,154 +1,179 @@
-// K2/K3 — fused in-batch pairwise logistic (BPR) loss, forward + backward, on the segmented batch.
+// K2/K3 -- fused in-batch pairwise logistic (BPR) loss, forward + backward, on the segmented batch.
 //
 // Replaces pairwise_loss_from_batch.py:254-274 + TF autodiff.  After K1 the rows are
 // sorted by (group, label, row), so for a row at sorted position p with group start a(p) and label-level
 // start l(p) the negatives of p are exactly the positions [a(p), l(p)): pair enumeration is position
 // arithmetic, pair COUNTS are exact integers (l - a), and the kept pairs of a group form a staircase of
-// dense rectangles.  The pair kernel walks that staircase in 32x32 micro-tiles, one warp per tile:
-// lane = one positive row i (kept in registers), the 32 negatives of the tile rotate through the lanes with
-// shfl.bfly, so each lane meets each negative exactly once; the dL/ds_j contribution travels back with a
-// second shfl.bfly and is summed in the lane that owns j.  No shared memory, no block barriers, no dense
-// contraction: per pair 3 MUFU (ex2, lg2, rcp) + ~14 FP32/INT ops, i.e. SFU-bound.
-#include "common.cuh"
+// dense rectangles.
+//
+// Two launches per call after k_init:
+//   k_seg<HeadsTail>  segmentation (segment.cuh) + heads: group / level starts, gathers into sorted order,
+//                     exact counts, per-I-block J ranges and the work list.
+//   k_pair            persistent cooperative kernel.  A warp owns an I-block of 64 positive rows (two per
+//                     lane, in registers) and walks its J range in blocks of 32 negatives that rotate through
+//                     the lanes with shfl.bfly: every lane meets every negative exactly once, the two rows share
+//                     the shuffled score and send ONE summed dL/ds_j back.  Fast path (both rows cover the whole
+//                     J block, weights constant over it): per pair ex2 + rcp on the SFU, the log is taken once
+//                     per 32 pairs of the running product of (1+e); ~12 FP32 ops per pair.  Edge tiles take the
+//                     masked general path.  After a grid barrier the same kernel finalises: exact counts (when
+//                     they depend on scores), occurrence weights, 1/n, un-permutation of the gradient, loss.
+// No shared memory in the pair loop, no dense contraction, no tensor cores: the roofline is the SFU pipe.
+#include <stdlib.h>
+#include "segment.cuh"
 
 namespace rn {
 
-constexpr u32 kTargetUnits = 12288;     // work-list granularity target (units of <= C micro-tiles)
+// developer tuning knobs (read once from the environment; defaults are the shipped configuration)
+static int tune_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
 constexpr u32 kMaxUnitC = 64;
+constexpr int kPairThreads = 1024;      // threads per CTA of the pair kernel (one CTA per SM, <= 64 registers)
+constexpr u32 kDone = 0xFFFFFFFFu;
+constexpr int kPairWarps = kPairThreads / 32;
 
 struct PairParams {
-  int64_t B; int K; int gbits;
+  u32 B; int K; int gbits;
   const float* logits; const float* labels; const float* rw_pos; const float* rw_neg;
   float c_log2;          // factor * log2(e)
-  float factor, power; int reduce_mean; int dyn_count;
+  float factor, power; int reduce_mean; int dyn_count; int debug;
   int part_rank, part_count;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
 };
 
-// ---- heads: group / label-level starts, gather into sorted order, per-I-block J ranges, work list ------
-__device__ __forceinline__ u32 lower_bound_gid(const u64* __restrict__ k, u32 n, u32 gid) {
-  u32 lo = 0, hi = n;            // first p with (k[p] >> 32) >= gid
-  while (lo < hi) { u32 mid = (lo + hi) >> 1; if ((u32)(k[mid] >> 32) < gid) lo = mid + 1; else hi = mid; }
-  return lo;
-}
-__device__ __forceinline__ u32 lower_bound_key(const u64* __restrict__ k, u32 n, u64 key) {
-  u32 lo = 0, hi = n;
-  while (lo < hi) { u32 mid = (lo + hi) >> 1; if (k[mid] < key) lo = mid + 1; else hi = mid; }
-  return lo;
-}
+// ---- heads tail of k_seg ---------------------------------------------------------------------------------
+struct HeadsTail {
+  PairParams P;
+  uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32* cnt;
+  uint2* blk; u32* ustart; u32 nib; u64* cprim; const u32* pgid;
+  u32 target_units;          // work-list granularity target (units of <= C J-blocks)
 
-// inclusive max-scan over the 1024 threads of the block of two values at once
-__device__ __forceinline__ void block_maxscan2(u32& x, u32& y, u32 (*sm)[2]) {
-  const u32 ln = lane_id(), w = threadIdx.x >> 5;
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
+                                      u32& epoch) const {
+    u32* sm_scan = smem;                       // [kSegWarps][2]
+    u32* sm_carry = smem + 2 * kSegWarps;      // [2]
+    u32* sm_wj = smem + 36;                    // [kSegWarps][2]
+    u64* sm_red = reinterpret_cast<u64*>(smem + 72);   // [kSegWarps]
+    Ctl* ctl = S.ctl;
+    const u32 B = S.B, ln = lane_id(), w = threadIdx.x >> 5;
+    const bool count_now = !P.dyn_count;
+    const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+      const u32 t0 = c * kSegThreads, p = t0 + threadIdx.x;
+      const bool in = p < B;
+      const u64 k = in ? key[p] : ~0ull;
+      const u64 kp = (in && p > 0) ? key[p - 1] : ~k;
+      const u32 gid = (u32)(k >> pl.labbits);
+      const bool head = in && (p == 0 || gid != (u32)(kp >> pl.labbits));
+      const bool lvl = in && (head || k != kp);
+      if (w == 0) { const u32 lb = coop_lower_bound(key, t0, pl.labbits); if (ln == 0) sm_carry[0] = lb; }
+      if (w == 1) { const u32 lb = coop_lower_bound(key, t0, 0); if (ln == 0) sm_carry[1] = lb; }
+      u32 xa = head ? p + 1 : 0, xl = lvl ? p + 1 : 0;
+      block_maxscan2(xa, xl, sm_scan);
+      const u32 a = xa ? xa - 1 : sm_carry[0];
+      const u32 l = xl ? xl - 1 : sm_carry[1];
+      u32 n = in ? l - a : 0;
+      const u32 row = in ? val[p] : 0;
+      if (in) {
+        float wp = 1.f, wn = 1.f;
+        if (P.rw_pos) { wp = P.rw_pos[row]; if (!(wp > 0.f)) n = 0; }     // PW:193  C = W > 0
+        if (P.rw_neg) wn = P.rw_neg[row];
+        aj[p] = make_uint2(a, n);
+        ss[p] = P.logits[row];
+        sy[p] = P.labels[row];
+        if (P.rw_pos) swp[p] = wp;
+        if (P.rw_neg) swn[p] = wn;
+        gacc[p] = 0.f; lossrow[p] = 0.f; cnt[p] = 0;
+      }
+      // J range needed by this warp's 32 rows; two warps make one I-block
+      const u32 jlo = warp_min(n ? a : 0xFFFFFFFFu), jhi = warp_max(n ? a + n : 0u);
+      if (ln == 0) { sm_wj[2 * w] = jlo; sm_wj[2 * w + 1] = jhi; }
+      // exact counts (position arithmetic): per row, per PRIMARY group (PW:286-289), total
+      u32 cn = 0;
+      if (count_now) {
+        cn = n;
+        if (in && P.row_pairs) P.row_pairs[row] = (int64_t)cn;
+        const u32 pg = cn ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
+        const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
+        const u32 tot = __reduce_add_sync(m, cn);
+        if (pg != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(cprim + pg, (u64)tot);
+      }
+      const u64 s = warp_sum((u64)cn);
+      if (ln == 0) sm_red[w] = s;
+      __syncthreads();
+      if (!(w & 1) && ln == 0) {
+        const u32 ib = (t0 + w * 32) / kIB;
+        if (ib < nib) blk[ib] = make_uint2(min(sm_wj[2 * w], sm_wj[2 * w + 2]), max(sm_wj[2 * w + 1], sm_wj[2 * w + 3]));
+      }
+      if (threadIdx.x == 0 && count_now) {
+        u64 t = 0;
+        for (int q = 0; q < kSegWarps; ++q) t += sm_red[q];
+        if (t) atomicAdd(&ctl->n_pair, t);
+      }
+      __syncthreads();
+    }
+    // ---- work list (CTA 0): units of <= C J-blocks per I-block -------------------------------------------
+    stamp(ctl, 17);
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+    stamp(ctl, 18);
+    if (blockIdx.x != 0) return;
+    auto ntile = [&](u32 b) -> u32 {
+      const uint2 v = blk[b];
+      return v.y > v.x ? ((v.y + 31) >> 5) - (v.x >> 5) : 0u;
+    };
+    u64 m = 0;
+    for (u32 b = threadIdx.x; b < nib; b += kSegThreads) m += ntile(b);
+    m = warp_sum(m);
+    if (ln == 0) sm_red[w] = m;
+    __syncthreads();
+    u64 M = 0;
+    for (int q = 0; q < kSegWarps; ++q) M += sm_red[q];
+    u32 C = (u32)((M + target_units - 1) / target_units);
+    C = C < 1 ? 1 : (C > kMaxUnitC ? kMaxUnitC : C);
+    u32* s_scan = smem;            // [kSegWarps]
+    u32* s_carry = smem + kSegWarps;
+    if (threadIdx.x == 0) *s_carry = 0;
+    __syncthreads();
+    for (u32 b0 = 0; b0 < nib; b0 += kSegThreads) {
+      const u32 b = b0 + threadIdx.x;
+      const u32 v = b < nib ? (ntile(b) + C - 1) / C : 0u;
+      u32 inc = v;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    u32 tx = __shfl_up_sync(0xFFFFFFFFu, x, o), ty = __shfl_up_sync(0xFFFFFFFFu, y, o);
-    if (ln >= (u32)o) { x = max(x, tx); y = max(y, ty); }
+      for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+      if (ln == 31) s_scan[w] = inc;
+      __syncthreads();
+      u32 off = *s_carry;
+      for (u32 q = 0; q < w; ++q) off += s_scan[q];
+      if (b < nib) ustart[b] = off + inc - v;
+      __syncthreads();
+      if (threadIdx.x == kSegThreads - 1) *s_carry = off + inc;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) { ustart[nib] = *s_carry; ctl->n_units = *s_carry; ctl->unit_c = C; ctl->n_tiles = M; }
   }
-  if (ln == 31) { sm[w][0] = x; sm[w][1] = y; }
-  __syncthreads();
-  u32 cx = 0, cy = 0;
-  for (u32 k = 0; k < w; ++k) { cx = max(cx, sm[k][0]); cy = max(cy, sm[k][1]); }
-  x = max(x, cx); y = max(y, cy);
-}
-
-__global__ void __launch_bounds__(1024) k_heads(PairParams P, const u64* keyA, const u64* keyB, const u32* valA,
-                                                const u32* valB, uint2* __restrict__ aj, float* __restrict__ ss,
-                                                float* __restrict__ sy, float* __restrict__ swp,
-                                                float* __restrict__ swn, uint2* __restrict__ blk,
-                                                u32* __restrict__ ustart, u32 nblk, Ctl* ctl, int use_label) {
-  const Plan pl = make_plan(ctl->lab_or, ctl->lab_nor, P.gbits, use_label != 0);
-  const u64* __restrict__ key = (pl.npass & 1) ? keyB : keyA;
-  const u32* __restrict__ val = (pl.npass & 1) ? valB : valA;
-  __shared__ u32 sm[32][2];
-  __shared__ u32 carry[2];
-  __shared__ u32 s_last;
-  const u32 B = (u32)P.B;
-  const u32 t0 = blockIdx.x * 1024u;
-  const u32 p = t0 + threadIdx.x;
-  const bool in = p < B;
-  u64 k = in ? key[p] : ~0ull;
-  u64 kp = (in && p > 0) ? key[p - 1] : ~k;
-  bool head = in && (p == 0 || (u32)(k >> 32) != (u32)(kp >> 32));
-  bool lvl = in && (head || k != kp);
-  if (threadIdx.x == 0) carry[0] = lower_bound_gid(key, t0 < B ? t0 + 1 : B, (u32)(k >> 32));
-  if (threadIdx.x == 32) { u64 k0 = key[t0 < B ? t0 : B - 1]; carry[1] = lower_bound_key(key, t0 < B ? t0 + 1 : B, k0); }
-  u32 xa = head ? p + 1 : 0, xl = lvl ? p + 1 : 0;
-  block_maxscan2(xa, xl, sm);
-  __syncthreads();
-  u32 a = xa ? xa - 1 : carry[0];
-  u32 l = xl ? xl - 1 : carry[1];
-  u32 n = l - a;
-  u32 row = in ? val[p] : 0;
-  float wp = 1.f, wn = 1.f;
-  if (in) {
-    if (P.rw_pos) { wp = P.rw_pos[row]; if (!(wp > 0.f)) n = 0; }
-    if (P.rw_neg) wn = P.rw_neg[row];
-    aj[p] = make_uint2(a, n);
-    ss[p] = P.logits[row];
-    sy[p] = P.labels[row];
-    if (P.rw_pos) swp[p] = wp;
-    if (P.rw_neg) swn[p] = wn;
-  } else {
-    n = 0;
-  }
-  // J range needed by this I-block (warp)
-  u32 jlo = warp_min(n ? a : 0xFFFFFFFFu), jhi = warp_max(n ? a + n : 0u);
-  if (lane_id() == 0 && (p >> 5) < nblk) blk[p >> 5] = make_uint2(jlo, jhi);
-  // ---- last block builds the work list ---------------------------------------------------------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(&ctl->heads_done, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  volatile uint2* vb = blk;
-  auto ntile = [&](u32 b) -> u32 {
-    u32 lo = vb[b].x, hi = vb[b].y;
-    return hi > lo ? ((hi + 31) >> 5) - (lo >> 5) : 0u;
-  };
-  __shared__ u64 s_red[32];
-  __shared__ u32 s_scan[32];
-  __shared__ u32 s_carry;
-  u64 m = 0;
-  for (u32 b = threadIdx.x; b < nblk; b += 1024) m += ntile(b);
-  m = warp_sum(m);
-  if (lane_id() == 0) s_red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x < 32) { u64 v = s_red[threadIdx.x]; v = warp_sum(v); if (threadIdx.x == 0) s_red[0] = v; }
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  const u64 M = s_red[0];
-  u32 C = (u32)((M + kTargetUnits - 1) / kTargetUnits);
-  C = C < 1 ? 1 : (C > kMaxUnitC ? kMaxUnitC : C);
-  for (u32 b0 = 0; b0 < nblk; b0 += 1024) {
-    u32 b = b0 + threadIdx.x;
-    u32 v = b < nblk ? (ntile(b) + C - 1) / C : 0u;
-    u32 inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane_id() >= (u32)o) inc += t; }
-    if (lane_id() == 31) s_scan[threadIdx.x >> 5] = inc;
-    __syncthreads();
-    u32 off = s_carry;
-    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) off += s_scan[w];
-    if (b < nblk) ustart[b] = off + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = off + inc;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { ustart[nblk] = s_carry; ctl->n_units = s_carry; ctl->unit_c = C; ctl->n_tiles = M; }
-}
+};
 
 // ---- the pair kernel ------------------------------------------------------------------------------
 enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8 };
 
+struct KpArgs {
+  const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* blk; const u32* ustart; u32 nib;
+  float *gacc, *lossrow; u32* cnt; Ctl* ctl;
+  // finalisation
+  const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
+  u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first unit start, loop exit, busy cycles, units | general tiles << 32}
+};
+
+// General (masked) 32x32 tile for one positive row per lane.
 template <int MODE, bool FULL>
-__device__ __forceinline__ void tile32(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
-                                       const u32 pjm, const float sjm, const float yjm, const float wnjm,
-                                       const float c, float& li, float& gi, u32& cnt, float& accj) {
+__device__ __forceinline__ void tile_general(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
+                                             const u32 pjm, const float sjm, const float yjm, const float wnjm,
+                                             const float c, float& li, float& gi, u32& cnt, float& accj) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
   float gi_t = 0.f, li_t = 0.f;
-#pragma unroll
+#pragma unroll 8
   for (int t = 0; t < 32; ++t) {
     const float sj = __shfl_xor_sync(0xFFFFFFFFu, sjm, t);
     const float x = si - sj;                           // PW:117 (float32 subtract, as the reference)
@@ -178,166 +203,243 @@ __device__ __forceinline__ void tile32(const float si, const float yi, const flo
   li += li_t; gi += gi_t;
 }
 
+// Fast 64x32 tile: both rows of every lane pair with ALL 32 negatives and their pair weight (wv0 / wv1) is constant
+// over the tile.  Per pair: ex2 + rcp (SFU), ~11 FP32 ops; per row and tile one lg2 of the product of the (1+e).
+template <bool HASW>
+__device__ __forceinline__ void tile_fast(const float si0, const float si1, const float wv0, const float wv1,
+                                          const float sjm, const float c, float& li0, float& li1, float& gi0,
+                                          float& gi1, float& accj) {
+  float p0 = 1.f, p1 = 1.f, m0 = 0.f, m1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll
+  for (int t = 0; t < 32; ++t) {
+    const float sj = __shfl_xor_sync(0xFFFFFFFFu, sjm, t);
+    const float x0 = (si0 - sj) * c, x1 = (si1 - sj) * c;           // PW:117-119 in log2 units
+    const float e0 = mufu_ex2(-fabsf(x0)), e1 = mufu_ex2(-fabsf(x1));
+    const float t0 = 1.0f + e0, t1 = 1.0f + e1;
+    float d0 = mufu_rcp(t0), d1 = mufu_rcp(t1);                     // sigma(-x) for x < 0
+    p0 *= t0; p1 *= t1;                                            // prod (1+e) <= 2^32
+    if (x0 >= 0.f) d0 *= e0; else m0 -= x0;                         // sigma(-x) = e/(1+e) for x >= 0; max(-x,0)
+    if (x1 >= 0.f) d1 *= e1; else m1 -= x1;
+    if (HASW) { d0 *= wv0; d1 *= wv1; }
+    g0 += d0; g1 += d1;
+    accj += __shfl_xor_sync(0xFFFFFFFFu, d0 + d1, t);
+  }
+  const float L0 = m0 + mufu_lg2(p0), L1 = m1 + mufu_lg2(p1);       // sum softplus(-x) / ln2   (PW:120-121)
+  li0 += HASW ? wv0 * L0 : L0; li1 += HASW ? wv1 * L1 : L1;
+  gi0 += g0; gi1 += g1;
+}
+
+// Work-unit hand-out: units are dealt round-robin to the CTAs (unit q * gridDim + cta belongs to this CTA), the
+// warps of a CTA take their CTA's units dynamically from a shared-memory counter.  The unit list is ordered by kind
+// (edge tiles of the small groups ... dense tiles of the big groups), so every SM receives the same mix; there is
+// no global ticket (one contended address would serialise every warp of the chip).
+__device__ __forceinline__ u32 take_unit(u32* s_cnt, u32 u_begin, u32 u_end) {
+  const u32 q = atomicAdd(s_cnt, 1u);
+  const u64 u = (u64)u_begin + (u64)q * gridDim.x + blockIdx.x;
+  return u < (u64)u_end ? (u32)u : kDone;
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(256) k_pair(PairParams P, const uint2* __restrict__ aj,
-                                              const float* __restrict__ ss, const float* __restrict__ sy,
-                                              const float* __restrict__ swp, const float* __restrict__ swn,
-                                              const uint2* __restrict__ blk, const u32* __restrict__ ustart,
-                                              u32 nblk, float* gacc, float* lossrow, u32* cntrow, Ctl* ctl) {
+__global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
+  __shared__ u32 s_cnt;
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
+  Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
-  const u32 U = ctl->n_units, C = ctl->unit_c;
-  const u32 B = (u32)P.B;
-  const u32 u_begin = (u32)(((u64)U * (u32)P.part_rank) / (u32)P.part_count);
-  const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
-  const float c = P.c_log2;
-  for (;;) {
-    u32 u = 0;
-    if (ln == 0) u = atomicAdd(&ctl->k2_ticket, 1u) + u_begin;
-    u = __shfl_sync(0xFFFFFFFFu, u, 0);
-    if (u >= u_end) break;
-    // unit -> (I-block b, chunk): largest b with ustart[b] <= u
-    u32 lo_b = 0, hi_b = nblk;
-    while (hi_b - lo_b > 1) { u32 mid = (lo_b + hi_b) >> 1; if (ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
-    const u32 b = lo_b;
-    const uint2 bj = blk[b];
-    const u32 chunk = u - ustart[b];
-    const u32 jb0 = (bj.x >> 5) + chunk * C;
-    u32 jb1 = (bj.y + 31) >> 5; if (jb1 > jb0 + C) jb1 = jb0 + C;
-    // positive side: one row per lane
-    const u32 pi = b * 32 + ln;
-    uint2 an = make_uint2(0, 0); float si = 0.f, yi = 0.f, wpi = 1.f;
-    if (pi < B) { an = aj[pi]; si = ss[pi]; if (DIFF) yi = sy[pi]; if (HASW && swp) wpi = swp[pi]; }
-    const u32 lo = an.x, hi = an.x + an.y;
-    float li = 0.f, gi = 0.f; u32 cnt = 0;
-    u32 pjm = jb0 * 32 + ln;
-    float sjm = pjm < B ? ss[pjm] : 0.f, yjm = 0.f, wnjm = 1.f;
-    if (DIFF) yjm = pjm < B ? sy[pjm] : 0.f;
-    if (RWN) wnjm = pjm < B ? swn[pjm] : 0.f;
-    for (u32 jb = jb0; jb < jb1; ++jb) {
-      // prefetch the next J-block while this one is being scored
-      const u32 pjn = pjm + 32;
-      const bool more = (jb + 1 < jb1) && pjn < B;
-      float sjn = more ? ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
-      if (DIFF) yjn = more ? sy[pjn] : 0.f;
-      if (RWN) wnjn = more ? swn[pjn] : 0.f;
-      float accj = 0.f;
-      const u32 j0 = jb * 32;
-      const bool full = __all_sync(0xFFFFFFFFu, lo <= j0 && j0 + 32 <= hi);
-      if (full) tile32<MODE, true>(si, yi, wpi, lo, hi, pjm, sjm, yjm, wnjm, c, li, gi, cnt, accj);
-      else      tile32<MODE, false>(si, yi, wpi, lo, hi, pjm, sjm, yjm, wnjm, c, li, gi, cnt, accj);
-      if (accj != 0.f) atomicAdd(gacc + pjm, accj);
-      pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
-    }
-    if (pi < B && an.y) {
-      if (gi != 0.f) atomicAdd(gacc + pi, -gi);
-      if (li != 0.f) atomicAdd(lossrow + pi, li);
-      if ((WRONG || RWN) && cnt) atomicAdd(cntrow + pi, cnt);
-    }
-  }
-}
-
-// ---- finalisation ---------------------------------------------------------------------------------
-// F_a: exact counts.  c_row = pairs with the row on the positive side; c_h accumulates per PRIMARY key
-// (pairwise_loss_from_batch.py:286-289); n = sum.
-__global__ void __launch_bounds__(256) k_fin_counts(PairParams P, const u32* valA, const u32* valB,
-                                                    const uint2* __restrict__ aj, const u32* __restrict__ cntrow,
-                                                    const u32* __restrict__ slotp, u64* cprim, Ctl* ctl,
-                                                    int use_label) {
-  const Plan pl = make_plan(ctl->lab_or, ctl->lab_nor, P.gbits, use_label != 0);
-  const u32* __restrict__ val = (pl.npass & 1) ? valB : valA;
-  const u32 p = blockIdx.x * 256u + threadIdx.x;
-  const bool in = p < (u32)P.B;
-  u32 c = 0, ps = kEmpty, row = 0;
-  if (in) {
-    row = val[p];
-    c = P.dyn_count ? cntrow[p] : aj[p].y;
-    if (c) ps = slotp[row];
-    if (P.row_pairs) P.row_pairs[row] = (int64_t)c;
-  }
-  const u32 m = __match_any_sync(0xFFFFFFFFu, ps);
-  const u32 tot = __reduce_add_sync(m, c);
-  if (ps != kEmpty && lane_id() == (u32)(__ffs(m) - 1)) atomicAdd(cprim + ps, (u64)tot);
-  __shared__ u64 red[8];
-  u64 s = warp_sum((u64)c);
-  if (lane_id() == 0) red[threadIdx.x >> 5] = s;
+  const u32 B = P.B;
+  stamp(ctl, 20);
+  if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    u64 t = 0;
-    for (int k = 0; k < 8; ++k) t += red[k];
-    if (t) atomicAdd(&ctl->n_pair, t);
+  {
+    const u32 U = ld_relaxed(&ctl->n_units), C = ld_relaxed(&ctl->unit_c);
+    const u32 u_begin = (u32)(((u64)U * (u32)P.part_rank) / (u32)P.part_count);
+    const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
+    const float c = P.c_log2;
+    // debug tallies (per warp, flushed once): longest unit, busy cycles, units, fast / general tiles
+    u64 d_max = 0, d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0; u64 d_gencyc = 0;
+    const u64 d_start = P.debug ? globaltimer() : 0;
+    for (;;) {
+      const long long d_t0 = P.debug ? clock64() : 0;
+      u32 u = 0;
+      if (ln == 0) u = take_unit(&s_cnt, u_begin, u_end);
+      u = __shfl_sync(0xFFFFFFFFu, u, 0);
+      if (u == kDone) break;
+      // hand the units out from the END of the list: the small groups (edge tiles, slow general path) come first,
+      // the dense fast tiles of the big groups last, so the tail of the kernel is made of short units
+      u = u_begin + (u_end - 1u - u);
+      // unit -> (I-block b, chunk): largest b with ustart[b] <= u
+      u32 lo_b = 0, hi_b = A.nib;
+      while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (A.ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
+      const u32 b = lo_b;
+      const uint2 bj = A.blk[b];
+      const u32 chunk = u - A.ustart[b];
+      const u32 jb0 = (bj.x >> 5) + chunk * C;
+      u32 jb1 = (bj.y + 31) >> 5; if (jb1 > jb0 + C) jb1 = jb0 + C;
+      // positive side: two rows per lane
+      const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
+      uint2 an0 = make_uint2(0, 0), an1 = make_uint2(0, 0);
+      float si0 = 0.f, si1 = 0.f, yi0 = 0.f, yi1 = 0.f, wp0 = 1.f, wp1 = 1.f;
+      if (pi0 < B) { an0 = A.aj[pi0]; si0 = A.ss[pi0]; if (DIFF) yi0 = A.sy[pi0]; if (HASW && A.swp) wp0 = A.swp[pi0]; }
+      if (pi1 < B) { an1 = A.aj[pi1]; si1 = A.ss[pi1]; if (DIFF) yi1 = A.sy[pi1]; if (HASW && A.swp) wp1 = A.swp[pi1]; }
+      const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
+      float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
+      u32 pjm = jb0 * 32 + ln;
+      float sjm = pjm < B ? A.ss[pjm] : 0.f, yjm = 0.f, wnjm = 1.f;
+      if (DIFF) yjm = pjm < B ? A.sy[pjm] : 0.f;
+      if (RWN) wnjm = pjm < B ? A.swn[pjm] : 0.f;
+      for (u32 jb = jb0; jb < jb1; ++jb) {
+        // prefetch the next J-block while this one is being scored
+        const u32 pjn = pjm + 32;
+        const bool more = (jb + 1 < jb1) && pjn < B;
+        float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
+        if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
+        if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
+        float accj = 0.f;
+        const u32 j0 = jb * 32;
+        const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
+        const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
+        bool fast = full0 && full1 && !RWN && !WRONG;
+        if (DIFF && fast) fast = __all_sync(0xFFFFFFFFu, yjm == __shfl_sync(0xFFFFFFFFu, yjm, 0));
+        if (P.debug) { if (fast) ++d_fast; else ++d_gen; }
+        const long long d_g0 = (P.debug && !fast) ? clock64() : 0;
+        if (fast) {
+          float wv0 = wp0, wv1 = wp1;
+          if (DIFF) { wv0 = (yi0 - yjm) * wp0; wv1 = (yi1 - yjm) * wp1; }    // yjm is uniform over the block
+          tile_fast<HASW>(si0, si1, wv0, wv1, sjm, c, li0, li1, gi0, gi1, accj);
+        } else {
+          const bool any0 = __any_sync(0xFFFFFFFFu, lo0 < j0 + 32 && hi0 > j0);
+          const bool any1 = __any_sync(0xFFFFFFFFu, lo1 < j0 + 32 && hi1 > j0);
+          if (any0) {
+            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+          }
+          if (any1) {
+            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+          }
+        }
+        if (P.debug && !fast) d_gencyc += (u64)(clock64() - d_g0);
+        if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
+        pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
+      }
+      if (pi0 < B && an0.y) {
+        if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
+        if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
+        if ((WRONG || RWN) && cnt0) atomicAdd(A.cnt + pi0, cnt0);
+      }
+      if (pi1 < B && an1.y) {
+        if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
+        if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
+        if ((WRONG || RWN) && cnt1) atomicAdd(A.cnt + pi1, cnt1);
+      }
+      if (P.debug) {
+        const u64 dt = (u64)(clock64() - d_t0);
+        d_busy += dt; ++d_units;
+        const u64 enc = (dt << 32) | u;
+        if (enc > d_max) d_max = enc;
+      }
+    }
+    if (P.debug && ln == 0) {
+      atomicMax(&ctl->dbg[0], d_max); atomicAdd(&ctl->dbg[1], d_busy);
+      const u64 now = globaltimer();
+      atomicMax(&ctl->dbg[2], now);
+      u64* rec = A.dbgbuf + 4 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5));
+      rec[0] = d_start; rec[1] = now; rec[2] = d_busy; rec[3] = (u64)d_units | ((u64)d_gen << 32);
+      atomicAdd(&ctl->dbg[4], (u64)d_units); atomicAdd(&ctl->dbg[5], (u64)d_fast);
+      atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc);
+    }
   }
-}
-
-// F_b: scale, apply the occurrence weight, un-permute the gradient, reduce the loss.
-__global__ void __launch_bounds__(256) k_fin_scale(PairParams P, const u32* valA, const u32* valB,
-                                                   const float* __restrict__ gacc, const float* __restrict__ lossrow,
-                                                   const u32* __restrict__ slotp, const u64* __restrict__ cprim,
-                                                   Ctl* ctl, int use_label) {
-  const Plan pl = make_plan(ctl->lab_or, ctl->lab_nor, P.gbits, use_label != 0);
-  const u32* __restrict__ val = (pl.npass & 1) ? valB : valA;
-  const u64 n = ctl->n_pair;
+  // ---- finalisation (all CTAs, after a grid barrier) --------------------------------------------------
+  u32 epoch = 0;
+  stamp(ctl, 21);
+  grid_sync(&ctl->bar2, epoch, &ctl->err);
+  stamp(ctl, 22);
+  const Plan pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), P.gbits, true);
+  const u64* key = (pl.npass & 1) ? A.keyB : A.keyA;
+  const u32* val = (pl.npass & 1) ? A.valB : A.valA;
+  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  __shared__ u64 red_u[kPairWarps];
+  __shared__ double red_d[kPairWarps];
+  if (P.dyn_count) {
+    // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
+    u64 tot_c = 0;
+    for (u32 p0 = 0; p0 < B; p0 += gthreads) {             // uniform trip count: the body uses warp collectives
+      const u32 p = p0 + gtid;
+      u32 cn = 0, pg = kEmpty;
+      if (p < B) {
+        const u32 row = val[p];
+        cn = A.cnt[p];
+        if (cn) pg = P.K > 1 ? A.pgid[row] : (u32)(key[p] >> pl.labbits);
+        if (P.row_pairs) P.row_pairs[row] = (int64_t)cn;
+      }
+      const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
+      const u32 tot = __reduce_add_sync(m, cn);
+      if (pg != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(A.cprim + pg, (u64)tot);
+      tot_c += cn;
+    }
+    tot_c = warp_sum(tot_c);
+    if (ln == 0) red_u[threadIdx.x >> 5] = tot_c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      u64 t = 0;
+      for (int q = 0; q < kPairWarps; ++q) t += red_u[q];
+      if (t) atomicAdd(&ctl->n_pair, t);
+    }
+    grid_sync(&ctl->bar2, epoch, &ctl->err);
+  }
+  // F_b: scale, apply the occurrence weight, un-permute the gradient, reduce the loss
+  const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
   const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
   const float gscale = P.factor / denom;
-  const u32 p = blockIdx.x * 256u + threadIdx.x;
   double lp = 0.0;
-  if (p < (u32)P.B) {
+  for (u32 p = gtid; p < B; p += gthreads) {
     const u32 row = val[p];
-    const float g = gacc[p], l = lossrow[p];
+    const float g = A.gacc[p], l = A.lossrow[p];
     float wocc = 1.f;
     if (P.power != 0.f && (g != 0.f || l != 0.f)) {
-      const u32 ps = slotp[row];
-      const u64 ch = ps != kEmpty ? cprim[ps] : 0ull;
+      const u32 pg = P.K > 1 ? A.pgid[row] : (u32)(key[p] >> pl.labbits);
+      const u64 ch = A.cprim[pg];
       wocc = ch ? ((P.power == 1.0f) ? (float)ch : powf((float)ch, P.power)) : 0.f;   // PW:147-149
     }
     P.dlogits[row] = g * wocc * gscale;
-    lp = (double)l * (double)wocc;
+    lp += (double)l * (double)wocc;
   }
-  __shared__ double red[8];
-  __shared__ u32 s_last;
   lp = warp_sum(lp);
-  if (lane_id() == 0) red[threadIdx.x >> 5] = lp;
+  if (ln == 0) red_d[threadIdx.x >> 5] = lp;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0;
-    for (int k = 0; k < 8; ++k) t += red[k];
+    for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
     if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     __threadfence();
-    s_last = (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) ? 1u : 0u;
-    if (s_last) {
-      __threadfence();
-      const double tot = *((volatile double*)&ctl->loss_sum) * 0.6931471805599453;
-      *P.loss = (float)(tot / (double)denom);
-      *P.n_pair_f32 = (float)n;                  // PW:276
-      *P.n_pair = (int64_t)n;
-    }
+    if (atomicAdd(&ctl->fin_done, 1u) != gridDim.x - 1) return;       // the last CTA writes the scalars
+    __threadfence();
+    ctl->ts[23] = globaltimer();
+    const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+    *P.loss = (float)(tot / (double)denom);
+    *P.n_pair_f32 = (float)n;                  // PW:276
+    *P.n_pair = (int64_t)n;
   }
 }
 
 template <int MODE>
-static cudaError_t launch_pair(const PairParams& P, const Layout& L, char* base, cudaStream_t st) {
+static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_t st) {
   static int blocks_per_sm = 0;
   if (!blocks_per_sm) {
     int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair<MODE>, 256, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair<MODE>, kPairThreads, 0);
     if (e != cudaSuccess) return e;
-    blocks_per_sm = nb > 0 ? nb : 1;
+    if (nb < 1) nb = 1;
+    int want = tune_int("RN_PAIR_BPS", 1);           // CTAs per SM (all co-resident: cooperative launch)
+    blocks_per_sm = want < nb ? (want < 1 ? 1 : want) : nb;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  k_pair<MODE><<<sms * blocks_per_sm, 256, 0, st>>>(P, at<uint2>(base, L.aj), at<float>(base, L.ss),
-                                                    at<float>(base, L.sy), P.rw_pos ? at<float>(base, L.swp) : nullptr,
-                                                    at<float>(base, L.swn), at<uint2>(base, L.blk),
-                                                    at<u32>(base, L.ustart), L.nblk, at<float>(base, L.gacc),
-                                                    at<float>(base, L.lossrow), at<u32>(base, L.cnt),
-                                                    at<Ctl>(base, L.ctl));
-  return cudaGetLastError();
+  PairParams p = P; KpArgs a = A;
+  void* args[] = {&p, &a};
+  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm, kPairThreads, args, st);
 }
 
-static cudaError_t dispatch_pair(int mode, const PairParams& P, const Layout& L, char* base, cudaStream_t st) {
+static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A, cudaStream_t st) {
   switch (mode) {
-#define RN_CASE(m) case m: return launch_pair<m>(P, L, base, st);
+#define RN_CASE(m) case m: return launch_pair<m>(P, A, st);
     RN_CASE(0) RN_CASE(M_WRONG)
     RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
     RN_CASE(M_HASW | M_DIFF) RN_CASE(M_HASW | M_DIFF | M_WRONG)
@@ -387,7 +489,7 @@ extern "C" size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K) {
 
 extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
   if (B <= 0 || K <= 0) return 0;
-  return seg_launch_count(make_layout(B, K)) + 4;
+  return 3;        // k_init, k_seg<HeadsTail>, k_pair
 }
 
 static int validate_pairwise(const rn_pairwise_args* a) {
@@ -412,21 +514,34 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
-  SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
-  if (seg_run(L, scratch, in, st) != cudaSuccess) return RN_ERR_LAUNCH;
   PairParams P{};
-  P.B = a->B; P.K = a->K; P.gbits = L.gbits;
+  P.B = (u32)a->B; P.K = a->K; P.gbits = L.gbits;
   P.logits = a->logits; P.labels = a->labels; P.rw_pos = a->rw_pos; P.rw_neg = a->rw_neg;
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;
   P.c_log2 = a->factor * 1.4426950408889634f;
+  static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
+  P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;
   P.loss = a->loss; P.n_pair_f32 = a->n_pair_f32; P.n_pair = a->n_pair; P.dlogits = a->dlogits; P.row_pairs = a->row_pairs;
-  Ctl* ctl = at<Ctl>(base, L.ctl);
-  const u32 nblk1024 = (u32)((a->B + 1023) / 1024);
-  k_heads<<<nblk1024, 1024, 0, st>>>(P, at<u64>(base, L.keyA), at<u64>(base, L.keyB), at<u32>(base, L.valA),
-                                     at<u32>(base, L.valB), at<uint2>(base, L.aj), at<float>(base, L.ss),
-                                     at<float>(base, L.sy), at<float>(base, L.swp), at<float>(base, L.swn),
-                                     at<uint2>(base, L.blk), at<u32>(base, L.ustart), L.nblk, ctl, 1);
+  HeadsTail H{};
+  H.P = P;
+  H.aj = at<uint2>(base, L.aj); H.ss = at<float>(base, L.ss); H.sy = at<float>(base, L.sy);
+  H.swp = at<float>(base, L.swp); H.swn = at<float>(base, L.swn);
+  H.gacc = at<float>(base, L.gacc); H.lossrow = at<float>(base, L.lossrow); H.cnt = at<u32>(base, L.cnt);
+  H.blk = at<uint2>(base, L.blk); H.ustart = at<u32>(base, L.ustart); H.nib = L.nib;
+  H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
+  static const int target_units = tune_int("RN_TARGET_UNITS", 16384);
+  H.target_units = (u32)(target_units > 0 ? target_units : 16384);
+  SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
+  if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  KpArgs A{};
+  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
+  A.blk = H.blk; A.ustart = H.ustart; A.nib = L.nib;
+  A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.ctl = at<Ctl>(base, L.ctl);
+  A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
+  A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
+  A.pgid = H.pgid; A.cprim = H.cprim;
+  A.dbgbuf = at<u64>(base, L.gstat);
   int mode = 0;
   if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
@@ -434,13 +549,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (a->only_wrong) mode |= M_WRONG;
   const bool prof = g_prof.on && g_prof.n < g_prof.cap;
   if (prof) cudaEventRecord(g_prof.ev[2 * g_prof.n], st);
-  if (dispatch_pair(mode, P, L, base, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  if (dispatch_pair(mode, P, A, st) != cudaSuccess) return RN_ERR_LAUNCH;
   if (prof) { cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st); ++g_prof.n; }
-  const u32* slotp = (a->K > 1) ? at<u32>(base, L.slot1) : at<u32>(base, L.slot);
-  const u32 g256 = (u32)((a->B + 255) / 256);
-  k_fin_counts<<<g256, 256, 0, st>>>(P, at<u32>(base, L.valA), at<u32>(base, L.valB), at<uint2>(base, L.aj),
-                                     at<u32>(base, L.cnt), slotp, at<u64>(base, L.cprim), ctl, 1);
-  k_fin_scale<<<g256, 256, 0, st>>>(P, at<u32>(base, L.valA), at<u32>(base, L.valB), at<float>(base, L.gacc),
-                                    at<float>(base, L.lossrow), slotp, at<u64>(base, L.cprim), ctl, 1);
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
 }

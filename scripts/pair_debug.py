@@ -1,0 +1,38 @@
+"""Dev tool: per-warp timeline of the pair kernel (RN_PAIR_DEBUG=1).  Usage: RN_PAIR_DEBUG=1 python scripts/pair_debug.py cfg3"""
+import ctypes as C, sys
+import numpy as np, torch
+sys.path.insert(0, ".")
+from oracle import generators as G
+from rec_now_b200 import ops, _lib
+
+d = getattr(G, sys.argv[1] if len(sys.argv) > 1 else "cfg3")()
+s, y = torch.tensor(d["s"]).cuda(), torch.tensor(d["y"]).cuda()
+keys = torch.tensor(d["g"]).cuda().reshape(1, -1)
+w = torch.tensor(d["w"]).cuda() if "w" in d else None
+kw = dict(label_func=d["label_func"], power=d["power"], rw_pos=w)
+for _ in range(5):
+    out = ops.pairwise_fwd_bwd(s, y, keys, **kw)
+torch.cuda.synchronize()
+scr = out["_scratch"]
+ts = (C.c_uint64 * 34)()
+_lib.lib().rn_debug_timestamps(scr.data_ptr(), ts, 34, None)
+t = list(ts)
+# locate gstat: the arena layout is deterministic; find it by scanning for the record pattern instead of
+# duplicating the layout here: records start at the gstat offset = total - align(8*4*B)
+B = s.numel()
+total = scr.numel()
+gstat_off = total - ((8 * 4 * B + 255) // 256) * 256
+rec = scr[gstat_off:gstat_off + 148 * 32 * 32].view(torch.int64).cpu().numpy().reshape(-1, 4)
+t20 = t[20]
+start = (rec[:, 0] - t20) / 1e3; end = (rec[:, 1] - t20) / 1e3
+busy = rec[:, 2]; units = rec[:, 3] & 0xFFFFFFFF; gen = rec[:, 3] >> 32
+ok = rec[:, 1] > 0
+print(f"warps {ok.sum()}  k_pair start->barrier {(t[22]-t20)/1e3:.1f} us; fin {(t[23]-t[22])/1e3:.1f} us")
+print(f"first-unit start: min {start[ok].min():.1f} med {np.median(start[ok]):.1f} max {start[ok].max():.1f} us")
+print(f"loop exit:        min {end[ok].min():.1f} p10 {np.percentile(end[ok],10):.1f} med {np.median(end[ok]):.1f} p90 {np.percentile(end[ok],90):.1f} max {end[ok].max():.1f} us")
+sm_end = end.reshape(148, 32).max(1); sm_busy = busy.reshape(148, 32).sum(1)
+print(f"per-SM last exit: min {sm_end.min():.1f} med {np.median(sm_end):.1f} max {sm_end.max():.1f} us")
+print(f"per-SM busy warp-cycles: min {sm_busy.min()/1e3:.0f}K med {np.median(sm_busy)/1e3:.0f}K max {sm_busy.max()/1e3:.0f}K")
+print(f"units/warp: min {units[ok].min()} med {np.median(units[ok])} max {units[ok].max()}; general tiles/warp max {gen[ok].max()}")
+o = np.argsort(-end)[:5]
+for i in o: print(f"  slow warp cta {i//32} w {i%32}: start {start[i]:.1f} end {end[i]:.1f} busy {busy[i]} units {units[i]} gen {gen[i]}")

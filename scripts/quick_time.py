@@ -23,6 +23,24 @@ def run(d, iters=50):
     n = int(out["n_pair"].item())
     print(f"{d['name']}: B={s.numel()} n_pair={n} {ms*1e3:.1f} us/call  {n/ms/1e6:.2f} Gpairs/s  "
           f"SFU-frac(3 MUFU, 4.65e12/s)={3*n/(ms*1e-3)/4.65e12:.3f} loss={out['loss'].item():.6f} err={ops.device_error(out['_scratch'])}")
+    stamps(out)
+
+def stamps(out):
+    import ctypes as C
+    from rec_now_b200 import _lib
+    ts = (C.c_uint64 * 34)()
+    _lib.lib().rn_debug_timestamps(out["_scratch"].data_ptr(), ts, 34, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    t = list(ts)
+    t0 = t[0]
+    print("   phase stamps (us from k_seg start):", " ".join(f"{i}:{(x - t0) / 1e3:.1f}" for i, x in enumerate(t[:24]) if x))
+    d = t[24:32]
+    print(f"   units={t[32] & 0xFFFFFFFF} C={t[32] >> 32} tiles={t[33]}")
+    if d[4]:
+        M = (1 << 64) - 1
+        print(f"   debug: longest unit {d[0] >> 32} cyc (u={d[0] & 0xFFFFFFFF}); busy/warp-avg {d[1] / 4736:.0f} cyc; "
+              f"loop exit first {((~d[3] & M) - t0) / 1e3:.1f} us last {(d[2] - t0) / 1e3:.1f} us; units {d[4]} fast tiles {d[5]} "
+              f"general {d[6]} general cyc/tile {d[7] / max(d[6], 1):.0f}")
+
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["cfg2", "cfg3"]
