@@ -209,133 +209,198 @@ template <bool HASW>
 __device__ __forceinline__ void tile_fast(const float si0, const float si1, const float wv0, const float wv1,
                                           const float sjm, const float c, float& li0, float& li1, float& gi0,
                                           float& gi1, float& accj) {
+  // Four rotation steps (8 independent pair chains) are issued in lock-step so that the SHFL / MUFU latencies of
+  // one chain are covered by the other seven: a warp issues in order, without this batching every step exposes
+  // its whole dependency chain.
+  constexpr int KB = 4;
   float p0 = 1.f, p1 = 1.f, m0 = 0.f, m1 = 0.f, g0 = 0.f, g1 = 0.f;
 #pragma unroll
-  for (int t = 0; t < 32; ++t) {
-    const float sj = __shfl_xor_sync(0xFFFFFFFFu, sjm, t);
-    const float x0 = (si0 - sj) * c, x1 = (si1 - sj) * c;           // PW:117-119 in log2 units
-    const float e0 = mufu_ex2(-fabsf(x0)), e1 = mufu_ex2(-fabsf(x1));
-    const float t0 = 1.0f + e0, t1 = 1.0f + e1;
-    float d0 = mufu_rcp(t0), d1 = mufu_rcp(t1);                     // sigma(-x) for x < 0
-    p0 *= t0; p1 *= t1;                                            // prod (1+e) <= 2^32
-    if (x0 >= 0.f) d0 *= e0; else m0 -= x0;                         // sigma(-x) = e/(1+e) for x >= 0; max(-x,0)
-    if (x1 >= 0.f) d1 *= e1; else m1 -= x1;
-    if (HASW) { d0 *= wv0; d1 *= wv1; }
-    g0 += d0; g1 += d1;
-    accj += __shfl_xor_sync(0xFFFFFFFFu, d0 + d1, t);
+  for (int tb = 0; tb < 32; tb += KB) {
+    float sj[KB], x0[KB], x1[KB], e0[KB], e1[KB], t0[KB], t1[KB], d0[KB], d1[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) sj[k] = __shfl_xor_sync(0xFFFFFFFFu, sjm, tb + k);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { x0[k] = (si0 - sj[k]) * c; x1[k] = (si1 - sj[k]) * c; }   // PW:117-119, log2 units
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { e0[k] = mufu_ex2(-fabsf(x0[k])); e1[k] = mufu_ex2(-fabsf(x1[k])); }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { t0[k] = 1.0f + e0[k]; t1[k] = 1.0f + e1[k]; }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) { d0[k] = mufu_rcp(t0[k]); d1[k] = mufu_rcp(t1[k]); }        // sigma(-x) for x < 0
+    p0 *= (t0[0] * t0[1]) * (t0[2] * t0[3]);                                               // prod (1+e) <= 2^32
+    p1 *= (t1[0] * t1[1]) * (t1[2] * t1[3]);
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+      if (x0[k] >= 0.f) d0[k] *= e0[k]; else m0 -= x0[k];          // sigma(-x) = e/(1+e) for x >= 0; max(-x,0)
+      if (x1[k] >= 0.f) d1[k] *= e1[k]; else m1 -= x1[k];
+      if (HASW) { d0[k] *= wv0; d1[k] *= wv1; }
+    }
+    g0 += (d0[0] + d0[1]) + (d0[2] + d0[3]);
+    g1 += (d1[0] + d1[1]) + (d1[2] + d1[3]);
+    float back[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) back[k] = __shfl_xor_sync(0xFFFFFFFFu, d0[k] + d1[k], tb + k);
+    accj += (back[0] + back[1]) + (back[2] + back[3]);
   }
   const float L0 = m0 + mufu_lg2(p0), L1 = m1 + mufu_lg2(p1);       // sum softplus(-x) / ln2   (PW:120-121)
   li0 += HASW ? wv0 * L0 : L0; li1 += HASW ? wv1 * L1 : L1;
   gi0 += g0; gi1 += g1;
 }
 
-// Work-unit hand-out: units are dealt round-robin to the CTAs (unit q * gridDim + cta belongs to this CTA), the
-// warps of a CTA take their CTA's units dynamically from a shared-memory counter.  The unit list is ordered by kind
-// (edge tiles of the small groups ... dense tiles of the big groups), so every SM receives the same mix; there is
-// no global ticket (one contended address would serialise every warp of the chip).
-__device__ __forceinline__ u32 take_unit(u32* s_cnt, u32 u_begin, u32 u_end) {
-  const u32 q = atomicAdd(s_cnt, 1u);
-  const u64 u = (u64)u_begin + (u64)q * gridDim.x + blockIdx.x;
-  return u < (u64)u_end ? (u32)u : kDone;
+// Positive-side rows of an I-block (two per lane) and the first J block of a unit: loaded one unit ahead.
+struct UnitRows {
+  uint2 an0, an1; float si0, si1, yi0, yi1, wp0, wp1; float sjm, yjm, wnjm;
+};
+
+template <int MODE>
+__device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, UnitRows& r) {
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
+  const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
+  r.an0 = make_uint2(0, 0); r.an1 = make_uint2(0, 0);
+  r.si0 = r.si1 = r.yi0 = r.yi1 = 0.f; r.wp0 = r.wp1 = 1.f;
+  if (pi0 < B) { r.an0 = A.aj[pi0]; r.si0 = A.ss[pi0]; if (DIFF) r.yi0 = A.sy[pi0]; if (HASW && A.swp) r.wp0 = A.swp[pi0]; }
+  if (pi1 < B) { r.an1 = A.aj[pi1]; r.si1 = A.ss[pi1]; if (DIFF) r.yi1 = A.sy[pi1]; if (HASW && A.swp) r.wp1 = A.swp[pi1]; }
+  const u32 pjm = jb0 * 32 + ln;
+  r.sjm = pjm < B ? A.ss[pjm] : 0.f; r.yjm = 0.f; r.wnjm = 1.f;
+  if (DIFF) r.yjm = pjm < B ? A.sy[pjm] : 0.f;
+  if (RWN) r.wnjm = pjm < B ? A.swn[pjm] : 0.f;
 }
+
+constexpr u32 kMaxRec = 512;            // unit records per CTA and round (shared memory)
 
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
+  // Units are dealt round-robin to the CTAs (the q-th unit of this CTA is unit q * gridDim + cta of the list taken
+  // from its END: edge tiles of the small groups first, dense tiles of the big groups last), so every SM gets the
+  // same mix and there is no global ticket.  The CTA resolves its units to (I-block, J range) records in shared
+  // memory once; its warps then take records dynamically from a shared-memory counter and load the rows of the
+  // NEXT unit while the current one is being scored.
   __shared__ u32 s_cnt;
+  __shared__ uint4 s_rec[kMaxRec];
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
   Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
   const u32 B = P.B;
   stamp(ctl, 20);
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
   {
     const u32 U = ld_relaxed(&ctl->n_units), C = ld_relaxed(&ctl->unit_c);
     const u32 u_begin = (u32)(((u64)U * (u32)P.part_rank) / (u32)P.part_count);
     const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
+    const u32 n_mine = (u_end - u_begin > blockIdx.x) ? (u_end - u_begin - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const float c = P.c_log2;
     // debug tallies (per warp, flushed once): longest unit, busy cycles, units, fast / general tiles
     u64 d_max = 0, d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0; u64 d_gencyc = 0;
     const u64 d_start = P.debug ? globaltimer() : 0;
-    for (;;) {
-      const long long d_t0 = P.debug ? clock64() : 0;
-      u32 u = 0;
-      if (ln == 0) u = take_unit(&s_cnt, u_begin, u_end);
-      u = __shfl_sync(0xFFFFFFFFu, u, 0);
-      if (u == kDone) break;
-      // hand the units out from the END of the list: the small groups (edge tiles, slow general path) come first,
-      // the dense fast tiles of the big groups last, so the tail of the kernel is made of short units
-      u = u_begin + (u_end - 1u - u);
-      // unit -> (I-block b, chunk): largest b with ustart[b] <= u
-      u32 lo_b = 0, hi_b = A.nib;
-      while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (A.ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
-      const u32 b = lo_b;
-      const uint2 bj = A.blk[b];
-      const u32 chunk = u - A.ustart[b];
-      const u32 jb0 = (bj.x >> 5) + chunk * C;
-      u32 jb1 = (bj.y + 31) >> 5; if (jb1 > jb0 + C) jb1 = jb0 + C;
-      // positive side: two rows per lane
-      const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
-      uint2 an0 = make_uint2(0, 0), an1 = make_uint2(0, 0);
-      float si0 = 0.f, si1 = 0.f, yi0 = 0.f, yi1 = 0.f, wp0 = 1.f, wp1 = 1.f;
-      if (pi0 < B) { an0 = A.aj[pi0]; si0 = A.ss[pi0]; if (DIFF) yi0 = A.sy[pi0]; if (HASW && A.swp) wp0 = A.swp[pi0]; }
-      if (pi1 < B) { an1 = A.aj[pi1]; si1 = A.ss[pi1]; if (DIFF) yi1 = A.sy[pi1]; if (HASW && A.swp) wp1 = A.swp[pi1]; }
-      const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
-      float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
-      u32 pjm = jb0 * 32 + ln;
-      float sjm = pjm < B ? A.ss[pjm] : 0.f, yjm = 0.f, wnjm = 1.f;
-      if (DIFF) yjm = pjm < B ? A.sy[pjm] : 0.f;
-      if (RWN) wnjm = pjm < B ? A.swn[pjm] : 0.f;
-      for (u32 jb = jb0; jb < jb1; ++jb) {
-        // prefetch the next J-block while this one is being scored
-        const u32 pjn = pjm + 32;
-        const bool more = (jb + 1 < jb1) && pjn < B;
-        float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
-        if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
-        if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
-        float accj = 0.f;
-        const u32 j0 = jb * 32;
-        const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
-        const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
-        bool fast = full0 && full1 && !RWN && !WRONG;
-        if (DIFF && fast) fast = __all_sync(0xFFFFFFFFu, yjm == __shfl_sync(0xFFFFFFFFu, yjm, 0));
-        if (P.debug) { if (fast) ++d_fast; else ++d_gen; }
-        const long long d_g0 = (P.debug && !fast) ? clock64() : 0;
-        if (fast) {
-          float wv0 = wp0, wv1 = wp1;
-          if (DIFF) { wv0 = (yi0 - yjm) * wp0; wv1 = (yi1 - yjm) * wp1; }    // yjm is uniform over the block
-          tile_fast<HASW>(si0, si1, wv0, wv1, sjm, c, li0, li1, gi0, gi1, accj);
-        } else {
-          const bool any0 = __any_sync(0xFFFFFFFFu, lo0 < j0 + 32 && hi0 > j0);
-          const bool any1 = __any_sync(0xFFFFFFFFu, lo1 < j0 + 32 && hi1 > j0);
-          if (any0) {
-            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
-            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+    for (u32 q0 = 0; q0 < n_mine; q0 += kMaxRec) {
+      const u32 nrec = min(kMaxRec, n_mine - q0);
+      __syncthreads();
+      if (threadIdx.x == 0) s_cnt = 0;
+      for (u32 k = threadIdx.x; k < nrec; k += kPairThreads) {
+        const u32 u = u_end - 1u - ((q0 + k) * gridDim.x + blockIdx.x);
+        // unit -> (I-block b, chunk): largest b with ustart[b] <= u
+        u32 lo_b = 0, hi_b = A.nib;
+        while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (A.ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
+        const uint2 bj = A.blk[lo_b];
+        const u32 jb0 = (bj.x >> 5) + (u - A.ustart[lo_b]) * C;
+        u32 jb1 = (bj.y + 31) >> 5; if (jb1 > jb0 + C) jb1 = jb0 + C;
+        s_rec[k] = make_uint4(lo_b, jb0, jb1, u);
+      }
+      __syncthreads();
+      auto take = [&](uint4& rec) -> bool {
+        u32 q = 0;
+        if (ln == 0) q = atomicAdd(&s_cnt, 1u);
+        q = __shfl_sync(0xFFFFFFFFu, q, 0);
+        if (q >= nrec) return false;
+        rec = s_rec[q];
+        return true;
+      };
+      uint4 rec, rec_n; UnitRows R, Rn;
+      bool have = take(rec);
+      if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y, ln, R);
+      while (have) {
+        const long long d_t0 = P.debug ? clock64() : 0;
+        const bool have_n = take(rec_n);
+        if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y, ln, Rn);      // in flight while this unit is scored
+        const u32 b = rec.x, jb0 = rec.y, jb1 = rec.z;
+        const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
+        const uint2 an0 = R.an0, an1 = R.an1;
+        const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
+        const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
+        float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
+        u32 pjm = jb0 * 32 + ln;
+        float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
+        for (u32 jb = jb0; jb < jb1; ++jb) {
+          // prefetch the next J-block while this one is being scored
+          const u32 pjn = pjm + 32;
+          const bool more = (jb + 1 < jb1) && pjn < B;
+          float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
+          if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
+          if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
+          float accj = 0.f;
+          const u32 j0 = jb * 32;
+          // Overlap of every row's negative range with this J block.  Row ranges start at a group start and end at
+          // a level start of the same group, so a row covers a (group, level) run of the block entirely or not at
+          // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
+          // value, the block is scored by the fast tile with out-of-range negatives replaced by a sentinel score
+          // (x = +inf: e = 0, sigma = 0, factor 1 in the product) and rows that do not touch it weighted 0.
+          const u32 s0 = max(lo0, j0), e0 = min(hi0, j0 + 32), s1 = max(lo1, j0), e1 = min(hi1, j0 + 32);
+          const bool in0 = s0 < e0, in1 = s1 < e1;
+          const u32 smin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? s0 : 0xFFFFFFFFu, in1 ? s1 : 0xFFFFFFFFu));
+          const u32 smax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? s0 : 0u, in1 ? s1 : 0u));
+          const u32 emin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? e0 : 0xFFFFFFFFu, in1 ? e1 : 0xFFFFFFFFu));
+          const u32 emax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? e0 : 0u, in1 ? e1 : 0u));
+          const bool any_in = smin != 0xFFFFFFFFu;
+          const bool jin = pjm >= smin && pjm < emax;                  // this lane's negative is inside the overlap
+          bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG;
+          float yref = 0.f;
+          if (DIFF && fast) {
+            yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
+            fast = __all_sync(0xFFFFFFFFu, !jin || yjm == yref);
           }
-          if (any1) {
-            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
-            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+          if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; }
+          const long long d_g0 = (P.debug && !fast) ? clock64() : 0;
+          if (fast) {
+            float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
+            if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
+            const float sje = jin ? sjm : -3.0e38f;
+            const bool whole = __all_sync(0xFFFFFFFFu, in0 && in1);
+            if (HASW || !whole) tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+            else                tile_fast<false>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+          } else if (any_in) {
+            const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
+            const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
+            const bool any0 = __any_sync(0xFFFFFFFFu, in0);
+            const bool any1 = __any_sync(0xFFFFFFFFu, in1);
+            if (any0) {
+              if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+              else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+            }
+            if (any1) {
+              if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+              else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+            }
           }
+          if (P.debug && !fast) d_gencyc += (u64)(clock64() - d_g0);
+          if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
+          pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
         }
-        if (P.debug && !fast) d_gencyc += (u64)(clock64() - d_g0);
-        if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
-        pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
-      }
-      if (pi0 < B && an0.y) {
-        if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
-        if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
-        if ((WRONG || RWN) && cnt0) atomicAdd(A.cnt + pi0, cnt0);
-      }
-      if (pi1 < B && an1.y) {
-        if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
-        if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
-        if ((WRONG || RWN) && cnt1) atomicAdd(A.cnt + pi1, cnt1);
-      }
-      if (P.debug) {
-        const u64 dt = (u64)(clock64() - d_t0);
-        d_busy += dt; ++d_units;
-        const u64 enc = (dt << 32) | u;
-        if (enc > d_max) d_max = enc;
+        if (pi0 < B && an0.y) {
+          if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
+          if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
+          if ((WRONG || RWN) && cnt0) atomicAdd(A.cnt + pi0, cnt0);
+        }
+        if (pi1 < B && an1.y) {
+          if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
+          if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
+          if ((WRONG || RWN) && cnt1) atomicAdd(A.cnt + pi1, cnt1);
+        }
+        if (P.debug) {
+          const u64 dt = (u64)(clock64() - d_t0);
+          d_busy += dt; ++d_units;
+          const u64 enc = (dt << 32) | rec.w;
+          if (enc > d_max) d_max = enc;
+        }
+        have = have_n; rec = rec_n; R = Rn;
       }
     }
     if (P.debug && ln == 0) {

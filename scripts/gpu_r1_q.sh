@@ -1,0 +1,2 @@
+timeout 900 python -m pytest tests/test_pairwise_gpu.py -m gpu -x -q 2>&1 | tail -2
+for tu in 8192 16384 32768; do echo "== TARGET_UNITS=$tu"; NW=32 RN_PAIR_DEBUG=1 RN_TARGET_UNITS=$tu timeout 120 python scripts/pair_debug.py cfg3 2>&1 | grep -E "loop exit|per-SM last|start->";  RN_TARGET_UNITS=$tu timeout 120 python scripts/quick_time.py cfg3 2>&1 | tail -3 | head -2; done

@@ -20,9 +20,10 @@ t = list(ts)
 # locate gstat: the arena layout is deterministic; find it by scanning for the record pattern instead of
 # duplicating the layout here: records start at the gstat offset = total - align(8*4*B)
 B = s.numel()
+NW = int(__import__('os').environ.get('NW', '16'))
 total = scr.numel()
 gstat_off = total - ((8 * 4 * B + 255) // 256) * 256
-rec = scr[gstat_off:gstat_off + 148 * 32 * 32].view(torch.int64).cpu().numpy().reshape(-1, 4)
+rec = scr[gstat_off:gstat_off + 148 * NW * 32].view(torch.int64).cpu().numpy().reshape(-1, 4)
 t20 = t[20]
 start = (rec[:, 0] - t20) / 1e3; end = (rec[:, 1] - t20) / 1e3
 busy = rec[:, 2]; units = rec[:, 3] & 0xFFFFFFFF; gen = rec[:, 3] >> 32
@@ -30,9 +31,16 @@ ok = rec[:, 1] > 0
 print(f"warps {ok.sum()}  k_pair start->barrier {(t[22]-t20)/1e3:.1f} us; fin {(t[23]-t[22])/1e3:.1f} us")
 print(f"first-unit start: min {start[ok].min():.1f} med {np.median(start[ok]):.1f} max {start[ok].max():.1f} us")
 print(f"loop exit:        min {end[ok].min():.1f} p10 {np.percentile(end[ok],10):.1f} med {np.median(end[ok]):.1f} p90 {np.percentile(end[ok],90):.1f} max {end[ok].max():.1f} us")
-sm_end = end.reshape(148, 32).max(1); sm_busy = busy.reshape(148, 32).sum(1)
+sm_end = end.reshape(148, NW).max(1); sm_busy = busy.reshape(148, NW).sum(1)
 print(f"per-SM last exit: min {sm_end.min():.1f} med {np.median(sm_end):.1f} max {sm_end.max():.1f} us")
 print(f"per-SM busy warp-cycles: min {sm_busy.min()/1e3:.0f}K med {np.median(sm_busy)/1e3:.0f}K max {sm_busy.max()/1e3:.0f}K")
 print(f"units/warp: min {units[ok].min()} med {np.median(units[ok])} max {units[ok].max()}; general tiles/warp max {gen[ok].max()}")
 o = np.argsort(-end)[:5]
-for i in o: print(f"  slow warp cta {i//32} w {i%32}: start {start[i]:.1f} end {end[i]:.1f} busy {busy[i]} units {units[i]} gen {gen[i]}")
+for i in o: print(f"  slow warp cta {i//NW} w {i%NW}: start {start[i]:.1f} end {end[i]:.1f} busy {busy[i]} units {units[i]} gen {gen[i]}")
+sm_units = units.reshape(148, NW).sum(1); sm_gen = gen.reshape(148, NW).sum(1)
+o = np.argsort(sm_end)
+print("per-SM (sorted by last exit): sm exit busyK units gen | warp exits sorted")
+for i in list(o[:3]) + list(o[-4:]):
+    we = np.sort(end.reshape(148, NW)[i])
+    print(f"  sm {i:3d} exit {sm_end[i]:.1f} busy {sm_busy[i]/1e3:.0f}K units {sm_units[i]} gen {sm_gen[i]} | " + " ".join(f"{x:.0f}" for x in we[::max(1,NW//8)]) + f" {we[-1]:.0f}")
+print("corr(exit, busy) =", np.corrcoef(sm_end, sm_busy)[0,1], " corr(exit, gen) =", np.corrcoef(sm_end, sm_gen)[0,1])
