@@ -1,5 +1,4 @@
 set -x
-python __graft_entry__.py smoke 2>&1 | tail -5
+python __graft_entry__.py smoke 2>&1 | tail -3
 python bench.py --steps 200 --warmup 20 2> gpurun_out/bench_err.log | tee gpurun_out/bench_n1.json
 tail -5 gpurun_out/bench_err.log
-python bench.py --impl reference --steps 5 --warmup 1 | tee gpurun_out/bench_ref.json

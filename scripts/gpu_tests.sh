@@ -1,3 +1,2 @@
 set -x
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -40
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -15

@@ -138,3 +138,60 @@ def test_partition_partials_sum_to_full(parts):
     ref = S.pairwise(d["s"], y, d["g"], spec)
     err = np.abs(grad.cpu().numpy() - ref["grad"])
     assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all()
+
+
+def test_cfg3_full_size():
+    """BASELINE.json config 3 at full size (B = 65536, graded labels, per-sample weights, power -0.5) against the
+    float64 segmented oracle: exact counts, 1e-5 loss / gradient."""
+    d = G.cfg3(0)
+    spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=d["w"])
+    out = run_pairwise(d["s"], d["y"], d["g"], spec)
+    r = check_pairwise(out, S.pairwise(d["s"], d["y"], d["g"], spec), ctx="cfg3")
+    print("cfg3 parity", r, "n_pair", int(out["n_pair"].item()))
+
+
+def test_size_independent_properties_full_size():
+    """Properties that need no oracle, at B = 65536: (1) the gradient sums to zero (every pair adds +d to one row
+    and -d to another); (2) n_pair == sum(row_pairs); (3) permuting the rows and relabelling the group ids permutes
+    the gradient and leaves n_pair / loss unchanged; (4) the loss of reduce_mean=False equals n_pair * mean loss."""
+    d = G.cfg3(1)
+    rng = np.random.default_rng(7)
+    spec = S.PairSpec(power=0.0, label_func="diff", rw_pos=d["w"])
+    out = run_pairwise(d["s"], d["y"], d["g"], spec)
+    g = out["dlogits"].double().cpu().numpy()
+    n = int(out["n_pair"].item())
+    assert abs(g.sum()) <= 1e-6 * np.abs(g).sum()
+    assert int(out["row_pairs"].sum().item()) == n
+    perm = rng.permutation(g.size)
+    ids2 = (d["g"] ^ np.int64(0x5DEECE66D))[perm]                 # bijective relabelling
+    w2 = d["w"][perm]
+    out2 = run_pairwise(d["s"][perm], d["y"][perm], ids2, S.PairSpec(power=0.0, label_func="diff", rw_pos=w2))
+    assert int(out2["n_pair"].item()) == n
+    l1, l2 = float(out["loss"].item()), float(out2["loss"].item())
+    assert abs(l1 - l2) <= 2e-6 * abs(l1)
+    g2 = out2["dlogits"].double().cpu().numpy()
+    scale = np.abs(g).max()
+    assert np.abs(g2 - g[perm]).max() <= 2e-6 * scale
+    assert np.array_equal(out2["row_pairs"].cpu().numpy(), out["row_pairs"].cpu().numpy()[perm])
+    out3 = run_pairwise(d["s"], d["y"], d["g"], S.PairSpec(power=0.0, label_func="diff", rw_pos=d["w"], reduce_mean=False))
+    assert abs(float(out3["loss"].item()) - l1 * n) <= 2e-6 * abs(l1 * n)
+
+
+def test_edge_tiles_and_wide_logits():
+    """Groups whose level runs straddle the 32-row J blocks and 64-row I blocks in every way (sizes 1..200, 1-7
+    label levels), logits spread over +-60 (softplus from ~1e-26 to ~60): exercises the sentinel / zero-weight fast
+    tile and the general tile against the oracle."""
+    rng = np.random.default_rng(11)
+    sizes = np.r_[np.arange(1, 201), rng.integers(1, 200, 150)]
+    gidx = np.repeat(np.arange(sizes.size), sizes)
+    b = gidx.size
+    perm = rng.permutation(b)
+    gidx = gidx[perm]
+    levels = rng.integers(1, 8, sizes.size)
+    y = (rng.integers(0, 1 << 30, b) % levels[gidx]).astype(np.float32)
+    s = (rng.standard_normal(b) * 20).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, b).astype(np.float32)
+    ids = gidx.astype(np.int64) * 1000003 + 17
+    for spec in (S.PairSpec(), S.PairSpec(power=-0.5, label_func="diff", rw_pos=w), S.PairSpec(rw_pos=w, factor=0.3)):
+        out = run_pairwise(s, y, ids, spec)
+        check_pairwise(out, S.pairwise(s, y, ids, spec), ctx=f"edge {spec.label_func}")
