@@ -24,110 +24,140 @@ __device__ __forceinline__ float warp_maxf(float v) {
   return v;
 }
 
-// One warp per 32 sorted positions; the warp processes every list whose head falls in its block.
-__global__ void __launch_bounds__(256) k_lw_group(LwParams P, const u32* __restrict__ astart,
-                                                  const u32* __restrict__ gend, const float* __restrict__ ss,
-                                                  const float* __restrict__ sy, float* __restrict__ rec, Ctl* ctl) {
-  const u32 ln = lane_id();
-  const u32 blk = (blockIdx.x * 256u + threadIdx.x) >> 5;
-  const u32 p = blk * 32 + ln;
-  const bool head = p < P.B && astart[p] == p;
-  u32 heads = __ballot_sync(0xFFFFFFFFu, head);
-  u32 ng = __popc(heads), nv = 0;
-  while (heads) {
-    const u32 h = __ffs(heads) - 1; heads &= heads - 1;
-    const u32 a = blk * 32 + h, e = gend[a];
-    float m = -INFINITY;
-    for (u32 q = a + ln; q < e; q += 32) m = fmaxf(m, ss[q]);
-    m = warp_maxf(m);
-    float z = 0.f, sumy = 0.f; int hp = 0, hn = 0;
-    for (u32 q = a + ln; q < e; q += 32) {
-      const float s = ss[q], y = sy[q];
-      z += expf(s - m); sumy += y;
-      hp |= (y > P.th); hn |= ((y - P.th) < 0.f);                // LW:135-136
-    }
-    z = warp_sum(z); sumy = warp_sum(sumy);
-    const bool valid = __any_sync(0xFFFFFFFFu, hp) && __any_sync(0xFFFFFFFFu, hn);   // LW:137
-    const float lse = logf(z);
-    float dot = 0.f;
-    if (valid)
-      for (u32 q = a + ln; q < e; q += 32) dot += (sy[q] / sumy) * (lse - (ss[q] - m));   // LW:144, LW:167
-    dot = warp_sum(dot);
-    if (ln == 0) {
-      rec[(size_t)R_MAX * P.B + a] = m; rec[(size_t)R_LSE * P.B + a] = lse; rec[(size_t)R_SY * P.B + a] = sumy;
-      rec[(size_t)R_LOSS * P.B + a] = dot; rec[(size_t)R_VALID * P.B + a] = valid ? 1.f : 0.f;
-    }
-    nv += valid ? 1u : 0u;
-  }
-  if (ln == 0) {
-    if (ng) atomicAdd(&ctl->n_groups, ng);
-    if (nv) atomicAdd(&ctl->n_valid, nv);
-  }
-}
+// Listwise tail of k_seg: bounds -> per-list statistics -> ranks of the valid lists + weighted losses -> gradient,
+// separated by grid barriers (one launch instead of five).
+struct ListwiseTail {
+  BoundsTail bounds;            // astart / gend / perm + gathers of logits (ss) and labels (sy)
+  LwParams P;
+  const float* ss; const float* sy; float* rec; u32* chunkcnt;
 
-// Single block: rank of every valid list (exclusive scan of the valid flags over head positions, which are in
-// first-occurrence order), per-list weighted losses and their sum in a fixed order.
-__global__ void __launch_bounds__(1024) k_lw_rank(LwParams P, const u32* __restrict__ astart, float* __restrict__ rec,
-                                                  Ctl* ctl) {
-  __shared__ u32 wsum[32];
-  __shared__ double dsum[32];
-  __shared__ u32 s_carry;
-  const u32 ln = lane_id(), w = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
-  __syncthreads();
-  double acc = 0.0;
-  for (u32 p0 = 0; p0 < P.B; p0 += 1024) {
-    const u32 p = p0 + threadIdx.x;
-    const bool v = p < P.B && astart[p] == p && rec[(size_t)R_VALID * P.B + p] != 0.f;
-    u32 inc = v ? 1u : 0u;
+  // One warp per 32 sorted positions; the warp processes every list whose head falls in its block.
+  __device__ __forceinline__ u32 group_block(u32 blk, Ctl* ctl) const {
+    const u32 ln = lane_id();
+    const u32 p = blk * 32 + ln;
+    const u32* astart = bounds.astart; const u32* gend = bounds.gend;
+    const bool head = p < P.B && astart[p] == p;
+    u32 heads = __ballot_sync(0xFFFFFFFFu, head);
+    u32 ng = __popc(heads), nv = 0;
+    while (heads) {
+      const u32 h = __ffs(heads) - 1; heads &= heads - 1;
+      const u32 a = blk * 32 + h, e = gend[a];
+      float m = -INFINITY;
+      for (u32 q = a + ln; q < e; q += 32) m = fmaxf(m, ss[q]);
+      m = warp_maxf(m);
+      float z = 0.f, sumy = 0.f; int hp = 0, hn = 0;
+      for (u32 q = a + ln; q < e; q += 32) {
+        const float s = ss[q], y = sy[q];
+        z += expf(s - m); sumy += y;
+        hp |= (y > P.th); hn |= ((y - P.th) < 0.f);                // LW:135-136
+      }
+      z = warp_sum(z); sumy = warp_sum(sumy);
+      const bool valid = __any_sync(0xFFFFFFFFu, hp) && __any_sync(0xFFFFFFFFu, hn);   // LW:137
+      const float lse = logf(z);
+      float dot = 0.f;
+      if (valid)
+        for (u32 q = a + ln; q < e; q += 32) dot += (sy[q] / sumy) * (lse - (ss[q] - m));   // LW:144, LW:167
+      dot = warp_sum(dot);
+      if (ln == 0) {
+        rec[(size_t)R_MAX * P.B + a] = m; rec[(size_t)R_LSE * P.B + a] = lse; rec[(size_t)R_SY * P.B + a] = sumy;
+        rec[(size_t)R_LOSS * P.B + a] = dot; rec[(size_t)R_VALID * P.B + a] = valid ? 1.f : 0.f;
+      }
+      nv += valid ? 1u : 0u;
+    }
+    if (ln == 0 && ng) atomicAdd(&ctl->n_groups, ng);
+    return nv;
+  }
+
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
+                                      u32& epoch) const {
+    Ctl* ctl = S.ctl;
+    const u32 B = P.B, ln = lane_id(), w = threadIdx.x >> 5;
+    const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
+    const u32* astart = bounds.astart;
+    bounds.run(S, pl, key, val, smem, epoch);
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+    // ---- per-list statistics; valid lists per 512-position chunk -------------------------------------------
+    u32* sm_cnt = smem;                    // [kSegWarps]
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+      const u32 nv = group_block(c * kSegWarps + w, ctl);
+      if (ln == 0) sm_cnt[w] = nv;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        u32 t = 0;
+        for (int q = 0; q < kSegWarps; ++q) t += sm_cnt[q];
+        chunkcnt[c] = t;
+        if (t) atomicAdd(&ctl->n_valid, t);
+      }
+      __syncthreads();
+    }
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+    // ---- rank of every valid list (exclusive scan of the valid flags over head positions = first-occurrence
+    //      order, LW:109), per-list weighted losses, their sum ------------------------------------------------
+    u32* sm_scan = smem;                   // [kSegWarps]
+    u32* sm_off = smem + kSegWarps;        // [1]
+    double* sm_d = reinterpret_cast<double*>(smem + 32);   // [kSegWarps]
+    double acc = 0.0;
+    for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+      u32 part = 0;
+      for (u32 q = threadIdx.x; q < c; q += kSegThreads) part += chunkcnt[q];
+      part = warp_sum(part);
+      if (ln == 0) sm_scan[w] = part;
+      __syncthreads();
+      if (threadIdx.x == 0) { u32 t = 0; for (int q = 0; q < kSegWarps; ++q) t += sm_scan[q]; *sm_off = t; }
+      __syncthreads();
+      const u32 base = *sm_off;
+      __syncthreads();
+      const u32 p = c * kSegThreads + threadIdx.x;
+      const bool v = p < B && astart[p] == p && rec[(size_t)R_VALID * B + p] != 0.f;
+      u32 inc = v ? 1u : 0u;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { u32 t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += t; }
-    if (ln == 31) wsum[w] = inc;
-    __syncthreads();
-    u32 off = s_carry;
-    for (u32 k = 0; k < w; ++k) off += wsum[k];
-    if (v) {
-      const u32 r = off + inc - 1;
-      float l = rec[(size_t)R_LOSS * P.B + p];
-      if (P.list_w) l *= P.list_w[r];                              // LW:168-169
-      rec[(size_t)R_RANK * P.B + p] = __uint_as_float(r);
-      if (P.list_loss) P.list_loss[r] = l;
-      acc += (double)l;
+      for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+      if (ln == 31) sm_scan[w] = inc;
+      __syncthreads();
+      u32 off = base;
+      for (u32 q = 0; q < w; ++q) off += sm_scan[q];
+      if (v) {
+        const u32 r = off + inc - 1;
+        float l = rec[(size_t)R_LOSS * B + p];
+        if (P.list_w) l *= P.list_w[r];                              // LW:168-169
+        rec[(size_t)R_RANK * B + p] = __uint_as_float(r);
+        if (P.list_loss) P.list_loss[r] = l;
+        acc += (double)l;
+      }
+      __syncthreads();
     }
+    acc = warp_sum(acc);
+    if (ln == 0) sm_d[w] = acc;
     __syncthreads();
-    if (threadIdx.x == 1023) s_carry = off + inc;
-    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int q = 0; q < kSegWarps; ++q) t += sm_d[q];
+      if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
+    }
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+    // ---- gradient + scalars -------------------------------------------------------------------------------
+    const u32 V = ld_relaxed(&ctl->n_valid);
+    const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;
+    for (u32 p = gtid; p < B; p += gthreads) {
+      const u32 a = astart[p];
+      float g = 0.f;
+      if (rec[(size_t)R_VALID * B + a] != 0.f) {
+        const float m = rec[(size_t)R_MAX * B + a], lse = rec[(size_t)R_LSE * B + a], sumy = rec[(size_t)R_SY * B + a];
+        float wr = 1.f;
+        if (P.list_w) wr = P.list_w[__float_as_uint(rec[(size_t)R_RANK * B + a])];
+        if (P.do_reduce) wr /= (float)V;
+        g = wr * (expf(ss[p] - m - lse) - sy[p] / sumy);               // xent backprop: softmax - labels
+      }
+      P.dlogits[bounds.perm[p]] = g;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const double t = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
+      if (P.do_reduce) *P.loss = V ? (float)(t / (double)V) : 0.f;   // LW:171-172 (mean; NaN -> 0)
+      *P.n_valid = (int32_t)V;
+      *P.n_group = (int32_t)ld_relaxed(&ctl->n_groups);
+    }
   }
-  acc = warp_sum(acc);
-  if (ln == 0) dsum[w] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = 0;
-    for (int k = 0; k < 32; ++k) t += dsum[k];
-    const u32 V = ctl->n_valid;
-    if (P.do_reduce) *P.loss = V ? (float)(t / (double)V) : 0.f;   // LW:171-172 (mean; NaN -> 0)
-    *P.n_valid = (int32_t)V;
-    *P.n_group = (int32_t)ctl->n_groups;
-  }
-}
-
-__global__ void __launch_bounds__(256) k_lw_grad(LwParams P, const u32* __restrict__ astart,
-                                                 const u32* __restrict__ perm, const float* __restrict__ ss,
-                                                 const float* __restrict__ sy, const float* __restrict__ rec,
-                                                 const Ctl* ctl) {
-  const u32 p = blockIdx.x * 256u + threadIdx.x;
-  if (p >= P.B) return;
-  const u32 a = astart[p];
-  float g = 0.f;
-  if (rec[(size_t)R_VALID * P.B + a] != 0.f) {
-    const float m = rec[(size_t)R_MAX * P.B + a], lse = rec[(size_t)R_LSE * P.B + a], sumy = rec[(size_t)R_SY * P.B + a];
-    float wr = 1.f;
-    if (P.list_w) wr = P.list_w[__float_as_uint(rec[(size_t)R_RANK * P.B + a])];
-    if (P.do_reduce) wr /= (float)ctl->n_valid;
-    g = wr * (expf(ss[p] - m - lse) - sy[p] / sumy);               // xent backprop: softmax - labels
-  }
-  P.dlogits[perm[p]] = g;
-}
+};
 
 __global__ void __launch_bounds__(256) k_lw_dense_fill(size_t n, uint8_t* __restrict__ dm, float* __restrict__ dl,
                                                        float* __restrict__ dz, float pad) {
@@ -163,7 +193,7 @@ extern "C" int rn_listwise_launch_count(int64_t B) {
   if (B <= 0) return 0;
   const Layout L = make_layout(B, 1);
   (void)L;
-  return 2 + 3;    // k_init, k_seg<BoundsTail>, k_lw_group, k_lw_rank, k_lw_grad
+  return 2;        // k_init, k_seg<ListwiseTail>
 }
 
 static int validate_listwise(const rn_listwise_args* a) {
@@ -192,15 +222,10 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   float* sy = at<float>(base, L.sy);
   float* rec = at<float>(base, L.gstat);
   GatherCols gc{{a->logits, a->labels, nullptr, nullptr}, {ss, sy, nullptr, nullptr}};
-  BoundsTail T{astart, gend, perm, gc};
-  if (seg_run(L, scratch, in, T, st) != cudaSuccess) return RN_ERR_LAUNCH;
   LwParams P{(u32)a->B, L.gbits, a->list_w, a->pos_neg_th, a->do_reduce, a->loss, a->list_loss, a->n_valid,
              a->n_group, a->dlogits};
-  Ctl* ctl = at<Ctl>(base, L.ctl);
-  const u32 g256 = (u32)((a->B + 255) / 256);
-  k_lw_group<<<g256, 256, 0, st>>>(P, astart, gend, ss, sy, rec, ctl);
-  k_lw_rank<<<1, 1024, 0, st>>>(P, astart, rec, ctl);
-  k_lw_grad<<<g256, 256, 0, st>>>(P, astart, perm, ss, sy, rec, ctl);
+  ListwiseTail T{BoundsTail{astart, gend, perm, gc}, P, ss, sy, rec, at<u32>(base, L.blk)};
+  if (seg_run(L, scratch, in, T, st) != cudaSuccess) return RN_ERR_LAUNCH;
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
 }
 

@@ -13,8 +13,43 @@ from . import _lib
 from ._lib import ListwiseArgs, PairwiseArgs, check, lib
 
 
-def _stream() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(dev=None) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+# Scratch arenas are reused per (device, stream, size): calls on one stream are ordered, so the next call may
+# overwrite the arena of the previous one (its outputs live in their own tensors).  Set to False to get a fresh
+# arena per call (needed when the control block of an earlier call is inspected after a later one was enqueued).
+REUSE_SCRATCH = True
+_scratch_cache: dict = {}
+
+
+def _scratch(nbytes: int, dev: torch.device, stream_ptr: int) -> torch.Tensor:
+    if not REUSE_SCRATCH:
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    key = (dev.index, stream_ptr, nbytes)
+    t = _scratch_cache.get(key)
+    if t is None:
+        if len(_scratch_cache) > 64:
+            _scratch_cache.clear()
+        t = _scratch_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    return t
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -30,6 +65,8 @@ def _need_cuda(*ts):
 def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t.detach().view(-1)
     return t.detach().reshape(-1).to(torch.float32).contiguous()
 
 
@@ -43,6 +80,9 @@ def canon_keys(groups, row_ok: Optional[torch.Tensor] = None):
     _need_cuda(*cols)
     b = cols[0].numel()
     dev = cols[0].device
+    if len(cols) == 1 and cols[0].dtype is torch.int64 and cols[0].is_contiguous():
+        ok = None if row_ok is None else row_ok.detach().reshape(-1).to(torch.uint8).contiguous()
+        return cols[0].detach().view(1, -1), ok                  # integer ids are canonical as they are
     keys = torch.empty((len(cols), b), dtype=torch.int64, device=dev)
     ok = None if row_ok is None else row_ok.detach().reshape(-1).to(torch.uint8).contiguous().clone()
     for k, g in enumerate(cols):
@@ -71,29 +111,31 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()
-    keys = keys.reshape(-1, b).contiguous()
+    if keys.dim() != 2 or not keys.is_contiguous():
+        keys = keys.reshape(-1, b).contiguous()
     kk = keys.shape[0]
     dev = s.device
     rwp, rwn = _f32(rw_pos), _f32(rw_neg)
     ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
-    out = torch.empty(2, dtype=torch.float32, device=dev)          # loss, n_pair_f32
-    n_pair = torch.empty(1, dtype=torch.int64, device=dev)
+    out = torch.empty(4, dtype=torch.float32, device=dev)          # loss, n_pair_f32, n_pair (int64 in [2:4])
     dlogits = torch.empty(b, dtype=torch.float32, device=dev)
     row_pairs = torch.empty(b, dtype=torch.int64, device=dev) if want_row_pairs else None
     nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    scratch = _scratch(nbytes, dev, st)
+    po = out.data_ptr()
     a = PairwiseArgs(
         B=b, K=kk, label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
         keys=keys.data_ptr(), logits=s.data_ptr(), labels=y.data_ptr(),
         row_ok=_ptr(ok), rw_pos=_ptr(rwp), rw_neg=_ptr(rwn),
         factor=float(factor), power=float(power), only_wrong=int(bool(only_wrong)),
         reduce_mean=int(bool(reduce_mean)), part_rank=int(part[0]), part_count=int(part[1]),
-        loss=out.data_ptr(), n_pair_f32=out.data_ptr() + 4, n_pair=n_pair.data_ptr(),
+        loss=po, n_pair_f32=po + 4, n_pair=po + 8,
         dlogits=dlogits.data_ptr(), row_pairs=_ptr(row_pairs))
-    with torch.cuda.device(dev):
-        check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, _stream()), "rn_pairwise_fwd_bwd")
-    return dict(loss=out[0], n_pair_f32=out[1], n_pair=n_pair[0], dlogits=dlogits, row_pairs=row_pairs,
-                _scratch=scratch)
+    with _on_device(dev):
+        check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, C.c_void_p(st)), "rn_pairwise_fwd_bwd")
+    return dict(loss=out[0], n_pair_f32=out[1], n_pair=out[2:4].view(torch.int64)[0], dlogits=dlogits,
+                row_pairs=row_pairs, _scratch=scratch)
 
 
 def device_error(scratch: torch.Tensor) -> int:
