@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include "../../include/recnow_b200.h"
 
 namespace rn {
@@ -70,10 +71,18 @@ struct Layout {
   // 0xFF-initialised region
   size_t table, table1;
   // plain
-  size_t slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, blk, ustart, misc, gstat;
+  size_t slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Work-list granularity of the pair kernel: the J ranges of the I-blocks are cut into about this many units
+// (developer knob RN_TARGET_UNITS).
+inline u32 target_units() {
+  static u32 n = 0;
+  if (!n) { const char* v = getenv("RN_TARGET_UNITS"); const long x = (v && *v) ? atol(v) : 0; n = (x > 0 && x <= (1 << 22)) ? (u32)x : 16384u; }
+  return n;
+}
 
 inline Layout make_layout(int64_t B, int K) {
   Layout L; L.B = B; L.K = K;
@@ -110,8 +119,9 @@ inline Layout make_layout(int64_t B, int K) {
   L.gacc = take(sizeof(float) * B);
   L.lossrow = take(sizeof(float) * B);
   L.cnt = take(sizeof(u32) * B);
+  L.perm = take(sizeof(u32) * B);
   L.blk = take(sizeof(uint2) * L.nib);
-  L.ustart = take(sizeof(u32) * (L.nib + 1));
+  L.units = take(sizeof(uint2) * ((size_t)L.nib + target_units() + 1));
   L.misc = take(sizeof(u64) * (B + 1));
   L.gstat = take(sizeof(float) * 8 * B);   // listwise per-list records
   L.total = o;

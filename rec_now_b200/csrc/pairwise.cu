@@ -20,6 +20,7 @@
 // No shared memory in the pair loop, no dense contraction, no tensor cores: the roofline is the SFU pipe.
 #include <stdlib.h>
 #include "segment.cuh"
+#include "pair_tiles.cuh"
 
 namespace rn {
 
@@ -39,15 +40,17 @@ struct PairParams {
   const float* logits; const float* labels; const float* rw_pos; const float* rw_neg;
   float c_log2;          // factor * log2(e)
   float factor, power; int reduce_mean; int dyn_count; int debug;
-  int part_rank, part_count;
+  int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
 };
 
 // ---- heads tail of k_seg ---------------------------------------------------------------------------------
+// Work units: an I-block (64 sorted rows) x up to C consecutive J-blocks (32 sorted rows each) of its J range.
+// Record = (I-block, first J-block | J-block count << 24).
 struct HeadsTail {
   PairParams P;
-  uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32* cnt;
-  uint2* blk; u32* ustart; u32 nib; u64* cprim; const u32* pgid;
+  uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32 *cnt, *perm;
+  uint2* blk; uint2* units; u32 nib; u64* cprim; const u32* pgid;
   u32 target_units;          // work-list granularity target (units of <= C J-blocks)
 
   __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
@@ -59,6 +62,7 @@ struct HeadsTail {
     Ctl* ctl = S.ctl;
     const u32 B = S.B, ln = lane_id(), w = threadIdx.x >> 5;
     const bool count_now = !P.dyn_count;
+    const bool has_swp = P.rw_pos || (count_now && P.power != 0.f);
     const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
       const u32 t0 = c * kSegThreads, p = t0 + threadIdx.x;
@@ -83,9 +87,10 @@ struct HeadsTail {
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[row];
         sy[p] = P.labels[row];
-        if (P.rw_pos) swp[p] = wp;
+        if (has_swp) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
-        gacc[p] = 0.f; lossrow[p] = 0.f; cnt[p] = 0;
+        gacc[p] = 0.f; perm[p] = row;
+        if (P.dyn_count) { lossrow[p] = 0.f; cnt[p] = 0; }
       }
       // J range needed by this warp's 32 rows; two warps make one I-block
       const u32 jlo = warp_min(n ? a : 0xFFFFFFFFu), jhi = warp_max(n ? a + n : 0u);
@@ -114,11 +119,23 @@ struct HeadsTail {
       }
       __syncthreads();
     }
-    // ---- work list (CTA 0): units of <= C J-blocks per I-block -------------------------------------------
     stamp(ctl, 17);
     grid_sync(&ctl->bar, epoch, &ctl->err);
     stamp(ctl, 18);
-    if (blockIdx.x != 0) return;
+    // ---- occurrence weights (PW:285-290): the counts are final, fold c_h^power into the positive-side weight ----
+    if (count_now && P.power != 0.f) {
+      for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const u32 p = c * kSegThreads + threadIdx.x;
+        if (p < B) {
+          const u32 pg = S.K > 1 ? pgid[val[p]] : (u32)(key[p] >> pl.labbits);
+          const u64 ch = cprim[pg];
+          const float wocc = ch ? ((P.power == 1.0f) ? (float)ch : powf((float)ch, P.power)) : 0.f;   // PW:147-149
+          swp[p] = (P.rw_pos ? swp[p] : 1.f) * wocc;
+        }
+      }
+    }
+    // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
+    //      the unit records of its own I-blocks ------------------------------------------------------------------
     auto ntile = [&](u32 b) -> u32 {
       const uint2 v = blk[b];
       return v.y > v.x ? ((v.y + 31) >> 5) - (v.x >> 5) : 0u;
@@ -126,6 +143,7 @@ struct HeadsTail {
     u64 m = 0;
     for (u32 b = threadIdx.x; b < nib; b += kSegThreads) m += ntile(b);
     m = warp_sum(m);
+    __syncthreads();
     if (ln == 0) sm_red[w] = m;
     __syncthreads();
     u64 M = 0;
@@ -134,11 +152,13 @@ struct HeadsTail {
     C = C < 1 ? 1 : (C > kMaxUnitC ? kMaxUnitC : C);
     u32* s_scan = smem;            // [kSegWarps]
     u32* s_carry = smem + kSegWarps;
+    __syncthreads();
     if (threadIdx.x == 0) *s_carry = 0;
     __syncthreads();
     for (u32 b0 = 0; b0 < nib; b0 += kSegThreads) {
       const u32 b = b0 + threadIdx.x;
-      const u32 v = b < nib ? (ntile(b) + C - 1) / C : 0u;
+      const u32 nt = b < nib ? ntile(b) : 0u;
+      const u32 v = (nt + C - 1) / C;
       u32 inc = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
@@ -146,106 +166,27 @@ struct HeadsTail {
       __syncthreads();
       u32 off = *s_carry;
       for (u32 q = 0; q < w; ++q) off += s_scan[q];
-      if (b < nib) ustart[b] = off + inc - v;
+      if (v && (b % gridDim.x) == blockIdx.x) {
+        const u32 jfirst = blk[b].x >> 5;
+        uint2* dst = units + (off + inc - v);
+        for (u32 q = 0; q < v; ++q) dst[q] = make_uint2(b, (jfirst + q * C) | (min(C, nt - q * C) << 24));
+      }
       __syncthreads();
       if (threadIdx.x == kSegThreads - 1) *s_carry = off + inc;
       __syncthreads();
     }
-    if (threadIdx.x == 0) { ustart[nib] = *s_carry; ctl->n_units = *s_carry; ctl->unit_c = C; ctl->n_tiles = M; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->n_units = *s_carry; ctl->unit_c = C; ctl->n_tiles = M; }
   }
 };
 
 // ---- the pair kernel ------------------------------------------------------------------------------
-enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8 };
-
 struct KpArgs {
-  const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* blk; const u32* ustart; u32 nib;
-  float *gacc, *lossrow; u32* cnt; Ctl* ctl;
+  const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units;
+  float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
   // finalisation
   const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first unit start, loop exit, busy cycles, units | general tiles << 32}
 };
-
-// General (masked) 32x32 tile for one positive row per lane.
-template <int MODE, bool FULL>
-__device__ __forceinline__ void tile_general(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
-                                             const u32 pjm, const float sjm, const float yjm, const float wnjm,
-                                             const float c, float& li, float& gi, u32& cnt, float& accj) {
-  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
-  float gi_t = 0.f, li_t = 0.f;
-#pragma unroll 8
-  for (int t = 0; t < 32; ++t) {
-    const float sj = __shfl_xor_sync(0xFFFFFFFFu, sjm, t);
-    const float x = si - sj;                           // PW:117 (float32 subtract, as the reference)
-    const float xs = x * c;                            // (x * factor) in log2 units
-    const float e = mufu_ex2(-fabsf(xs));              // exp(-|x|)
-    const float t1 = 1.0f + e;
-    const float L = mufu_lg2(t1);                      // log1p(exp(-|x|)) / ln2
-    const float r = mufu_rcp(t1);
-    const float lo2 = fmaxf(-xs, 0.f) + L;             // softplus(-x) / ln2        (PW:120-121, TF stable form)
-    float d = (xs >= 0.f ? e : 1.0f) * r;              // sigma(-x)
-    bool valid = true;
-    if (!FULL) { const u32 pj = pjm ^ (u32)t; valid = (pj >= lo) && (pj < hi); }
-    if (WRONG) valid = valid && (x < 0.f);             // PW:200-202  s_i < s_j
-    float wv = 1.f;
-    if (HASW) {
-      wv = wpi;
-      if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = (yi - yj) * wpi; }
-      if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
-      d *= wv;
-    }
-    if (!FULL || WRONG || RWN) d = valid ? d : 0.f;
-    if (WRONG || RWN) cnt += valid ? 1u : 0u;
-    if (HASW) { if (valid) li_t = fmaf(wv, lo2, li_t); } else { if (valid) li_t += lo2; }
-    gi_t += d;
-    accj += __shfl_xor_sync(0xFFFFFFFFu, d, t);
-  }
-  li += li_t; gi += gi_t;
-}
-
-// Fast 64x32 tile: both rows of every lane pair with ALL 32 negatives and their pair weight (wv0 / wv1) is constant
-// over the tile.  Per pair: ex2 + rcp (SFU), ~11 FP32 ops; per row and tile one lg2 of the product of the (1+e).
-template <bool HASW>
-__device__ __forceinline__ void tile_fast(const float si0, const float si1, const float wv0, const float wv1,
-                                          const float sjm, const float c, float& li0, float& li1, float& gi0,
-                                          float& gi1, float& accj) {
-  // Four rotation steps (8 independent pair chains) are issued in lock-step so that the SHFL / MUFU latencies of
-  // one chain are covered by the other seven: a warp issues in order, without this batching every step exposes
-  // its whole dependency chain.
-  constexpr int KB = 4;
-  float p0 = 1.f, p1 = 1.f, m0 = 0.f, m1 = 0.f, g0 = 0.f, g1 = 0.f;
-#pragma unroll
-  for (int tb = 0; tb < 32; tb += KB) {
-    float sj[KB], x0[KB], x1[KB], e0[KB], e1[KB], t0[KB], t1[KB], d0[KB], d1[KB];
-#pragma unroll
-    for (int k = 0; k < KB; ++k) sj[k] = __shfl_xor_sync(0xFFFFFFFFu, sjm, tb + k);
-#pragma unroll
-    for (int k = 0; k < KB; ++k) { x0[k] = (si0 - sj[k]) * c; x1[k] = (si1 - sj[k]) * c; }   // PW:117-119, log2 units
-#pragma unroll
-    for (int k = 0; k < KB; ++k) { e0[k] = mufu_ex2(-fabsf(x0[k])); e1[k] = mufu_ex2(-fabsf(x1[k])); }
-#pragma unroll
-    for (int k = 0; k < KB; ++k) { t0[k] = 1.0f + e0[k]; t1[k] = 1.0f + e1[k]; }
-#pragma unroll
-    for (int k = 0; k < KB; ++k) { d0[k] = mufu_rcp(t0[k]); d1[k] = mufu_rcp(t1[k]); }        // sigma(-x) for x < 0
-    p0 *= (t0[0] * t0[1]) * (t0[2] * t0[3]);                                               // prod (1+e) <= 2^32
-    p1 *= (t1[0] * t1[1]) * (t1[2] * t1[3]);
-#pragma unroll
-    for (int k = 0; k < KB; ++k) {
-      if (x0[k] >= 0.f) d0[k] *= e0[k]; else m0 -= x0[k];          // sigma(-x) = e/(1+e) for x >= 0; max(-x,0)
-      if (x1[k] >= 0.f) d1[k] *= e1[k]; else m1 -= x1[k];
-      if (HASW) { d0[k] *= wv0; d1[k] *= wv1; }
-    }
-    g0 += (d0[0] + d0[1]) + (d0[2] + d0[3]);
-    g1 += (d1[0] + d1[1]) + (d1[2] + d1[3]);
-    float back[KB];
-#pragma unroll
-    for (int k = 0; k < KB; ++k) back[k] = __shfl_xor_sync(0xFFFFFFFFu, d0[k] + d1[k], tb + k);
-    accj += (back[0] + back[1]) + (back[2] + back[3]);
-  }
-  const float L0 = m0 + mufu_lg2(p0), L1 = m1 + mufu_lg2(p1);       // sum softplus(-x) / ln2   (PW:120-121)
-  li0 += HASW ? wv0 * L0 : L0; li1 += HASW ? wv1 * L1 : L1;
-  gi0 += g0; gi1 += g1;
-}
 
 // Positive-side rows of an I-block (two per lane) and the first J block of a unit: loaded one unit ahead.
 struct UnitRows {
@@ -266,142 +207,137 @@ __device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u3
   if (RWN) r.wnjm = pjm < B ? A.swn[pjm] : 0.f;
 }
 
-constexpr u32 kMaxRec = 512;            // unit records per CTA and round (shared memory)
-
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
-  // Units are dealt round-robin to the CTAs (the q-th unit of this CTA is unit q * gridDim + cta of the list taken
-  // from its END: edge tiles of the small groups first, dense tiles of the big groups last), so every SM gets the
-  // same mix and there is no global ticket.  The CTA resolves its units to (I-block, J range) records in shared
-  // memory once; its warps then take records dynamically from a shared-memory counter and load the rows of the
-  // NEXT unit while the current one is being scored.
+  // Units are dealt round-robin to the CTAs (the q-th unit of this CTA is unit q * gridDim + cta of this rank's share
+  // of the list), so every SM gets the same mix and there is no global ticket; the warps of a CTA take the CTA's units
+  // dynamically from a shared-memory counter and load the record and rows of the NEXT unit while the current one is
+  // being scored.  When the pair set does not depend on scores (DYN = false) the occurrence weights are already
+  // folded into the positive-side weights, so the kernel accumulates final values: per-row gradient sums (global
+  // RED) and one loss partial per warp (registers).
   __shared__ u32 s_cnt;
-  __shared__ uint4 s_rec[kMaxRec];
+  __shared__ u64 red_u[kPairWarps];
+  __shared__ double red_d[kPairWarps];
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
+  constexpr bool DYN = RWN || WRONG;
   Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
   const u32 B = P.B;
   stamp(ctl, 20);
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  double lsum = 0.0;
   {
-    const u32 U = ld_relaxed(&ctl->n_units), C = ld_relaxed(&ctl->unit_c);
+    const u32 U = ld_relaxed(&ctl->n_units);
     const u32 u_begin = (u32)(((u64)U * (u32)P.part_rank) / (u32)P.part_count);
     const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
     const u32 n_mine = (u_end - u_begin > blockIdx.x) ? (u_end - u_begin - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const float c = P.c_log2;
     // debug tallies (per warp, flushed once): longest unit, busy cycles, units, fast / general tiles
-    u64 d_max = 0, d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0; u64 d_gencyc = 0;
+    u64 d_max = 0, d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0; u64 d_gencyc = 0, d_fastcyc = 0;
     const u64 d_start = P.debug ? globaltimer() : 0;
-    for (u32 q0 = 0; q0 < n_mine; q0 += kMaxRec) {
-      const u32 nrec = min(kMaxRec, n_mine - q0);
-      __syncthreads();
-      if (threadIdx.x == 0) s_cnt = 0;
-      for (u32 k = threadIdx.x; k < nrec; k += kPairThreads) {
-        const u32 u = u_end - 1u - ((q0 + k) * gridDim.x + blockIdx.x);
-        // unit -> (I-block b, chunk): largest b with ustart[b] <= u
-        u32 lo_b = 0, hi_b = A.nib;
-        while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (A.ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
-        const uint2 bj = A.blk[lo_b];
-        const u32 jb0 = (bj.x >> 5) + (u - A.ustart[lo_b]) * C;
-        u32 jb1 = (bj.y + 31) >> 5; if (jb1 > jb0 + C) jb1 = jb0 + C;
-        s_rec[k] = make_uint4(lo_b, jb0, jb1, u);
-      }
-      __syncthreads();
-      auto take = [&](uint4& rec) -> bool {
-        u32 q = 0;
-        if (ln == 0) q = atomicAdd(&s_cnt, 1u);
-        q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        if (q >= nrec) return false;
-        rec = s_rec[q];
-        return true;
-      };
-      uint4 rec, rec_n; UnitRows R, Rn;
-      bool have = take(rec);
-      if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y, ln, R);
-      while (have) {
-        const long long d_t0 = P.debug ? clock64() : 0;
-        const bool have_n = take(rec_n);
-        if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y, ln, Rn);      // in flight while this unit is scored
-        const u32 b = rec.x, jb0 = rec.y, jb1 = rec.z;
-        const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
-        const uint2 an0 = R.an0, an1 = R.an1;
-        const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
-        const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
-        float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
-        u32 pjm = jb0 * 32 + ln;
-        float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
-        for (u32 jb = jb0; jb < jb1; ++jb) {
-          // prefetch the next J-block while this one is being scored
-          const u32 pjn = pjm + 32;
-          const bool more = (jb + 1 < jb1) && pjn < B;
-          float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
-          if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
-          if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
-          float accj = 0.f;
-          const u32 j0 = jb * 32;
-          // Overlap of every row's negative range with this J block.  Row ranges start at a group start and end at
-          // a level start of the same group, so a row covers a (group, level) run of the block entirely or not at
-          // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
-          // value, the block is scored by the fast tile with out-of-range negatives replaced by a sentinel score
-          // (x = +inf: e = 0, sigma = 0, factor 1 in the product) and rows that do not touch it weighted 0.
-          const u32 s0 = max(lo0, j0), e0 = min(hi0, j0 + 32), s1 = max(lo1, j0), e1 = min(hi1, j0 + 32);
-          const bool in0 = s0 < e0, in1 = s1 < e1;
-          const u32 smin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? s0 : 0xFFFFFFFFu, in1 ? s1 : 0xFFFFFFFFu));
-          const u32 smax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? s0 : 0u, in1 ? s1 : 0u));
-          const u32 emin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? e0 : 0xFFFFFFFFu, in1 ? e1 : 0xFFFFFFFFu));
-          const u32 emax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? e0 : 0u, in1 ? e1 : 0u));
-          const bool any_in = smin != 0xFFFFFFFFu;
-          const bool jin = pjm >= smin && pjm < emax;                  // this lane's negative is inside the overlap
-          bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG;
-          float yref = 0.f;
-          if (DIFF && fast) {
-            yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
-            fast = __all_sync(0xFFFFFFFFu, !jin || yjm == yref);
+    auto take = [&](uint2& rec) -> bool {
+      u32 q = 0;
+      if (ln == 0) q = atomicAdd(&s_cnt, 1u);
+      q = __shfl_sync(0xFFFFFFFFu, q, 0);
+      if (q >= n_mine) return false;
+      const u32 idx = q * gridDim.x + blockIdx.x;
+      rec = A.units[P.ascending ? u_begin + idx : u_end - 1u - idx];
+      return true;
+    };
+    uint2 rec, rec_n; UnitRows R, Rn;
+    bool have = take(rec);
+    if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y & 0xFFFFFFu, ln, R);
+    while (have) {
+      const long long d_t0 = P.debug ? clock64() : 0;
+      const u64 d_gt0 = P.debug > 1 ? globaltimer() : 0;
+      const u64 d_tc0 = d_fastcyc + d_gencyc; const u32 d_gen0 = d_gen;
+      const bool have_n = take(rec_n);
+      if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y & 0xFFFFFFu, ln, Rn);      // in flight while this unit is scored
+      const u32 b = rec.x, jb0 = rec.y & 0xFFFFFFu, jb1 = jb0 + (rec.y >> 24);
+      const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
+      const uint2 an0 = R.an0, an1 = R.an1;
+      const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
+      const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
+      float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
+      u32 pjm = jb0 * 32 + ln;
+      float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
+      for (u32 jb = jb0; jb < jb1; ++jb) {
+        // prefetch the next J-block while this one is being scored
+        const u32 pjn = pjm + 32;
+        const bool more = (jb + 1 < jb1) && pjn < B;
+        float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
+        if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
+        if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
+        float accj = 0.f;
+        const u32 j0 = jb * 32;
+        // Overlap of every row's negative range with this J block.  Row ranges start at a group start and end at
+        // a level start of the same group, so a row covers a (group, level) run of the block entirely or not at
+        // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
+        // value, the block is scored by the fast tile with out-of-range negatives replaced by a sentinel score
+        // (x = +inf: e = 0, sigma = 0, factor 1 in the product) and rows that do not touch it weighted 0.
+        const u32 s0 = max(lo0, j0), e0 = min(hi0, j0 + 32), s1 = max(lo1, j0), e1 = min(hi1, j0 + 32);
+        const bool in0 = s0 < e0, in1 = s1 < e1;
+        const u32 smin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? s0 : 0xFFFFFFFFu, in1 ? s1 : 0xFFFFFFFFu));
+        const u32 smax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? s0 : 0u, in1 ? s1 : 0u));
+        const u32 emin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? e0 : 0xFFFFFFFFu, in1 ? e1 : 0xFFFFFFFFu));
+        const u32 emax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? e0 : 0u, in1 ? e1 : 0u));
+        const bool any_in = smin != 0xFFFFFFFFu;
+        const bool jin = pjm >= smin && pjm < emax;                  // this lane's negative is inside the overlap
+        bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG;
+        float yref = 0.f;
+        if (DIFF && fast) {
+          yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
+          fast = __all_sync(0xFFFFFFFFu, !jin || yjm == yref);
+        }
+        if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; }
+        const long long d_g0 = P.debug ? clock64() : 0;
+        if (fast) {
+          float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
+          if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
+          const float sje = jin ? sjm : -3.0e38f;
+          const bool whole = __all_sync(0xFFFFFFFFu, in0 && in1);
+          if (HASW || !whole) tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+          else                tile_fast<false>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+        } else if (any_in) {
+          const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
+          const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
+          const bool any0 = __any_sync(0xFFFFFFFFu, in0);
+          const bool any1 = __any_sync(0xFFFFFFFFu, in1);
+          if (any0) {
+            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
           }
-          if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; }
-          const long long d_g0 = (P.debug && !fast) ? clock64() : 0;
-          if (fast) {
-            float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
-            if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
-            const float sje = jin ? sjm : -3.0e38f;
-            const bool whole = __all_sync(0xFFFFFFFFu, in0 && in1);
-            if (HASW || !whole) tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
-            else                tile_fast<false>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
-          } else if (any_in) {
-            const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
-            const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
-            const bool any0 = __any_sync(0xFFFFFFFFu, in0);
-            const bool any1 = __any_sync(0xFFFFFFFFu, in1);
-            if (any0) {
-              if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
-              else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
-            }
-            if (any1) {
-              if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
-              else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
-            }
+          if (any1) {
+            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
           }
-          if (P.debug && !fast) d_gencyc += (u64)(clock64() - d_g0);
-          if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
-          pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
         }
-        if (pi0 < B && an0.y) {
-          if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
-          if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
-          if ((WRONG || RWN) && cnt0) atomicAdd(A.cnt + pi0, cnt0);
-        }
-        if (pi1 < B && an1.y) {
-          if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
-          if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
-          if ((WRONG || RWN) && cnt1) atomicAdd(A.cnt + pi1, cnt1);
-        }
-        if (P.debug) {
-          const u64 dt = (u64)(clock64() - d_t0);
-          d_busy += dt; ++d_units;
-          const u64 enc = (dt << 32) | rec.w;
-          if (enc > d_max) d_max = enc;
-        }
-        have = have_n; rec = rec_n; R = Rn;
+        if (P.debug) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
+        if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
+        pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
       }
+      if (pi0 < B && an0.y) {
+        if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
+        if (DYN) { if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0); if (cnt0) atomicAdd(A.cnt + pi0, cnt0); }
+      }
+      if (pi1 < B && an1.y) {
+        if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
+        if (DYN) { if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1); if (cnt1) atomicAdd(A.cnt + pi1, cnt1); }
+      }
+      if (!DYN) lsum += (double)li0 + (double)li1;
+      if (P.debug) {
+        const u64 dt = (u64)(clock64() - d_t0);
+        if (P.debug > 1 && ln == 0 && d_units < 6) {       // per-unit trace (RN_PAIR_DEBUG=2, B >= 65536 only)
+          u64* tr = A.dbgbuf + 4 * (size_t)(gridDim.x * kPairWarps) + 48 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5)) + 6 * d_units;
+          tr[0] = d_gt0; tr[1] = globaltimer(); tr[2] = ((u64)(u32)(b * 4096u + (jb0 & 4095u)) << 32) | ((u64)(jb1 - jb0) << 16) | (d_gen - d_gen0);
+          tr[3] = (dt << 32) | (d_fastcyc + d_gencyc - d_tc0); tr[4] = 0; tr[5] = 0;
+        }
+        d_busy += dt; ++d_units;
+        const u64 enc = (dt << 32) | b;
+        if (enc > d_max) d_max = enc;
+      }
+      have = have_n; rec = rec_n; R = Rn;
     }
     if (P.debug && ln == 0) {
       atomicMax(&ctl->dbg[0], d_max); atomicAdd(&ctl->dbg[1], d_busy);
@@ -410,21 +346,48 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       u64* rec = A.dbgbuf + 4 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5));
       rec[0] = d_start; rec[1] = now; rec[2] = d_busy; rec[3] = (u64)d_units | ((u64)d_gen << 32);
       atomicAdd(&ctl->dbg[4], (u64)d_units); atomicAdd(&ctl->dbg[5], (u64)d_fast);
-      atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc);
+      atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc); atomicAdd(&ctl->dbg[3], d_fastcyc);
     }
   }
-  // ---- finalisation (all CTAs, after a grid barrier) --------------------------------------------------
+  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   u32 epoch = 0;
+  if (!DYN) {
+    // ---- this CTA's share of sum w * loss, then (after the grid barrier) un-permute and scale the gradient ----
+    lsum = warp_sum(lsum);
+    if (ln == 0) red_d[threadIdx.x >> 5] = lsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
+      if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
+    }
+    // the row permutation and the pair count are final before this kernel starts: fetch them ahead of the barrier
+    const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
+    const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
+    const float gscale = P.factor / denom;
+    const u32 row0 = gtid < B ? A.perm[gtid] : 0u;
+    stamp(ctl, 21);
+    grid_sync(&ctl->bar2, epoch, &ctl->err);
+    stamp(ctl, 22);
+    if (gtid < B) P.dlogits[row0] = A.gacc[gtid] * gscale;
+    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[A.perm[p]] = A.gacc[p] * gscale;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+      *P.loss = (float)(tot / (double)denom);
+      *P.n_pair_f32 = (float)n;                  // PW:276
+      *P.n_pair = (int64_t)n;
+      ctl->ts[23] = globaltimer();
+    }
+    return;
+  }
+  // ---- finalisation when the pair set depends on scores / negative-side weights (all CTAs, after a grid barrier) ----
   stamp(ctl, 21);
   grid_sync(&ctl->bar2, epoch, &ctl->err);
   stamp(ctl, 22);
   const Plan pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), P.gbits, true);
   const u64* key = (pl.npass & 1) ? A.keyB : A.keyA;
   const u32* val = (pl.npass & 1) ? A.valB : A.valA;
-  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  __shared__ u64 red_u[kPairWarps];
-  __shared__ double red_d[kPairWarps];
-  if (P.dyn_count) {
+  {
     // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
     u64 tot_c = 0;
     for (u32 p0 = 0; p0 < B; p0 += gthreads) {             // uniform trip count: the body uses warp collectives
@@ -587,28 +550,31 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
   P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;
+  static const int ascending = tune_int("RN_PAIR_ASCENDING", 0);
+  P.ascending = ascending;
   P.loss = a->loss; P.n_pair_f32 = a->n_pair_f32; P.n_pair = a->n_pair; P.dlogits = a->dlogits; P.row_pairs = a->row_pairs;
   HeadsTail H{};
   H.P = P;
   H.aj = at<uint2>(base, L.aj); H.ss = at<float>(base, L.ss); H.sy = at<float>(base, L.sy);
   H.swp = at<float>(base, L.swp); H.swn = at<float>(base, L.swn);
   H.gacc = at<float>(base, L.gacc); H.lossrow = at<float>(base, L.lossrow); H.cnt = at<u32>(base, L.cnt);
-  H.blk = at<uint2>(base, L.blk); H.ustart = at<u32>(base, L.ustart); H.nib = L.nib;
+  H.perm = at<u32>(base, L.perm);
+  H.blk = at<uint2>(base, L.blk); H.units = at<uint2>(base, L.units); H.nib = L.nib;
   H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
-  static const int target_units = tune_int("RN_TARGET_UNITS", 16384);
-  H.target_units = (u32)(target_units > 0 ? target_units : 16384);
+  H.target_units = target_units();
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
   KpArgs A{};
-  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
-  A.blk = H.blk; A.ustart = H.ustart; A.nib = L.nib;
-  A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.ctl = at<Ctl>(base, L.ctl);
+  const bool fold_occ = !dyn && a->power != 0.f;        // occurrence weights folded into the positive-side weights
+  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = (a->rw_pos || fold_occ) ? H.swp : nullptr; A.swn = H.swn;
+  A.units = H.units;
+  A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
   A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
   A.pgid = H.pgid; A.cprim = H.cprim;
   A.dbgbuf = at<u64>(base, L.gstat);
   int mode = 0;
-  if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
+  if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg || fold_occ) mode |= M_HASW;
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
