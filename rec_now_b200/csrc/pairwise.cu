@@ -31,6 +31,7 @@ static int tune_int(const char* name, int dflt) {
 }
 
 constexpr u32 kMaxUnitC = 64;
+constexpr u32 kMaxNibS = 4096;           // I-blocks whose work list fits k_pair's shared memory (B <= 262144)
 constexpr int kPairThreads = 1024;      // threads per CTA of the pair kernel (one CTA per SM, <= 64 registers)
 constexpr u32 kDone = 0xFFFFFFFFu;
 constexpr int kPairWarps = kPairThreads / 32;
@@ -62,7 +63,6 @@ struct HeadsTail {
     Ctl* ctl = S.ctl;
     const u32 B = S.B, ln = lane_id(), w = threadIdx.x >> 5;
     const bool count_now = !P.dyn_count;
-    const bool has_swp = P.rw_pos || (count_now && P.power != 0.f);
     const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
       const u32 t0 = c * kSegThreads, p = t0 + threadIdx.x;
@@ -87,7 +87,7 @@ struct HeadsTail {
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[row];
         sy[p] = P.labels[row];
-        if (has_swp) swp[p] = wp;
+        if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
         if (P.dyn_count) { lossrow[p] = 0.f; cnt[p] = 0; }
@@ -100,7 +100,9 @@ struct HeadsTail {
       if (count_now) {
         cn = n;
         if (in && P.row_pairs) P.row_pairs[row] = (int64_t)cn;
-        const u32 pg = cn ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
+        const u32 pgi = in ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
+        if (in) cnt[p] = pgi;                   // index of the row's occurrence count: k_pair weights the row by c_h^power
+        const u32 pg = cn ? pgi : kEmpty;
         const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
         const u32 tot = __reduce_add_sync(m, cn);
         if (pg != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(cprim + pg, (u64)tot);
@@ -120,20 +122,11 @@ struct HeadsTail {
       __syncthreads();
     }
     stamp(ctl, 17);
+    // Small batches: k_pair builds the work list itself (shared-memory scan of the per-I-block J ranges), the kernel
+    // ends here without another grid barrier.  Large batches: explicit unit records.
+    if (nib <= kMaxNibS) return;
     grid_sync(&ctl->bar, epoch, &ctl->err);
     stamp(ctl, 18);
-    // ---- occurrence weights (PW:285-290): the counts are final, fold c_h^power into the positive-side weight ----
-    if (count_now && P.power != 0.f) {
-      for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const u32 p = c * kSegThreads + threadIdx.x;
-        if (p < B) {
-          const u32 pg = S.K > 1 ? pgid[val[p]] : (u32)(key[p] >> pl.labbits);
-          const u64 ch = cprim[pg];
-          const float wocc = ch ? ((P.power == 1.0f) ? (float)ch : powf((float)ch, P.power)) : 0.f;   // PW:147-149
-          swp[p] = (P.rw_pos ? swp[p] : 1.f) * wocc;
-        }
-      }
-    }
     // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
     //      the unit records of its own I-blocks ------------------------------------------------------------------
     auto ntile = [&](u32 b) -> u32 {
@@ -181,7 +174,7 @@ struct HeadsTail {
 
 // ---- the pair kernel ------------------------------------------------------------------------------
 struct KpArgs {
-  const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units;
+  const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units; const uint2* blk; u32 nib; u32 target_units;
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
   // finalisation
   const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
@@ -191,16 +184,31 @@ struct KpArgs {
 // Positive-side rows of an I-block (two per lane) and the first J block of a unit: loaded one unit ahead.
 struct UnitRows {
   uint2 an0, an1; float si0, si1, yi0, yi1, wp0, wp1; float sjm, yjm, wnjm;
+  u32 pg0, pg1;                     // occurrence-count index of the two rows (fetched with the rows, one unit ahead)
 };
 
+// Occurrence weight c_h^power of a row's primary group (PW:147-149, 285-290).  Both rows of a pair share the group, so
+// the weight is applied per ROW, not per pair: to the row's loss sum when its unit ends and to its gradient in the
+// final pass.  The counts are final before k_pair starts; row -> count index -> count is a chain of two L2 round
+// trips that is kept off the critical path (index fetched with the rows one unit ahead, count fetched when the unit
+// starts and used when it ends).
+__device__ __forceinline__ float occ_pow(u64 ch, float power) {
+  return ch ? ((power == 1.0f) ? (float)ch : powf((float)ch, power)) : 0.f;
+}
+
 template <int MODE>
-__device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, UnitRows& r) {
+__device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, float fold_power, UnitRows& r) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
   const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
   r.an0 = make_uint2(0, 0); r.an1 = make_uint2(0, 0);
   r.si0 = r.si1 = r.yi0 = r.yi1 = 0.f; r.wp0 = r.wp1 = 1.f;
   if (pi0 < B) { r.an0 = A.aj[pi0]; r.si0 = A.ss[pi0]; if (DIFF) r.yi0 = A.sy[pi0]; if (HASW && A.swp) r.wp0 = A.swp[pi0]; }
   if (pi1 < B) { r.an1 = A.aj[pi1]; r.si1 = A.ss[pi1]; if (DIFF) r.yi1 = A.sy[pi1]; if (HASW && A.swp) r.wp1 = A.swp[pi1]; }
+  r.pg0 = r.pg1 = kEmpty;
+  if (fold_power != 0.f) {
+    if (pi0 < B) r.pg0 = A.cnt[pi0];
+    if (pi1 < B) r.pg1 = A.cnt[pi1];
+  }
   const u32 pjm = jb0 * 32 + ln;
   r.sjm = pjm < B ? A.ss[pjm] : 0.f; r.yjm = 0.f; r.wnjm = 1.f;
   if (DIFF) r.yjm = pjm < B ? A.sy[pjm] : 0.f;
@@ -218,6 +226,9 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   __shared__ u32 s_cnt;
   __shared__ u64 red_u[kPairWarps];
   __shared__ double red_d[kPairWarps];
+  __shared__ u32 s_ustart[kMaxNibS + 1];          // first unit of every I-block (work list built here for small batches)
+  __shared__ u32 s_jn[kMaxNibS];                  // first J-block | J-block count << 16
+  __shared__ u32 s_scan[kPairWarps + 2];
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
   constexpr bool DYN = RWN || WRONG;
   Ctl* ctl = A.ctl;
@@ -225,10 +236,54 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   const u32 B = P.B;
   stamp(ctl, 20);
   if (threadIdx.x == 0) s_cnt = 0;
+  const bool own_list = A.nib <= kMaxNibS;
+  const float fold_power = DYN ? 0.f : P.power;
+  u32 U = 0, C = 1;
+  if (own_list) {
+    // ---- work list: units of <= C J-blocks per I-block, C from the total tile count (every CTA, redundantly) ----
+    const u32 wq = threadIdx.x >> 5;
+    u32 msum = 0;
+    for (u32 b = threadIdx.x; b < A.nib; b += kPairThreads) {
+      const uint2 v = A.blk[b];
+      const u32 nt = v.y > v.x ? ((v.y + 31) >> 5) - (v.x >> 5) : 0u;
+      s_jn[b] = nt ? ((v.x >> 5) | (nt << 16)) : 0u;
+      msum += nt;
+    }
+    msum = warp_sum(msum);
+    if (ln == 0) s_scan[wq] = msum;
+    __syncthreads();
+    u32 Mt = 0;
+    for (int q = 0; q < kPairWarps; ++q) Mt += s_scan[q];
+    C = (Mt + A.target_units - 1) / A.target_units;
+    C = C < 1 ? 1 : (C > kMaxUnitC ? kMaxUnitC : C);
+    __syncthreads();
+    if (threadIdx.x == 0) s_scan[kPairWarps] = 0;                    // running carry
+    __syncthreads();
+    for (u32 b0 = 0; b0 < A.nib; b0 += kPairThreads) {
+      const u32 b = b0 + threadIdx.x;
+      const u32 v = b < A.nib ? ((s_jn[b] >> 16) + C - 1) / C : 0u;
+      u32 inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+      if (ln == 31) s_scan[wq] = inc;
+      __syncthreads();
+      u32 off = s_scan[kPairWarps];
+      for (u32 q = 0; q < wq; ++q) off += s_scan[q];
+      if (b < A.nib) s_ustart[b] = off + inc - v;
+      __syncthreads();
+      if (threadIdx.x == kPairThreads - 1) s_scan[kPairWarps] = off + inc;
+      __syncthreads();
+    }
+    U = s_scan[kPairWarps];
+    if (threadIdx.x == 0) s_ustart[A.nib] = U;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->n_units = U; ctl->unit_c = C; ctl->n_tiles = Mt; }
+  } else {
+    U = ld_relaxed(&ctl->n_units);
+  }
   __syncthreads();
+  stamp(ctl, 16);
   double lsum = 0.0;
   {
-    const u32 U = ld_relaxed(&ctl->n_units);
     const u32 u_begin = (u32)(((u64)U * (u32)P.part_rank) / (u32)P.part_count);
     const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
     const u32 n_mine = (u_end - u_begin > blockIdx.x) ? (u_end - u_begin - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
@@ -242,23 +297,34 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       q = __shfl_sync(0xFFFFFFFFu, q, 0);
       if (q >= n_mine) return false;
       const u32 idx = q * gridDim.x + blockIdx.x;
-      rec = A.units[P.ascending ? u_begin + idx : u_end - 1u - idx];
+      const u32 u = P.ascending ? u_begin + idx : u_end - 1u - idx;
+      if (own_list) {
+        u32 lo_b = 0, hi_b = A.nib;                  // largest b with ustart[b] <= u
+        while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (s_ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
+        const u32 jn = s_jn[lo_b], k = u - s_ustart[lo_b];
+        rec = make_uint2(lo_b, ((jn & 0xFFFFu) + k * C) | (min(C, (jn >> 16) - k * C) << 24));
+      } else {
+        rec = A.units[u];
+      }
       return true;
     };
     uint2 rec, rec_n; UnitRows R, Rn;
     bool have = take(rec);
-    if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y & 0xFFFFFFu, ln, R);
+    const bool fold = fold_power != 0.f;
+    if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y & 0xFFFFFFu, ln, fold_power, R);
     while (have) {
       const long long d_t0 = P.debug ? clock64() : 0;
       const u64 d_gt0 = P.debug > 1 ? globaltimer() : 0;
       const u64 d_tc0 = d_fastcyc + d_gencyc; const u32 d_gen0 = d_gen;
       const bool have_n = take(rec_n);
-      if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y & 0xFFFFFFu, ln, Rn);      // in flight while this unit is scored
+      if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y & 0xFFFFFFu, ln, fold_power, Rn);      // in flight while this unit is scored
       const u32 b = rec.x, jb0 = rec.y & 0xFFFFFFu, jb1 = jb0 + (rec.y >> 24);
       const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
       const uint2 an0 = R.an0, an1 = R.an1;
       const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
       const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
+      u64 ch0 = 0, ch1 = 0;                           // occurrence counts of the two rows: in flight during the unit
+      if (fold) { if (R.pg0 != kEmpty) ch0 = A.cprim[R.pg0]; if (R.pg1 != kEmpty) ch1 = A.cprim[R.pg1]; }
       float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
       u32 pjm = jb0 * 32 + ln;
       float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
@@ -325,7 +391,10 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
         if (DYN) { if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1); if (cnt1) atomicAdd(A.cnt + pi1, cnt1); }
       }
-      if (!DYN) lsum += (double)li0 + (double)li1;
+      if (!DYN) {
+        if (fold) { li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power); }
+        lsum += (double)li0 + (double)li1;
+      }
       if (P.debug) {
         const u64 dt = (u64)(clock64() - d_t0);
         if (P.debug > 1 && ln == 0 && d_units < 6) {       // per-unit trace (RN_PAIR_DEBUG=2, B >= 65536 only)
@@ -365,12 +434,18 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
     const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
     const float gscale = P.factor / denom;
+    auto row_scale = [&](u32 p) -> float {
+      if (fold_power == 0.f) return gscale;
+      const u32 pg = A.cnt[p];
+      return pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) * gscale : 0.f;
+    };
     const u32 row0 = gtid < B ? A.perm[gtid] : 0u;
+    const float sc0 = gtid < B ? row_scale(gtid) : 0.f;
     stamp(ctl, 21);
     grid_sync(&ctl->bar2, epoch, &ctl->err);
     stamp(ctl, 22);
-    if (gtid < B) P.dlogits[row0] = A.gacc[gtid] * gscale;
-    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[A.perm[p]] = A.gacc[p] * gscale;
+    if (gtid < B) P.dlogits[row0] = A.gacc[gtid] * sc0;
+    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[A.perm[p]] = A.gacc[p] * row_scale(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
       *P.loss = (float)(tot / (double)denom);
@@ -565,16 +640,15 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
   KpArgs A{};
-  const bool fold_occ = !dyn && a->power != 0.f;        // occurrence weights folded into the positive-side weights
-  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = (a->rw_pos || fold_occ) ? H.swp : nullptr; A.swn = H.swn;
-  A.units = H.units;
+  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
+  A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
   A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
   A.pgid = H.pgid; A.cprim = H.cprim;
   A.dbgbuf = at<u64>(base, L.gstat);
   int mode = 0;
-  if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg || fold_occ) mode |= M_HASW;
+  if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
