@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RN_VERSION 100 /* 0.1.0 */
+#define RN_VERSION 101 /* 0.1.1: blocked rows + reduce-scatter output layout in rn_pairwise_args */
 
 enum {
   RN_OK = 0,
@@ -83,6 +83,17 @@ typedef struct rn_pairwise_args {
   int64_t* n_pair;         /* [1]  exact n */
   float* dlogits;          /* [B]  d loss / d logits */
   int64_t* row_pairs;      /* NULL or [B]: number of kept pairs with row i on the positive side */
+  /* Blocked rows (multi-GPU global mode; 0 = contiguous columns).  After ONE all-gather of packed per-rank blocks
+   * the B rows are B / block_rows blocks of block_rows rows, block_stride BYTES apart (a multiple of 16).  Every
+   * input column pointer addresses its column inside block 0: element i lives at
+   * column + (i / block_rows) * block_stride bytes + (i % block_rows) elements; key column k starts block_rows
+   * int64 after key column k-1.  If out_chunk > block_rows, the outputs are laid out for ONE reduce-scatter:
+   * d loss / d logits of row i goes to dlogits[(i / block_rows) * out_chunk + i % block_rows] and the (partial) loss
+   * to dlogits[r * out_chunk + block_rows] of every block r (remaining pad floats are zeroed); dlogits then holds
+   * (B / block_rows) * out_chunk floats.  row_pairs stays [B], indexed by row. */
+  int64_t block_rows;
+  int64_t block_stride;
+  int64_t out_chunk;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {

@@ -44,6 +44,7 @@ class PairwiseArgs(C.Structure):
         ("part_rank", C.c_int32), ("part_count", C.c_int32),
         ("loss", C.c_void_p), ("n_pair_f32", C.c_void_p), ("n_pair", C.c_void_p),
         ("dlogits", C.c_void_p), ("row_pairs", C.c_void_p),
+        ("block_rows", C.c_int64), ("block_stride", C.c_int64), ("out_chunk", C.c_int64),
     ]
 
 

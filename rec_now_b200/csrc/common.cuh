@@ -18,6 +18,16 @@ constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kIB = 64;                       // rows per I-block of the pair kernel (two per lane)
 constexpr u32 kEmpty = 0xFFFFFFFFu;
 
+// Blocked row layout of the input columns (multi-GPU global mode: an all-gather of packed per-rank blocks leaves the
+// rows as B / Bl blocks of Bl rows, `stride` bytes apart).  Element i of a column lives at block i / Bl, offset
+// i % Bl; the strides below are in ELEMENTS of 8-, 4- and 1-byte columns.  Bl = 0: contiguous columns.
+struct RowMap {
+  u32 Bl, s8, s4, s1;
+  __host__ __device__ __forceinline__ size_t i8(u32 i) const { return Bl ? (size_t)(i / Bl) * s8 + (i % Bl) : i; }
+  __host__ __device__ __forceinline__ size_t i4(u32 i) const { return Bl ? (size_t)(i / Bl) * s4 + (i % Bl) : i; }
+  __host__ __device__ __forceinline__ size_t i1(u32 i) const { return Bl ? (size_t)(i / Bl) * s1 + (i % Bl) : i; }
+};
+
 // Device-side control block (zero-initialised by k_init at the start of every call).
 struct Ctl {
   u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range

@@ -130,6 +130,7 @@ using namespace rn;
 extern "C" size_t rn_pair_indices_scratch_bytes(int64_t B, int32_t K) { return (B > 0 && K > 0) ? make_layout(B, K).total : 0; }
 
 static int pi_common(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, Layout& L) {
+  if (a && a->block_rows) return RN_ERR_UNSUPPORTED;      // pair materialisation reads contiguous columns only
   if (!a || a->B <= 0 || a->B > (1ll << 28) || a->K <= 0 || a->K > 8) return RN_ERR_ARG;
   if (!a->keys || !a->logits || !a->labels) return RN_ERR_ARG;
   if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF) return RN_ERR_UNSUPPORTED;

@@ -43,6 +43,7 @@ struct PairParams {
   float factor, power; int reduce_mean; int dyn_count; int debug;
   int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
+  RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
 };
 
 // ---- heads tail of k_seg ---------------------------------------------------------------------------------
@@ -82,11 +83,12 @@ struct HeadsTail {
       const u32 row = in ? val[p] : 0;
       if (in) {
         float wp = 1.f, wn = 1.f;
-        if (P.rw_pos) { wp = P.rw_pos[row]; if (!(wp > 0.f)) n = 0; }     // PW:193  C = W > 0
-        if (P.rw_neg) wn = P.rw_neg[row];
+        const size_t ro = P.rm.i4(row);
+        if (P.rw_pos) { wp = P.rw_pos[ro]; if (!(wp > 0.f)) n = 0; }      // PW:193  C = W > 0
+        if (P.rw_neg) wn = P.rw_neg[ro];
         aj[p] = make_uint2(a, n);
-        ss[p] = P.logits[row];
-        sy[p] = P.labels[row];
+        ss[p] = P.logits[ro];
+        sy[p] = P.labels[ro];
         if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       }
       have = have_n; rec = rec_n; R = Rn;
     }
-    if (P.debug && ln == 0) {
+    if ((P.debug & 1) && ln == 0) {
       atomicMax(&ctl->dbg[0], d_max); atomicAdd(&ctl->dbg[1], d_busy);
       const u64 now = globaltimer();
       atomicMax(&ctl->dbg[2], now);
@@ -444,13 +446,22 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     stamp(ctl, 21);
     grid_sync(&ctl->bar2, epoch, &ctl->err);
     stamp(ctl, 22);
-    if (gtid < B) P.dlogits[row0] = A.gacc[gtid] * sc0;
-    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[A.perm[p]] = A.gacc[p] * row_scale(p);
+    // output index: plain, or chunked for a following reduce-scatter (row i -> (i / Bl) * out_chunk + i % Bl)
+    auto out_at = [&](u32 row) -> size_t { return P.out_chunk ? (size_t)(row / P.rm.Bl) * P.out_chunk + (row % P.rm.Bl) : row; };
+    if (gtid < B) P.dlogits[out_at(row0)] = A.gacc[gtid] * sc0;
+    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
-      *P.loss = (float)(tot / (double)denom);
+      const float lossv = (float)(tot / (double)denom);
+      *P.loss = lossv;
       *P.n_pair_f32 = (float)n;                  // PW:276
       *P.n_pair = (int64_t)n;
+      if (P.out_chunk)                           // the (partial) loss rides in every chunk of the reduce-scatter
+        for (u32 r = 0; r * P.rm.Bl < B; ++r) {
+          float* tail = P.dlogits + (size_t)r * P.out_chunk + P.rm.Bl;
+          tail[0] = lossv;
+          for (u32 q = 1; P.rm.Bl + q < P.out_chunk; ++q) tail[q] = 0.f;
+        }
       ctl->ts[23] = globaltimer();
     }
     return;
@@ -600,6 +611,12 @@ static int validate_pairwise(const rn_pairwise_args* a) {
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
   if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF) return RN_ERR_UNSUPPORTED;
   if (a->part_count < 1 || a->part_rank < 0 || a->part_rank >= a->part_count) return RN_ERR_ARG;
+  if (a->block_rows) {
+    if (a->block_rows < 0 || a->B % a->block_rows || a->block_stride <= 0 || (a->block_stride & 15) ||
+        a->block_stride / 4 > 0xFFFFFFFFll) return RN_ERR_ARG;
+    if (a->out_chunk && (a->out_chunk <= a->block_rows || a->out_chunk > 0x7FFFFFFFll)) return RN_ERR_ARG;
+    if (a->only_wrong || a->rw_neg) return RN_ERR_UNSUPPORTED;
+  } else if (a->out_chunk) return RN_ERR_ARG;
   const void* ptrs[] = {a->keys, a->logits, a->labels, a->row_ok, a->rw_pos, a->rw_neg, a->dlogits, a->row_pairs};
   for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
   return RN_OK;
@@ -628,6 +645,11 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   static const int ascending = tune_int("RN_PAIR_ASCENDING", 0);
   P.ascending = ascending;
   P.loss = a->loss; P.n_pair_f32 = a->n_pair_f32; P.n_pair = a->n_pair; P.dlogits = a->dlogits; P.row_pairs = a->row_pairs;
+  P.rm = RowMap{0, 0, 0, 0}; P.out_chunk = 0;
+  if (a->block_rows) {
+    P.rm.Bl = (u32)a->block_rows; P.rm.s8 = (u32)(a->block_stride / 8); P.rm.s4 = (u32)(a->block_stride / 4);
+    P.rm.s1 = (u32)a->block_stride; P.out_chunk = (u32)a->out_chunk;
+  }
   HeadsTail H{};
   H.P = P;
   H.aj = at<uint2>(base, L.aj); H.ss = at<float>(base, L.ss); H.sy = at<float>(base, L.sy);
@@ -638,6 +660,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
   H.target_units = target_units();
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
+  in.rm = P.rm;
   if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;

@@ -25,6 +25,7 @@ namespace rn {
 
 struct SegParams {
   u32 B; int K; int gbits; int use_label; int nan_trash;
+  RowMap rm; u32 kpitch;          // input row layout; elements between key columns (B, or the block rows when blocked)
   const int64_t* keys; const uint8_t* row_ok; const float* labels;
   u32 capmask, ntiles;
   u32 *table, *table1, *slot, *slot1;
@@ -37,9 +38,11 @@ constexpr int kSegSmemWords = kSegWarps * kBins + kBins + 64;
 
 // Open-addressing insert of row i's key tuple (nk columns); the slot's value converges to the smallest row
 // holding that tuple (any representative has the same key, so probing stays consistent while it changes).
-__device__ __forceinline__ u32 hash_insert(const int64_t* keys, u32 B, int nk, u32 i, u32* table, u32 capmask) {
+__device__ __forceinline__ u32 hash_insert(const SegParams& S, int nk, u32 i, u32* table) {
+  const int64_t* keys = S.keys; const u32 capmask = S.capmask;
+  const size_t oi = S.rm.i8(i);
   u64 h = 0x9E3779B97F4A7C15ull;
-  for (int k = 0; k < nk; ++k) h = mix64(h ^ (u64)keys[(size_t)k * B + i]);
+  for (int k = 0; k < nk; ++k) h = mix64(h ^ (u64)keys[(size_t)k * S.kpitch + oi]);
   u32 s = (u32)h & capmask;
   for (;;) {
     u32 cur = ld_relaxed(table + s);
@@ -49,7 +52,8 @@ __device__ __forceinline__ u32 hash_insert(const int64_t* keys, u32 B, int nk, u
       cur = prev;
     }
     bool eq = true;
-    for (int k = 0; k < nk; ++k) eq = eq && (keys[(size_t)k * B + cur] == keys[(size_t)k * B + i]);
+    const size_t oc = S.rm.i8(cur);
+    for (int k = 0; k < nk; ++k) eq = eq && (keys[(size_t)k * S.kpitch + oc] == keys[(size_t)k * S.kpitch + oi]);
     if (eq) {
       if (i < cur) atomicMin(table + s, i);
       return s;
@@ -75,12 +79,13 @@ __device__ __forceinline__ void seg_hash_pass(const SegParams& S, int nk, u32* t
     bool ok = false;
     u32 ls = 0;
     if (i < S.B) {
-      const float y = S.labels ? S.labels[i] : 0.f;
-      ok = (S.row_ok ? S.row_ok[i] != 0 : true) && !(S.nan_trash && (y != y));
+      const float y = S.labels ? S.labels[S.rm.i4(i)] : 0.f;
+      ok = (S.row_ok ? S.row_ok[S.rm.i1(i)] != 0 : true) && !(S.nan_trash && (y != y));
       if (ok) {
         if (first) { const u32 e = enc_label(y); vor |= e; vnor |= ~e; }
         u64 h = 0x9E3779B97F4A7C15ull;
-        for (int k = 0; k < nk; ++k) h = mix64(h ^ (u64)S.keys[(size_t)k * S.B + i]);
+        const size_t oi = S.rm.i8(i);
+        for (int k = 0; k < nk; ++k) h = mix64(h ^ (u64)S.keys[(size_t)k * S.kpitch + oi]);
         ls = (u32)(h >> 40) & (kLoc - 1);
         for (;;) {
           u32 cur = sm_tab[ls];
@@ -90,14 +95,15 @@ __device__ __forceinline__ void seg_hash_pass(const SegParams& S, int nk, u32* t
             cur = prev;
           }
           bool eq = true;
-          for (int k = 0; k < nk; ++k) eq = eq && (S.keys[(size_t)k * S.B + r0 + cur] == S.keys[(size_t)k * S.B + i]);
+          const size_t oc = S.rm.i8(r0 + cur);
+          for (int k = 0; k < nk; ++k) eq = eq && (S.keys[(size_t)k * S.kpitch + oc] == S.keys[(size_t)k * S.kpitch + oi]);
           if (eq) { if (tid < cur) atomicMin(&sm_tab[ls], tid); break; }
           ls = (ls + 1) & (kLoc - 1);
         }
       }
     }
     __syncthreads();
-    if (ok && sm_tab[ls] == tid) sm_gslot[ls] = hash_insert(S.keys, S.B, nk, i, table, S.capmask);
+    if (ok && sm_tab[ls] == tid) sm_gslot[ls] = hash_insert(S, nk, i, table);
     __syncthreads();
     if (i < S.B) slot_out[i] = ok ? sm_gslot[ls] : kEmpty;
     __syncthreads();
@@ -136,7 +142,7 @@ __device__ __forceinline__ void seg_vkey(const SegParams& S, const Plan& pl, u32
         const u32 s = S.slot[i];
         const u32 gid = (s == kEmpty) ? i : S.table[s];
         u32 lab = 0;
-        if (S.use_label && s != kEmpty) lab = (enc_label(S.labels[i]) >> pl.labshift) & labmask;
+        if (S.use_label && s != kEmpty) lab = (enc_label(S.labels[S.rm.i4(i)]) >> pl.labshift) & labmask;
         const u64 key = ((u64)gid << pl.labbits) | lab;
         S.keyA[i] = key; S.valA[i] = i;
         if (S.K > 1) { const u32 s1 = S.slot1[i]; S.slot1[i] = (s1 == kEmpty) ? i : S.table1[s1]; }   // primary gid
@@ -344,6 +350,7 @@ struct SegInputs {
   const int64_t* keys; const float* labels; const uint8_t* row_ok;
   bool use_label;        // sort by (group, label, row) instead of (group, row)
   bool nan_label_is_trash;
+  RowMap rm = RowMap{0, 0, 0, 0};
 };
 
 inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs& in) {
@@ -352,6 +359,7 @@ inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs
   S.B = (u32)in.B; S.K = in.K; S.gbits = L.gbits; S.use_label = in.use_label ? 1 : 0;
   S.nan_trash = in.nan_label_is_trash ? 1 : 0;
   S.keys = in.keys; S.row_ok = in.row_ok; S.labels = in.labels;
+  S.rm = in.rm; S.kpitch = in.rm.Bl ? in.rm.Bl : (u32)in.B;
   S.capmask = L.cap - 1; S.ntiles = L.ntiles;
   S.table = at<u32>(base, L.table); S.table1 = at<u32>(base, L.table1);
   S.slot = at<u32>(base, L.slot); S.slot1 = at<u32>(base, L.slot1);

@@ -4,13 +4,18 @@ Semantics: ``pairwise_loss`` evaluated on the concatenation of all ranks' rows (
 reference has no multi-GPU mode; this is the data-parallel extension the north star defines.
 
 One process per GPU.  Per step and rank:
-  1. all-gather the compact rows (group key(s) int64, logit f32, label f32 [, weight f32]) over NCCL/NVLink;
+  1. all-gather the compact rows (group key(s) int64, logit f32, label f32 [, weight f32]) over NCCL/NVLink --
+     packed into ONE block per rank, so it is a single collective; the kernels read the blocked rows in place
+     (rn_pairwise_args.block_rows / block_stride);
   2. every rank segments the SAME global rows (replicated, deterministic) -> pair counts n and c_h are
      globally consistent without communication;
   3. the pair space (32x32 micro-tile work units of the sorted batch) is split evenly across ranks
      (rn_pairwise_args.part_rank/part_count); each rank scores its share and accumulates partial
      d loss / d logits for ALL global rows, already scaled by the global 1/n and occurrence weights;
-  4. reduce-scatter(sum) returns every rank the gradient of its own rows; the scalar loss is all-reduced.
+  4. ONE reduce-scatter(sum) returns every rank the gradient of its own rows; the partial loss rides in a spare
+     slot of every chunk (rn_pairwise_args.out_chunk), so the same collective also sums the loss.
+(Rows per rank not a multiple of 16, or the CPU plumbing test: one all-gather per column, reduce-scatter +
+all-reduce.)
 The even tile split (instead of "positive side is local") keeps the ranks balanced for any row placement,
 e.g. a loader that shards by user.
 
@@ -40,6 +45,35 @@ def _all_gather_cols(cols, group):
     return outs
 
 
+def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
+                   _compute_blocked=None):
+    """The two-collective path: pack this rank's columns into one block -> ONE all-gather -> the kernels read the
+    blocked rows in place and write gradient chunks with the partial loss riding in each -> ONE reduce-scatter."""
+    from . import ops
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b_loc = logits.numel()
+    kk = keys.shape[0]
+    lay = ops.packed_block_layout(b_loc, kk, rw_pos is not None, row_ok is not None)
+    cols = [keys.reshape(-1).view(torch.uint8), logits.reshape(-1).to(torch.float32).view(torch.uint8),
+            labels.reshape(-1).to(torch.float32).view(torch.uint8)]
+    if rw_pos is not None:
+        cols.append(rw_pos.reshape(-1).to(torch.float32).view(torch.uint8))
+    if row_ok is not None:
+        cols.append(row_ok.reshape(-1).to(torch.uint8))
+    used = sum(c.numel() for c in cols)
+    if used != lay["stride"]:
+        cols.append(torch.zeros(lay["stride"] - used, dtype=torch.uint8, device=logits.device))
+    block = torch.cat(cols)
+    gbuf = torch.empty(world * lay["stride"], dtype=torch.uint8, device=logits.device)
+    dist.all_gather_into_tensor(gbuf, block, group=group)
+    compute = _compute_blocked or ops.pairwise_fwd_bwd_blocked
+    res = compute(gbuf, world, b_loc, kk, rw_pos is not None, row_ok is not None, label_func=label_func,
+                  factor=factor, power=power, reduce_mean=reduce_mean, part=(rank, world))
+    mine = torch.empty(res["chunk"], dtype=torch.float32, device=logits.device)
+    dist.reduce_scatter_tensor(mine, res["out"], op=dist.ReduceOp.SUM, group=group)
+    return dict(loss=mine[b_loc], n_pair=res["n_pair"], dlogits=mine[:b_loc])
+
+
 def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: torch.Tensor,
                             rw_pos: Optional[torch.Tensor] = None, row_ok: Optional[torch.Tensor] = None,
                             label_func: str = "step", factor: float = 1.0, power: float = 0.0,
@@ -54,6 +88,8 @@ def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: to
     b_loc = logits.numel()
     keys = keys.reshape(-1, b_loc)
     kk = keys.shape[0]
+    if _compute is None and b_loc % 16 == 0 and keys.dtype is torch.int64 and keys.is_contiguous():
+        return _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group)
     cols = [keys[k] for k in range(kk)] + [logits.reshape(-1).to(torch.float32), labels.reshape(-1).to(torch.float32),
                                            None if rw_pos is None else rw_pos.reshape(-1).to(torch.float32),
                                            None if row_ok is None else row_ok.reshape(-1).to(torch.uint8)]

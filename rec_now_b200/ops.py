@@ -138,6 +138,53 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
                 row_pairs=row_pairs, _scratch=scratch)
 
 
+def packed_block_layout(b_loc: int, kk: int, has_w: bool, has_ok: bool) -> dict:
+    """Byte layout of one rank's packed row block (global mode): [keys K x int64][logits f32][labels f32][w f32]
+    [row_ok u8], every column 16-byte aligned, block size a multiple of 16."""
+    assert b_loc % 16 == 0
+    off, o = {}, 0
+    off["keys"] = o; o += 8 * kk * b_loc
+    off["logits"] = o; o += 4 * b_loc
+    off["labels"] = o; o += 4 * b_loc
+    if has_w:
+        off["w"] = o; o += 4 * b_loc
+    if has_ok:
+        off["ok"] = o; o += b_loc
+    off["stride"] = (o + 15) // 16 * 16
+    return off
+
+
+def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int, has_w: bool, has_ok: bool,
+                             label_func="step", factor=1.0, power=0.0, reduce_mean=True, part=(0, 1)):
+    """rn_pairwise_fwd_bwd on `world` packed row blocks (packed_block_layout) as ONE all-gather leaves them, with the
+    outputs laid out for ONE reduce-scatter: returns dict(out=float32[world * chunk] with chunk = b_loc + 4:
+    d loss / d logits of global row r * b_loc + i at out[r * chunk + i], the partial loss at out[r * chunk + b_loc];
+    n_pair (global, exact), chunk)."""
+    _need_cuda(gbuf)
+    lay = packed_block_layout(b_loc, kk, has_w, has_ok)
+    assert gbuf.dtype is torch.uint8 and gbuf.numel() == world * lay["stride"] and gbuf.is_contiguous()
+    dev = gbuf.device
+    b = world * b_loc
+    chunk = b_loc + 4
+    scal = torch.empty(4, dtype=torch.float32, device=dev)
+    out = torch.empty(world * chunk, dtype=torch.float32, device=dev)
+    nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    scratch = _scratch(nbytes, dev, st)
+    base, po = gbuf.data_ptr(), scal.data_ptr()
+    a = PairwiseArgs(
+        B=b, K=kk, label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
+        keys=base + lay["keys"], logits=base + lay["logits"], labels=base + lay["labels"],
+        row_ok=(base + lay["ok"]) if has_ok else None, rw_pos=(base + lay["w"]) if has_w else None, rw_neg=None,
+        factor=float(factor), power=float(power), only_wrong=0, reduce_mean=int(bool(reduce_mean)),
+        part_rank=int(part[0]), part_count=int(part[1]),
+        loss=po, n_pair_f32=po + 4, n_pair=po + 8, dlogits=out.data_ptr(), row_pairs=None,
+        block_rows=b_loc, block_stride=lay["stride"], out_chunk=chunk)
+    with _on_device(dev):
+        check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, C.c_void_p(st)), "rn_pairwise_fwd_bwd")
+    return dict(out=out, n_pair=scal[2:4].view(torch.int64)[0], chunk=chunk, _scratch=scratch)
+
+
 def device_error(scratch: torch.Tensor) -> int:
     err = C.c_int32(0)
     check(lib().rn_last_device_error(scratch.data_ptr(), C.byref(err), _stream()), "rn_last_device_error")

@@ -45,7 +45,32 @@ def _worker(rank, world, port, b_loc, ret):
     ok = (abs(float(out["loss"]) - ref["loss"]) < 1e-6 * abs(ref["loss"]) + 1e-9
           and int(out["n_pair"]) == ref["n_pair"]
           and np.abs(out["dlogits"].numpy() - ref["grad"][lo:hi]).max() < 1e-6 * np.abs(ref["grad"]).max() + 1e-9)
-    ret[rank] = bool(ok)
+    # the two-collective path (packed blocks -> one all-gather; chunked outputs + loss slot -> one reduce-scatter)
+    from rec_now_b200 import ops
+
+    def fake_blocked(gbuf, world_, b_loc_, kk, has_w, has_ok, label_func="step", factor=1.0, power=0.0,
+                     reduce_mean=True, part=(0, 1)):
+        lay = ops.packed_block_layout(b_loc_, kk, has_w, has_ok)
+        blk = gbuf.numpy().reshape(world_, lay["stride"])
+        col = lambda name, dt, n: np.concatenate([blk[r, lay[name]:lay[name] + n].copy().view(dt) for r in range(world_)])
+        gk, gs, gy = col("keys", np.int64, 8 * b_loc_), col("logits", np.float32, 4 * b_loc_), col("labels", np.float32, 4 * b_loc_)
+        gw = col("w", np.float32, 4 * b_loc_) if has_w else None
+        r = S.pairwise(gs, gy, gk, S.PairSpec(factor=factor, power=power, label_func=label_func, rw_pos=gw))
+        chunk = b_loc_ + 4
+        o = np.zeros((world_, chunk), np.float32)
+        o[:, :b_loc_] = (r["grad"] / part[1]).reshape(world_, b_loc_)
+        o[:, b_loc_] = r["loss"] / part[1]
+        seen["blocked_part"] = part
+        return dict(out=torch.tensor(o.reshape(-1)), n_pair=torch.tensor(r["n_pair"]), chunk=chunk)
+
+    out2 = global_mode._packed_global(
+        torch.tensor(d["s"][lo:hi]), torch.tensor(d["y"][lo:hi]), torch.tensor(d["g"][lo:hi]).reshape(1, -1),
+        torch.tensor(d["w"][lo:hi]), None, "diff", 1.0, -0.5, True, None, _compute_blocked=fake_blocked)
+    ok2 = (seen["blocked_part"] == (rank, world)
+           and abs(float(out2["loss"]) - ref["loss"]) < 1e-6 * abs(ref["loss"]) + 1e-9
+           and int(out2["n_pair"]) == ref["n_pair"]
+           and np.abs(out2["dlogits"].numpy() - ref["grad"][lo:hi]).max() < 1e-6 * np.abs(ref["grad"]).max() + 1e-9)
+    ret[rank] = bool(ok and ok2)
     dist.destroy_process_group()
 
 

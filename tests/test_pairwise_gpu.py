@@ -140,6 +140,46 @@ def test_partition_partials_sum_to_full(parts):
     assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all()
 
 
+@pytest.mark.parametrize("world,kk,with_ok", [(2, 1, False), (4, 2, True)])
+def test_blocked_rows_match_contiguous(world, kk, with_ok):
+    """Global-mode layouts of the C ABI: rows as packed per-rank blocks (block_rows / block_stride) and outputs laid
+    out for one reduce-scatter (out_chunk) give the same numbers as the contiguous call on the concatenated rows."""
+    import torch
+    from rec_now_b200 import ops
+    b_loc = 2048
+    d = G.cfg5(world, seed=5, rows_per_rank=b_loc, groups_per_rank=64)
+    rng = np.random.default_rng(2)
+    b = world * b_loc
+    cols = [d["g"]] + ([rng.integers(0, 3, b).astype(np.int64)] if kk > 1 else [])
+    ok = (rng.random(b) > 0.1) if with_ok else None
+    spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=d["w"])
+    ref = S.pairwise(d["s"], d["y"], cols if kk > 1 else cols[0], spec, mask=ok)
+    lay = ops.packed_block_layout(b_loc, kk, True, with_ok)
+    blocks = []
+    for r in range(world):
+        sl = slice(r * b_loc, (r + 1) * b_loc)
+        parts = [np.ascontiguousarray(c[sl]).view(np.uint8) for c in cols]
+        parts += [np.ascontiguousarray(d[k][sl]).view(np.uint8) for k in ("s", "y", "w")]
+        if with_ok:
+            parts.append(ok[sl].astype(np.uint8))
+        blk = np.concatenate(parts)
+        blocks.append(np.concatenate([blk, np.zeros(lay["stride"] - blk.size, np.uint8)]))
+    gbuf = torch.tensor(np.concatenate(blocks)).cuda()
+    loss, grad = 0.0, np.zeros(b)
+    nparts = 3
+    for r in range(nparts):
+        res = ops.pairwise_fwd_bwd_blocked(gbuf, world, b_loc, kk, True, with_ok, label_func="diff", power=-0.5,
+                                           part=(r, nparts))
+        o = res["out"].cpu().numpy().reshape(world, res["chunk"])
+        assert int(res["n_pair"].item()) == ref["n_pair"]
+        assert np.all(o[:, b_loc] == o[0, b_loc]) and np.all(o[:, b_loc + 1:] == 0)       # loss slot + zeroed pad
+        loss += float(o[0, b_loc])
+        grad += o[:, :b_loc].reshape(-1).astype(np.float64)
+    assert abs(loss - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    err = np.abs(grad - ref["grad"])
+    assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all(), err.max()
+
+
 def test_cfg3_full_size():
     """BASELINE.json config 3 at full size (B = 65536, graded labels, per-sample weights, power -0.5) against the
     float64 segmented oracle: exact counts, 1e-5 loss / gradient."""
