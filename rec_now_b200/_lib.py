@@ -79,6 +79,7 @@ def lib() -> C.CDLL:
     L.rn_pairwise_scratch_bytes.restype = sz
     L.rn_pairwise_scratch_bytes.argtypes = [i64, i32]
     L.rn_pairwise_fwd_bwd.argtypes = [C.POINTER(PairwiseArgs), vp, sz, vp]
+    L.rn_pairwise_fwd_bwd.restype = C.c_int
     L.rn_pair_indices_scratch_bytes.restype = sz
     L.rn_pair_indices_scratch_bytes.argtypes = [i64, i32]
     L.rn_pair_indices_count.argtypes = [C.POINTER(PairwiseArgs), i32, vp, sz, C.POINTER(i64), vp]

@@ -104,10 +104,25 @@ def canon_keys(groups, row_ok: Optional[torch.Tensor] = None):
     return keys, ok
 
 
+class _PairCall:
+    """Per-thread reusable argument struct of rn_pairwise_fwd_bwd (building a 25-field ctypes struct per call costs
+    more host time than the three kernel launches)."""
+    __slots__ = ("args", "ref", "fn")
+
+    def __init__(self):
+        self.args = PairwiseArgs()
+        self.ref = C.byref(self.args)
+        self.fn = lib().rn_pairwise_fwd_bwd
+
+
+_pair_call = None
+
+
 def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
                      factor=1.0, power=0.0, only_wrong=False, reduce_mean=True, part=(0, 1),
                      want_row_pairs=False):
     """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors."""
+    global _pair_call
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()
@@ -124,18 +139,50 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     st = torch.cuda.current_stream(dev).cuda_stream
     scratch = _scratch(nbytes, dev, st)
     po = out.data_ptr()
-    a = PairwiseArgs(
-        B=b, K=kk, label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
-        keys=keys.data_ptr(), logits=s.data_ptr(), labels=y.data_ptr(),
-        row_ok=_ptr(ok), rw_pos=_ptr(rwp), rw_neg=_ptr(rwn),
-        factor=float(factor), power=float(power), only_wrong=int(bool(only_wrong)),
-        reduce_mean=int(bool(reduce_mean)), part_rank=int(part[0]), part_count=int(part[1]),
-        loss=po, n_pair_f32=po + 4, n_pair=po + 8,
-        dlogits=dlogits.data_ptr(), row_pairs=_ptr(row_pairs))
+    pc = _pair_call
+    if pc is None:
+        pc = _pair_call = _PairCall()
+    a = pc.args
+    a.B = b; a.K = kk; a.label_func = _lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP
+    a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
+    a.row_ok = _ptr(ok); a.rw_pos = _ptr(rwp); a.rw_neg = _ptr(rwn)
+    a.factor = factor; a.power = power; a.only_wrong = 1 if only_wrong else 0; a.reduce_mean = 1 if reduce_mean else 0
+    a.part_rank, a.part_count = part
+    a.loss = po; a.n_pair_f32 = po + 4; a.n_pair = po + 8
+    a.dlogits = dlogits.data_ptr(); a.row_pairs = _ptr(row_pairs)
+    a.block_rows = 0; a.block_stride = 0; a.out_chunk = 0
     with _on_device(dev):
-        check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, C.c_void_p(st)), "rn_pairwise_fwd_bwd")
-    return dict(loss=out[0], n_pair_f32=out[1], n_pair=out[2:4].view(torch.int64)[0], dlogits=dlogits,
-                row_pairs=row_pairs, _scratch=scratch)
+        rc = pc.fn(pc.ref, scratch.data_ptr(), nbytes, st)
+    if rc:
+        check(rc, "rn_pairwise_fwd_bwd")
+    return _PairOut(out, dlogits, row_pairs, scratch)
+
+
+class _PairOut(dict):
+    """Result of pairwise_fwd_bwd: a dict whose scalar views (loss, n_pair_f32, n_pair) are made on first use (each
+    tensor slice costs a few microseconds of host time)."""
+
+    def __init__(self, out, dlogits, row_pairs, scratch):
+        super().__init__(dlogits=dlogits, row_pairs=row_pairs, _scratch=scratch, _out=out)
+
+    def __missing__(self, key):
+        out = dict.__getitem__(self, "_out")
+        if key == "loss":
+            v = out[0]
+        elif key == "n_pair_f32":
+            v = out[1]
+        elif key == "n_pair":
+            v = out[2:4].view(torch.int64)[0]
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
 
 
 def packed_block_layout(b_loc: int, kk: int, has_w: bool, has_ok: bool) -> dict:

@@ -139,7 +139,11 @@ class _FusedPairwiseLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_n):
         (dlogits,) = ctx.saved_tensors
-        g = (g_loss * dlogits).reshape(ctx.out_shape).to(ctx.out_dtype)
+        g = g_loss * dlogits
+        if g.shape != ctx.out_shape:
+            g = g.reshape(ctx.out_shape)
+        if g.dtype != ctx.out_dtype:
+            g = g.to(ctx.out_dtype)
         return (g,) + (None,) * 10
 
 
