@@ -17,6 +17,7 @@ constexpr int kSegThreads = 512;              // threads per CTA of the segmenta
 constexpr int kSegWarps = kSegThreads / 32;
 constexpr int kIB = 64;                       // rows per I-block of the pair kernel (two per lane)
 constexpr u32 kEmpty = 0xFFFFFFFFu;
+constexpr int kInitMaxCtas = 1024;            // upper bound of k_init's grid (label-range partials)
 
 // Blocked row layout of the input columns (multi-GPU global mode: an all-gather of packed per-rank blocks leaves the
 // rows as B / Bl blocks of Bl rows, `stride` bytes apart).  Element i of a column lives at block i / Bl, offset
@@ -77,11 +78,11 @@ struct Layout {
   int64_t B; int K; int gbits; int ipt; u32 cap; u32 tile; u32 ntiles; u32 nib;
   size_t zero_begin, zero_end, ones_begin, ones_end, total;
   // zero-initialised region
-  size_t ctl, hist, cprim;
+  size_t ctl, hist, cprim, th0;
   // 0xFF-initialised region
   size_t table, table1;
   // plain
-  size_t slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
+  size_t labpart, slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
 };
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -108,19 +109,21 @@ inline Layout make_layout(int64_t B, int K) {
   L.zero_begin = o;
   L.ctl = take(sizeof(Ctl));
   L.hist = take(sizeof(u32) * kMaxPass * kBins);
-  L.cprim = take(sizeof(u64) * B);
+  L.cprim = take(sizeof(u64) * cap);                   // pair totals per group id (first-occurrence row < B, or table slot < cap)
+  L.th0 = take(sizeof(u32) * (size_t)L.ntiles * kBins);  // tile histograms, buffer 0 (accumulated with atomics in the merged first phase)
   L.zero_end = o;
   L.ones_begin = o;
   L.table = take(sizeof(u32) * cap);
   L.table1 = K > 1 ? take(sizeof(u32) * cap) : L.table;
   L.ones_end = o;
+  L.labpart = take(sizeof(u32) * 2 * kInitMaxCtas);
   L.slot = take(sizeof(u32) * B);
   L.slot1 = take(sizeof(u32) * B);
   L.keyA = take(sizeof(u64) * B);
   L.keyB = take(sizeof(u64) * B);
   L.valA = take(sizeof(u32) * B);
   L.valB = take(sizeof(u32) * B);
-  L.tilehist = take(sizeof(u32) * 3 * (size_t)L.ntiles * kBins);
+  L.tilehist = take(sizeof(u32) * 2 * (size_t)L.ntiles * kBins);    // buffers 1 and 2 (buffer 0 is L.th0)
   L.aj = take(sizeof(uint2) * B);
   L.ss = take(sizeof(float) * B);
   L.sy = take(sizeof(float) * B);
@@ -210,7 +213,10 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
 
 // ---- host plumbing (segment.cu) ---------------------------------------------------------------------
 // Zero / 0xFF-fill the initialised regions of the arena (one ordinary launch; it also resets the barriers).
-cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st);
+// Optionally (labels != nullptr) the same launch OR-reduces the label bits of the pairable rows into per-CTA partials
+// (Layout::labpart), which lets k_seg build the sort keys in its first phase; returns the grid size in *ncta.
+cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels = nullptr,
+                     const uint8_t* row_ok = nullptr, int* ncta = nullptr);
 int device_sm_count();
 // Cooperative launch of `kernel` with `grid` CTAs of `threads` threads (grid must not exceed the co-resident limit).
 cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st);

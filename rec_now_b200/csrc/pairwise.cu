@@ -102,7 +102,8 @@ struct HeadsTail {
       if (count_now) {
         cn = n;
         if (in && P.row_pairs) P.row_pairs[row] = (int64_t)cn;
-        const u32 pgi = in ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
+        // (merged first phase: ids are table slots; the id `cap` collects the rows that cannot pair)
+        const u32 pgi = (in && !(S.merged && gid > S.capmask)) ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
         if (in) cnt[p] = pgi;                   // index of the row's occurrence count: k_pair weights the row by c_h^power
         const u32 pg = cn ? pgi : kEmpty;
         const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
@@ -661,6 +662,9 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   H.target_units = target_units();
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   in.rm = P.rm;
+  static const int allow_merged = tune_int("RN_SEG_MERGED", 1);
+  in.allow_merged = allow_merged && a->part_count == 1;      // ranks of the global mode need identical ids
+  if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }
   if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;

@@ -30,8 +30,14 @@ struct SegParams {
   u32 capmask, ntiles;
   u32 *table, *table1, *slot, *slot1;
   u64 *keyA, *keyB; u32 *valA, *valB;
-  u32 *hist, *tilehist;
+  u32 *hist, *tilehist, *th0;
   Ctl* ctl;
+  // merged first phase (single key column, contiguous rows, no cross-rank determinism needed): the label bit range
+  // comes from k_init's per-CTA partials, the group id is the table SLOT (known right after the insert), so the sort
+  // keys and histograms are built in the hash phase and one phase + grid barrier disappear.  Rows that cannot pair
+  // get the id `cap` (one group, one label level: no pairs), which sorts last.
+  int merged; const u32* labpart; int npart;
+  __device__ __forceinline__ u32* th_buf(u32 k) const { return k ? tilehist + (size_t)(k - 1) * ntiles * kBins : th0; }
 };
 
 constexpr int kSegSmemWords = kSegWarps * kBins + kBins + 64;
@@ -123,7 +129,67 @@ __device__ __forceinline__ void seg_hash(const SegParams& S, u32* smem) {
   }
   // tile-histogram buffer 1 is accumulated during pass 0: clear it here (buffer 0 is stored by vkey, buffer 2 is
   // cleared during pass 0)
-  u32* th1 = S.tilehist + (size_t)S.ntiles * kBins;
+  u32* th1 = S.th_buf(1);
+  for (u32 k = gtid; k < S.ntiles * kBins; k += gthreads) th1[k] = 0;
+}
+
+// Merged first phase: hash + sort keys + histograms in one pass over this CTA's 512-row chunks (see SegParams::merged).
+template <int IPT>
+__device__ __forceinline__ void seg_hash_keys(const SegParams& S, const Plan& pl, u32* smem) {
+  constexpr u32 kLoc = 2 * kSegThreads;
+  constexpr u32 T = kSegThreads * IPT;
+  u32* sm_tab = smem;                                 // [kLoc] representative (local thread id)
+  u32* sm_gslot = smem + kLoc;                        // [kLoc] its global slot
+  u32* sm_hist = smem + 2 * kLoc;                     // [npass][kBins]
+  const u32 tid = threadIdx.x;
+  const u32 gtid = blockIdx.x * kSegThreads + tid, gthreads = gridDim.x * kSegThreads;
+  const u32 labmask = pl.labbits >= 32 ? 0xFFFFFFFFu : ((1u << pl.labbits) - 1u);
+  const u32 trash = S.capmask + 1u;
+  const u32 nchunks = (S.B + kSegThreads - 1) / kSegThreads;
+  for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const u32 r0 = c * kSegThreads, i = r0 + tid;
+    sm_tab[tid] = kEmpty; sm_tab[tid + kSegThreads] = kEmpty;
+    for (u32 k = tid; k < (u32)pl.npass * kBins; k += kSegThreads) sm_hist[k] = 0;
+    __syncthreads();
+    bool ok = false;
+    u32 ls = 0; float y = 0.f;
+    if (i < S.B) {
+      y = S.labels[i];
+      ok = (S.row_ok ? S.row_ok[i] != 0 : true) && !(y != y);
+      if (ok) {
+        const u64 key = (u64)S.keys[i];
+        ls = (u32)(mix64(0x9E3779B97F4A7C15ull ^ key) >> 40) & (kLoc - 1);
+        for (;;) {
+          u32 cur = sm_tab[ls];
+          if (cur == kEmpty) {
+            const u32 prev = atomicCAS(&sm_tab[ls], kEmpty, tid);
+            if (prev == kEmpty) break;
+            cur = prev;
+          }
+          if ((u64)S.keys[r0 + cur] == key) { if (tid < cur) atomicMin(&sm_tab[ls], tid); break; }
+          ls = (ls + 1) & (kLoc - 1);
+        }
+      }
+    }
+    __syncthreads();
+    if (ok && sm_tab[ls] == tid) sm_gslot[ls] = hash_insert(S, 1, i, S.table);
+    __syncthreads();
+    if (i < S.B) {
+      const u32 gid = ok ? sm_gslot[ls] : trash;
+      const u32 lab = ok ? ((enc_label(y) >> pl.labshift) & labmask) : 0u;
+      const u64 key = ((u64)gid << pl.labbits) | lab;
+      S.keyA[i] = key; S.valA[i] = i;
+#pragma unroll 1
+      for (int p = 0; p < pl.npass; ++p)
+        atomicAdd(&sm_hist[p * kBins + (u32)((key >> pl.shift[p]) & ((1u << pl.nbits[p]) - 1u))], 1u);
+    }
+    __syncthreads();
+    for (u32 k = tid; k < (u32)pl.npass * kBins; k += kSegThreads)
+      if (sm_hist[k]) atomicAdd(S.hist + k, sm_hist[k]);
+    if (sm_hist[tid]) atomicAdd(S.th0 + (size_t)(r0 / T) * kBins + tid, sm_hist[tid]);   // pass-0 histogram of the row's tile
+    __syncthreads();
+  }
+  u32* th1 = S.th_buf(1);
   for (u32 k = gtid; k < S.ntiles * kBins; k += gthreads) th1[k] = 0;
 }
 
@@ -154,7 +220,7 @@ __device__ __forceinline__ void seg_vkey(const SegParams& S, const Plan& pl, u32
     __syncthreads();
     for (u32 k = tid; k < (u32)pl.npass * kBins; k += kSegThreads)
       if (smem[k]) atomicAdd(S.hist + k, smem[k]);
-    S.tilehist[(size_t)t * kBins + tid] = smem[tid];           // pass-0 histogram of this tile (buffer 0)
+    S.th0[(size_t)t * kBins + tid] = smem[tid];                // pass-0 histogram of this tile (buffer 0)
     __syncthreads();
   }
 }
@@ -172,10 +238,9 @@ __device__ __forceinline__ void seg_sort_pass(const SegParams& S, const Plan& pl
   const bool more = pass + 1 < pl.npass;
   const int nshift = more ? pl.shift[pass + 1] : 0;
   const u32 ndmask = more ? ((1u << pl.nbits[pass + 1]) - 1u) : 0u;
-  const size_t thsz = (size_t)S.ntiles * kBins;
-  const u32* th_cur = S.tilehist + (size_t)(pass % 3) * thsz;
-  u32* th_next = S.tilehist + (size_t)((pass + 1) % 3) * thsz;
-  u32* th_zero = S.tilehist + (size_t)((pass + 2) % 3) * thsz;
+  const u32* th_cur = S.th_buf(pass % 3);
+  u32* th_next = S.th_buf((pass + 1) % 3);
+  u32* th_zero = S.th_buf((pass + 2) % 3);
   const u32 tid = threadIdx.x, w = tid >> 5, ln = tid & 31u;
   for (u32 t = blockIdx.x; t < S.ntiles; t += gridDim.x) {
     for (u32 k = tid; k < kSegWarps * kBins; k += kSegThreads) smem[k] = 0;
@@ -324,14 +389,32 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   u32 epoch = 0;
   Ctl* ctl = S.ctl;
   stamp(ctl, 0);
-  seg_hash(S, smem);
-  stamp(ctl, 1);
-  grid_sync(&ctl->bar, epoch, &ctl->err);
-  stamp(ctl, 2);
-  const Plan pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), S.gbits, S.use_label != 0);
-  seg_vkey<IPT>(S, pl, smem);
-  stamp(ctl, 3);
-  grid_sync(&ctl->bar, epoch, &ctl->err);
+  Plan pl;
+  if (S.merged) {
+    // label bit range from k_init's partials
+    u32 vor = 0, vnor = 0;
+    for (int k = threadIdx.x; k < S.npart; k += kSegThreads) { vor |= S.labpart[2 * k]; vnor |= S.labpart[2 * k + 1]; }
+    vor = __reduce_or_sync(0xFFFFFFFFu, vor); vnor = __reduce_or_sync(0xFFFFFFFFu, vnor);
+    if ((threadIdx.x & 31u) == 0) { smem[2 * (threadIdx.x >> 5)] = vor; smem[2 * (threadIdx.x >> 5) + 1] = vnor; }
+    __syncthreads();
+    vor = 0; vnor = 0;
+    for (int q = 0; q < kSegWarps; ++q) { vor |= smem[2 * q]; vnor |= smem[2 * q + 1]; }
+    __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->lab_or = vor; ctl->lab_nor = vnor; }
+    pl = make_plan(vor, vnor, S.gbits, true);
+    seg_hash_keys<IPT>(S, pl, smem);
+    stamp(ctl, 3);
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+  } else {
+    seg_hash(S, smem);
+    stamp(ctl, 1);
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+    stamp(ctl, 2);
+    pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), S.gbits, S.use_label != 0);
+    seg_vkey<IPT>(S, pl, smem);
+    stamp(ctl, 3);
+    grid_sync(&ctl->bar, epoch, &ctl->err);
+  }
   stamp(ctl, 4);
   for (int p = 0; p < pl.npass; ++p) {
     seg_sort_pass<IPT>(S, pl, p, smem);
@@ -351,6 +434,7 @@ struct SegInputs {
   bool use_label;        // sort by (group, label, row) instead of (group, row)
   bool nan_label_is_trash;
   RowMap rm = RowMap{0, 0, 0, 0};
+  bool allow_merged = false;   // the caller accepts table-slot group ids (not deterministic across calls / ranks)
 };
 
 inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs& in) {
@@ -365,17 +449,24 @@ inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs
   S.slot = at<u32>(base, L.slot); S.slot1 = at<u32>(base, L.slot1);
   S.keyA = at<u64>(base, L.keyA); S.keyB = at<u64>(base, L.keyB);
   S.valA = at<u32>(base, L.valA); S.valB = at<u32>(base, L.valB);
-  S.hist = at<u32>(base, L.hist); S.tilehist = at<u32>(base, L.tilehist);
+  S.hist = at<u32>(base, L.hist); S.tilehist = at<u32>(base, L.tilehist); S.th0 = at<u32>(base, L.th0);
+  S.merged = 0; S.labpart = at<u32>(base, L.labpart); S.npart = 0;
   S.ctl = at<Ctl>(base, L.ctl);
   return S;
 }
 
+// group-id bits of the merged first phase: table slots < cap plus the id `cap` of the rows that cannot pair
+inline int seg_merged_gbits(const Layout& L) { return bit_width_u64((uint64_t)L.cap); }
+
 // Enqueue init + the segmentation kernel with the given tail (2 launches).
 template <class Tail>
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const Tail& tail, cudaStream_t st) {
-  cudaError_t e = seg_init(L, scratch, st);
+  const bool merged = in.allow_merged && in.K == 1 && in.use_label && in.labels && !in.rm.Bl;
+  int npart = 0;
+  cudaError_t e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart) : seg_init(L, scratch, st);
   if (e != cudaSuccess) return e;
   SegParams S = make_seg_params(L, scratch, in);
+  if (merged) { S.merged = 1; S.npart = npart; S.gbits = seg_merged_gbits(L); }
   Tail T = tail;
   int grid = (int)((in.B + kSegThreads - 1) / kSegThreads);
   const int sms = device_sm_count();
