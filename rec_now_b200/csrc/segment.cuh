@@ -37,6 +37,7 @@ struct SegParams {
   // keys and histograms are built in the hash phase and one phase + grid barrier disappear.  Rows that cannot pair
   // get the id `cap` (one group, one label level: no pairs), which sorts last.
   int merged; const u32* labpart; int npart;
+  u64* dbgts;                     // RN_SEG_DEBUG=1: per-CTA arrival stamps [phase][cta] (dev tool), else nullptr
   __device__ __forceinline__ u32* th_buf(u32 k) const { return k ? tilehist + (size_t)(k - 1) * ntiles * kBins : th0; }
 };
 
@@ -271,12 +272,22 @@ __device__ __forceinline__ void seg_sort_pass(const SegParams& S, const Plan& pl
     u32 tp = 0;
     if (tid < nb) {
       u32 t2 = 0;
-      for (; t2 + 16 <= t; t2 += 16) {
+      // all loads of a batch are independent: the deeper the batch, the fewer dependent L2 round trips (the prefix
+      // over the earlier tiles is the longest chain of a pass)
+      for (; t2 + 32 <= t; t2 += 32) {
+        u32 x[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = th_cur[(size_t)(t2 + k) * kBins + tid];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) tp += x[k];
+      }
+      if (t2 + 16 <= t) {
         u32 x[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = th_cur[(size_t)(t2 + k) * kBins + tid];
 #pragma unroll
         for (int k = 0; k < 16; ++k) tp += x[k];
+        t2 += 16;
       }
       if (t2 + 8 <= t) {
         u32 x[8];
@@ -403,6 +414,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->lab_or = vor; ctl->lab_nor = vnor; }
     pl = make_plan(vor, vnor, S.gbits, true);
     seg_hash_keys<IPT>(S, pl, smem);
+    if (S.dbgts && threadIdx.x == 0) S.dbgts[blockIdx.x] = globaltimer();
     stamp(ctl, 3);
     grid_sync(&ctl->bar, epoch, &ctl->err);
   } else {
@@ -418,6 +430,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   stamp(ctl, 4);
   for (int p = 0; p < pl.npass; ++p) {
     seg_sort_pass<IPT>(S, pl, p, smem);
+    if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)(1 + p) * gridDim.x + blockIdx.x] = globaltimer();
     stamp(ctl, 5 + 2 * p);
     grid_sync(&ctl->bar, epoch, &ctl->err);
     stamp(ctl, 6 + 2 * p);
@@ -451,6 +464,8 @@ inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs
   S.valA = at<u32>(base, L.valA); S.valB = at<u32>(base, L.valB);
   S.hist = at<u32>(base, L.hist); S.tilehist = at<u32>(base, L.tilehist); S.th0 = at<u32>(base, L.th0);
   S.merged = 0; S.labpart = at<u32>(base, L.labpart); S.npart = 0;
+  static const char* segdbg = getenv("RN_SEG_DEBUG");
+  S.dbgts = (segdbg && *segdbg == '1') ? at<u64>(base, L.gstat) : nullptr;
   S.ctl = at<Ctl>(base, L.ctl);
   return S;
 }

@@ -237,21 +237,27 @@ def test_edge_tiles_and_wide_logits():
         check_pairwise(out, S.pairwise(s, y, ids, spec), ctx=f"edge {spec.label_func}")
 
 
-def test_large_batch_wide_tiles():
+@pytest.mark.parametrize("b", [200_000, 300_000])
+def test_large_batch_wide_tiles(b):
     """B > 148 * 1024 switches the segmentation kernel to 4096-row sort tiles (several tiles per CTA) and needs
-    18 group bits: the size of the all-gathered batch in global mode at 4+ GPUs."""
+    18+ group bits: the size of the all-gathered batch in global mode at 4+ GPUs.  B > 262144 (8 GPUs) also takes
+    the explicit work-unit records written by the segmentation kernel instead of the pair kernel's own list; there
+    the 2-way partition of the global mode is checked too."""
     rng = np.random.default_rng(21)
-    b = 200_000
     gidx = np.r_[np.repeat([0, 1], 3000), 2 + rng.integers(0, 4000, b - 6000)][rng.permutation(b)]
     ids = (gidx.astype(np.int64) * 2654435761 + 12345) ^ np.int64(0x0123456789ABCDEF)
     y = rng.integers(0, 5, b).astype(np.float32)
     s = rng.standard_normal(b).astype(np.float32)
     w = rng.uniform(0.5, 1.5, b).astype(np.float32)
     spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=w)
+    ref = S.pairwise(s, y, ids, spec)
     out = run_pairwise(s, y, ids, spec)
-    check_pairwise(out, S.pairwise(s, y, ids, spec), ctx="B=200000")
-    # partial evaluation (global mode) adds up
-    parts = [run_pairwise(s, y, ids, spec, part=(r, 3)) for r in range(3)]
-    tot = sum(p["dlogits"].double() for p in parts).cpu().numpy()
-    ref = out["dlogits"].double().cpu().numpy()
-    assert np.abs(tot - ref).max() <= 2e-6 * np.abs(ref).max()
+    check_pairwise(out, ref, ctx=f"B={b}")
+    if b > 262144:
+        loss, grad = 0.0, 0.0
+        for r in range(2):
+            o = run_pairwise(s, y, ids, spec, part=(r, 2))
+            assert int(o["n_pair"].item()) == ref["n_pair"]
+            loss += float(o["loss"].item()); grad = grad + o["dlogits"].double()
+        assert abs(loss - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+        assert (np.abs(grad.cpu().numpy() - ref["grad"]) <= 1e-5 * ref["grad_abs"] + 1e-12).all()
