@@ -133,8 +133,8 @@ inline Layout make_layout(int64_t B, int K) {
   L.lossrow = take(sizeof(float) * B);
   L.cnt = take(sizeof(u32) * B);
   L.perm = take(sizeof(u32) * B);
-  L.blk = take(sizeof(uint2) * L.nib);
-  L.units = take(sizeof(uint2) * ((size_t)L.nib + target_units() + 1));
+  L.blk = take(sizeof(uint2) * 2 * (size_t)L.nib);     // two J ranges per I-block
+  L.units = take(sizeof(uint2) * (2 * (size_t)L.nib + target_units() + 1));
   L.misc = take(sizeof(u64) * (B + 1));
   L.gstat = take(sizeof(float) * 8 * B);   // listwise per-list records
   L.total = o;
@@ -219,7 +219,7 @@ cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const floa
                      const uint8_t* row_ok = nullptr, int* ncta = nullptr);
 int device_sm_count();
 // Cooperative launch of `kernel` with `grid` CTAs of `threads` threads (grid must not exceed the co-resident limit).
-cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st);
+cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st, size_t smem = 0);
 
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 

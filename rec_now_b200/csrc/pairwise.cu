@@ -31,7 +31,7 @@ static int tune_int(const char* name, int dflt) {
 }
 
 constexpr u32 kMaxUnitC = 64;
-constexpr u32 kMaxNibS = 4096;           // I-blocks whose work list fits k_pair's shared memory (B <= 262144)
+constexpr u32 kMaxNibS = 8192;           // I-blocks whose cost prefixes fit k_pair's shared memory (B <= 524288)
 constexpr int kPairThreads = 1024;      // threads per CTA of the pair kernel (one CTA per SM, <= 64 registers)
 constexpr u32 kDone = 0xFFFFFFFFu;
 constexpr int kPairWarps = kPairThreads / 32;
@@ -46,6 +46,17 @@ struct PairParams {
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
 };
 
+// J-block range of virtual block v (2b = range R1 of I-block b, 2b + 1 = range R2, see HeadsTail): first J-block and
+// J-block count; R2 is trimmed so that no (I-block, J-block) tile is listed twice.
+__device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst) {
+  const uint2 r = blk[v];
+  u32 lo = 0, hi = 0;
+  if (r.y > r.x) { lo = r.x >> 5; hi = (r.y + 31) >> 5; }
+  if (v & 1) { const uint2 r1 = blk[v - 1]; if (r1.y > r1.x) lo = max(lo, (r1.y + 31) >> 5); }
+  jfirst = lo;
+  return hi > lo ? hi - lo : 0u;
+}
+
 // ---- heads tail of k_seg ---------------------------------------------------------------------------------
 // Work units: an I-block (64 sorted rows) x up to C consecutive J-blocks (32 sorted rows each) of its J range.
 // Record = (I-block, first J-block | J-block count << 24).
@@ -59,8 +70,8 @@ struct HeadsTail {
                                       u32& epoch) const {
     u32* sm_scan = smem;                       // [kSegWarps][2]
     u32* sm_carry = smem + 2 * kSegWarps;      // [2]
-    u32* sm_wj = smem + 36;                    // [kSegWarps][2]
-    u64* sm_red = reinterpret_cast<u64*>(smem + 72);   // [kSegWarps]
+    u32* sm_wj = smem + 36;                    // [kSegWarps][4]
+    u64* sm_red = reinterpret_cast<u64*>(smem + 104);  // [kSegWarps]
     Ctl* ctl = S.ctl;
     const u32 B = S.B, ln = lane_id(), w = threadIdx.x >> 5;
     const bool count_now = !P.dyn_count;
@@ -92,11 +103,20 @@ struct HeadsTail {
         if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
-        if (P.dyn_count) { lossrow[p] = 0.f; cnt[p] = 0; }
+        lossrow[p] = 0.f;
+        if (P.dyn_count) cnt[p] = 0;
       }
-      // J range needed by this warp's 32 rows; two warps make one I-block
-      const u32 jlo = warp_min(n ? a : 0xFFFFFFFFu), jhi = warp_max(n ? a + n : 0u);
-      if (ln == 0) { sm_wj[2 * w] = jlo; sm_wj[2 * w + 1] = jhi; }
+      // J ranges needed by this warp's 32 rows (two warps make one I-block): R1 = the range of the rows whose group
+      // began before the I-block (one group: it can reach far to the left), R2 = the hull of the ranges of the rows
+      // whose group begins inside the I-block (those lie inside the I-block's own 64 positions).  Keeping them apart
+      // keeps the gap between them -- the top label level of a big group -- out of the work list.
+      {
+        const u32 p0 = p & ~(u32)(kIB - 1);
+        const bool r1 = n && a < p0, r2 = n && a >= p0;
+        const u32 r1lo = warp_min(r1 ? a : 0xFFFFFFFFu), r1hi = warp_max(r1 ? a + n : 0u);
+        const u32 r2lo = warp_min(r2 ? a : 0xFFFFFFFFu), r2hi = warp_max(r2 ? a + n : 0u);
+        if (ln == 0) { sm_wj[4 * w] = r1lo; sm_wj[4 * w + 1] = r1hi; sm_wj[4 * w + 2] = r2lo; sm_wj[4 * w + 3] = r2hi; }
+      }
       // exact counts (position arithmetic): per row, per PRIMARY group (PW:286-289), total
       u32 cn = 0;
       if (count_now) {
@@ -115,7 +135,10 @@ struct HeadsTail {
       __syncthreads();
       if (!(w & 1) && ln == 0) {
         const u32 ib = (t0 + w * 32) / kIB;
-        if (ib < nib) blk[ib] = make_uint2(min(sm_wj[2 * w], sm_wj[2 * w + 2]), max(sm_wj[2 * w + 1], sm_wj[2 * w + 3]));
+        if (ib < nib) {
+          blk[2 * ib] = make_uint2(min(sm_wj[4 * w], sm_wj[4 * w + 4]), max(sm_wj[4 * w + 1], sm_wj[4 * w + 5]));
+          blk[2 * ib + 1] = make_uint2(min(sm_wj[4 * w + 2], sm_wj[4 * w + 6]), max(sm_wj[4 * w + 3], sm_wj[4 * w + 7]));
+        }
       }
       if (threadIdx.x == 0 && count_now) {
         u64 t = 0;
@@ -125,19 +148,17 @@ struct HeadsTail {
       __syncthreads();
     }
     stamp(ctl, 17);
-    // Small batches: k_pair builds the work list itself (shared-memory scan of the per-I-block J ranges), the kernel
-    // ends here without another grid barrier.  Large batches: explicit unit records.
+    // Batches up to 524288 rows: k_pair partitions the work itself (cost prefixes in shared memory), the kernel ends here
+    // without another grid barrier.  Larger batches: explicit unit records.
     if (nib <= kMaxNibS) return;
     grid_sync(&ctl->bar, epoch, &ctl->err);
     stamp(ctl, 18);
     // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
     //      the unit records of its own I-blocks ------------------------------------------------------------------
-    auto ntile = [&](u32 b) -> u32 {
-      const uint2 v = blk[b];
-      return v.y > v.x ? ((v.y + 31) >> 5) - (v.x >> 5) : 0u;
-    };
+    const u32 nvb = 2 * nib;
+    auto ntile = [&](u32 v) -> u32 { u32 jf; return vblock_tiles(blk, v, jf); };
     u64 m = 0;
-    for (u32 b = threadIdx.x; b < nib; b += kSegThreads) m += ntile(b);
+    for (u32 b = threadIdx.x; b < nvb; b += kSegThreads) m += ntile(b);
     m = warp_sum(m);
     __syncthreads();
     if (ln == 0) sm_red[w] = m;
@@ -151,9 +172,10 @@ struct HeadsTail {
     __syncthreads();
     if (threadIdx.x == 0) *s_carry = 0;
     __syncthreads();
-    for (u32 b0 = 0; b0 < nib; b0 += kSegThreads) {
+    for (u32 b0 = 0; b0 < nvb; b0 += kSegThreads) {
       const u32 b = b0 + threadIdx.x;
-      const u32 nt = b < nib ? ntile(b) : 0u;
+      u32 jfirst = 0;
+      const u32 nt = b < nvb ? vblock_tiles(blk, b, jfirst) : 0u;
       const u32 v = (nt + C - 1) / C;
       u32 inc = v;
 #pragma unroll
@@ -163,9 +185,8 @@ struct HeadsTail {
       u32 off = *s_carry;
       for (u32 q = 0; q < w; ++q) off += s_scan[q];
       if (v && (b % gridDim.x) == blockIdx.x) {
-        const u32 jfirst = blk[b].x >> 5;
         uint2* dst = units + (off + inc - v);
-        for (u32 q = 0; q < v; ++q) dst[q] = make_uint2(b, (jfirst + q * C) | (min(C, nt - q * C) << 24));
+        for (u32 q = 0; q < v; ++q) dst[q] = make_uint2(b >> 1, (jfirst + q * C) | (min(C, nt - q * C) << 24));
       }
       __syncthreads();
       if (threadIdx.x == kSegThreads - 1) *s_carry = off + inc;
@@ -178,40 +199,88 @@ struct HeadsTail {
 // ---- the pair kernel ------------------------------------------------------------------------------
 struct KpArgs {
   const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units; const uint2* blk; u32 nib; u32 target_units;
+  u32 cost_gen;              // cost of a J-block of a range R2 in eighths of a fast tile (see vcost)
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
   // finalisation
   const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
-  u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first unit start, loop exit, busy cycles, units | general tiles << 32}
-};
-
-// Positive-side rows of an I-block (two per lane) and the first J block of a unit: loaded one unit ahead.
-struct UnitRows {
-  uint2 an0, an1; float si0, si1, yi0, yi1, wp0, wp1; float sjm, yjm, wnjm;
-  u32 pg0, pg1;                     // occurrence-count index of the two rows (fetched with the rows, one unit ahead)
+  u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
 };
 
 // Occurrence weight c_h^power of a row's primary group (PW:147-149, 285-290).  Both rows of a pair share the group, so
-// the weight is applied per ROW, not per pair: to the row's loss sum when its unit ends and to its gradient in the
-// final pass.  The counts are final before k_pair starts; row -> count index -> count is a chain of two L2 round
-// trips that is kept off the critical path (index fetched with the rows one unit ahead, count fetched when the unit
-// starts and used when it ends).
+// the weight is applied per ROW, not per pair: to the row's loss sum when its segment ends and to its gradient in the
+// final pass.  The counts are final before k_pair starts.
 __device__ __forceinline__ float occ_pow(u64 ch, float power) {
   return ch ? ((power == 1.0f) ? (float)ch : powf((float)ch, power)) : 0.f;
 }
 
+// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
+// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
+// a[n] receives the total (sc: kPairWarps + 2 words).  All threads of the CTA must call it.
+constexpr u32 kScanThreads = 256;
+__device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
+  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
+  const bool act = threadIdx.x < kScanThreads;
+  const u32 per = (n + kScanThreads - 1) / kScanThreads;
+  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
+  u32 sum = 0, inc = 0;
+  if (act) {
+    for (u32 i = i0; i < i1; ++i) sum += a[i];
+    inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+    if (ln == 31) sc[wq] = inc;
+  }
+  __syncthreads();
+  if (act) {
+    u32 off = inc - sum;
+    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
+    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
+    if (threadIdx.x == kScanThreads - 1) a[n] = off;
+  }
+  __syncthreads();
+}
+
+// Largest idx in [lo, hi) with arr[idx] <= key (arr nondecreasing, arr[lo] <= key); one thread, binary search.
+__device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) {
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (arr[mid] <= key) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// Cost of one J-block (32 negatives) of a virtual block in eighths of a fast tile.  Range R1 of an I-block (the rows of
+// the group that began before the block) is almost all fast tiles; range R2 (groups that begin inside the block) is
+// general tiles (~2x, measured; a warp that finishes early costs little -- its SMSP neighbours speed up -- while a late
+// one runs alone and cannot fill the SFU pipe, so the estimate leans to the pessimistic side).
+constexpr u32 kCostFast = 8;
+__device__ __forceinline__ u32 vcost(u32 v, u32 cgen) { return (v & 1u) ? cgen : kCostFast; }
+
+// Position `pos` of the cost line -> (virtual block, J-block, eighth).  s_pi: cost prefix over the virtual blocks,
+// s_jn: first J-block | J-block count << 16 of every virtual block.
+__device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32& v, u32& jb,
+                                            u32& e) {
+  if (pos >= tot) { v = nvb; jb = 0; e = 0; return; }
+  v = last_le(s_pi, 0, nvb, pos);
+  const u32 o = pos - s_pi[v], c = vcost(v, cgen), q = o / c;
+  jb = (s_jn[v] & 0xFFFFu) + q;
+  e = ((o - q * c) * 8u) / c;
+}
+
+// Positive-side rows of an I-block (two per lane) and the first J block of a segment: loaded one segment ahead.
+struct UnitRows {
+  uint2 an0, an1; float si0, si1, yi0, yi1, wp0, wp1; float sjm, yjm, wnjm;
+};
+
+// One piece of work of a warp: I-block b x J-blocks [jb0, jb1); of the first J-block only the rotation-step eighths
+// from ea on, of the last one only those below eb (a whole tile is [0, 8)).
+struct Seg { u32 b, jb0, jb1, ea, eb; };
+
 template <int MODE>
-__device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, float fold_power, UnitRows& r) {
+__device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, UnitRows& r) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
   const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
   r.an0 = make_uint2(0, 0); r.an1 = make_uint2(0, 0);
   r.si0 = r.si1 = r.yi0 = r.yi1 = 0.f; r.wp0 = r.wp1 = 1.f;
   if (pi0 < B) { r.an0 = A.aj[pi0]; r.si0 = A.ss[pi0]; if (DIFF) r.yi0 = A.sy[pi0]; if (HASW && A.swp) r.wp0 = A.swp[pi0]; }
   if (pi1 < B) { r.an1 = A.aj[pi1]; r.si1 = A.ss[pi1]; if (DIFF) r.yi1 = A.sy[pi1]; if (HASW && A.swp) r.wp1 = A.swp[pi1]; }
-  r.pg0 = r.pg1 = kEmpty;
-  if (fold_power != 0.f) {
-    if (pi0 < B) r.pg0 = A.cnt[pi0];
-    if (pi1 < B) r.pg1 = A.cnt[pi1];
-  }
   const u32 pjm = jb0 * 32 + ln;
   r.sjm = pjm < B ? A.ss[pjm] : 0.f; r.yjm = 0.f; r.wnjm = 1.f;
   if (DIFF) r.yjm = pjm < B ? A.sy[pjm] : 0.f;
@@ -220,18 +289,21 @@ __device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u3
 
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
-  // Units are dealt round-robin to the CTAs (the q-th unit of this CTA is unit q * gridDim + cta of this rank's share
-  // of the list), so every SM gets the same mix and there is no global ticket; the warps of a CTA take the CTA's units
-  // dynamically from a shared-memory counter and load the record and rows of the NEXT unit while the current one is
-  // being scored.  When the pair set does not depend on scores (DYN = false) the occurrence weights are already
-  // folded into the positive-side weights, so the kernel accumulates final values: per-row gradient sums (global
-  // RED) and one loss partial per warp (registers).
+  // Work = the (I-block x J-block) tiles of the staircase, laid out on a COST LINE: virtual block after virtual block
+  // (the two J ranges of every I-block), J-block after J-block, a J-block of range R1 costing 8 and one of range R2
+  // costing 13 (see vcost).  For B <= 524288 the kernel partitions the line STATICALLY: the costs are prefix-summed
+  // over the virtual blocks (shared memory, every CTA redundantly) and every warp of the grid takes ONE contiguous
+  // piece of exactly the same length, cut at a granularity of one eighth of a tile (4 of the 32 rotation steps).
+  // Pieces are dealt to the warps interleaved over the SMs (piece r -> CTA r % grid), so every SM gets the same mix.
+  // No tickets, no atomics for scheduling, a few row loads per warp (the rows of the next I-block of a piece are
+  // fetched while the current one is scored).  Larger batches use explicit unit records (built by k_seg) that the
+  // warps of a CTA take dynamically.
+  extern __shared__ __align__(16) u32 dsm[];
   __shared__ u32 s_cnt;
   __shared__ u64 red_u[kPairWarps];
   __shared__ double red_d[kPairWarps];
-  __shared__ u32 s_ustart[kMaxNibS + 1];          // first unit of every I-block (work list built here for small batches)
-  __shared__ u32 s_jn[kMaxNibS];                  // first J-block | J-block count << 16
   __shared__ u32 s_scan[kPairWarps + 2];
+  __shared__ u32 s_bnd[6 * kPairWarps];
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
   constexpr bool DYN = RWN || WRONG;
   Ctl* ctl = A.ctl;
@@ -241,49 +313,60 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   if (threadIdx.x == 0) s_cnt = 0;
   const bool own_list = A.nib <= kMaxNibS;
   const float fold_power = DYN ? 0.f : P.power;
-  u32 U = 0, C = 1;
+  const u32 nvb = 2 * A.nib;                 // virtual blocks: the two J ranges of every I-block
+  u32* s_pi = dsm;                           // [nvb + 1]
+  u32* s_jn = s_pi + nvb + 1;                // [nvb]
+  // static partition: this warp's piece [cur, end) of the cost line; explicit list: U units
+  u32 cb = 0, cj = 0, ce = 0, zb = 0, zj = 0, ze = 0;
+  bool st_done = true;
+  u32 U = 0;
   if (own_list) {
-    // ---- work list: units of <= C J-blocks per I-block, C from the total tile count (every CTA, redundantly) ----
-    const u32 wq = threadIdx.x >> 5;
     u32 msum = 0;
-    for (u32 b = threadIdx.x; b < A.nib; b += kPairThreads) {
-      const uint2 v = A.blk[b];
-      const u32 nt = v.y > v.x ? ((v.y + 31) >> 5) - (v.x >> 5) : 0u;
-      s_jn[b] = nt ? ((v.x >> 5) | (nt << 16)) : 0u;
+    for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
+      u32 jf;
+      const u32 nt = vblock_tiles(A.blk, v, jf);
+      s_jn[v] = nt ? (jf | (nt << 16)) : 0u;
+      s_pi[v] = nt * vcost(v, A.cost_gen);
       msum += nt;
     }
-    msum = warp_sum(msum);
-    if (ln == 0) s_scan[wq] = msum;
     __syncthreads();
-    u32 Mt = 0;
-    for (int q = 0; q < kPairWarps; ++q) Mt += s_scan[q];
-    C = (Mt + A.target_units - 1) / A.target_units;
-    C = C < 1 ? 1 : (C > kMaxUnitC ? kMaxUnitC : C);
-    __syncthreads();
-    if (threadIdx.x == 0) s_scan[kPairWarps] = 0;                    // running carry
-    __syncthreads();
-    for (u32 b0 = 0; b0 < A.nib; b0 += kPairThreads) {
-      const u32 b = b0 + threadIdx.x;
-      const u32 v = b < A.nib ? ((s_jn[b] >> 16) + C - 1) / C : 0u;
-      u32 inc = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
-      if (ln == 31) s_scan[wq] = inc;
-      __syncthreads();
-      u32 off = s_scan[kPairWarps];
-      for (u32 q = 0; q < wq; ++q) off += s_scan[q];
-      if (b < A.nib) s_ustart[b] = off + inc - v;
-      __syncthreads();
-      if (threadIdx.x == kPairThreads - 1) s_scan[kPairWarps] = off + inc;
-      __syncthreads();
+    stamp(ctl, 11);
+    block_excl_scan(s_pi, nvb, s_scan);
+    stamp(ctl, 12);
+    const u32 tot = s_pi[nvb];
+    // this rank's share [r0, r1) of the cost line, one equal piece per warp; the 2 x 32 piece boundaries of this CTA's
+    // warps are resolved by 64 threads at once (s_bnd: [64][v, jb, e])
+    u32 r0 = 0, r1 = tot;
+    if (P.part_count > 1) {
+      r0 = (u32)(((u64)tot * (u32)P.part_rank) / (u32)P.part_count);
+      r1 = (u32)(((u64)tot * ((u32)P.part_rank + 1)) / (u32)P.part_count);
     }
-    U = s_scan[kPairWarps];
-    if (threadIdx.x == 0) s_ustart[A.nib] = U;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->n_units = U; ctl->unit_c = C; ctl->n_tiles = Mt; }
+    if (threadIdx.x < 2 * kPairWarps) {
+      const u32 wpr = gridDim.x * kPairWarps;                       // pieces per rank (< 65536)
+      const u32 r = (threadIdx.x >> 1) * gridDim.x + blockIdx.x + (threadIdx.x & 1u);
+      const u32 len = r1 - r0, q = len / wpr, rem = len - q * wpr;  // len * r / wpr without 64-bit division
+      const u32 pos = r0 + q * r + (rem * r) / wpr;
+      u32 v, jb, e;
+      resolve_pos(pos, tot, nvb, s_pi, s_jn, A.cost_gen, v, jb, e);
+      s_bnd[3 * threadIdx.x] = v; s_bnd[3 * threadIdx.x + 1] = jb; s_bnd[3 * threadIdx.x + 2] = e;
+    }
+    __syncthreads();
+    {
+      // (warp-uniform values are passed through shfl so that the compiler keeps them in uniform registers)
+      const u32 wq = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
+      const u32* bd = s_bnd + 6 * wq;
+      cb = bd[0]; cj = bd[1]; ce = bd[2]; zb = bd[3]; zj = bd[4]; ze = bd[5];
+      st_done = !(cb < zb || (cb == zb && (cj < zj || (cj == zj && ce < ze))));
+    }
+    if (blockIdx.x == 0) {
+      msum = warp_sum(msum);
+      if (ln == 0 && msum) atomicAdd((u64*)&ctl->n_tiles, (u64)msum);
+      if (threadIdx.x == 0) { ctl->n_units = tot; ctl->unit_c = 0; }
+    }
   } else {
     U = ld_relaxed(&ctl->n_units);
+    __syncthreads();
   }
-  __syncthreads();
   stamp(ctl, 16);
   double lsum = 0.0;
   {
@@ -291,44 +374,55 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     const u32 u_end = (u32)(((u64)U * ((u32)P.part_rank + 1)) / (u32)P.part_count);
     const u32 n_mine = (u_end - u_begin > blockIdx.x) ? (u_end - u_begin - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const float c = P.c_log2;
-    // debug tallies (per warp, flushed once): longest unit, busy cycles, units, fast / general tiles
-    u64 d_max = 0, d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0; u64 d_gencyc = 0, d_fastcyc = 0;
+    // debug tallies (per warp, flushed once): busy cycles, segments, fast / general tiles, eighths
+    u64 d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0, d_eighths = 0; u64 d_gencyc = 0, d_fastcyc = 0;
     const u64 d_start = P.debug ? globaltimer() : 0;
-    auto take = [&](uint2& rec) -> bool {
+    auto take = [&](Seg& sg) -> bool {
+      if (own_list) {
+        // next I-block segment of this warp's piece
+        for (;;) {
+          if (st_done || cb >= nvb) return false;
+          if (cb > zb || (cb == zb && (cj > zj || (cj == zj && ce >= ze)))) { st_done = true; return false; }
+          const u32 jn = s_jn[cb], jend = (jn & 0xFFFFu) + (jn >> 16);
+          if (cj >= jend) {                       // (also skips virtual blocks without tiles)
+            ++cb; cj = cb < nvb ? (s_jn[cb] & 0xFFFFu) : 0u; ce = 0;
+            continue;
+          }
+          sg.b = cb >> 1; sg.jb0 = cj; sg.ea = ce;
+          if (cb == zb) { sg.jb1 = ze ? zj + 1 : zj; sg.eb = ze ? ze : 8u; st_done = true; }
+          else { sg.jb1 = jend; sg.eb = 8u; ++cb; cj = cb < nvb ? (s_jn[cb] & 0xFFFFu) : 0u; ce = 0; }
+          sg.b = __shfl_sync(0xFFFFFFFFu, sg.b, 0); sg.jb0 = __shfl_sync(0xFFFFFFFFu, sg.jb0, 0);
+          sg.jb1 = __shfl_sync(0xFFFFFFFFu, sg.jb1, 0);
+          const u32 ee = __shfl_sync(0xFFFFFFFFu, sg.ea | (sg.eb << 4), 0);
+          sg.ea = ee & 15u; sg.eb = ee >> 4;
+          return true;
+        }
+      }
       u32 q = 0;
       if (ln == 0) q = atomicAdd(&s_cnt, 1u);
       q = __shfl_sync(0xFFFFFFFFu, q, 0);
       if (q >= n_mine) return false;
       const u32 idx = q * gridDim.x + blockIdx.x;
-      const u32 u = P.ascending ? u_begin + idx : u_end - 1u - idx;
-      if (own_list) {
-        u32 lo_b = 0, hi_b = A.nib;                  // largest b with ustart[b] <= u
-        while (hi_b - lo_b > 1) { const u32 mid = (lo_b + hi_b) >> 1; if (s_ustart[mid] <= u) lo_b = mid; else hi_b = mid; }
-        const u32 jn = s_jn[lo_b], k = u - s_ustart[lo_b];
-        rec = make_uint2(lo_b, ((jn & 0xFFFFu) + k * C) | (min(C, (jn >> 16) - k * C) << 24));
-      } else {
-        rec = A.units[u];
-      }
+      const uint2 rec = A.units[P.ascending ? u_begin + idx : u_end - 1u - idx];
+      sg.b = rec.x; sg.jb0 = rec.y & 0xFFFFFFu; sg.jb1 = sg.jb0 + (rec.y >> 24); sg.ea = 0; sg.eb = 8u;
       return true;
     };
-    uint2 rec, rec_n; UnitRows R, Rn;
-    bool have = take(rec);
+    Seg sg, sg_n; UnitRows R, Rn;
+    bool have = take(sg);
     const bool fold = fold_power != 0.f;
-    if (have) load_unit_rows<MODE>(A, B, rec.x, rec.y & 0xFFFFFFu, ln, fold_power, R);
+    if (have) load_unit_rows<MODE>(A, B, sg.b, sg.jb0, ln, R);
     while (have) {
       const long long d_t0 = P.debug ? clock64() : 0;
-      const u64 d_gt0 = P.debug > 1 ? globaltimer() : 0;
-      const u64 d_tc0 = d_fastcyc + d_gencyc; const u32 d_gen0 = d_gen;
-      const bool have_n = take(rec_n);
-      if (have_n) load_unit_rows<MODE>(A, B, rec_n.x, rec_n.y & 0xFFFFFFu, ln, fold_power, Rn);      // in flight while this unit is scored
-      const u32 b = rec.x, jb0 = rec.y & 0xFFFFFFu, jb1 = jb0 + (rec.y >> 24);
+      const bool have_n = take(sg_n);
+      if (have_n) load_unit_rows<MODE>(A, B, sg_n.b, sg_n.jb0, ln, Rn);      // in flight while this segment is scored
+      const u32 b = sg.b, jb0 = sg.jb0, jb1 = sg.jb1;
       const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
       const uint2 an0 = R.an0, an1 = R.an1;
       const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
       const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
-      u64 ch0 = 0, ch1 = 0;                           // occurrence counts of the two rows: in flight during the unit
-      if (fold) { if (R.pg0 != kEmpty) ch0 = A.cprim[R.pg0]; if (R.pg1 != kEmpty) ch1 = A.cprim[R.pg1]; }
       float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
+      u32 pg0 = kEmpty, pg1 = kEmpty;             // occurrence-count index of the two rows (count fetched when the segment ends)
+      if (fold) { if (pi0 < B) pg0 = A.cnt[pi0]; if (pi1 < B) pg1 = A.cnt[pi1]; }
       u32 pjm = jb0 * 32 + ln;
       float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
       for (u32 jb = jb0; jb < jb1; ++jb) {
@@ -340,6 +434,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
         float accj = 0.f;
         const u32 j0 = jb * 32;
+        const int ts = (jb == jb0) ? 4 * (int)sg.ea : 0, te = (jb + 1 == jb1) ? 4 * (int)sg.eb : 32;   // rotation steps
+        const bool part = (te - ts) != 32;
         // Overlap of every row's negative range with this J block.  Row ranges start at a group start and end at
         // a level start of the same group, so a row covers a (group, level) run of the block entirely or not at
         // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
@@ -359,27 +455,26 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
           fast = __all_sync(0xFFFFFFFFu, !jin || yjm == yref);
         }
-        if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; }
+        if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; d_eighths += (u32)(te - ts) >> 2; }
         const long long d_g0 = P.debug ? clock64() : 0;
         if (fast) {
           float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
           if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
           const float sje = jin ? sjm : -3.0e38f;
-          const bool whole = __all_sync(0xFFFFFFFFu, in0 && in1);
-          if (HASW || !whole) tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
-          else                tile_fast<false>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+          if (part) tile_fast<true, true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj, ts, te);
+          else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
         } else if (any_in) {
           const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
           const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
           const bool any0 = __any_sync(0xFFFFFFFFu, in0);
           const bool any1 = __any_sync(0xFFFFFFFFu, in1);
           if (any0) {
-            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
-            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, li0, gi0, cnt0, accj);
+            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
+            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
           }
           if (any1) {
-            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
-            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, li1, gi1, cnt1, accj);
+            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
+            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
           }
         }
         if (P.debug) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
@@ -388,35 +483,31 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       }
       if (pi0 < B && an0.y) {
         if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
-        if (DYN) { if (li0 != 0.f) atomicAdd(A.lossrow + pi0, li0); if (cnt0) atomicAdd(A.cnt + pi0, cnt0); }
+        if (DYN && li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
+        if (DYN && cnt0) atomicAdd(A.cnt + pi0, cnt0);
       }
       if (pi1 < B && an1.y) {
         if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
-        if (DYN) { if (li1 != 0.f) atomicAdd(A.lossrow + pi1, li1); if (cnt1) atomicAdd(A.cnt + pi1, cnt1); }
+        if (DYN && li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
+        if (DYN && cnt1) atomicAdd(A.cnt + pi1, cnt1);
       }
       if (!DYN) {
-        if (fold) { li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power); }
+        if (fold) {
+          const u64 ch0 = pg0 != kEmpty ? A.cprim[pg0] : 0ull, ch1 = pg1 != kEmpty ? A.cprim[pg1] : 0ull;
+          li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
+        }
         lsum += (double)li0 + (double)li1;
       }
-      if (P.debug) {
-        const u64 dt = (u64)(clock64() - d_t0);
-        if (P.debug > 1 && ln == 0 && d_units < 6) {       // per-unit trace (RN_PAIR_DEBUG=2, B >= 65536 only)
-          u64* tr = A.dbgbuf + 4 * (size_t)(gridDim.x * kPairWarps) + 48 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5)) + 6 * d_units;
-          tr[0] = d_gt0; tr[1] = globaltimer(); tr[2] = ((u64)(u32)(b * 4096u + (jb0 & 4095u)) << 32) | ((u64)(jb1 - jb0) << 16) | (d_gen - d_gen0);
-          tr[3] = (dt << 32) | (d_fastcyc + d_gencyc - d_tc0); tr[4] = 0; tr[5] = 0;
-        }
-        d_busy += dt; ++d_units;
-        const u64 enc = (dt << 32) | b;
-        if (enc > d_max) d_max = enc;
-      }
-      have = have_n; rec = rec_n; R = Rn;
+      if (P.debug) { d_busy += (u64)(clock64() - d_t0); ++d_units; }
+      have = have_n; sg = sg_n; R = Rn;
     }
     if ((P.debug & 1) && ln == 0) {
-      atomicMax(&ctl->dbg[0], d_max); atomicAdd(&ctl->dbg[1], d_busy);
+      atomicAdd(&ctl->dbg[1], d_busy);
       const u64 now = globaltimer();
       atomicMax(&ctl->dbg[2], now);
-      u64* rec = A.dbgbuf + 4 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5));
+      u64* rec = A.dbgbuf + 8 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5));
       rec[0] = d_start; rec[1] = now; rec[2] = d_busy; rec[3] = (u64)d_units | ((u64)d_gen << 32);
+      rec[4] = d_fast; rec[5] = d_fastcyc; rec[6] = d_gencyc; rec[7] = d_eighths;
       atomicAdd(&ctl->dbg[4], (u64)d_units); atomicAdd(&ctl->dbg[5], (u64)d_fast);
       atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc); atomicAdd(&ctl->dbg[3], d_fastcyc);
     }
@@ -433,7 +524,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
       if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
-    // the row permutation and the pair count are final before this kernel starts: fetch them ahead of the barrier
+    // the row permutation, the pair count and the occurrence counts are final before this kernel starts: fetch them
+    // ahead of the barrier
     const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
     const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
     const float gscale = P.factor / denom;
@@ -549,7 +641,16 @@ static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_
   }
   PairParams p = P; KpArgs a = A;
   void* args[] = {&p, &a};
-  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm, kPairThreads, args, st);
+  // cost prefix of the static partition: s_pi[2 nib + 1], s_jn[2 nib]
+  const size_t smem = A.nib <= kMaxNibS ? sizeof(u32) * (4 * (size_t)A.nib + 2) : 0;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    const size_t want = sizeof(u32) * (4 * (size_t)kMaxNibS + 2);
+    cudaError_t e = cudaFuncSetAttribute(k_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    if (e != cudaSuccess) return e;
+    smem_set = want;
+  }
+  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm, kPairThreads, args, st, smem);
 }
 
 static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A, cudaStream_t st) {
@@ -669,6 +770,8 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
+  static const int cost_gen = tune_int("RN_PAIR_COST_GEN", 17);
+  A.cost_gen = (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
   A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);

@@ -6,7 +6,7 @@
 using namespace rn;
 
 template <int VAR>
-__global__ void __launch_bounds__(1024) k_tb(int iters, float* out, unsigned long long* cyc) {
+__global__ void __launch_bounds__(VAR >= 2 ? 512 : 1024) k_tb(int iters, float* out, unsigned long long* cyc) {
   const u32 ln = threadIdx.x & 31;
   float si0 = 0.01f * ln, si1 = -0.02f * ln, sjm = 0.03f * ln - 0.5f;
   float li0 = 0, li1 = 0, gi0 = 0, gi1 = 0, accj = 0;
@@ -14,6 +14,7 @@ __global__ void __launch_bounds__(1024) k_tb(int iters, float* out, unsigned lon
   for (int i = 0; i < iters; ++i) {
     if (VAR == 0) tile_fast<true>(si0, si1, 1.1f, 0.9f, sjm, 1.4427f, li0, li1, gi0, gi1, accj);
     if (VAR == 1) tile_fast<false>(si0, si1, 1.1f, 0.9f, sjm, 1.4427f, li0, li1, gi0, gi1, accj);
+    if (VAR == 2) tile_fast<true, false, 8>(si0, si1, 1.1f, 0.9f, sjm, 1.4427f, li0, li1, gi0, gi1, accj);
     sjm += 1e-3f;
   }
   const long long t1 = clock64();
@@ -27,6 +28,7 @@ void run(const char* name) {
   cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&cyc, 148 * 32 * 8);
   const int iters = 64;
   for (int nw : {1, 2, 4, 8, 12, 16, 24, 32}) {
+    if (VAR >= 2 && nw > 16) continue;
     for (int rep = 0; rep < 3; ++rep) k_tb<VAR><<<148, 32 * nw>>>(iters, out, cyc);
     cudaDeviceSynchronize();
     std::vector<unsigned long long> h(148 * nw);
@@ -43,5 +45,6 @@ void run(const char* name) {
 int main() {
   run<0>("fast<HASW>");
   run<1>("fast<noW> ");
+  run<2>("fast<HASW,KB=8,512thr>");
   return 0;
 }

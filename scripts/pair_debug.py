@@ -33,7 +33,7 @@ B = s.numel()
 NW = int(__import__('os').environ.get('NW', '16'))
 total = scr.numel()
 gstat_off = total - ((8 * 4 * B + 255) // 256) * 256
-rec = scr[gstat_off:gstat_off + 148 * NW * 32].view(torch.int64).cpu().numpy().reshape(-1, 4)
+rec = scr[gstat_off:gstat_off + 148 * NW * 64].view(torch.int64).cpu().numpy().reshape(-1, 8)
 t20 = t[20]
 start = (rec[:, 0] - t20) / 1e3; end = (rec[:, 1] - t20) / 1e3
 busy = rec[:, 2]; units = rec[:, 3] & 0xFFFFFFFF; gen = rec[:, 3] >> 32
@@ -54,3 +54,19 @@ for i in list(o[:3]) + list(o[-4:]):
     we = np.sort(end.reshape(148, NW)[i])
     print(f"  sm {i:3d} exit {sm_end[i]:.1f} busy {sm_busy[i]/1e3:.0f}K units {sm_units[i]} gen {sm_gen[i]} | " + " ".join(f"{x:.0f}" for x in we[::max(1,NW//8)]) + f" {we[-1]:.0f}")
 print("corr(exit, busy) =", np.corrcoef(sm_end, sm_busy)[0,1], " corr(exit, gen) =", np.corrcoef(sm_end, sm_gen)[0,1])
+
+fast = rec[:, 4]; fcyc = rec[:, 5]; gcyc = rec[:, 6]; eig = rec[:, 7]
+print(f"eighths/warp: min {eig[ok].min()} med {np.median(eig[ok])} max {eig[ok].max()}; fast tiles/warp med {np.median(fast[ok])} max {fast[ok].max()}")
+dur = (end - start)
+for name, m in (("gen==0", ok & (gen == 0)), ("gen>=1", ok & (gen >= 1)), ("gen>=3", ok & (gen >= 3))):
+    if m.sum(): print(f"  {name}: n {m.sum()} dur med {np.median(dur[m]):.1f} p90 {np.percentile(dur[m],90):.1f} max {dur[m].max():.1f} us; eighths med {np.median(eig[m])}; busy med {np.median(busy[m])}; fastcyc/fast-eighth med {np.median(fcyc[m]/np.maximum(eig[m]-0,1)):.0f}")
+print("corr(dur, eighths) =", np.corrcoef(dur[ok], eig[ok])[0,1], " corr(dur, gen) =", np.corrcoef(dur[ok], gen[ok])[0,1], " corr(dur, units) =", np.corrcoef(dur[ok], units[ok])[0,1])
+wq = np.arange(len(dur)) % NW
+print("dur by warp%4 (SMSP):", [round(float(np.median(dur[ok & (wq % 4 == k)])), 1) for k in range(4)])
+print("dur by warp idx/8:", [round(float(np.median(dur[ok & (wq // 8 == k)])), 1) for k in range(NW // 8)])
+cta = np.arange(len(dur)) // NW
+o = np.argsort(-dur)[:12]
+for i in o: print(f"  slow warp cta {cta[i]} w {wq[i]}: dur {dur[i]:.1f} busy {busy[i]} segs {units[i]} gen {gen[i]} fast {fast[i]} eighths {eig[i]} fastcyc {fcyc[i]} gencyc {gcyc[i]}")
+o = np.argsort(dur)[:6]
+for i in o: print(f"  quick warp cta {cta[i]} w {wq[i]}: dur {dur[i]:.1f} busy {busy[i]} segs {units[i]} gen {gen[i]} fast {fast[i]} eighths {eig[i]} fastcyc {fcyc[i]} gencyc {gcyc[i]}")
+np.savez("gpurun_out/pair_debug.npz", rec=rec, t20=t20, ts=np.array(t, dtype=np.uint64))
