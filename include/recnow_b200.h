@@ -169,6 +169,10 @@ int rn_debug_timestamps(void* scratch, uint64_t* ts_host, int32_t capacity, void
 /* Stage timing breakdown helper: number of kernel launches the last-built pipeline enqueues per call. */
 int rn_pairwise_launch_count(int64_t B, int32_t K);
 int rn_listwise_launch_count(int64_t B);
+/* Calls of the calling thread that were enqueued as ONE launch of a cached CUDA graph (rn_pairwise_fwd_bwd does that
+ * unless RN_GRAPH=0, the stream is under capture, or rn_profile_enable is active); negative (-count - 1) after a graph
+ * API failure switched the thread back to plain launches. */
+int64_t rn_debug_graph_launches(void);
 
 #ifdef __cplusplus
 }

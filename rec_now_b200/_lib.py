@@ -24,6 +24,7 @@ EXPORTS = [
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
     "rn_bench_mufu", "rn_profile_enable", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
+    "rn_debug_graph_launches",
 ]
 
 
@@ -98,6 +99,8 @@ def lib() -> C.CDLL:
     L.rn_debug_timestamps.argtypes = [vp, C.POINTER(C.c_uint64), i32, vp]
     L.rn_pairwise_launch_count.argtypes = [i64, i32]
     L.rn_listwise_launch_count.argtypes = [i64]
+    L.rn_debug_graph_launches.restype = i64
+    L.rn_debug_graph_launches.argtypes = []
     _lib = L
     return L
 

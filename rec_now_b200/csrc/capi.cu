@@ -95,3 +95,5 @@ extern "C" int rn_debug_timestamps(void* scratch, uint64_t* ts_host, int32_t cap
   if (capacity > 34) ts_host[34] = (uint64_t)make_layout(1, 1).gstat;   // (layout probe for debug tools: see scripts/)
   return RN_OK;
 }
+
+extern "C" int64_t rn_debug_graph_launches(void) { return (int64_t)graph_launch_count(); }

@@ -177,6 +177,10 @@ __device__ __forceinline__ void grid_sync(u32* bar, u32& epoch, u32* err) {
   __syncthreads();
 }
 
+// Wait for the previous kernel of the stream (programmatic dependent launch, see launch_coop); a no-op when the kernel
+// was launched without the attribute.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ u64 globaltimer() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // phase timestamp i (CTA 0, thread 0 only)
 __device__ __forceinline__ void stamp(Ctl* ctl, int i) {
@@ -220,6 +224,18 @@ cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const floa
 int device_sm_count();
 // Cooperative launch of `kernel` with `grid` CTAs of `threads` threads (grid must not exceed the co-resident limit).
 cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st, size_t smem = 0);
+
+// One pairwise call as ONE launch of a cached CUDA graph (see segment.cu).  Construct it before the launches of the
+// call, enqueue them on run_stream, then finish().  Falls back to plain launches on the caller's stream when graphs
+// are disabled (RN_GRAPH=0), the stream is being captured by the caller, or a graph API call has failed.
+struct GraphSlot;
+const void* seg_init_func();
+long long graph_launch_count();
+struct GraphCall {
+  cudaStream_t st, run_stream; GraphSlot* slot = nullptr; int mode = 0;     // 0 direct, 1 node update, 2 capture
+  GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow);
+  cudaError_t finish(bool ok);
+};
 
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 

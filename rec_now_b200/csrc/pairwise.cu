@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
   const u32 B = P.B;
+  grid_dep_wait();
   stamp(ctl, 20);
   if (threadIdx.x == 0) s_cnt = 0;
   const bool own_list = A.nib <= kMaxNibS;
@@ -653,6 +654,19 @@ static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_
   return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm, kPairThreads, args, st, smem);
 }
 
+static const void* pair_func(int mode) {
+  switch (mode) {
+#define RN_CASE(m) case m: return (const void*)k_pair<m>;
+    RN_CASE(0) RN_CASE(M_WRONG)
+    RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF) RN_CASE(M_HASW | M_DIFF | M_WRONG)
+    RN_CASE(M_HASW | M_RWN) RN_CASE(M_HASW | M_RWN | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF | M_RWN) RN_CASE(M_HASW | M_DIFF | M_RWN | M_WRONG)
+#undef RN_CASE
+  }
+  return nullptr;
+}
+
 static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A, cudaStream_t st) {
   switch (mode) {
 #define RN_CASE(m) case m: return launch_pair<m>(P, A, st);
@@ -766,7 +780,6 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   static const int allow_merged = tune_int("RN_SEG_MERGED", 1);
   in.allow_merged = allow_merged && a->part_count == 1;      // ranks of the global mode need identical ids
   if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }
-  if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
@@ -783,8 +796,22 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
   const bool prof = g_prof.on && g_prof.n < g_prof.cap;
-  if (prof) cudaEventRecord(g_prof.ev[2 * g_prof.n], st);
-  if (dispatch_pair(mode, P, A, st) != cudaSuccess) return RN_ERR_LAUNCH;
-  if (prof) { cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], st); ++g_prof.n; }
+  // the three launches of the call (k_init, k_seg, k_pair) on stream s
+  auto enqueue = [&](cudaStream_t s) -> bool {
+    if (seg_run(L, scratch, in, H, s) != cudaSuccess) return false;
+    if (prof) cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+    if (dispatch_pair(mode, P, A, s) != cudaSuccess) return false;
+    if (prof) { cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s); ++g_prof.n; }
+    return true;
+  };
+  const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;
+  // one launch of a cached CUDA graph (not while the pair kernel is being timed with events)
+  GraphCall gc(seg_init_func(), f_seg, pair_func(mode), st, !prof);
+  const bool ok = enqueue(gc.run_stream);
+  if (gc.finish(ok) != cudaSuccess) {
+    if (gc.mode == 0) return RN_ERR_LAUNCH;
+    cudaGetLastError();
+    if (!enqueue(st)) return RN_ERR_LAUNCH;       // (graphs are switched off for this thread from now on)
+  }
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
 }

@@ -1,5 +1,6 @@
 // Host plumbing of the segmentation kernel: arena initialisation and cooperative launches.
 // (The device code lives in segment.cuh and is instantiated by the three consumers.)
+#include <stdio.h>
 #include "common.cuh"
 
 namespace rn {
@@ -30,6 +31,114 @@ __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4
   }
 }
 
+// ---- launch plumbing --------------------------------------------------------------------------------------------
+// A call of the pairwise path is three dependent launches (k_init, k_seg, k_pair) of a few tens of microseconds
+// each, so the gaps between them count.  When a GraphCall is active on this thread the launches below do not go to
+// the stream: they set the parameters of the three kernel nodes of a cached, instantiated CUDA graph, which the
+// caller then launches once (smaller inter-kernel gaps, one driver call instead of three).
+struct GraphSlot { int dev; const void* f[3]; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
+static thread_local GraphSlot tl_slots[24];
+static thread_local int tl_nslots = 0;
+static thread_local GraphSlot* tl_update = nullptr;      // slot whose nodes receive the launches of this thread
+static thread_local int tl_next = 0;
+static thread_local bool tl_capturing = false;           // launches go to the private capture stream (graph build)
+static thread_local bool tl_graph_broken = false;        // a graph API call failed: direct launches from now on
+static thread_local cudaStream_t tl_cap_stream = nullptr;
+static thread_local long long tl_graph_launches = 0;   // calls of this thread that went out as one graph launch
+long long graph_launch_count() { return tl_graph_broken ? -tl_graph_launches - 1 : tl_graph_launches; }
+
+static cudaError_t emit(const void* f, dim3 grid, dim3 block, size_t smem, void** args, bool coop, cudaStream_t st) {
+  if (tl_update) {
+    const int i = tl_next++;
+    if (i >= 3 || tl_update->f[i] != f) { if (getenv("RN_GRAPH_DEBUG")) fprintf(stderr, "[recnow] graph node %d: unexpected kernel\n", i); return cudaErrorInvalidValue; }
+    cudaKernelNodeParams p{};
+    p.func = const_cast<void*>(f); p.gridDim = grid; p.blockDim = block; p.sharedMemBytes = (unsigned)smem;
+    p.kernelParams = args; p.extra = nullptr;
+    const cudaError_t e = cudaGraphExecKernelNodeSetParams(tl_update->exec, tl_update->node[i], &p);
+    if (e != cudaSuccess && getenv("RN_GRAPH_DEBUG")) fprintf(stderr, "[recnow] graph node %d update: %s\n", i, cudaGetErrorString(e));
+    return e;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (coop) {
+    attr[na].id = cudaLaunchAttributeCooperative; attr[na].val.cooperative = 1; ++na;
+    // programmatic dependent launch: the launch is processed while the previous kernel of the stream still runs; the
+    // kernel itself waits for that kernel's completion and memory flush with griddepcontrol.wait (grid_dep_wait)
+    static const char* nopdl = getenv("RN_NO_PDL");
+    if (!tl_capturing && !(nopdl && *nopdl == '1')) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1; ++na;
+    }
+  }
+  cfg.attrs = attr; cfg.numAttrs = (unsigned)na;
+  return cudaLaunchKernelExC(&cfg, f, args);
+}
+
+const void* seg_init_func() { return (const void*)k_init; }
+
+GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow)
+    : st(user_stream), run_stream(user_stream) {
+  static const char* off = getenv("RN_GRAPH");
+  if (!allow || tl_graph_broken || (off && *off == '0')) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(user_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  for (int i = 0; i < tl_nslots; ++i) {
+    GraphSlot& g = tl_slots[i];
+    if (g.dev == dev && g.f[0] == f_init && g.f[1] == f_seg && g.f[2] == f_pair) {
+      slot = &g; tl_update = slot; tl_next = 0; mode = 1;
+      return;
+    }
+  }
+  if (tl_nslots >= (int)(sizeof(tl_slots) / sizeof(tl_slots[0]))) return;
+  if (!tl_cap_stream && cudaStreamCreateWithFlags(&tl_cap_stream, cudaStreamNonBlocking) != cudaSuccess) { tl_graph_broken = true; return; }
+  if (cudaStreamBeginCapture(tl_cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { tl_graph_broken = true; cudaGetLastError(); return; }
+  slot = &tl_slots[tl_nslots];
+  slot->dev = dev; slot->f[0] = f_init; slot->f[1] = f_seg; slot->f[2] = f_pair;
+  run_stream = tl_cap_stream; tl_capturing = true; mode = 2;
+}
+
+cudaError_t GraphCall::finish(bool ok) {
+  if (mode == 0) return ok ? cudaSuccess : cudaErrorUnknown;
+  if (mode == 1) {
+    const bool all = tl_next == 3;
+    tl_update = nullptr;
+    if (!ok || !all) { tl_graph_broken = true; return cudaErrorUnknown; }
+    ++tl_graph_launches;
+    return cudaGraphLaunch(slot->exec, st);
+  }
+  // mode 2: end the capture, instantiate, find the three kernel nodes, launch
+  tl_capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(tl_cap_stream, &graph);
+  if (e != cudaSuccess || !ok || !graph) { tl_graph_broken = true; if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return ok ? e : cudaErrorUnknown; }
+  cudaGraphNode_t nodes[8]; size_t n = 8;
+  bool found[3] = {false, false, false};
+  if (cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess && n == 3) {
+    for (size_t i = 0; i < n; ++i) {
+      cudaKernelNodeParams p{};
+      if (cudaGraphKernelNodeGetParams(nodes[i], &p) != cudaSuccess) continue;
+      for (int k = 0; k < 3; ++k) if (!found[k] && p.func == slot->f[k]) { slot->node[k] = nodes[i]; found[k] = true; break; }
+    }
+  }
+  if (!(found[0] && found[1] && found[2]) || cudaGraphInstantiate(&slot->exec, graph, 0) != cudaSuccess) {
+    // (still run this call: the captured work was not executed)
+    tl_graph_broken = true; cudaGetLastError();
+    cudaGraphExec_t once = nullptr;
+    e = cudaGraphInstantiate(&once, graph, 0);
+    if (e == cudaSuccess) { e = cudaGraphLaunch(once, st); cudaGraphExecDestroy(once); }
+    cudaGraphDestroy(graph);
+    return e;
+  }
+  // (the graph stays alive: its node handles address the nodes of the executable graph in later updates)
+  slot->graph = graph;
+  ++tl_nslots; ++tl_graph_launches;
+  return cudaGraphLaunch(slot->exec, st);
+}
+
 cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels, const uint8_t* row_ok, int* ncta) {
   char* base = static_cast<char*>(scratch);
   const size_t nz = (L.zero_end - L.zero_begin) / 16, no = (L.ones_end - L.ones_begin) / 16;
@@ -39,9 +148,10 @@ cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const floa
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   if (ncta) *ncta = grid;
-  k_init<<<grid, 256, 0, st>>>(at<uint4>(base, L.zero_begin), nz, at<uint4>(base, L.ones_begin), no,
-                               labels, row_ok, (u32)L.B, at<u32>(base, L.labpart));
-  return cudaGetLastError();
+  uint4* zp = at<uint4>(base, L.zero_begin); uint4* op = at<uint4>(base, L.ones_begin);
+  size_t nzv = nz, nov = no; u32 Bv = (u32)L.B; u32* lp = at<u32>(base, L.labpart);
+  void* args[] = {&zp, &nzv, &op, &nov, &labels, &row_ok, &Bv, &lp};
+  return emit((const void*)k_init, dim3((unsigned)grid), dim3(256), 0, args, false, st);
 }
 
 int device_sm_count() {
@@ -57,17 +167,7 @@ int device_sm_count() {
 }
 
 cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st, size_t smem) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)threads);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelExC(&cfg, kernel, args);
+  return emit(kernel, dim3((unsigned)grid), dim3((unsigned)threads), smem, args, true, st);
 }
 
 }  // namespace rn

@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   __shared__ __align__(16) u32 smem[kSegSmemWords];
   u32 epoch = 0;
   Ctl* ctl = S.ctl;
+  grid_dep_wait();
   stamp(ctl, 0);
   Plan pl;
   if (S.merged) {

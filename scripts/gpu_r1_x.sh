@@ -1,2 +1,5 @@
-for cg in 13 17 21 26; do echo "== COST_GEN=$cg"; RN_PAIR_COST_GEN=$cg python scripts/quick_time.py cfg3 2>&1 | grep -E "us/call|stamps"; done
-RN_PAIR_DEBUG=1 NW=32 python scripts/pair_debug.py cfg3 2>&1 | grep -E "loop exit|per-SM last|eighths/warp|gen==0|gen>=3"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python scripts/quick_time.py cfg1 cfg2 cfg3 2>&1 | grep -E "us/call|stamps"
+RN_GRAPH=0 python scripts/quick_time.py cfg3 2>&1 | grep -E "us/call|stamps"
+python scripts/host_overhead.py 2>&1 | head -2
+RN_GRAPH=0 python scripts/host_overhead.py 2>&1 | head -2

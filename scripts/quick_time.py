@@ -34,6 +34,8 @@ def run(d, iters=200):
     n = int(out["n_pair"].item())
     print(f"{d['name']}: B={s.numel()} n_pair={n} {ms*1e3:.1f} us/call  {n/ms/1e6:.2f} Gpairs/s  "
           f"SFU-frac(3 MUFU, 4.65e12/s)={3*n/(ms*1e-3)/4.65e12:.3f} loss={out['loss'].item():.6f} err={ops.device_error(out['_scratch'])}")
+    from rec_now_b200 import _lib
+    print('   graph launches on this thread:', _lib.lib().rn_debug_graph_launches())
     stamps(out)
 
 def stamps(out):
