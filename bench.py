@@ -52,6 +52,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def kpair_traffic(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pair launch from the committed `ncu --set full` capture
+    of this round (profiles/kpair_traffic.json, written by scripts/ncu_summary.py); None if there is none."""
+    p = os.path.join(ROOT, "profiles", "kpair_traffic.json")
+    if world != 1 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+
+
 # ----------------------------------------------------------------------------------------------------------
 # clocks sampler (NVML) -- runs in a thread during warm-up + timed region
 # ----------------------------------------------------------------------------------------------------------
@@ -240,8 +251,8 @@ def ours(args):
     for _ in range(W):
         out = step()
     barrier()
-    lib.rn_profile_enable(K)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    g0 = int(lib.rn_debug_graph_launches())
     barrier()
     if sampler:
         sampler.timed[0] = time.perf_counter()
@@ -254,8 +265,17 @@ def ours(args):
     if sampler:
         sampler.timed[1] = time.perf_counter()
     t_ms = sum(a.elapsed_time(b) for a, b in evs)
-    ms = (C.c_float * K)(); nget = C.c_int32(0)
-    lib.rn_profile_collect(ms, K, C.byref(nget))
+    graph_calls = int(lib.rn_debug_graph_launches()) - g0       # steps that went out as one CUDA-graph launch
+    # ---- the dominant kernel alone: the same steps again with CUDA events around the k_pair launch (the events sit
+    #      between the kernels of a call, so this pass uses plain launches instead of the cached graph) -----------
+    KP = min(K, 100)
+    lib.rn_profile_enable(KP)
+    for k in range(KP):
+        flush.fill_(k & 0xFF)
+        out = step()
+    barrier()
+    ms = (C.c_float * KP)(); nget = C.c_int32(0)
+    lib.rn_profile_collect(ms, KP, C.byref(nget))
     lib.rn_profile_disable()
     pair_ms = float(np.mean(list(ms)[:nget.value])) if nget.value else float("nan")
     n_pair = int(out["n_pair"].item())
@@ -266,41 +286,88 @@ def ours(args):
     # over); it is copied to the device every step and the column tensors are views of the device buffer
     sizes = {"g": 8 * ROWS_PER_GPU, "s": 4 * ROWS_PER_GPU, "y": 4 * ROWS_PER_GPU, "w": 4 * ROWS_PER_GPU}
     pin_all = torch.empty(sum(sizes.values()), dtype=torch.uint8).pin_memory()
-    dev_all = torch.empty_like(pin_all, device=dev)
-    pin, dbuf, o = {}, {}, 0
+    o = 0
     for k, dt in (("g", torch.int64), ("s", torch.float32), ("y", torch.float32), ("w", torch.float32)):
-        pin[k] = pin_all[o:o + sizes[k]].view(dt); pin[k].copy_(torch.tensor(host[k]))
-        dbuf[k] = dev_all[o:o + sizes[k]].view(dt)
+        pin_all[o:o + sizes[k]].view(dt).copy_(torch.tensor(host[k]))
         o += sizes[k]
+    # two device buffers: the copy of step k+1's inputs (copy stream) overlaps the compute of step k -- what an input
+    # prefetcher does; every step still copies its own inputs from pinned host memory inside the timed region
+    dev_all = [torch.empty_like(pin_all, device=dev) for _ in range(2)]
+    dbuf = []
+    for q in range(2):
+        cols, o = {}, 0
+        for k, dt in (("g", torch.int64), ("s", torch.float32), ("y", torch.float32), ("w", torch.float32)):
+            cols[k] = dev_all[q][o:o + sizes[k]].view(dt)
+            o += sizes[k]
+        dbuf.append(cols)
     h_loss = torch.empty(1, dtype=torch.float32).pin_memory()
     h_grad = torch.empty(ROWS_PER_GPU, dtype=torch.float32).pin_memory()
+    main = torch.cuda.current_stream(dev)
+    cs = torch.cuda.Stream(dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step():
-        dev_all.copy_(pin_all, non_blocking=True)
-        logits = dbuf["s"].requires_grad_(True)
-        if world == 1:
-            loss = PW.pairwise_loss(logits, dbuf["y"], dbuf["g"], click_occurance_power=-0.5,
-                                    label_pair_to_weight_func=PW.label_gain_times_sample_weight,
-                                    sample_weight=dbuf["w"])
+    # (cudaMemcpyAsync on the copy stream through ctypes: torch's stream context manager costs ~10 us of host time)
+    try:
+        rt = C.CDLL("libcudart.so.12")
+        rt.cudaMemcpyAsync.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+        rt.cudaMemcpyAsync.restype = C.c_int
+    except OSError:
+        rt = None
+    nbytes_in, cs_ptr, pin_ptr = pin_all.numel(), C.c_void_p(cs.cuda_stream), pin_all.data_ptr()
+    dev_ptr = [t.data_ptr() for t in dev_all]
+    h_loss_ptr, h_grad_ptr, main_ptr = h_loss.data_ptr(), h_grad.data_ptr(), C.c_void_p(main.cuda_stream)
+
+    def enqueue_copy(q):
+        cs.wait_event(consumed[q])                       # the step that last read this buffer is done with it
+        if rt is not None:
+            if rt.cudaMemcpyAsync(dev_ptr[q], pin_ptr, nbytes_in, 1, cs_ptr) != 0:
+                raise RuntimeError("cudaMemcpyAsync failed")
         else:
-            loss = global_mode.global_pairwise_loss(logits, dbuf["y"], dbuf["g"], click_occurance_power=-0.5,
-                                                    label_pair_to_weight_func=PW.label_gain_times_sample_weight,
-                                                    sample_weight=dbuf["w"])
-        loss.backward()
-        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-        h_grad.copy_(logits.grad, non_blocking=True)
-        logits.grad = None
-        dbuf["s"].requires_grad_(False)
+            with torch.cuda.stream(cs):
+                dev_all[q].copy_(pin_all, non_blocking=True)
+        copied[q].record(cs)
 
-    for _ in range(W):
-        e2e_step()
-    barrier()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(K):
-        e2e_step()
-    b.record()
-    barrier()
+    def e2e_steps(n):
+        for q in range(2):
+            consumed[q].record(main)
+        enqueue_copy(0)
+        for k in range(n):
+            q = k & 1
+            if k + 1 < n:
+                enqueue_copy(1 - q)
+            main.wait_event(copied[q])
+            cols = dbuf[q]
+            logits = cols["s"].requires_grad_(True)
+            if world == 1:
+                loss = PW.pairwise_loss(logits, cols["y"], cols["g"], click_occurance_power=-0.5,
+                                        label_pair_to_weight_func=PW.label_gain_times_sample_weight,
+                                        sample_weight=cols["w"])
+            else:
+                loss = global_mode.global_pairwise_loss(logits, cols["y"], cols["g"], click_occurance_power=-0.5,
+                                                        label_pair_to_weight_func=PW.label_gain_times_sample_weight,
+                                                        sample_weight=cols["w"])
+            loss.backward()
+            if rt is not None:                           # D2H of the step's results on the compute stream
+                rt.cudaMemcpyAsync(h_loss_ptr, loss.data_ptr(), 4, 2, main_ptr)
+                rt.cudaMemcpyAsync(h_grad_ptr, logits.grad.data_ptr(), 4 * ROWS_PER_GPU, 2, main_ptr)
+            else:
+                h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+                h_grad.copy_(logits.grad, non_blocking=True)
+            consumed[q].record(main)
+            logits.grad = None
+            cols["s"].requires_grad_(False)
+
+    # the backward graph is one node: running the autograd engine on the calling thread saves its thread hand-off
+    with torch.autograd.set_multithreading_enabled(False):
+        e2e_steps(W)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        e2e_steps(K)
+        cs.synchronize()
+        b.record()
+        barrier()
     e2e_ms = a.elapsed_time(b)
     h2d = pin_all.numel()
     d2h = h_loss.numel() * 4 + h_grad.numel() * 4
@@ -337,7 +404,7 @@ def ours(args):
                          "nominal_peak": NOMINAL_MUFU_PER_S / 1e9, "frac_of_nominal": achieved / NOMINAL_MUFU_PER_S,
                          "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / (t_ms / K),
                          "algorithmic_mufu_per_pair": MUFU_PER_PAIR, "pairs_per_launch": pairs_per_launch,
-                         "traffic": None,
+                         "traffic": kpair_traffic(world),
                          "hbm_view": {"bound": "hbm", "achieved": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9,
                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peak_src,
                                       "frac": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
@@ -345,8 +412,13 @@ def ours(args):
                     "samples_per_s": rows_total * K / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "rec_block.pairwise_loss_from_batch.pairwise_loss + backward" if world == 1
-                           else "global_mode.global_pairwise_loss + backward"},
+                           else "global_mode.global_pairwise_loss + backward",
+                    "pipeline": "inputs of step k+1 copied H2D on a copy stream (two device buffers) while step k "
+                                "computes; loss and gradient copied D2H every step; autograd engine single-threaded "
+                                "(torch.autograd.set_multithreading_enabled(False))"},
             "gpu_launches": int(lib.rn_pairwise_launch_count(rows_total, 1)) * K,
+            "launch_mode": {"kernels_per_step": int(lib.rn_pairwise_launch_count(rows_total, 1)),
+                            "steps_enqueued_as_one_cuda_graph_launch": graph_calls},
             "clocks": clocks, "device_error": err,
         }
         if world == 1 and not args.no_cpu:

@@ -35,3 +35,5 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(300): fb()
 pr.disable(); torch.cuda.synchronize()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+with torch.autograd.set_multithreading_enabled(False):
+    t("forward + backward(), engine single-threaded", fb)

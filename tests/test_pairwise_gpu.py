@@ -237,12 +237,13 @@ def test_edge_tiles_and_wide_logits():
         check_pairwise(out, S.pairwise(s, y, ids, spec), ctx=f"edge {spec.label_func}")
 
 
-@pytest.mark.parametrize("b", [200_000, 300_000])
+@pytest.mark.parametrize("b", [200_000, 300_000, 600_000])
 def test_large_batch_wide_tiles(b):
     """B > 148 * 1024 switches the segmentation kernel to 4096-row sort tiles (several tiles per CTA) and needs
-    18+ group bits: the size of the all-gathered batch in global mode at 4+ GPUs.  B > 262144 (8 GPUs) also takes
-    the explicit work-unit records written by the segmentation kernel instead of the pair kernel's own list; there
-    the 2-way partition of the global mode is checked too."""
+    18+ group bits: the size of the all-gathered batch in global mode at 4+ GPUs.  Up to B = 524288 (8 GPUs) the pair
+    kernel partitions the tile staircase statically (cost prefix in shared memory); B = 600000 takes the explicit
+    work-unit records written by the segmentation kernel.  For the two larger sizes the 2-way partition of the global
+    mode is checked too."""
     rng = np.random.default_rng(21)
     gidx = np.r_[np.repeat([0, 1], 3000), 2 + rng.integers(0, 4000, b - 6000)][rng.permutation(b)]
     ids = (gidx.astype(np.int64) * 2654435761 + 12345) ^ np.int64(0x0123456789ABCDEF)
