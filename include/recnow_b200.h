@@ -94,6 +94,14 @@ typedef struct rn_pairwise_args {
   int64_t block_rows;
   int64_t block_stride;
   int64_t out_chunk;
+  /* Peer-memory gather (global mode over NVLink peer mappings; gather_dst == NULL: off).  peer_blocks[r] is the packed
+   * row block of rank r (this rank's own included, r < B / block_rows <= 8) in peer-mapped device memory.  The FIRST
+   * kernel of the call copies the blocks with peer loads into the local blocked input buffer starting at gather_dst
+   * (block r at gather_dst + r * block_stride; the column pointers above address that buffer) before anything reads
+   * it: the all-gather happens inside the compute path, without a collective call.  The caller makes sure that all
+   * ranks have written their blocks (a device-side barrier on the stream) before the call is enqueued. */
+  const void* peer_blocks[8];
+  void* gather_dst;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {
@@ -124,6 +132,19 @@ int rn_canon_keys_f64(const double* ids, int64_t B, int64_t* keys_out, uint8_t* 
 /* ---- pairwise --------------------------------------------------------------------------------------- */
 size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K);
 int rn_pairwise_fwd_bwd(const rn_pairwise_args* args, void* scratch, size_t scratch_bytes, void* stream);
+
+/* Global mode (one process per GPU): pack this rank's row block for ONE all-gather -- [keys K x int64[B_loc]]
+ * [logits f32][labels f32][rw_pos f32 if given][row_ok u8 if given], every column 16-byte aligned, zero padded to
+ * `stride` bytes (a multiple of 16): the layout rn_pairwise_args.block_rows / block_stride reads in place.  B_loc must
+ * be a multiple of 16.  One launch. */
+int rn_pack_row_block(const int64_t* keys, int32_t K, const float* logits, const float* labels, const float* rw_pos,
+                      const uint8_t* row_ok, int64_t B_loc, void* block_out, int64_t stride, void* stream);
+
+/* Global mode, return path: dst[i] = sum over r < world of peer_out[r][my_rank * chunk + i], i < chunk -- the
+ * reduce-scatter of the chunked gradient buffers (rn_pairwise_args.out_chunk) read straight from the peers' mapped
+ * memory.  The caller synchronises the ranks (all calls finished) before it is enqueued.  One launch. */
+int rn_reduce_peer_chunks(const void* const* peer_out, int32_t world, int32_t my_rank, int64_t chunk, float* dst,
+                          void* stream);
 
 /* Pair materialisation in the reference's row-major order (i ascending, then j ascending; PW:217).
  * Two phases because P is data dependent: _count enqueues the segmentation + counting, then synchronises

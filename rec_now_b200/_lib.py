@@ -24,7 +24,7 @@ EXPORTS = [
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
     "rn_bench_mufu", "rn_profile_enable", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
-    "rn_debug_graph_launches",
+    "rn_debug_graph_launches", "rn_pack_row_block", "rn_reduce_peer_chunks",
 ]
 
 
@@ -46,6 +46,7 @@ class PairwiseArgs(C.Structure):
         ("loss", C.c_void_p), ("n_pair_f32", C.c_void_p), ("n_pair", C.c_void_p),
         ("dlogits", C.c_void_p), ("row_pairs", C.c_void_p),
         ("block_rows", C.c_int64), ("block_stride", C.c_int64), ("out_chunk", C.c_int64),
+        ("peer_blocks", C.c_void_p * 8), ("gather_dst", C.c_void_p),
     ]
 
 
@@ -99,6 +100,8 @@ def lib() -> C.CDLL:
     L.rn_debug_timestamps.argtypes = [vp, C.POINTER(C.c_uint64), i32, vp]
     L.rn_pairwise_launch_count.argtypes = [i64, i32]
     L.rn_listwise_launch_count.argtypes = [i64]
+    L.rn_pack_row_block.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, i64, vp]
+    L.rn_reduce_peer_chunks.argtypes = [C.POINTER(C.c_void_p), i32, i32, i64, vp, vp]
     L.rn_debug_graph_launches.restype = i64
     L.rn_debug_graph_launches.argtypes = []
     _lib = L

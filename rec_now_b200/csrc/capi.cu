@@ -28,9 +28,80 @@ __global__ void __launch_bounds__(256) k_mufu(int iters, float* sink) {
   if (a + b + c + d == -1.f) sink[0] = a;      // never true; keeps the chains alive
 }
 
+// One rank's row block of the global mode: the columns copied back to back as 16-byte words (see rn_pack_row_block).
+struct PackCols { const uint4* src[12]; u32 n16[12]; int ncol; u32 total16, pad_from16; };
+__global__ void __launch_bounds__(256) k_pack(PackCols P, uint4* __restrict__ dst) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.total16; i += gridDim.x * blockDim.x) {
+    u32 o = i;
+    uint4 v = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+    for (int c = 0; c < P.ncol; ++c) {
+      if (o < P.n16[c]) { v = P.src[c][o]; break; }
+      o -= P.n16[c];
+    }
+    dst[i] = v;
+  }
+}
+
+struct PeerChunks { const float4* src[8]; int world; };
+__global__ void __launch_bounds__(256) k_reduce_chunks(PeerChunks P, u32 n4, float4* __restrict__ dst) {
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    float4 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) if (r < P.world) v[r] = P.src[r][i];          // all peer loads in flight at once
+    float4 a = v[0];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) if (r < P.world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+    dst[i] = a;
+  }
+}
+
 }  // namespace rn
 
 using namespace rn;
+
+extern "C" int rn_reduce_peer_chunks(const void* const* peer_out, int32_t world, int32_t my_rank, int64_t chunk, float* dst,
+                                     void* stream) {
+  if (!peer_out || !dst || world < 1 || world > 8 || my_rank < 0 || my_rank >= world || chunk <= 0 || (chunk & 3)) return RN_ERR_ARG;
+  if (check_align(dst)) return RN_ERR_ALIGN;
+  PeerChunks P{};
+  P.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_out[r] || check_align(peer_out[r])) return RN_ERR_ARG;
+    P.src[r] = reinterpret_cast<const float4*>(static_cast<const float*>(peer_out[r]) + (size_t)my_rank * chunk);
+  }
+  const u32 n4 = (u32)(chunk / 4);
+  int grid = (int)((n4 + 255) / 256);
+  const int cap = device_sm_count() * 4;
+  if (grid > cap) grid = cap;
+  k_reduce_chunks<<<grid, 256, 0, (cudaStream_t)stream>>>(P, n4, reinterpret_cast<float4*>(dst));
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+extern "C" int rn_pack_row_block(const int64_t* keys, int32_t K, const float* logits, const float* labels,
+                                 const float* rw_pos, const uint8_t* row_ok, int64_t B_loc, void* block_out,
+                                 int64_t stride, void* stream) {
+  if (!keys || !logits || !labels || !block_out || K <= 0 || K > 8 || B_loc <= 0 || (B_loc & 15) || (stride & 15)) return RN_ERR_ARG;
+  const void* ptrs[] = {keys, logits, labels, rw_pos, row_ok, block_out};
+  for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
+  PackCols P{};
+  int c = 0;
+  for (int k = 0; k < K; ++k) { P.src[c] = reinterpret_cast<const uint4*>(keys + (size_t)k * B_loc); P.n16[c++] = (u32)(B_loc / 2); }
+  P.src[c] = reinterpret_cast<const uint4*>(logits); P.n16[c++] = (u32)(B_loc / 4);
+  P.src[c] = reinterpret_cast<const uint4*>(labels); P.n16[c++] = (u32)(B_loc / 4);
+  if (rw_pos) { P.src[c] = reinterpret_cast<const uint4*>(rw_pos); P.n16[c++] = (u32)(B_loc / 4); }
+  if (row_ok) { P.src[c] = reinterpret_cast<const uint4*>(row_ok); P.n16[c++] = (u32)(B_loc / 16); }
+  P.ncol = c;
+  u64 used = 0;
+  for (int k = 0; k < c; ++k) used += P.n16[k];
+  if ((u64)stride / 16 < used || (u64)stride / 16 > 0xFFFFFFFFull) return RN_ERR_ARG;
+  P.total16 = (u32)(stride / 16);
+  int grid = (int)((P.total16 + 255) / 256);
+  const int cap = device_sm_count() * 8;
+  if (grid > cap) grid = cap;
+  k_pack<<<grid, 256, 0, (cudaStream_t)stream>>>(P, static_cast<uint4*>(block_out));
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
 
 extern "C" int rn_version(void) { return RN_VERSION; }
 

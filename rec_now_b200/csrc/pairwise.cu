@@ -732,7 +732,12 @@ static int validate_pairwise(const rn_pairwise_args* a) {
         a->block_stride / 4 > 0xFFFFFFFFll) return RN_ERR_ARG;
     if (a->out_chunk && (a->out_chunk <= a->block_rows || a->out_chunk > 0x7FFFFFFFll)) return RN_ERR_ARG;
     if (a->only_wrong || a->rw_neg) return RN_ERR_UNSUPPORTED;
-  } else if (a->out_chunk) return RN_ERR_ARG;
+    if (a->gather_dst) {
+      const int64_t world = a->B / a->block_rows;
+      if (world > 8 || check_align(a->gather_dst)) return RN_ERR_ARG;
+      for (int64_t r = 0; r < world; ++r) if (!a->peer_blocks[r] || check_align(a->peer_blocks[r])) return RN_ERR_ARG;
+    }
+  } else if (a->out_chunk || a->gather_dst) return RN_ERR_ARG;
   const void* ptrs[] = {a->keys, a->logits, a->labels, a->row_ok, a->rw_pos, a->rw_neg, a->dlogits, a->row_pairs};
   for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
   return RN_OK;
@@ -777,6 +782,11 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   H.target_units = target_units();
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   in.rm = P.rm;
+  if (a->gather_dst) {
+    in.gather.world = (u32)(a->B / a->block_rows); in.gather.n16 = (u32)(a->block_stride / 16);
+    in.gather.dst = static_cast<uint4*>(a->gather_dst);
+    for (u32 r = 0; r < in.gather.world; ++r) in.gather.src[r] = static_cast<const uint4*>(a->peer_blocks[r]);
+  }
   static const int allow_merged = tune_int("RN_SEG_MERGED", 1);
   in.allow_merged = allow_merged && a->part_count == 1;      // ranks of the global mode need identical ids
   if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }

@@ -6,10 +6,26 @@
 namespace rn {
 
 __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4* ones, size_t nones16,
-                                              const float* labels, const uint8_t* row_ok, u32 B, u32* labpart) {
+                                              const float* labels, const uint8_t* row_ok, u32 B, u32* labpart,
+                                              GatherArgs G) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
   const uint4 z = make_uint4(0, 0, 0, 0), f = make_uint4(~0u, ~0u, ~0u, ~0u);
+  if (G.world) {
+    // global mode: the all-gather -- every rank's packed row block, read over NVLink from its peer mapping (4 loads
+    // in flight per thread: the round trip is a few microseconds)
+    const size_t tot = (size_t)G.world * G.n16;
+    for (size_t k0 = i; k0 < tot; k0 += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const size_t k = k0 + q * stride;
+        if (k < tot) { const u32 r = (u32)(k / G.n16); v[q] = G.src[r][k - (size_t)r * G.n16]; }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { const size_t k = k0 + q * stride; if (k < tot) G.dst[k] = v[q]; }
+    }
+  }
   for (size_t k = i; k < nzero16; k += stride) zero[k] = z;
   for (size_t k = i; k < nones16; k += stride) ones[k] = f;
   if (labels) {
@@ -139,10 +155,13 @@ cudaError_t GraphCall::finish(bool ok) {
   return cudaGraphLaunch(slot->exec, st);
 }
 
-cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels, const uint8_t* row_ok, int* ncta) {
+cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels, const uint8_t* row_ok, int* ncta,
+                     const GatherArgs* gather) {
   char* base = static_cast<char*>(scratch);
   const size_t nz = (L.zero_end - L.zero_begin) / 16, no = (L.ones_end - L.ones_begin) / 16;
-  int grid = (int)((nz + no + 255) / 256);
+  GatherArgs G{};
+  if (gather) G = *gather;
+  int grid = (int)((nz + no + (size_t)G.world * G.n16 + 255) / 256);
   int cap = device_sm_count() * 4;
   if (cap > kInitMaxCtas) cap = kInitMaxCtas;
   if (grid > cap) grid = cap;
@@ -150,7 +169,7 @@ cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const floa
   if (ncta) *ncta = grid;
   uint4* zp = at<uint4>(base, L.zero_begin); uint4* op = at<uint4>(base, L.ones_begin);
   size_t nzv = nz, nov = no; u32 Bv = (u32)L.B; u32* lp = at<u32>(base, L.labpart);
-  void* args[] = {&zp, &nzv, &op, &nov, &labels, &row_ok, &Bv, &lp};
+  void* args[] = {&zp, &nzv, &op, &nov, &labels, &row_ok, &Bv, &lp, &G};
   return emit((const void*)k_init, dim3((unsigned)grid), dim3(256), 0, args, false, st);
 }
 

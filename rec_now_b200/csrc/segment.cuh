@@ -449,6 +449,7 @@ struct SegInputs {
   bool nan_label_is_trash;
   RowMap rm = RowMap{0, 0, 0, 0};
   bool allow_merged = false;   // the caller accepts table-slot group ids (not deterministic across calls / ranks)
+  GatherArgs gather = GatherArgs{};   // peer-memory gather of the blocked input rows by k_init (world = 0: off)
 };
 
 inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs& in) {
@@ -479,7 +480,8 @@ template <class Tail>
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const Tail& tail, cudaStream_t st) {
   const bool merged = in.allow_merged && in.K == 1 && in.use_label && in.labels && !in.rm.Bl;
   int npart = 0;
-  cudaError_t e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart) : seg_init(L, scratch, st);
+  cudaError_t e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart)
+                         : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr);
   if (e != cudaSuccess) return e;
   SegParams S = make_seg_params(L, scratch, in);
   if (merged) { S.merged = 1; S.npart = npart; S.gbits = seg_merged_gbits(L); }

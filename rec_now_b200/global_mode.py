@@ -45,6 +45,77 @@ def _all_gather_cols(cols, group):
     return outs
 
 
+class _PeerState:
+    """Peer-mapped (symmetric) buffers of one (group, block layout): two input blocks and two chunked gradient buffers
+    per rank, alternating between consecutive steps, so that a rank that runs ahead never overwrites what a peer
+    still reads (every step passes two device-side barriers; see _peer_global)."""
+
+    def __init__(self, group, dev, stride: int, out_floats: int):
+        import torch.distributed._symmetric_memory as symm_mem
+        g = dist.group.WORLD if group is None else group
+        self.in_off = [0, stride]
+        self.out_off = [2 * stride, 2 * stride + 4 * out_floats]
+        total = 2 * stride + 8 * out_floats
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, g.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.stride, self.out_floats, self.step = stride, out_floats, 0
+
+    def in_block(self, p):
+        return self.buf[self.in_off[p]:self.in_off[p] + self.stride]
+
+    def out_buf(self, p):
+        return self.buf[self.out_off[p]:self.out_off[p] + 4 * self.out_floats].view(torch.float32)
+
+
+_peer_states: dict = {}
+_peer_broken = False
+
+
+def _peer_state(group, dev, stride, out_floats) -> Optional[_PeerState]:
+    """The cached peer-memory state, or None when it is switched off (RN_GLOBAL_P2P=0) or symmetric memory is not
+    available on this box (then the NCCL collectives are used)."""
+    global _peer_broken
+    import os
+    if _peer_broken or os.environ.get("RN_GLOBAL_P2P", "1") == "0" or dist.get_world_size(group) > 8:
+        return None
+    key = (id(group), dev.index, stride, out_floats)
+    st = _peer_states.get(key)
+    if st is None:
+        try:
+            st = _peer_states[key] = _PeerState(group, dev, stride, out_floats)
+        except Exception as e:               # no peer access / no symmetric memory: fall back to the collectives
+            import warnings
+            warnings.warn(f"rec_now_b200 global mode: peer memory unavailable ({e!r}); using NCCL collectives")
+            _peer_broken = True
+            return None
+    return st
+
+
+def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
+    """Global step over NVLink peer mappings, no collective calls: pack this rank's block into its symmetric buffer ->
+    device-side barrier -> ONE graph launch whose first kernel gathers all ranks' blocks with peer loads and whose
+    last kernel leaves the chunked partial gradients in the symmetric buffer -> barrier -> one kernel sums this
+    rank's chunk over the peers' buffers."""
+    from . import ops
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    b_loc = logits.numel()
+    kk = keys.shape[0]
+    lay = ops.packed_block_layout(b_loc, kk, rw_pos is not None, row_ok is not None)
+    p = st.step & 1
+    st.step += 1
+    ops.pack_row_block(keys, logits, labels, rw_pos, row_ok, lay["stride"], out=st.in_block(p))
+    st.hdl.barrier(channel=0)                                   # every rank's block of this step is written
+    gbuf = torch.empty(world * lay["stride"], dtype=torch.uint8, device=logits.device)
+    res = ops.pairwise_fwd_bwd_blocked(gbuf, world, b_loc, kk, rw_pos is not None, row_ok is not None,
+                                       label_func=label_func, factor=factor, power=power, reduce_mean=reduce_mean,
+                                       part=(rank, world), peer_blocks=[b + st.in_off[p] for b in st.ptrs],
+                                       out=st.out_buf(p))
+    st.hdl.barrier(channel=1)                                   # every rank's partial gradients are written
+    mine = ops.reduce_peer_chunks([b + st.out_off[p] for b in st.ptrs], rank, res["chunk"], logits.device)
+    return dict(loss=mine[b_loc], n_pair=res["n_pair"], dlogits=mine[:b_loc])
+
+
 def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
                    _compute_blocked=None):
     """The two-collective path: pack this rank's columns into one block -> ONE all-gather -> the kernels read the
@@ -54,16 +125,23 @@ def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, pow
     b_loc = logits.numel()
     kk = keys.shape[0]
     lay = ops.packed_block_layout(b_loc, kk, rw_pos is not None, row_ok is not None)
-    cols = [keys.reshape(-1).view(torch.uint8), logits.reshape(-1).to(torch.float32).view(torch.uint8),
-            labels.reshape(-1).to(torch.float32).view(torch.uint8)]
-    if rw_pos is not None:
-        cols.append(rw_pos.reshape(-1).to(torch.float32).view(torch.uint8))
-    if row_ok is not None:
-        cols.append(row_ok.reshape(-1).to(torch.uint8))
-    used = sum(c.numel() for c in cols)
-    if used != lay["stride"]:
-        cols.append(torch.zeros(lay["stride"] - used, dtype=torch.uint8, device=logits.device))
-    block = torch.cat(cols)
+    if _compute_blocked is None:
+        st = _peer_state(group, logits.device, lay["stride"], world * (b_loc + 4))
+        if st is not None:
+            return _peer_global(st, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group)
+    if _compute_blocked is None:
+        block = ops.pack_row_block(keys, logits, labels, rw_pos, row_ok, lay["stride"])        # one launch
+    else:                                   # (CPU/gloo test of the collective plumbing: same layout with torch ops)
+        cols = [keys.reshape(-1).view(torch.uint8), logits.reshape(-1).to(torch.float32).view(torch.uint8),
+                labels.reshape(-1).to(torch.float32).view(torch.uint8)]
+        if rw_pos is not None:
+            cols.append(rw_pos.reshape(-1).to(torch.float32).view(torch.uint8))
+        if row_ok is not None:
+            cols.append(row_ok.reshape(-1).to(torch.uint8))
+        used = sum(c.numel() for c in cols)
+        if used != lay["stride"]:
+            cols.append(torch.zeros(lay["stride"] - used, dtype=torch.uint8, device=logits.device))
+        block = torch.cat(cols)
     gbuf = torch.empty(world * lay["stride"], dtype=torch.uint8, device=logits.device)
     dist.all_gather_into_tensor(gbuf, block, group=group)
     compute = _compute_blocked or ops.pairwise_fwd_bwd_blocked

@@ -66,7 +66,7 @@ def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
     if t.dtype is torch.float32 and t.is_contiguous():
-        return t.detach().view(-1)
+        return t                       # only the data pointer and numel() are used: no detach / view (each costs ~1.5 us)
     return t.detach().reshape(-1).to(torch.float32).contiguous()
 
 
@@ -116,6 +116,7 @@ class _PairCall:
 
 
 _pair_call = None
+_pair_scratch_bytes: dict = {}
 
 
 def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
@@ -135,7 +136,9 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     out = torch.empty(4, dtype=torch.float32, device=dev)          # loss, n_pair_f32, n_pair (int64 in [2:4])
     dlogits = torch.empty(b, dtype=torch.float32, device=dev)
     row_pairs = torch.empty(b, dtype=torch.int64, device=dev) if want_row_pairs else None
-    nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
+    nbytes = _pair_scratch_bytes.get((b, kk))
+    if nbytes is None:
+        nbytes = _pair_scratch_bytes[(b, kk)] = lib().rn_pairwise_scratch_bytes(b, kk)
     st = torch.cuda.current_stream(dev).cuda_stream
     scratch = _scratch(nbytes, dev, st)
     po = out.data_ptr()
@@ -201,9 +204,41 @@ def packed_block_layout(b_loc: int, kk: int, has_w: bool, has_ok: bool) -> dict:
     return off
 
 
+def pack_row_block(keys, logits, labels, rw_pos, row_ok, stride: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """rn_pack_row_block: this rank's columns as one packed uint8 block (packed_block_layout), one launch.  `out`: a
+    uint8 buffer of `stride` bytes to pack into (e.g. a peer-mapped symmetric buffer)."""
+    _need_cuda(keys, logits, labels, rw_pos, row_ok)
+    s, y, rwp = _f32(logits), _f32(labels), _f32(rw_pos)
+    b_loc = s.numel()
+    keys = keys.reshape(-1, b_loc)
+    if keys.dtype is not torch.int64 or not keys.is_contiguous():
+        keys = keys.to(torch.int64).contiguous()
+    ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    block = torch.empty(stride, dtype=torch.uint8, device=s.device) if out is None else out
+    assert block.numel() == stride and block.dtype is torch.uint8
+    with _on_device(s.device):
+        check(lib().rn_pack_row_block(keys.data_ptr(), keys.shape[0], s.data_ptr(), y.data_ptr(), _ptr(rwp), _ptr(ok),
+                                      b_loc, block.data_ptr(), stride, _stream(s.device)), "rn_pack_row_block")
+    return block
+
+
+def reduce_peer_chunks(peer_out_ptrs: Sequence[int], rank: int, chunk: int, dev: torch.device) -> torch.Tensor:
+    """rn_reduce_peer_chunks: this rank's chunk of the chunked gradient buffers summed over all ranks, read from the
+    peers' mapped memory (the reduce-scatter of the global mode without a collective call)."""
+    world = len(peer_out_ptrs)
+    mine = torch.empty(chunk, dtype=torch.float32, device=dev)
+    arr = (C.c_void_p * world)(*peer_out_ptrs)
+    with _on_device(dev):
+        check(lib().rn_reduce_peer_chunks(arr, world, rank, chunk, mine.data_ptr(), _stream(dev)), "rn_reduce_peer_chunks")
+    return mine
+
+
 def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int, has_w: bool, has_ok: bool,
-                             label_func="step", factor=1.0, power=0.0, reduce_mean=True, part=(0, 1)):
-    """rn_pairwise_fwd_bwd on `world` packed row blocks (packed_block_layout) as ONE all-gather leaves them, with the
+                             label_func="step", factor=1.0, power=0.0, reduce_mean=True, part=(0, 1),
+                             peer_blocks: Optional[Sequence[int]] = None, out: Optional[torch.Tensor] = None):
+    """rn_pairwise_fwd_bwd on `world` packed row blocks (packed_block_layout) as ONE all-gather leaves them (or, with
+    `peer_blocks` = the device pointers of every rank's block in peer-mapped memory, as the call's first kernel
+    gathers them into `gbuf` itself), with the
     outputs laid out for ONE reduce-scatter: returns dict(out=float32[world * chunk] with chunk = b_loc + 4:
     d loss / d logits of global row r * b_loc + i at out[r * chunk + i], the partial loss at out[r * chunk + b_loc];
     n_pair (global, exact), chunk)."""
@@ -214,7 +249,9 @@ def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int
     b = world * b_loc
     chunk = b_loc + 4
     scal = torch.empty(4, dtype=torch.float32, device=dev)
-    out = torch.empty(world * chunk, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty(world * chunk, dtype=torch.float32, device=dev)
+    assert out.numel() == world * chunk and out.dtype is torch.float32
     nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
     st = torch.cuda.current_stream(dev).cuda_stream
     scratch = _scratch(nbytes, dev, st)
@@ -227,6 +264,11 @@ def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int
         part_rank=int(part[0]), part_count=int(part[1]),
         loss=po, n_pair_f32=po + 4, n_pair=po + 8, dlogits=out.data_ptr(), row_pairs=None,
         block_rows=b_loc, block_stride=lay["stride"], out_chunk=chunk)
+    if peer_blocks is not None:          # k_init gathers the ranks' blocks into gbuf over NVLink (no all-gather call)
+        assert len(peer_blocks) == world
+        for r in range(world):
+            a.peer_blocks[r] = peer_blocks[r]
+        a.gather_dst = base
     with _on_device(dev):
         check(lib().rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, C.c_void_p(st)), "rn_pairwise_fwd_bwd")
     return dict(out=out, n_pair=scal[2:4].view(torch.int64)[0], chunk=chunk, _scratch=scratch)

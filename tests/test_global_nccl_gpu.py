@@ -1,5 +1,7 @@
-"""Global in-batch mode over NCCL (needs >= 2 GPUs on the box; skipped otherwise): every rank's loss / n_pair /
-gradient slice equals the single-batch oracle on the concatenated rows."""
+"""Global in-batch mode (needs >= 2 GPUs on the box; skipped otherwise): every rank's loss / n_pair / gradient slice
+equals the single-batch oracle on the concatenated rows -- over NVLink peer mappings (the default: gather inside
+the first kernel, peer-read reduction, three consecutive steps to exercise the alternating buffers) and over the NCCL
+collectives (RN_GLOBAL_P2P=0)."""
 import os
 import socket
 
@@ -15,11 +17,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, b_loc, q):
+def _worker(rank, world, port, b_loc, q, p2p):
     import torch
     import torch.distributed as dist
     from oracle import generators as G
     from rec_now_b200 import global_mode
+    os.environ["RN_GLOBAL_P2P"] = "1" if p2p else "0"
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -27,16 +30,20 @@ def _worker(rank, world, port, b_loc, q):
         d = G.cfg5(world, seed=3, rows_per_rank=b_loc, groups_per_rank=256)
         lo, hi = rank * b_loc, (rank + 1) * b_loc
         t = lambda k: torch.tensor(np.ascontiguousarray(d[k][lo:hi]), device="cuda")
-        out = global_mode.global_pairwise_fwd_bwd(t("s"), t("y"), t("g").reshape(1, -1), rw_pos=t("w"),
-                                                  label_func="diff", power=-0.5)
+        for _ in range(3 if p2p else 1):
+            out = global_mode.global_pairwise_fwd_bwd(t("s"), t("y"), t("g").reshape(1, -1), rw_pos=t("w"),
+                                                      label_func="diff", power=-0.5)
         torch.cuda.synchronize()
+        if p2p:
+            assert global_mode._peer_states and not global_mode._peer_broken, "peer-memory path was not taken"
         q.put((rank, float(out["loss"].item()), int(out["n_pair"].item()), out["dlogits"].cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [True, False])
 @pytest.mark.parametrize("world", [2])
-def test_global_pairwise_matches_oracle(world):
+def test_global_pairwise_matches_oracle(world, p2p):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
@@ -47,7 +54,7 @@ def test_global_pairwise_matches_oracle(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, b_loc, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, b_loc, q, p2p)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in range(world))
