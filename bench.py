@@ -187,7 +187,7 @@ def reference_arm(args):
         "e2e": {"value": r["pairs_per_s"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -429,12 +429,23 @@ def ours(args):
                 "sample": f"first {r['rows']} rows of the cfg3 batch through the dense (B,B) torch-CPU restatement of "
                           f"the reference (fwd+bwd, {r['n_pair']} pairs/step, {r['sec_per_step']:.2f} s/step); the "
                           "full B=65536 needs >= 155 GB of dense temporaries"}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE line, the JSON: everything else that a library prints there (the NCCL version banner
+    # at communicator creation, for one) is sent to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    global emit_line
+
+    def emit_line(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
