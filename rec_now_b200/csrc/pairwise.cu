@@ -200,6 +200,7 @@ struct HeadsTail {
 struct KpArgs {
   const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units; const uint2* blk; u32 nib; u32 target_units;
   u32 cost_gen;              // cost of a J-block of a range R2 in eighths of a fast tile (see vcost)
+  u32 cost_switch;           // fixed cost of a virtual block (row loads, flush of the row accumulators), same unit
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
   // finalisation
   const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
@@ -255,11 +256,13 @@ __device__ __forceinline__ u32 vcost(u32 v, u32 cgen) { return (v & 1u) ? cgen :
 
 // Position `pos` of the cost line -> (virtual block, J-block, eighth).  s_pi: cost prefix over the virtual blocks,
 // s_jn: first J-block | J-block count << 16 of every virtual block.
-__device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32& v, u32& jb,
-                                            u32& e) {
+__device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32 csw,
+                                            u32& v, u32& jb, u32& e) {
   if (pos >= tot) { v = nvb; jb = 0; e = 0; return; }
   v = last_le(s_pi, 0, nvb, pos);
-  const u32 o = pos - s_pi[v], c = vcost(v, cgen), q = o / c;
+  u32 o = pos - s_pi[v];
+  o = o > csw ? o - csw : 0u;                      // (the first csw units of a block stand for its row loads / flush)
+  const u32 c = vcost(v, cgen), q = o / c;
   jb = (s_jn[v] & 0xFFFFu) + q;
   e = ((o - q * c) * 8u) / c;
 }
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       u32 jf;
       const u32 nt = vblock_tiles(A.blk, v, jf);
       s_jn[v] = nt ? (jf | (nt << 16)) : 0u;
-      s_pi[v] = nt * vcost(v, A.cost_gen);
+      s_pi[v] = nt ? nt * vcost(v, A.cost_gen) + A.cost_switch : 0u;
       msum += nt;
     }
     __syncthreads();
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 len = r1 - r0, q = len / wpr, rem = len - q * wpr;  // len * r / wpr without 64-bit division
       const u32 pos = r0 + q * r + (rem * r) / wpr;
       u32 v, jb, e;
-      resolve_pos(pos, tot, nvb, s_pi, s_jn, A.cost_gen, v, jb, e);
+      resolve_pos(pos, tot, nvb, s_pi, s_jn, A.cost_gen, A.cost_switch, v, jb, e);
       s_bnd[3 * threadIdx.x] = v; s_bnd[3 * threadIdx.x + 1] = jb; s_bnd[3 * threadIdx.x + 2] = e;
     }
     __syncthreads();
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         float accj = 0.f;
         const u32 j0 = jb * 32;
         const int ts = (jb == jb0) ? 4 * (int)sg.ea : 0, te = (jb + 1 == jb1) ? 4 * (int)sg.eb : 32;   // rotation steps
-        const bool part = (te - ts) != 32;
+        const bool part = (te - ts) != 32 || (P.debug & 8);      // (debug bit 8: every fast tile through the looped variant)
         // Overlap of every row's negative range with this J block.  Row ranges start at a group start and end at
         // a level start of the same group, so a row covers a (group, level) run of the block entirely or not at
         // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           }
         }
         if (P.debug) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
-        if (accj != 0.f) atomicAdd(A.gacc + pjm, accj);
+        if (accj != 0.f && !(P.debug & 4)) atomicAdd(A.gacc + pjm, accj);      // (debug bit 4: timing experiment without the RED)
         pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
       }
       if (pi0 < B && an0.y) {
@@ -795,6 +798,8 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
   static const int cost_gen = tune_int("RN_PAIR_COST_GEN", 17);
   A.cost_gen = (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));
+  static const int cost_switch = tune_int("RN_PAIR_COST_SWITCH", 0);
+  A.cost_switch = (u32)(cost_switch < 0 ? 0 : (cost_switch > 64 ? 64 : cost_switch));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
   A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
