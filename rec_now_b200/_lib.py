@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librecnow_b200.so")
+# (RN_LIB_PATH: developer override used to A/B compile-time variants of the kernels on the GPU box)
+LIB_PATH = os.environ.get("RN_LIB_PATH") or os.path.join(HERE, "librecnow_b200.so")
 
 RN_OK = 0
 RN_LABEL_STEP, RN_LABEL_DIFF = 0, 1

@@ -102,4 +102,69 @@ __device__ __forceinline__ void tile_fast(const float si0, const float si1, cons
   gi0 += g0; gi1 += g1;
 }
 
+// ---- product-form fast tile ------------------------------------------------------------------------------------
+// Packed FP32x2 arithmetic (sm_100a FMUL2 / FADD2 / FFMA2: two FP32 operations per issue slot).
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 f2_mul(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// |c * (s - m)| bound under which a tile may use the product form: u <= 2^24, four factors (1 + u) <= 2^97
+constexpr float kProdRange = 12.0f;
+
+// The same 64x32 tile as tile_fast with ONE SFU operation per pair.  With a reference score m of the tile,
+//   2^(-c (s_i - s_j)) = E_i * F_j,   E_i = 2^(-c (s_i - m))  (once per row),  F_j = 2^(c (s_j - m))  (once per negative),
+// so exp(-x) of a pair is one multiplication; sigma(-x) = u / (1 + u) needs the reciprocal (the one SFU operation) and
+// softplus(-x) = log(1 + u) is taken once per row and tile on the running product of the (1 + u), whose exponent is
+// split off after every four factors (integer operations) so that it cannot overflow.  Preconditions (checked by the
+// caller, else tile_fast): |c (s - m)| <= kProdRange for every row and negative of the tile; F = 0 for the negatives
+// outside the overlap.  The arithmetic runs on pairs of rotation steps in packed FP32x2 instructions.
+template <bool PART = false>
+__device__ __forceinline__ void tile_prod(const float E0, const float E1, const float wv0, const float wv1, const float Fm,
+                                          float& li0, float& li1, float& gi0, float& gi1, float& accj,
+                                          const int ts = 0, const int te = 32) {
+  const u64 EE0 = f2_pack(E0, E0), EE1 = f2_pack(E1, E1), one2 = f2_pack(1.f, 1.f);
+  const u64 W0 = f2_pack(wv0, wv0), W1 = f2_pack(wv1, wv1);
+  float p0 = 1.f, p1 = 1.f;                 // mantissas of the running products, in [1, 2)
+  u32 x0 = 0, x1 = 0;                       // their exponents (biased, summed)
+  u64 g0 = 0, g1 = 0, acc = 0;              // packed partial sums (two rotation steps side by side)
+#pragma unroll (PART ? 1 : 8)
+  for (int tb = (PART ? ts : 0); tb < (PART ? te : 32); tb += 4) {
+    float f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = __shfl_xor_sync(0xFFFFFFFFu, Fm, tb + k);
+    const u64 fa = f2_pack(f[0], f[1]), fb = f2_pack(f[2], f[3]);
+    const u64 u0a = f2_mul(EE0, fa), u0b = f2_mul(EE0, fb), u1a = f2_mul(EE1, fa), u1b = f2_mul(EE1, fb);   // exp(-x)
+    const u64 t0a = f2_add(u0a, one2), t0b = f2_add(u0b, one2), t1a = f2_add(u1a, one2), t1b = f2_add(u1b, one2);
+    float t0[4], t1[4], r0[4], r1[4];
+    f2_unpack(t0a, t0[0], t0[1]); f2_unpack(t0b, t0[2], t0[3]); f2_unpack(t1a, t1[0], t1[1]); f2_unpack(t1b, t1[2], t1[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { r0[k] = mufu_rcp(t0[k]); r1[k] = mufu_rcp(t1[k]); }
+    {
+      float ql, qh;
+      f2_unpack(f2_mul(t0a, t0b), ql, qh); p0 *= ql * qh;
+      f2_unpack(f2_mul(t1a, t1b), ql, qh); p1 *= ql * qh;
+      const u32 b0 = __float_as_uint(p0), b1 = __float_as_uint(p1);
+      x0 += b0 >> 23; x1 += b1 >> 23;
+      p0 = __uint_as_float((b0 & 0x007FFFFFu) | 0x3F800000u); p1 = __uint_as_float((b1 & 0x007FFFFFu) | 0x3F800000u);
+    }
+    const u64 d0a = f2_mul(u0a, f2_pack(r0[0], r0[1])), d0b = f2_mul(u0b, f2_pack(r0[2], r0[3]));            // sigma(-x)
+    const u64 d1a = f2_mul(u1a, f2_pack(r1[0], r1[1])), d1b = f2_mul(u1b, f2_pack(r1[2], r1[3]));
+    g0 = f2_add(g0, f2_add(d0a, d0b)); g1 = f2_add(g1, f2_add(d1a, d1b));
+    float b[4];
+    f2_unpack(f2_fma(d1a, W1, f2_mul(d0a, W0)), b[0], b[1]); f2_unpack(f2_fma(d1b, W1, f2_mul(d0b, W0)), b[2], b[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b[k] = __shfl_xor_sync(0xFFFFFFFFu, b[k], tb + k);
+    acc = f2_add(acc, f2_add(f2_pack(b[0], b[1]), f2_pack(b[2], b[3])));
+  }
+  const int nb = ((PART ? te : 32) - (PART ? ts : 0)) >> 2;
+  const float L0 = (float)((int)x0 - 127 * nb) + mufu_lg2(p0), L1 = (float)((int)x1 - 127 * nb) + mufu_lg2(p1);
+  float lo, hi;
+  li0 = fmaf(wv0, L0, li0); li1 = fmaf(wv1, L1, li1);
+  f2_unpack(g0, lo, hi); gi0 = fmaf(wv0, lo + hi, gi0);
+  f2_unpack(g1, lo, hi); gi1 = fmaf(wv1, lo + hi, gi1);
+  f2_unpack(acc, lo, hi); accj += lo + hi;
+}
+
 }  // namespace rn

@@ -381,6 +381,15 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     // debug tallies (per warp, flushed once): busy cycles, segments, fast / general tiles, eighths
     u64 d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0, d_eighths = 0; u64 d_gencyc = 0, d_fastcyc = 0;
     const u64 d_start = P.debug ? globaltimer() : 0;
+#ifdef RN_TRACE
+    // dev build: where a warp's time goes (clock cycles): taking segments, per-J-block preamble, tiles, RED + loop end, flush
+    u64 tr_take = 0, tr_pre = 0, tr_tile = 0, tr_post = 0, tr_flush = 0; long long tr_t = 0;
+#define TR_BEGIN() (tr_t = clock64())
+#define TR_ADD(acc) do { const long long now_ = clock64(); acc += (u64)(now_ - tr_t); tr_t = now_; } while (0)
+#else
+#define TR_BEGIN() do {} while (0)
+#define TR_ADD(acc) do {} while (0)
+#endif
     auto take = [&](Seg& sg) -> bool {
       if (own_list) {
         // next I-block segment of this warp's piece
@@ -414,19 +423,21 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     Seg sg, sg_n; UnitRows R, Rn;
     bool have = take(sg);
     const bool fold = fold_power != 0.f;
+    const bool use_prod = !(P.debug & 16);        // (debug bit 16: fast tiles without the product form)
+    u32 occ_a = 0xFFFFFFFFu; float occ_w = 0.f;   // group start the cached occurrence weight belongs to
     if (have) load_unit_rows<MODE>(A, B, sg.b, sg.jb0, ln, R);
     while (have) {
       const long long d_t0 = P.debug ? clock64() : 0;
+      TR_BEGIN();
       const bool have_n = take(sg_n);
       if (have_n) load_unit_rows<MODE>(A, B, sg_n.b, sg_n.jb0, ln, Rn);      // in flight while this segment is scored
+      TR_ADD(tr_take);
       const u32 b = sg.b, jb0 = sg.jb0, jb1 = sg.jb1;
       const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
       const uint2 an0 = R.an0, an1 = R.an1;
       const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
       const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
       float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
-      u32 pg0 = kEmpty, pg1 = kEmpty;             // occurrence-count index of the two rows (count fetched when the segment ends)
-      if (fold) { if (pi0 < B) pg0 = A.cnt[pi0]; if (pi1 < B) pg1 = A.cnt[pi1]; }
       u32 pjm = jb0 * 32 + ln;
       float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
       for (u32 jb = jb0; jb < jb1; ++jb) {
@@ -461,12 +472,26 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         }
         if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; d_eighths += (u32)(te - ts) >> 2; }
         const long long d_g0 = P.debug ? clock64() : 0;
+        TR_ADD(tr_pre);
         if (fast) {
           float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
           if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
           const float sje = jin ? sjm : -3.0e38f;
-          if (part) tile_fast<true, true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj, ts, te);
-          else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+          // product form (one SFU operation per pair) when the scores of the tile lie within 2^+-kProdRange of a
+          // reference score -- here the first negative of the overlap; otherwise exp(-|x|) per pair
+          const float mref = __shfl_sync(0xFFFFFFFFu, sjm, smin - j0);
+          const float aj = (sjm - mref) * c, a0 = (si0 - mref) * c, a1 = (si1 - mref) * c;
+          const bool prod = use_prod && __all_sync(0xFFFFFFFFu, (!jin || fabsf(aj) <= kProdRange) &&
+                                                   (!in0 || fabsf(a0) <= kProdRange) && (!in1 || fabsf(a1) <= kProdRange));
+          if (prod) {
+            const float Fm = jin ? mufu_ex2(aj) : 0.f;
+            const float E0 = in0 ? mufu_ex2(-a0) : 0.f, E1 = in1 ? mufu_ex2(-a1) : 0.f;
+            if (part) tile_prod<true>(E0, E1, wv0, wv1, Fm, li0, li1, gi0, gi1, accj, ts, te);
+            else      tile_prod<false>(E0, E1, wv0, wv1, Fm, li0, li1, gi0, gi1, accj);
+          } else {
+            if (part) tile_fast<true, true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj, ts, te);
+            else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
+          }
         } else if (any_in) {
           const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
           const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
@@ -482,8 +507,10 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           }
         }
         if (P.debug) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
+        TR_ADD(tr_tile);
         if (accj != 0.f && !(P.debug & 4)) atomicAdd(A.gacc + pjm, accj);      // (debug bit 4: timing experiment without the RED)
         pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
+        TR_ADD(tr_post);
       }
       if (pi0 < B && an0.y) {
         if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
@@ -497,23 +524,44 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       }
       if (!DYN) {
         if (fold) {
-          const u64 ch0 = pg0 != kEmpty ? A.cprim[pg0] : 0ull, ch1 = pg1 != kEmpty ? A.cprim[pg1] : 0ull;
-          li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
+          // Occurrence weight of the rows' primary group.  Usually all rows of the I-block that have pairs belong to ONE
+          // group (equal group start): its weight is computed once per warp and kept while the group stays the same.
+          const bool act0 = pi0 < B && an0.y, act1 = pi1 < B && an1.y;
+          const u32 qmin = __reduce_min_sync(0xFFFFFFFFu, min(act0 ? lo0 : 0xFFFFFFFFu, act1 ? lo1 : 0xFFFFFFFFu));
+          const u32 qmax = __reduce_max_sync(0xFFFFFFFFu, max(act0 ? lo0 : 0u, act1 ? lo1 : 0u));
+          if (qmin == qmax) {
+            if (qmin != occ_a) {
+              const u32 pg = A.cnt[qmin];
+              occ_w = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
+              occ_a = qmin;
+            }
+            li0 *= occ_w; li1 *= occ_w;
+          } else if (qmin != 0xFFFFFFFFu) {
+            const u32 pg0 = act0 ? A.cnt[pi0] : kEmpty, pg1 = act1 ? A.cnt[pi1] : kEmpty;
+            const u64 ch0 = pg0 != kEmpty ? A.cprim[pg0] : 0ull, ch1 = pg1 != kEmpty ? A.cprim[pg1] : 0ull;
+            li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
+          }
         }
         lsum += (double)li0 + (double)li1;
       }
+      TR_ADD(tr_flush);
       if (P.debug) { d_busy += (u64)(clock64() - d_t0); ++d_units; }
       have = have_n; sg = sg_n; R = Rn;
     }
     if ((P.debug & 1) && ln == 0) {
-      atomicAdd(&ctl->dbg[1], d_busy);
       const u64 now = globaltimer();
-      atomicMax(&ctl->dbg[2], now);
       u64* rec = A.dbgbuf + 8 * (size_t)(blockIdx.x * kPairWarps + (threadIdx.x >> 5));
       rec[0] = d_start; rec[1] = now; rec[2] = d_busy; rec[3] = (u64)d_units | ((u64)d_gen << 32);
       rec[4] = d_fast; rec[5] = d_fastcyc; rec[6] = d_gencyc; rec[7] = d_eighths;
-      atomicAdd(&ctl->dbg[4], (u64)d_units); atomicAdd(&ctl->dbg[5], (u64)d_fast);
-      atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc); atomicAdd(&ctl->dbg[3], d_fastcyc);
+#ifdef RN_TRACE
+      rec[2] = d_busy | ((u64)d_units << 40) | ((u64)(d_fast + d_gen) << 48);
+      rec[3] = tr_take; rec[4] = tr_pre; rec[5] = tr_tile; rec[6] = tr_post; rec[7] = tr_flush;
+#endif
+      if (P.debug & 2) {      // grid-wide tallies: ~33 000 same-address atomics when the warps finish -- they perturb the timeline
+        atomicAdd(&ctl->dbg[1], d_busy); atomicMax(&ctl->dbg[2], now);
+        atomicAdd(&ctl->dbg[4], (u64)d_units); atomicAdd(&ctl->dbg[5], (u64)d_fast);
+        atomicAdd(&ctl->dbg[6], (u64)d_gen); atomicAdd(&ctl->dbg[7], d_gencyc); atomicAdd(&ctl->dbg[3], d_fastcyc);
+      }
     }
   }
   const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
@@ -798,7 +846,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
   static const int cost_gen = tune_int("RN_PAIR_COST_GEN", 17);
   A.cost_gen = (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));
-  static const int cost_switch = tune_int("RN_PAIR_COST_SWITCH", 0);
+  static const int cost_switch = tune_int("RN_PAIR_COST_SWITCH", 4);
   A.cost_switch = (u32)(cost_switch < 0 ? 0 : (cost_switch > 64 ? 64 : cost_switch));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
