@@ -371,12 +371,57 @@ def ours(args):
     e2e_ms = a.elapsed_time(b)
     h2d = pin_all.numel()
     d2h = h_loss.numel() * 4 + h_grad.numel() * 4
+    e2e_api_ms = e2e_ms
+    e2e_api = ("rec_block.pairwise_loss_from_batch.pairwise_loss + backward" if world == 1
+               else "global_mode.global_pairwise_loss + backward")
+    e2e_pipeline = ("inputs of step k+1 copied H2D on a copy stream (two device buffers) while step k computes; loss and "
+                    "gradient copied D2H every step; autograd engine single-threaded "
+                    "(torch.autograd.set_multithreading_enabled(False))")
+    e2e_timing = "CUDA events on the compute stream around the K steps"
+    if world == 1:
+        # ---- e2e through the C ABI with HOST buffers (rn_host_pairwise_*): every step copies its pinned host columns
+        #      to the device, runs the three kernels and copies loss, pair count and gradient back; two slots in flight
+        from rec_now_b200.host import HostPairwise
+        hp = HostPairwise(ROWS_PER_GPU, K=1, depth=2)
+        hin = {k: torch.from_numpy(host[k]).pin_memory() for k in ("g", "s", "y", "w")}
+        houts = [dict(loss=torch.empty(1, dtype=torch.float32).pin_memory(),
+                      n_pair_f32=torch.empty(1, dtype=torch.float32).pin_memory(),
+                      n_pair=torch.empty(1, dtype=torch.int64).pin_memory(),
+                      dlogits=torch.empty(ROWS_PER_GPU, dtype=torch.float32).pin_memory()) for _ in range(2)]
+
+        # (the loader's staging buffers are bound once; every submit copies what they hold at that moment)
+        bound = [hp.bind(hin["g"], hin["s"], hin["y"], rw_pos=hin["w"], label_func="diff", power=-0.5, **houts[q])
+                 for q in range(2)]
+
+        def host_steps(n):
+            prev = None
+            for k in range(n):
+                t = bound[k & 1].submit()
+                if prev is not None:
+                    hp.wait(prev)                # the results of step k-1 are in host memory
+                prev = t
+            hp.wait(prev)
+
+        host_steps(W)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        host_steps(K)
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert int(houts[(K - 1) & 1]["n_pair"]) == n_pair
+        hp.close()
+        h2d = sum(int(t.numel() * t.element_size()) for t in hin.values())
+        d2h = 4 + 4 + 8 + 4 * ROWS_PER_GPU
+        e2e_api = "C ABI with host buffers: rn_host_pairwise_submit / rn_host_pairwise_wait (rec_now_b200.host.HostPairwise)"
+        e2e_pipeline = ("every step: H2D of its pinned host columns (copy-in stream) -> k_init, k_seg, k_pair (compute "
+                        "stream) -> D2H of loss, n_pair and the gradient (copy-out stream); two device slots, the host "
+                        "waits for step k-1 after submitting step k")
+        e2e_timing = "host wall clock from the first submit to the last wait (device idle before, results in host memory after)"
 
     # ---- max over ranks ------------------------------------------------------------------------------
-    times = torch.tensor([t_ms, e2e_ms, pair_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([t_ms, e2e_ms, pair_ms, e2e_api_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_ms, e2e_ms, pair_ms = (float(x) for x in times.tolist())
+    t_ms, e2e_ms, pair_ms, e2e_api_ms = (float(x) for x in times.tolist())
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -411,11 +456,12 @@ def ours(args):
             "e2e": {"value": n_pair * K / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms / K,
                     "samples_per_s": rows_total * K / (e2e_ms * 1e-3),
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "rec_block.pairwise_loss_from_batch.pairwise_loss + backward" if world == 1
-                           else "global_mode.global_pairwise_loss + backward",
-                    "pipeline": "inputs of step k+1 copied H2D on a copy stream (two device buffers) while step k "
-                                "computes; loss and gradient copied D2H every step; autograd engine single-threaded "
-                                "(torch.autograd.set_multithreading_enabled(False))"},
+                    "api": e2e_api, "pipeline": e2e_pipeline, "timing": e2e_timing,
+                    "dropin_api": {"value": n_pair * K / (e2e_api_ms * 1e-3), "unit": "pairs/s",
+                                   "ms_per_step": e2e_api_ms / K,
+                                   "api": "rec_block.pairwise_loss_from_batch.pairwise_loss + backward on torch tensors "
+                                          "(H2D / D2H every step, Python + autograd-engine host time included)"}
+                                  if world == 1 else None},
             "gpu_launches": int(lib.rn_pairwise_launch_count(rows_total, 1)) * K,
             "launch_mode": {"kernels_per_step": int(lib.rn_pairwise_launch_count(rows_total, 1)),
                             "steps_enqueued_as_one_cuda_graph_launch": graph_calls},

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define RN_VERSION 101 /* 0.1.1: blocked rows + reduce-scatter output layout in rn_pairwise_args */
+#define RN_VERSION 102 /* 0.1.2: host-buffer front end (rn_host_pairwise_*) */
 
 enum {
   RN_OK = 0,
@@ -145,6 +145,21 @@ int rn_pack_row_block(const int64_t* keys, int32_t K, const float* logits, const
  * memory.  The caller synchronises the ranks (all calls finished) before it is enqueued.  One launch. */
 int rn_reduce_peer_chunks(const void* const* peer_out, int32_t world, int32_t my_rank, int64_t chunk, float* dst,
                           void* stream);
+
+/* ---- pairwise, HOST buffers ------------------------------------------------------------------------------
+ * Front end for callers whose tensors live in host memory (a CPU-placed TF2 op, a data loader): the same call as
+ * rn_pairwise_fwd_bwd, but EVERY pointer of rn_pairwise_args is a HOST pointer (pinned memory, or the copies are
+ * synchronous).  The object owns `depth` slots of device memory (input columns, outputs, scratch arena), a copy-in, a
+ * compute and a copy-out stream; it allocates at create time only.  submit enqueues copy-in -> kernels -> copy-out of
+ * one batch and returns a ticket without waiting (it blocks only while all `depth` slots are in flight); wait returns
+ * when that batch's loss, n_pair_f32, n_pair, dlogits (and row_pairs) are in the host buffers given to submit.  With
+ * depth >= 2 the copies of one batch overlap the kernels of its neighbours.  The multi-GPU fields of the args
+ * (part_*, block_*, out_chunk, peer_blocks, gather_dst) must be 0 / {0, 1}.  One object per thread. */
+typedef struct rn_host_pairwise rn_host_pairwise;
+int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, rn_host_pairwise** out);
+int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_args* host_args, int32_t* ticket);
+int rn_host_pairwise_wait(rn_host_pairwise* p, int32_t ticket);
+int rn_host_pairwise_destroy(rn_host_pairwise* p);
 
 /* Pair materialisation in the reference's row-major order (i ascending, then j ascending; PW:217).
  * Two phases because P is data dependent: _count enqueues the segmentation + counting, then synchronises

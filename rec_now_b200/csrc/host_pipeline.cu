@@ -1,0 +1,155 @@
+// Host-buffer front end of rn_pairwise_fwd_bwd (rn_host_pairwise_*, see recnow_b200.h).
+//
+// The reference's pairwise_loss (pairwise_loss_from_batch.py:228-279) is called with tensors that live wherever the
+// framework put them; a TF2 CPU placement, a data loader or a parameter server hands over HOST buffers.  This front
+// end owns everything between those buffers and the kernels: `depth` slots of device memory (input columns, outputs,
+// the scratch arena of the call), one stream for the host->device copies, one for the kernels and one for the
+// device->host copies.  A submit enqueues copy-in -> rn_pairwise_fwd_bwd -> copy-out for one batch and returns at
+// once; with depth >= 2 the copies of one batch overlap the kernels of its neighbours.  Nothing is allocated after
+// create, and the only host synchronisation is the wait for a slot's results.
+#include <new>
+#include "common.cuh"
+
+namespace {
+
+struct Slot {
+  char* dev = nullptr;                 // one allocation: [keys][logits][labels][rw_pos][rw_neg][row_ok][outs][dlogits][row_pairs][scratch]
+  float* outs_host = nullptr;          // pinned staging of the three scalars: [loss f32][n_pair f32][n_pair i64]
+  float* loss = nullptr; float* n_pair_f32 = nullptr; int64_t* n_pair = nullptr;      // where the caller wants them
+  cudaEvent_t in_done = nullptr, cmp_done = nullptr, out_done = nullptr;
+  bool busy = false;
+};
+
+}  // namespace
+
+struct rn_host_pairwise {
+  int64_t B_max = 0; int32_t K = 0; int32_t depth = 0; int device = 0;
+  size_t o_keys = 0, o_logits = 0, o_labels = 0, o_rwp = 0, o_rwn = 0, o_ok = 0, o_outs = 0, o_dl = 0, o_rp = 0, o_scr = 0;
+  size_t scratch_bytes = 0, slot_bytes = 0;
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  Slot* slots = nullptr;
+  int32_t next = 0;
+};
+
+extern "C" int rn_host_pairwise_destroy(rn_host_pairwise* p) {
+  if (!p) return RN_OK;
+  cudaSetDevice(p->device);
+  if (p->slots) {
+    for (int q = 0; q < p->depth; ++q) {
+      Slot& s = p->slots[q];
+      if (s.out_done) cudaEventSynchronize(s.out_done);
+      if (s.dev) cudaFree(s.dev);
+      if (s.outs_host) cudaFreeHost(s.outs_host);
+      if (s.in_done) cudaEventDestroy(s.in_done);
+      if (s.cmp_done) cudaEventDestroy(s.cmp_done);
+      if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    delete[] p->slots;
+  }
+  if (p->s_in) cudaStreamDestroy(p->s_in);
+  if (p->s_cmp) cudaStreamDestroy(p->s_cmp);
+  if (p->s_out) cudaStreamDestroy(p->s_out);
+  delete p;
+  return RN_OK;
+}
+
+extern "C" int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, rn_host_pairwise** out) {
+  if (!out || B_max <= 0 || B_max > (1ll << 28) || K <= 0 || K > 8 || depth < 1 || depth > 8) return RN_ERR_ARG;
+  *out = nullptr;
+  rn_host_pairwise* p = new (std::nothrow) rn_host_pairwise;
+  if (!p) return RN_ERR_LAUNCH;
+  p->B_max = B_max; p->K = K; p->depth = depth;
+  if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return RN_ERR_NO_DEVICE; }
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t r = o; o = rn::align_up(o + bytes); return r; };
+  const size_t B = (size_t)B_max;
+  p->o_keys = take(8 * B * (size_t)K); p->o_logits = take(4 * B); p->o_labels = take(4 * B);
+  p->o_rwp = take(4 * B); p->o_rwn = take(4 * B); p->o_ok = take(B);
+  p->o_outs = take(32); p->o_dl = take(4 * B); p->o_rp = take(8 * B);
+  p->scratch_bytes = rn_pairwise_scratch_bytes(B_max, K);
+  p->o_scr = take(p->scratch_bytes);
+  p->slot_bytes = o;
+  p->slots = new (std::nothrow) Slot[depth];
+  bool ok = p->slots != nullptr;
+  ok = ok && cudaStreamCreateWithFlags(&p->s_in, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&p->s_cmp, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&p->s_out, cudaStreamNonBlocking) == cudaSuccess;
+  for (int q = 0; ok && q < depth; ++q) {
+    Slot& s = p->slots[q];
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.dev), p->slot_bytes) == cudaSuccess;
+    ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.outs_host), 32, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.cmp_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) { cudaGetLastError(); rn_host_pairwise_destroy(p); return RN_ERR_LAUNCH; }
+  *out = p;
+  return RN_OK;
+}
+
+extern "C" int rn_host_pairwise_wait(rn_host_pairwise* p, int32_t ticket) {
+  if (!p || ticket < 0 || ticket >= p->depth) return RN_ERR_ARG;
+  Slot& s = p->slots[ticket];
+  if (!s.busy) return RN_OK;
+  if (cudaEventSynchronize(s.out_done) != cudaSuccess) return RN_ERR_LAUNCH;
+  *s.loss = s.outs_host[0]; *s.n_pair_f32 = s.outs_host[1]; *s.n_pair = *reinterpret_cast<const int64_t*>(s.outs_host + 2);
+  s.busy = false;
+  return RN_OK;
+}
+
+extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_args* h, int32_t* ticket) {
+  if (!p || !h || !ticket) return RN_ERR_ARG;
+  if (h->B <= 0 || h->B > p->B_max || h->K != p->K) return RN_ERR_ARG;
+  if (!h->keys || !h->logits || !h->labels || !h->loss || !h->n_pair_f32 || !h->n_pair || !h->dlogits) return RN_ERR_ARG;
+  if (h->block_rows || h->out_chunk || h->gather_dst || h->part_count != 1 || h->part_rank != 0) return RN_ERR_UNSUPPORTED;
+  const int32_t q = p->next;
+  int rc = rn_host_pairwise_wait(p, q);                 // the slot's previous batch has left the device
+  if (rc) return rc;
+  Slot& s = p->slots[q];
+  const size_t B = (size_t)h->B;
+  char* d = s.dev;
+  bool ok = true;
+  auto h2d = [&](size_t off, const void* src, size_t bytes) {
+    ok = ok && cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, p->s_in) == cudaSuccess;
+  };
+  // ---- copy-in (key column k of the device block starts B int64 after column k-1, as rn_pairwise_args wants it)
+  h2d(p->o_keys, h->keys, 8 * B * (size_t)p->K);
+  h2d(p->o_logits, h->logits, 4 * B);
+  h2d(p->o_labels, h->labels, 4 * B);
+  if (h->rw_pos) h2d(p->o_rwp, h->rw_pos, 4 * B);
+  if (h->rw_neg) h2d(p->o_rwn, h->rw_neg, 4 * B);
+  if (h->row_ok) h2d(p->o_ok, h->row_ok, B);
+  ok = ok && cudaEventRecord(s.in_done, p->s_in) == cudaSuccess;
+  // ---- kernels
+  ok = ok && cudaStreamWaitEvent(p->s_cmp, s.in_done, 0) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return RN_ERR_LAUNCH; }
+  rn_pairwise_args a = *h;
+  a.keys = reinterpret_cast<const int64_t*>(d + p->o_keys);
+  a.logits = reinterpret_cast<const float*>(d + p->o_logits);
+  a.labels = reinterpret_cast<const float*>(d + p->o_labels);
+  a.rw_pos = h->rw_pos ? reinterpret_cast<const float*>(d + p->o_rwp) : nullptr;
+  a.rw_neg = h->rw_neg ? reinterpret_cast<const float*>(d + p->o_rwn) : nullptr;
+  a.row_ok = h->row_ok ? reinterpret_cast<const uint8_t*>(d + p->o_ok) : nullptr;
+  float* outs = reinterpret_cast<float*>(d + p->o_outs);          // [loss f32][n_pair f32][n_pair i64]
+  a.loss = outs; a.n_pair_f32 = outs + 1; a.n_pair = reinterpret_cast<int64_t*>(outs + 2);
+  a.dlogits = reinterpret_cast<float*>(d + p->o_dl);
+  a.row_pairs = h->row_pairs ? reinterpret_cast<int64_t*>(d + p->o_rp) : nullptr;
+  rc = rn_pairwise_fwd_bwd(&a, d + p->o_scr, p->scratch_bytes, p->s_cmp);
+  if (rc) return rc;
+  ok = ok && cudaEventRecord(s.cmp_done, p->s_cmp) == cudaSuccess;
+  // ---- copy-out
+  ok = ok && cudaStreamWaitEvent(p->s_out, s.cmp_done, 0) == cudaSuccess;
+  auto d2h = [&](void* dst, size_t off, size_t bytes) {
+    ok = ok && cudaMemcpyAsync(dst, d + off, bytes, cudaMemcpyDeviceToHost, p->s_out) == cudaSuccess;
+  };
+  d2h(h->dlogits, p->o_dl, 4 * B);
+  if (h->row_pairs) d2h(h->row_pairs, p->o_rp, 8 * B);
+  d2h(s.outs_host, p->o_outs, 16);                      // (handed to the caller's three pointers by the wait)
+  s.loss = h->loss; s.n_pair_f32 = h->n_pair_f32; s.n_pair = h->n_pair;
+  ok = ok && cudaEventRecord(s.out_done, p->s_out) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); return RN_ERR_LAUNCH; }
+  s.busy = true;
+  *ticket = q;
+  p->next = (q + 1) % p->depth;
+  return RN_OK;
+}

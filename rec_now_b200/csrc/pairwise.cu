@@ -290,6 +290,41 @@ __device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u3
   if (RWN) r.wnjm = pjm < B ? A.swn[pjm] : 0.f;
 }
 
+// A block whose negatives span several label levels of ONE group (label-gain weights): every row covers a level of the
+// block entirely or not at all, so the block is the sum of one product-form pass per level, each with the other levels'
+// negatives switched off (F = 0).  Up to three levels (a general tile costs about four fast ones); false = not taken.
+__device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const u32 lo0, const u32 lo1, const u32 hi0,
+                                          const u32 hi1, const float si0, const float si1, const float yi0, const float yi1,
+                                          const float wp0, const float wp1, const u32 pjm, const float sjm, const float yjm,
+                                          const bool jin, const u32 smin, const u32 j0, const float c, const int ts,
+                                          const int te, float& li0, float& li1, float& gi0, float& gi1, float& accj) {
+  const u32 ln = lane_id();
+  const u32 gl = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? lo0 : 0xFFFFFFFFu, in1 ? lo1 : 0xFFFFFFFFu));
+  const u32 gh = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? lo0 : 0u, in1 ? lo1 : 0u));
+  if (gl != gh) return false;                                        // rows of several groups touch the block
+  const float yprev = __shfl_up_sync(0xFFFFFFFFu, yjm, 1);
+  const u32 heads = __ballot_sync(0xFFFFFFFFu, jin && (pjm == smin || yjm != yprev));
+  if (__popc(heads) > 3) return false;
+  const float mref = __shfl_sync(0xFFFFFFFFu, sjm, smin - j0);
+  const float aj = (sjm - mref) * c, a0 = (si0 - mref) * c, a1 = (si1 - mref) * c;
+  if (!__all_sync(0xFFFFFFFFu, (!jin || fabsf(aj) <= kProdRange) && (!in0 || fabsf(a0) <= kProdRange) &&
+                               (!in1 || fabsf(a1) <= kProdRange))) return false;
+  const float Fm = jin ? mufu_ex2(aj) : 0.f;
+  const float E0 = in0 ? mufu_ex2(-a0) : 0.f, E1 = in1 ? mufu_ex2(-a1) : 0.f;
+  u32 rem = __ballot_sync(0xFFFFFFFFu, jin);
+  while (rem) {
+    const int lead = __ffs(rem) - 1;
+    const float yv = __shfl_sync(0xFFFFFFFFu, yjm, lead);
+    const u32 runm = __ballot_sync(0xFFFFFFFFu, jin && yjm == yv) | (1u << lead);
+    const u32 rs = j0 + (u32)(__ffs(runm) - 1), re = j0 + 32u - (u32)__clz(runm);
+    const float wv0 = (in0 && lo0 <= rs && re <= hi0) ? wp0 * (yi0 - yv) : 0.f;
+    const float wv1 = (in1 && lo1 <= rs && re <= hi1) ? wp1 * (yi1 - yv) : 0.f;
+    tile_prod<true>(E0, E1, wv0, wv1, ((runm >> ln) & 1u) ? Fm : 0.f, li0, li1, gi0, gi1, accj, ts, te);
+    rem &= ~runm;
+  }
+  return true;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // Work = the (I-block x J-block) tiles of the staircase, laid out on a COST LINE: virtual block after virtual block
@@ -380,7 +415,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     const float c = P.c_log2;
     // debug tallies (per warp, flushed once): busy cycles, segments, fast / general tiles, eighths
     u64 d_busy = 0; u32 d_units = 0, d_fast = 0, d_gen = 0, d_eighths = 0; u64 d_gencyc = 0, d_fastcyc = 0;
-    const u64 d_start = P.debug ? globaltimer() : 0;
+    const bool tally = (P.debug & 3) != 0;          // (bits 1, 2: per-warp records / grid tallies; the higher bits only switch code paths)
+    const u64 d_start = tally ? globaltimer() : 0;
 #ifdef RN_TRACE
     // dev build: where a warp's time goes (clock cycles): taking segments, per-J-block preamble, tiles, RED + loop end, flush
     u64 tr_take = 0, tr_pre = 0, tr_tile = 0, tr_post = 0, tr_flush = 0; long long tr_t = 0;
@@ -427,7 +463,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     u32 occ_a = 0xFFFFFFFFu; float occ_w = 0.f;   // group start the cached occurrence weight belongs to
     if (have) load_unit_rows<MODE>(A, B, sg.b, sg.jb0, ln, R);
     while (have) {
-      const long long d_t0 = P.debug ? clock64() : 0;
+      const long long d_t0 = tally ? clock64() : 0;
       TR_BEGIN();
       const bool have_n = take(sg_n);
       if (have_n) load_unit_rows<MODE>(A, B, sg_n.b, sg_n.jb0, ln, Rn);      // in flight while this segment is scored
@@ -440,6 +476,10 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
       u32 pjm = jb0 * 32 + ln;
       float sjm = R.sjm, yjm = R.yjm, wnjm = R.wnjm;
+      // J blocks inside [seg_lomax, seg_himin) are covered entirely by every row of the I-block that has pairs
+      const bool act0 = an0.y != 0, act1 = an1.y != 0;
+      const u32 seg_lomax = __reduce_max_sync(0xFFFFFFFFu, max(act0 ? lo0 : 0u, act1 ? lo1 : 0u));
+      const u32 seg_himin = __reduce_min_sync(0xFFFFFFFFu, min(act0 ? hi0 : 0xFFFFFFFFu, act1 ? hi1 : 0xFFFFFFFFu));
       for (u32 jb = jb0; jb < jb1; ++jb) {
         // prefetch the next J-block while this one is being scored
         const u32 pjn = pjm + 32;
@@ -456,12 +496,18 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         // all: if all rows that touch the block share ONE overlap [s, e) and (label weights) its labels are one
         // value, the block is scored by the fast tile with out-of-range negatives replaced by a sentinel score
         // (x = +inf: e = 0, sigma = 0, factor 1 in the product) and rows that do not touch it weighted 0.
-        const u32 s0 = max(lo0, j0), e0 = min(hi0, j0 + 32), s1 = max(lo1, j0), e1 = min(hi1, j0 + 32);
-        const bool in0 = s0 < e0, in1 = s1 < e1;
-        const u32 smin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? s0 : 0xFFFFFFFFu, in1 ? s1 : 0xFFFFFFFFu));
-        const u32 smax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? s0 : 0u, in1 ? s1 : 0u));
-        const u32 emin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? e0 : 0xFFFFFFFFu, in1 ? e1 : 0xFFFFFFFFu));
-        const u32 emax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? e0 : 0u, in1 ? e1 : 0u));
+        bool in0, in1; u32 smin, smax, emin, emax;
+        if (j0 >= seg_lomax && j0 + 32 <= seg_himin && seg_himin != 0xFFFFFFFFu && !(P.debug & 64)) {   // (debug bit 64: always the general overlap test)
+          // the usual block of a big group: every row of the I-block that has pairs covers all 32 negatives
+          in0 = act0; in1 = act1; smin = smax = j0; emin = emax = j0 + 32;
+        } else {
+          const u32 s0 = max(lo0, j0), e0 = min(hi0, j0 + 32), s1 = max(lo1, j0), e1 = min(hi1, j0 + 32);
+          in0 = s0 < e0; in1 = s1 < e1;
+          smin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? s0 : 0xFFFFFFFFu, in1 ? s1 : 0xFFFFFFFFu));
+          smax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? s0 : 0u, in1 ? s1 : 0u));
+          emin = __reduce_min_sync(0xFFFFFFFFu, min(in0 ? e0 : 0xFFFFFFFFu, in1 ? e1 : 0xFFFFFFFFu));
+          emax = __reduce_max_sync(0xFFFFFFFFu, max(in0 ? e0 : 0u, in1 ? e1 : 0u));
+        }
         const bool any_in = smin != 0xFFFFFFFFu;
         const bool jin = pjm >= smin && pjm < emax;                  // this lane's negative is inside the overlap
         bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG;
@@ -470,8 +516,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
           fast = __all_sync(0xFFFFFFFFu, !jin || yjm == yref);
         }
-        if (P.debug) { if (fast) ++d_fast; else if (any_in) ++d_gen; d_eighths += (u32)(te - ts) >> 2; }
-        const long long d_g0 = P.debug ? clock64() : 0;
+        if (tally) { if (fast) ++d_fast; else if (any_in) ++d_gen; d_eighths += (u32)(te - ts) >> 2; }
+        const long long d_g0 = tally ? clock64() : 0;
         TR_ADD(tr_pre);
         if (fast) {
           float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
@@ -492,6 +538,10 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
             if (part) tile_fast<true, true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj, ts, te);
             else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
           }
+        } else if (any_in && DIFF && !RWN && !WRONG && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
+                   runs_tile(in0, in1, lo0, lo1, hi0, hi1, si0, si1, yi0, yi1, wp0, wp1, pjm, sjm, yjm, jin, smin, j0, c, ts, te,
+                             li0, li1, gi0, gi1, accj)) {
+          // (scored as up to three product-form passes, one per label level of the negatives)
         } else if (any_in) {
           const bool full0 = __all_sync(0xFFFFFFFFu, lo0 <= j0 && j0 + 32 <= hi0);
           const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
@@ -506,7 +556,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
             else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
           }
         }
-        if (P.debug) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
+        if (tally) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
         TR_ADD(tr_tile);
         if (accj != 0.f && !(P.debug & 4)) atomicAdd(A.gacc + pjm, accj);      // (debug bit 4: timing experiment without the RED)
         pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
@@ -526,7 +576,6 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         if (fold) {
           // Occurrence weight of the rows' primary group.  Usually all rows of the I-block that have pairs belong to ONE
           // group (equal group start): its weight is computed once per warp and kept while the group stays the same.
-          const bool act0 = pi0 < B && an0.y, act1 = pi1 < B && an1.y;
           const u32 qmin = __reduce_min_sync(0xFFFFFFFFu, min(act0 ? lo0 : 0xFFFFFFFFu, act1 ? lo1 : 0xFFFFFFFFu));
           const u32 qmax = __reduce_max_sync(0xFFFFFFFFu, max(act0 ? lo0 : 0u, act1 ? lo1 : 0u));
           if (qmin == qmax) {
@@ -545,7 +594,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         lsum += (double)li0 + (double)li1;
       }
       TR_ADD(tr_flush);
-      if (P.debug) { d_busy += (u64)(clock64() - d_t0); ++d_units; }
+      if (tally) { d_busy += (u64)(clock64() - d_t0); ++d_units; }
       have = have_n; sg = sg_n; R = Rn;
     }
     if ((P.debug & 1) && ln == 0) {

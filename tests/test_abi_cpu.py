@@ -33,7 +33,7 @@ def test_exports_match_header(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.rn_version() == 101
+    assert lib.rn_version() == 102
     assert lib.rn_strerror(0) == b"ok"
     for code in range(1, 8):
         assert lib.rn_strerror(code) not in (b"ok", b"unknown error")

@@ -1,0 +1,102 @@
+"""GPU parity of the host-buffer front end (rn_host_pairwise_*): host arrays in, host arrays out, several batches in
+flight; results against the float64 segmented oracle and bit-identical pair counts."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import generators as G
+from oracle import seg_ref as S
+from tests.util import check_pairwise
+
+pytestmark = pytest.mark.gpu
+
+
+def _outs(B, pinned):
+    mk = (lambda n, dt: torch.empty(n, dtype=dt).pin_memory()) if pinned else (lambda n, dt: torch.empty(n, dtype=dt))
+    return dict(loss=mk(1, torch.float32), n_pair_f32=mk(1, torch.float32), n_pair=mk(1, torch.int64),
+                dlogits=mk(B, torch.float32), row_pairs=mk(B, torch.int64))
+
+
+def _as_out(o):
+    return {k: v.clone() for k, v in o.items()}
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_batches_in_flight(pinned):
+    from rec_now_b200.host import HostPairwise
+    B = 20000
+    hp = HostPairwise(B, K=1, depth=3)
+    batches, outs, tickets = [], [], []
+    for seed in range(5):                      # more batches than slots: submit has to recycle them
+        rng = np.random.default_rng(seed)
+        n = B - 1000 * seed                    # ragged sizes below B_max
+        g = rng.integers(0, 300, n).astype(np.int64)
+        s = rng.standard_normal(n).astype(np.float32)
+        y = rng.integers(0, 5, n).astype(np.float32)
+        w = rng.uniform(0.5, 1.5, n).astype(np.float32)
+        o = _outs(n, pinned)
+        if pinned:
+            g_, s_, y_, w_ = (torch.from_numpy(x).pin_memory() for x in (g, s, y, w))
+        else:
+            g_, s_, y_, w_ = g, s, y, w
+        t = hp.submit(g_, s_, y_, rw_pos=w_, label_func="diff", power=-0.5, **o)
+        batches.append((g, s, y, w)); outs.append(o); tickets.append(t)
+        if seed >= 2:                          # results of an older batch while newer ones are in flight
+            hp.wait(tickets[seed - 2])
+    for t in tickets:
+        hp.wait(t)
+    hp.close()
+    for (g, s, y, w), o in zip(batches, outs):
+        ref = S.pairwise(s, y, g, S.PairSpec(label_func="diff", rw_pos=w, power=-0.5))
+        check_pairwise(_as_out(o), ref, ctx="host pipeline")
+
+
+def test_matches_device_path_cfg3():
+    """Same batch through the device-pointer ABI and through the host front end: identical counts, loss and gradient
+    equal up to the run-to-run jitter of the floating-point atomics."""
+    from rec_now_b200 import ops
+    from rec_now_b200.host import HostPairwise
+    d = G.cfg3()
+    B = d["s"].size
+    dev_out = ops.pairwise_fwd_bwd(torch.tensor(d["s"]).cuda(), torch.tensor(d["y"]).cuda(),
+                                   torch.tensor(d["g"]).cuda().reshape(1, -1), rw_pos=torch.tensor(d["w"]).cuda(),
+                                   label_func="diff", power=-0.5)
+    o = _outs(B, True); o.pop("row_pairs")
+    hp = HostPairwise(B)
+    hp.wait(hp.submit(d["g"], d["s"], d["y"], rw_pos=d["w"], label_func="diff", power=-0.5, **o))
+    hp.close()
+    assert int(o["n_pair"]) == int(dev_out["n_pair"].item())
+    assert abs(float(o["loss"]) - float(dev_out["loss"].item())) <= 1e-6 * abs(float(o["loss"]))
+    gd = dev_out["dlogits"].cpu().numpy()
+    assert np.abs(o["dlogits"].numpy() - gd).max() <= 1e-6 * np.abs(gd).max()
+
+
+def test_argument_errors():
+    from rec_now_b200 import _lib
+    from rec_now_b200.host import HostPairwise
+    hp = HostPairwise(1000)
+    o = _outs(2000, False)
+    with pytest.raises(_lib.RnError):          # batch larger than B_max
+        hp.submit(np.zeros(2000, np.int64), np.zeros(2000, np.float32), np.zeros(2000, np.float32), **o)
+    with pytest.raises(ValueError):            # device tensor where a host buffer is expected
+        hp.submit(torch.zeros(10, dtype=torch.int64).cuda(), np.zeros(10, np.float32), np.zeros(10, np.float32), **_outs(10, False))
+    hp.close()
+
+
+def test_bound_buffers_are_read_at_submit():
+    """bind() validates the staging buffers once; every submit() copies what they hold at that moment."""
+    from rec_now_b200.host import HostPairwise
+    B = 5000
+    rng = np.random.default_rng(7)
+    g = torch.from_numpy(rng.integers(0, 50, B).astype(np.int64)).pin_memory()
+    s = torch.from_numpy(rng.standard_normal(B).astype(np.float32)).pin_memory()
+    y = torch.from_numpy(rng.integers(0, 2, B).astype(np.float32)).pin_memory()
+    o = _outs(B, True)
+    hp = HostPairwise(B)
+    batch = hp.bind(g, s, y, **o)
+    for rep in range(3):
+        hp.wait(batch.submit())
+        check_pairwise(_as_out(o), S.pairwise(s.numpy(), y.numpy(), g.numpy()), ctx=f"bound rep {rep}")
+        s.copy_(torch.from_numpy(rng.standard_normal(B).astype(np.float32)))       # the loader refills its buffer
+        y.copy_(torch.from_numpy(rng.integers(0, 2, B).astype(np.float32)))
+    hp.close()

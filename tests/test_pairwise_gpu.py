@@ -262,3 +262,19 @@ def test_large_batch_wide_tiles(b):
             loss += float(o["loss"].item()); grad = grad + o["dlogits"].double()
         assert abs(loss - ref["loss"]) <= 1e-5 * abs(ref["loss"])
         assert (np.abs(grad.cpu().numpy() - ref["grad"]) <= 1e-5 * ref["grad_abs"] + 1e-12).all()
+
+
+@pytest.mark.parametrize("scale", [0.2, 1.0, 4.0, 9.0, 30.0, 300.0])
+@pytest.mark.parametrize("shift", [0.0, -40.0])
+def test_score_range_product_and_exp_tiles(scale, shift):
+    """The fast tile has two forms: the product form (exp(-x) = E_i * F_j, scores within 2^+-12 of the tile's reference
+    score) and exp-per-pair.  Wide and shifted score distributions exercise both and the switch between them."""
+    rng = np.random.default_rng(int(scale * 10) + int(-shift))
+    b = 12000
+    g = np.minimum(rng.zipf(1.3, b), 40).astype(np.int64)          # a few big groups -> many fast tiles
+    s = (rng.standard_normal(b) * scale + shift).astype(np.float32)
+    y = rng.integers(0, 5, b).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, b).astype(np.float32)
+    for spec in (S.PairSpec(), S.PairSpec(label_func="diff", rw_pos=w, power=-0.5)):
+        out = run_pairwise(s, y, g, spec)
+        check_pairwise(out, S.pairwise(s, y, g, spec), ctx=f"scale {scale} shift {shift}")
