@@ -167,4 +167,41 @@ __device__ __forceinline__ void tile_prod(const float E0, const float E1, const 
   f2_unpack(acc, lo, hi); accj += lo + hi;
 }
 
+// General (masked) tile in product form: exp(-x) = E_i * F_j as in tile_prod (same range precondition), so a pair costs
+// TWO SFU operations (reciprocal, log) instead of three, and no max(-x, 0) branch: softplus(-x) = log(1 + u) directly
+// (u <= 2^24).  Not for the wrong-order filter: s_i < s_j must be decided on the scores themselves.
+template <int MODE, bool FULL>
+__device__ __forceinline__ void tile_general_prod(const float Ei, const float yi, const float wpi, const u32 lo, const u32 hi,
+                                                  const u32 pjm, const float Fm, const float yjm, const float wnjm,
+                                                  const int t0, const int t1, float& li, float& gi, u32& cnt, float& accj) {
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
+  float gi_t = 0.f, li_t = 0.f;
+#pragma unroll 2
+  for (int tb = t0; tb < t1; tb += 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int t = tb + k;
+      const float u = Ei * __shfl_xor_sync(0xFFFFFFFFu, Fm, t);        // exp(-x)
+      const float t1p = 1.0f + u;
+      const float L = mufu_lg2(t1p);                                   // softplus(-x) / ln2
+      float d = u * mufu_rcp(t1p);                                     // sigma(-x)
+      bool valid = true;
+      if (!FULL) { const u32 pj = pjm ^ (u32)t; valid = (pj >= lo) && (pj < hi); }
+      float wv = 1.f;
+      if (HASW) {
+        wv = wpi;
+        if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = (yi - yj) * wpi; }
+        if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
+        d *= wv;
+      }
+      if (!FULL || RWN) d = valid ? d : 0.f;
+      if (RWN) cnt += valid ? 1u : 0u;
+      if (HASW) { if (valid) li_t = fmaf(wv, L, li_t); } else { if (valid) li_t += L; }
+      gi_t += d;
+      accj += __shfl_xor_sync(0xFFFFFFFFu, d, t);
+    }
+  }
+  li += li_t; gi += gi_t;
+}
+
 }  // namespace rn

@@ -547,6 +547,25 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           const bool full1 = __all_sync(0xFFFFFFFFu, lo1 <= j0 && j0 + 32 <= hi1);
           const bool any0 = __any_sync(0xFFFFFFFFu, in0);
           const bool any1 = __any_sync(0xFFFFFFFFu, in1);
+          // product form of the general tile (two SFU operations per pair) under the same range test as tile_prod
+          bool gprod = false; float Fg = 0.f, Eg0 = 0.f, Eg1 = 0.f;
+          if (!WRONG && use_prod && !(P.debug & 128)) {                  // (debug bit 128: general tiles with exp per pair)
+            const float mref = __shfl_sync(0xFFFFFFFFu, sjm, smin - j0);
+            const float aj = (sjm - mref) * c, a0 = (si0 - mref) * c, a1 = (si1 - mref) * c;
+            gprod = __all_sync(0xFFFFFFFFu, (!jin || fabsf(aj) <= kProdRange) && (!in0 || fabsf(a0) <= kProdRange) &&
+                                            (!in1 || fabsf(a1) <= kProdRange));
+            if (gprod) { Fg = jin ? mufu_ex2(aj) : 0.f; Eg0 = in0 ? mufu_ex2(-a0) : 0.f; Eg1 = in1 ? mufu_ex2(-a1) : 0.f; }
+          }
+          if (gprod) {
+            if (any0) {
+              if (full0) tile_general_prod<MODE, true>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj);
+              else       tile_general_prod<MODE, false>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj);
+            }
+            if (any1) {
+              if (full1) tile_general_prod<MODE, true>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj);
+              else       tile_general_prod<MODE, false>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj);
+            }
+          } else {
           if (any0) {
             if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
             else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
@@ -554,6 +573,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           if (any1) {
             if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
             else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
+          }
           }
         }
         if (tally) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
