@@ -440,9 +440,15 @@ def ours(args):
             "config": {"workload": name, "rows_per_gpu": ROWS_PER_GPU, "seed": 0,
                        "l2": "flushed between timed steps (256 MiB write); inputs ~1.6 MB/GPU",
                        "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks",
-                       "multi_gpu": None if world == 1 else "ONE NCCL all-gather of packed per-rank row blocks -> replicated "
-                                    "segmentation on the blocked rows -> even work-unit split -> ONE NCCL "
-                                    "reduce-scatter (gradient chunks, partial loss in a spare slot)"},
+                       "multi_gpu": None if world == 1 else (
+                           "peer memory over NVLink (torch symmetric memory), no collective calls: pack kernel -> device "
+                           "barrier -> ONE graph launch whose first kernel gathers every rank's row block with peer loads "
+                           "-> replicated segmentation -> even split of the pair work -> barrier -> one kernel sums this "
+                           "rank's gradient chunk from the peers' buffers"
+                           if global_mode.exchange_path() == "peer" else
+                           "ONE NCCL all-gather of packed per-rank row blocks -> replicated segmentation on the blocked "
+                           "rows -> even work-unit split -> ONE NCCL reduce-scatter (gradient chunks, partial loss in a "
+                           "spare slot)")},
             "roofline": {"bound": "sfu", "kernel": "k_pair", "achieved": achieved / 1e9, "peak": mufu_peak / 1e9,
                          "unit": "GMUFU/s", "frac": achieved / mufu_peak,
                          "peak_source": "measured in this run (rn_bench_mufu ex2/lg2/rcp chains)",

@@ -92,6 +92,14 @@ def _peer_state(group, dev, stride, out_floats) -> Optional[_PeerState]:
     return st
 
 
+def exchange_path() -> str:
+    """Which data path the global mode has used so far in this process: 'peer' (NVLink peer mappings, no collective
+    calls), 'nccl' (all-gather + reduce-scatter) or 'unused'."""
+    if _peer_states:
+        return "peer"
+    return "nccl" if _peer_broken or __import__("os").environ.get("RN_GLOBAL_P2P", "1") == "0" else "unused"
+
+
 def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
     """Global step over NVLink peer mappings, no collective calls: pack this rank's block into its symmetric buffer ->
     device-side barrier -> ONE graph launch whose first kernel gathers all ranks' blocks with peer loads and whose
