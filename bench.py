@@ -269,15 +269,22 @@ def ours(args):
     # ---- the dominant kernel alone: the same steps again with CUDA events around the k_pair launch (the events sit
     #      between the kernels of a call, so this pass uses plain launches instead of the cached graph) -----------
     KP = min(K, 100)
-    lib.rn_profile_enable(KP)
-    for k in range(KP):
-        flush.fill_(k & 0xFF)
-        out = step()
-    barrier()
-    ms = (C.c_float * KP)(); nget = C.c_int32(0)
-    lib.rn_profile_collect(ms, KP, C.byref(nget))
-    lib.rn_profile_disable()
-    pair_ms = float(np.mean(list(ms)[:nget.value])) if nget.value else float("nan")
+
+    def time_pair_kernel(in_graph):
+        lib.rn_profile_enable_ex(KP, in_graph)
+        for k in range(KP):
+            flush.fill_(k & 0xFF)
+            o = step()
+        barrier()
+        ms = (C.c_float * KP)(); nget = C.c_int32(0)
+        lib.rn_profile_collect(ms, KP, C.byref(nget))
+        lib.rn_profile_disable()
+        return (float(np.mean(list(ms)[:nget.value])) if nget.value else float("nan")), o
+
+    # on the default path (the step's cached CUDA graph with two event-record nodes around the pair kernel) ...
+    pair_ms, out = time_pair_kernel(1)
+    # ... and with plain launches and stream events between the kernels (includes the cooperative launch's latency)
+    pair_ms_plain, out = time_pair_kernel(0)
     n_pair = int(out["n_pair"].item())
     err = ops.device_error(out["_scratch"]) if world == 1 else 0
 
@@ -382,46 +389,47 @@ def ours(args):
         # ---- e2e through the C ABI with HOST buffers (rn_host_pairwise_*): every step copies its pinned host columns
         #      to the device, runs the three kernels and copies loss, pair count and gradient back; two slots in flight
         from rec_now_b200.host import HostPairwise
-        hp = HostPairwise(ROWS_PER_GPU, K=1, depth=2)
+        DEPTH = 3
+        hp = HostPairwise(ROWS_PER_GPU, K=1, depth=DEPTH)
         hin = {k: torch.from_numpy(host[k]).pin_memory() for k in ("g", "s", "y", "w")}
         houts = [dict(loss=torch.empty(1, dtype=torch.float32).pin_memory(),
                       n_pair_f32=torch.empty(1, dtype=torch.float32).pin_memory(),
                       n_pair=torch.empty(1, dtype=torch.int64).pin_memory(),
-                      dlogits=torch.empty(ROWS_PER_GPU, dtype=torch.float32).pin_memory()) for _ in range(2)]
+                      dlogits=torch.empty(ROWS_PER_GPU, dtype=torch.float32).pin_memory()) for _ in range(DEPTH)]
 
         # (the loader's staging buffers are bound once; every submit copies what they hold at that moment)
         bound = [hp.bind(hin["g"], hin["s"], hin["y"], rw_pos=hin["w"], label_func="diff", power=-0.5, **houts[q])
-                 for q in range(2)]
+                 for q in range(DEPTH)]
 
         def host_steps(n):
-            prev = None
+            pending = []
             for k in range(n):
-                t = bound[k & 1].submit()
-                if prev is not None:
-                    hp.wait(prev)                # the results of step k-1 are in host memory
-                prev = t
-            hp.wait(prev)
+                pending.append(bound[k % DEPTH].submit())
+                if len(pending) == DEPTH:
+                    hp.wait(pending.pop(0))      # the results of step k-2 are in host memory
+            for t in pending:
+                hp.wait(t)
 
         host_steps(W)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         host_steps(K)
         e2e_ms = (time.perf_counter() - t0) * 1e3
-        assert int(houts[(K - 1) & 1]["n_pair"]) == n_pair
+        assert int(houts[(K - 1) % DEPTH]["n_pair"]) == n_pair
         hp.close()
         h2d = sum(int(t.numel() * t.element_size()) for t in hin.values())
         d2h = 4 + 4 + 8 + 4 * ROWS_PER_GPU
         e2e_api = "C ABI with host buffers: rn_host_pairwise_submit / rn_host_pairwise_wait (rec_now_b200.host.HostPairwise)"
         e2e_pipeline = ("every step: H2D of its pinned host columns (copy-in stream) -> k_init, k_seg, k_pair (compute "
-                        "stream) -> D2H of loss, n_pair and the gradient (copy-out stream); two device slots, the host "
-                        "waits for step k-1 after submitting step k")
+                        "stream) -> D2H of loss, n_pair and the gradient (copy-out stream); three device slots, the host "
+                        "waits for step k-2 after submitting step k")
         e2e_timing = "host wall clock from the first submit to the last wait (device idle before, results in host memory after)"
 
     # ---- max over ranks ------------------------------------------------------------------------------
-    times = torch.tensor([t_ms, e2e_ms, pair_ms, e2e_api_ms], dtype=torch.float64, device=dev)
+    times = torch.tensor([t_ms, e2e_ms, pair_ms, e2e_api_ms, pair_ms_plain], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    t_ms, e2e_ms, pair_ms, e2e_api_ms = (float(x) for x in times.tolist())
+    t_ms, e2e_ms, pair_ms, e2e_api_ms, pair_ms_plain = (float(x) for x in times.tolist())
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -454,6 +462,10 @@ def ours(args):
                          "peak_source": "measured in this run (rn_bench_mufu ex2/lg2/rcp chains)",
                          "nominal_peak": NOMINAL_MUFU_PER_S / 1e9, "frac_of_nominal": achieved / NOMINAL_MUFU_PER_S,
                          "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / (t_ms / K),
+                         "kernel_timing": "CUDA event-record nodes around the k_pair node of the step's CUDA graph (the "
+                                          "default launch path), L2 flushed before every step",
+                         "kernel_ms_plain_launches": pair_ms_plain,
+                         "frac_plain_launches": MUFU_PER_PAIR * pairs_per_launch / (pair_ms_plain * 1e-3) / mufu_peak,
                          "algorithmic_mufu_per_pair": MUFU_PER_PAIR, "pairs_per_launch": pairs_per_launch,
                          "traffic": kpair_traffic(world),
                          "hbm_view": {"bound": "hbm", "achieved": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9,

@@ -195,6 +195,11 @@ int rn_bench_mufu(int32_t iters, float* sink, int64_t* mufu_ops_out_host, void* 
  * calls).  rn_profile_collect synchronises those events and returns the elapsed milliseconds per call.
  * Measurement aid only (process-global, not thread-safe, not for use under graph capture). */
 int rn_profile_enable(int32_t max_calls);
+/* in_graph != 0 (what rn_profile_enable does): the timed calls stay on the default path -- one launch of a cached CUDA
+ * graph that also holds two event-record nodes around the pair kernel; each timed call then waits for the stream and
+ * reads the elapsed time.  in_graph == 0: plain launches with stream events between the kernels (the figure then
+ * includes the launch latency of a cooperative launch behind an event). */
+int rn_profile_enable_ex(int32_t max_calls, int32_t in_graph);
 int rn_profile_collect(float* ms_out_host, int32_t capacity, int32_t* n_out_host);
 int rn_profile_disable(void);
 /* Device-side status word of the last call that used `scratch` (0 = ok); reads it back (synchronises). */

@@ -24,7 +24,7 @@ EXPORTS = [
     "rn_pair_indices_scratch_bytes", "rn_pair_indices_count", "rn_pair_indices_fill",
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
-    "rn_bench_mufu", "rn_profile_enable", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
+    "rn_bench_mufu", "rn_profile_enable", "rn_profile_enable_ex", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
     "rn_debug_graph_launches", "rn_pack_row_block", "rn_reduce_peer_chunks",
     "rn_host_pairwise_create", "rn_host_pairwise_submit", "rn_host_pairwise_wait", "rn_host_pairwise_destroy",
 ]
@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
     L.rn_listwise_dense.argtypes = [C.POINTER(ListwiseArgs), vp, sz, i64, vp, vp, vp, i32, f32, vp]
     L.rn_bench_mufu.argtypes = [i32, vp, C.POINTER(i64), vp]
     L.rn_profile_enable.argtypes = [i32]
+    L.rn_profile_enable_ex.argtypes = [i32, i32]
     L.rn_profile_collect.argtypes = [C.POINTER(f32), i32, C.POINTER(i32)]
     L.rn_last_device_error.argtypes = [vp, C.POINTER(i32), vp]
     L.rn_debug_timestamps.argtypes = [vp, C.POINTER(C.c_uint64), i32, vp]

@@ -236,9 +236,15 @@ const void* seg_init_func();
 long long graph_launch_count();
 struct GraphCall {
   cudaStream_t st, run_stream; GraphSlot* slot = nullptr; int mode = 0;     // 0 direct, 1 node update, 2 capture
-  GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow);
+  // timed = true: the graph also holds two event-record nodes around the pair kernel (see timed_events)
+  GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow,
+            bool timed = false);
   cudaError_t finish(bool ok);
+  bool capturing() const { return mode == 2; }
+  bool updating() const { return mode == 1; }
 };
+// The two events recorded by the timed graphs of this thread (created on first use; nullptr on failure).
+cudaEvent_t* timed_events();
 
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 

@@ -33,7 +33,6 @@ static int tune_int(const char* name, int dflt) {
 constexpr u32 kMaxUnitC = 64;
 constexpr u32 kMaxNibS = 8192;           // I-blocks whose cost prefixes fit k_pair's shared memory (B <= 524288)
 constexpr int kPairThreads = 1024;      // threads per CTA of the pair kernel (one CTA per SM, <= 64 registers)
-constexpr u32 kDone = 0xFFFFFFFFu;
 constexpr int kPairWarps = kPairThreads / 32;
 
 struct PairParams {
@@ -805,26 +804,37 @@ static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A,
 using namespace rn;
 
 // ---- pair-kernel timing (measurement aid, see recnow_b200.h) ------------------------------------------
-static struct { bool on = false; int cap = 0; int n = 0; cudaEvent_t* ev = nullptr; } g_prof;
+// (graph = true: the call stays on the product's default path, one launch of a cached CUDA graph that also holds two
+// event-record nodes around the pair kernel; the call then waits for the stream and reads the elapsed time itself)
+static struct { bool on = false; bool graph = false; int cap = 0; int n = 0; cudaEvent_t* ev = nullptr; float* ms = nullptr; } g_prof;
 
 extern "C" int rn_profile_disable(void) {
   if (g_prof.ev) { for (int i = 0; i < 2 * g_prof.cap; ++i) cudaEventDestroy(g_prof.ev[i]); delete[] g_prof.ev; }
-  g_prof.ev = nullptr; g_prof.on = false; g_prof.cap = g_prof.n = 0;
+  delete[] g_prof.ms;
+  g_prof.ev = nullptr; g_prof.ms = nullptr; g_prof.on = false; g_prof.graph = false; g_prof.cap = g_prof.n = 0;
   return RN_OK;
 }
+extern "C" int rn_profile_enable_ex(int32_t max_calls, int32_t in_graph);
 extern "C" int rn_profile_enable(int32_t max_calls) {
+  static const int in_graph = tune_int("RN_PROFILE_GRAPH", 1);
+  return rn_profile_enable_ex(max_calls, in_graph);
+}
+extern "C" int rn_profile_enable_ex(int32_t max_calls, int32_t in_graph) {
   rn_profile_disable();
   if (max_calls <= 0 || max_calls > (1 << 20)) return RN_ERR_ARG;
   g_prof.ev = new cudaEvent_t[2 * max_calls];
   for (int i = 0; i < 2 * max_calls; ++i)
     if (cudaEventCreate(&g_prof.ev[i]) != cudaSuccess) return RN_ERR_LAUNCH;
+  g_prof.ms = new float[max_calls];
   g_prof.cap = max_calls; g_prof.n = 0; g_prof.on = true;
+  g_prof.graph = in_graph != 0;
   return RN_OK;
 }
 extern "C" int rn_profile_collect(float* ms_out_host, int32_t capacity, int32_t* n_out_host) {
   if (!ms_out_host || !n_out_host) return RN_ERR_ARG;
   int n = g_prof.n < capacity ? g_prof.n : capacity;
   for (int i = 0; i < n; ++i) {
+    if (g_prof.ms[i] >= 0.f) { ms_out_host[i] = g_prof.ms[i]; continue; }          // (timed inside a graph launch)
     if (cudaEventSynchronize(g_prof.ev[2 * i + 1]) != cudaSuccess) return RN_ERR_LAUNCH;
     if (cudaEventElapsedTime(&ms_out_host[i], g_prof.ev[2 * i], g_prof.ev[2 * i + 1]) != cudaSuccess) return RN_ERR_LAUNCH;
   }
@@ -928,22 +938,39 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
   const bool prof = g_prof.on && g_prof.n < g_prof.cap;
+  cudaEvent_t* tev = (prof && g_prof.graph) ? timed_events() : nullptr;
+  const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;
+  // one launch of a cached CUDA graph; while the pair kernel is being timed: the timed variant of the graph (two
+  // event-record nodes around the pair kernel), or plain launches with stream events (RN_PROFILE_GRAPH=0)
+  GraphCall gc(seg_init_func(), f_seg, pair_func(mode), st, !prof || tev != nullptr, tev != nullptr);
+  const bool in_graph = gc.capturing() || gc.updating();
   // the three launches of the call (k_init, k_seg, k_pair) on stream s
-  auto enqueue = [&](cudaStream_t s) -> bool {
+  auto enqueue = [&](cudaStream_t s, bool graph) -> bool {
     if (seg_run(L, scratch, in, H, s) != cudaSuccess) return false;
-    if (prof) cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+    if (prof && !graph) cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+    if (prof && graph && gc.capturing() && cudaEventRecordWithFlags(tev[0], s, cudaEventRecordExternal) != cudaSuccess) return false;
     if (dispatch_pair(mode, P, A, s) != cudaSuccess) return false;
-    if (prof) { cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s); ++g_prof.n; }
+    if (prof && !graph) cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s);
+    if (prof && graph && gc.capturing() && cudaEventRecordWithFlags(tev[1], s, cudaEventRecordExternal) != cudaSuccess) return false;
     return true;
   };
-  const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;
-  // one launch of a cached CUDA graph (not while the pair kernel is being timed with events)
-  GraphCall gc(seg_init_func(), f_seg, pair_func(mode), st, !prof);
-  const bool ok = enqueue(gc.run_stream);
+  const bool ok = enqueue(gc.run_stream, in_graph);
+  bool timed_in_graph = prof && in_graph;
   if (gc.finish(ok) != cudaSuccess) {
     if (gc.mode == 0) return RN_ERR_LAUNCH;
     cudaGetLastError();
-    if (!enqueue(st)) return RN_ERR_LAUNCH;       // (graphs are switched off for this thread from now on)
+    timed_in_graph = false;
+    if (!enqueue(st, false)) return RN_ERR_LAUNCH;       // (graphs are switched off for this thread from now on)
+  }
+  if (prof) {
+    g_prof.ms[g_prof.n] = -1.f;
+    if (timed_in_graph) {
+      // measurement pass: wait for the call and read the pair kernel's time from the graph's two events
+      float ms = 0.f;
+      if (cudaStreamSynchronize(st) != cudaSuccess || cudaEventElapsedTime(&ms, tev[0], tev[1]) != cudaSuccess) return RN_ERR_LAUNCH;
+      g_prof.ms[g_prof.n] = ms;
+    }
+    ++g_prof.n;
   }
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
 }

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4
 // each, so the gaps between them count.  When a GraphCall is active on this thread the launches below do not go to
 // the stream: they set the parameters of the three kernel nodes of a cached, instantiated CUDA graph, which the
 // caller then launches once (smaller inter-kernel gaps, one driver call instead of three).
-struct GraphSlot { int dev; const void* f[3]; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
+struct GraphSlot { int dev; const void* f[3]; bool timed; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
 static thread_local GraphSlot tl_slots[24];
 static thread_local int tl_nslots = 0;
 static thread_local GraphSlot* tl_update = nullptr;      // slot whose nodes receive the launches of this thread
@@ -94,7 +94,18 @@ static cudaError_t emit(const void* f, dim3 grid, dim3 block, size_t smem, void*
 
 const void* seg_init_func() { return (const void*)k_init; }
 
-GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow)
+cudaEvent_t* timed_events() {
+  static thread_local cudaEvent_t ev[2] = {nullptr, nullptr};
+  static thread_local bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaEventCreate(&ev[0]) != cudaSuccess || cudaEventCreate(&ev[1]) != cudaSuccess) { ev[0] = ev[1] = nullptr; cudaGetLastError(); }
+  }
+  return ev[0] && ev[1] ? ev : nullptr;
+}
+
+GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, cudaStream_t user_stream, bool allow,
+                     bool timed)
     : st(user_stream), run_stream(user_stream) {
   static const char* off = getenv("RN_GRAPH");
   if (!allow || tl_graph_broken || (off && *off == '0')) return;
@@ -104,7 +115,7 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (cudaGetDevice(&dev) != cudaSuccess) return;
   for (int i = 0; i < tl_nslots; ++i) {
     GraphSlot& g = tl_slots[i];
-    if (g.dev == dev && g.f[0] == f_init && g.f[1] == f_seg && g.f[2] == f_pair) {
+    if (g.dev == dev && g.f[0] == f_init && g.f[1] == f_seg && g.f[2] == f_pair && g.timed == timed) {
       slot = &g; tl_update = slot; tl_next = 0; mode = 1;
       return;
     }
@@ -113,7 +124,7 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (!tl_cap_stream && cudaStreamCreateWithFlags(&tl_cap_stream, cudaStreamNonBlocking) != cudaSuccess) { tl_graph_broken = true; return; }
   if (cudaStreamBeginCapture(tl_cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { tl_graph_broken = true; cudaGetLastError(); return; }
   slot = &tl_slots[tl_nslots];
-  slot->dev = dev; slot->f[0] = f_init; slot->f[1] = f_seg; slot->f[2] = f_pair;
+  slot->dev = dev; slot->f[0] = f_init; slot->f[1] = f_seg; slot->f[2] = f_pair; slot->timed = timed;
   run_stream = tl_cap_stream; tl_capturing = true; mode = 2;
 }
 
@@ -133,8 +144,10 @@ cudaError_t GraphCall::finish(bool ok) {
   if (e != cudaSuccess || !ok || !graph) { tl_graph_broken = true; if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return ok ? e : cudaErrorUnknown; }
   cudaGraphNode_t nodes[8]; size_t n = 8;
   bool found[3] = {false, false, false};
-  if (cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess && n == 3) {
+  if (cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess && n == (slot->timed ? 5u : 3u)) {
     for (size_t i = 0; i < n; ++i) {
+      cudaGraphNodeType ty;
+      if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
       cudaKernelNodeParams p{};
       if (cudaGraphKernelNodeGetParams(nodes[i], &p) != cudaSuccess) continue;
       for (int k = 0; k < 3; ++k) if (!found[k] && p.func == slot->f[k]) { slot->node[k] = nodes[i]; found[k] = true; break; }

@@ -62,7 +62,6 @@ class HostPairwise:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().rn_host_pairwise_create(B_max, K, depth, C.byref(self._h)), "rn_host_pairwise_create")
         self.B_max, self.K, self.depth = B_max, K, depth
-        self._args = [_lib.PairwiseArgs() for _ in range(depth)]
         self._keep = [None] * depth                  # the buffers of a submit stay referenced until its wait
 
     def submit(self, keys, logits, labels, *, loss, n_pair_f32, n_pair, dlogits, rw_pos=None, rw_neg=None, row_ok=None,

@@ -120,3 +120,25 @@ def test_gather_in_first_kernel_and_peer_reduce():
     assert all(abs(l - ref["loss"]) <= 1e-5 * abs(ref["loss"]) for l in losses), (losses, ref["loss"])
     err = np.abs(np.concatenate(grad) - ref["grad"])
     assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all(), err.max()
+
+
+@pytest.mark.parametrize("in_graph", [1, 0])
+def test_pair_kernel_timing_aid(in_graph):
+    """rn_profile_enable_ex: the pair kernel's time per call, from event-record nodes inside the call's CUDA graph
+    (in_graph = 1) or from stream events around a plain launch (0); results stay correct while it is on."""
+    from rec_now_b200 import _lib
+    lib = _lib.lib()
+    d = G.cfg2()
+    ref = S.pairwise(d["s"], d["y"], d["g"])
+    assert lib.rn_profile_enable_ex(4, in_graph) == 0
+    try:
+        for _ in range(6):                     # two more calls than slots: the extra ones are simply not timed
+            out = run_pairwise(d["s"], d["y"], d["g"])
+        torch.cuda.synchronize()
+        ms = (C.c_float * 4)(); n = C.c_int32(0)
+        assert lib.rn_profile_collect(ms, 4, C.byref(n)) == 0
+    finally:
+        lib.rn_profile_disable()
+    assert n.value == 4
+    assert all(0.002 < t < 5.0 for t in ms), list(ms)
+    check_pairwise(out, ref, ctx=f"timing aid in_graph={in_graph}")
