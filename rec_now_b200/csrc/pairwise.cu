@@ -200,6 +200,7 @@ struct KpArgs {
   const uint2* aj; const float *ss, *sy, *swp, *swn; const uint2* units; const uint2* blk; u32 nib; u32 target_units;
   u32 cost_gen;              // cost of a J-block of a range R2 in eighths of a fast tile (see vcost)
   u32 cost_switch;           // fixed cost of a virtual block (row loads, flush of the row accumulators), same unit
+  u32 cost_straddle, cost_levels;   // extra cost of a block that holds a label-level boundary; boundaries per range (see vcost)
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
   // finalisation
   const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
@@ -246,22 +247,30 @@ __device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) 
   return lo;
 }
 
-// Cost of one J-block (32 negatives) of a virtual block in eighths of a fast tile.  Range R1 of an I-block (the rows of
-// the group that began before the block) is almost all fast tiles; range R2 (groups that begin inside the block) is
-// general tiles (~2x, measured; a warp that finishes early costs little -- its SMSP neighbours speed up -- while a late
-// one runs alone and cannot fill the SFU pipe, so the estimate leans to the pessimistic side).
-constexpr u32 kCostFast = 8;
-__device__ __forceinline__ u32 vcost(u32 v, u32 cgen) { return (v & 1u) ? cgen : kCostFast; }
+// Cost of one J-block (32 negatives) of a virtual block; a fast tile costs 8 * kCostUnit.  Range R1 of an I-block (the
+// rows of the group that began before the block) is fast tiles plus the blocks that hold a label-level boundary; range
+// R2 (groups that begin inside the block) is general tiles (a warp that finishes early costs little -- its SMSP
+// neighbours speed up -- while a late one runs alone and cannot fill the SFU pipe, so the estimates lean to the
+// pessimistic side).
+constexpr u32 kCostUnit = 4;                 // cost units per eighth of a fast tile (sub-eighth resolution for the averages below)
+constexpr u32 kCostFast = 8 * kCostUnit;
+// A range R1 of nt J-blocks crosses up to `lv` label-level boundaries of its group; a block that holds one is scored in
+// 2-3 passes (runs_tile) or as a general tile.  Short ranges (medium-sized groups) consist mostly of such blocks, long
+// ones hardly notice: cost per block = 8 + cstr * min(nt, lv) / nt (rounded up).  lv = 0: label levels play no role.
+__device__ __forceinline__ u32 vcost(u32 v, u32 nt, u32 cgen, u32 cstr, u32 lv) {
+  if (v & 1u) return cgen;
+  return kCostFast + (cstr * min(nt, lv) + nt - 1u) / max(nt, 1u);
+}
 
 // Position `pos` of the cost line -> (virtual block, J-block, eighth).  s_pi: cost prefix over the virtual blocks,
 // s_jn: first J-block | J-block count << 16 of every virtual block.
 __device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32 csw,
-                                            u32& v, u32& jb, u32& e) {
+                                            u32 cstr, u32 lv, u32& v, u32& jb, u32& e) {
   if (pos >= tot) { v = nvb; jb = 0; e = 0; return; }
   v = last_le(s_pi, 0, nvb, pos);
   u32 o = pos - s_pi[v];
   o = o > csw ? o - csw : 0u;                      // (the first csw units of a block stand for its row loads / flush)
-  const u32 c = vcost(v, cgen), q = o / c;
+  const u32 c = vcost(v, s_jn[v] >> 16, cgen, cstr, lv), q = o / c;
   jb = (s_jn[v] & 0xFFFFu) + q;
   e = ((o - q * c) * 8u) / c;
 }
@@ -327,8 +336,8 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // Work = the (I-block x J-block) tiles of the staircase, laid out on a COST LINE: virtual block after virtual block
-  // (the two J ranges of every I-block), J-block after J-block, a J-block of range R1 costing 8 and one of range R2
-  // costing 13 (see vcost).  For B <= 524288 the kernel partitions the line STATICALLY: the costs are prefix-summed
+  // (the two J ranges of every I-block), J-block after J-block, each with the cost vcost() estimates for it (a fast tile
+  // = 8 eighths; more for general tiles and for blocks that hold a label-level boundary).  For B <= 524288 the kernel partitions the line STATICALLY: the costs are prefix-summed
   // over the virtual blocks (shared memory, every CTA redundantly) and every warp of the grid takes ONE contiguous
   // piece of exactly the same length, cut at a granularity of one eighth of a tile (4 of the 32 rotation steps).
   // Pieces are dealt to the warps interleaved over the SMs (piece r -> CTA r % grid), so every SM gets the same mix.
@@ -358,13 +367,14 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   u32 cb = 0, cj = 0, ce = 0, zb = 0, zj = 0, ze = 0;
   bool st_done = true;
   u32 U = 0;
+  const u32 lv_cost = DIFF ? A.cost_levels : 0u;     // (label levels only split blocks under label-gain weights)
   if (own_list) {
     u32 msum = 0;
     for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
       u32 jf;
       const u32 nt = vblock_tiles(A.blk, v, jf);
       s_jn[v] = nt ? (jf | (nt << 16)) : 0u;
-      s_pi[v] = nt ? nt * vcost(v, A.cost_gen) + A.cost_switch : 0u;
+      s_pi[v] = nt ? nt * vcost(v, nt, A.cost_gen, A.cost_straddle, lv_cost) + A.cost_switch : 0u;
       msum += nt;
     }
     __syncthreads();
@@ -385,7 +395,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 len = r1 - r0, q = len / wpr, rem = len - q * wpr;  // len * r / wpr without 64-bit division
       const u32 pos = r0 + q * r + (rem * r) / wpr;
       u32 v, jb, e;
-      resolve_pos(pos, tot, nvb, s_pi, s_jn, A.cost_gen, A.cost_switch, v, jb, e);
+      resolve_pos(pos, tot, nvb, s_pi, s_jn, A.cost_gen, A.cost_switch, A.cost_straddle, lv_cost, v, jb, e);
       s_bnd[3 * threadIdx.x] = v; s_bnd[3 * threadIdx.x + 1] = jb; s_bnd[3 * threadIdx.x + 2] = e;
     }
     __syncthreads();
@@ -924,9 +934,13 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
   static const int cost_gen = tune_int("RN_PAIR_COST_GEN", 17);
-  A.cost_gen = (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));
+  A.cost_gen = kCostUnit * (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));            // (knobs are in eighths of a fast tile)
   static const int cost_switch = tune_int("RN_PAIR_COST_SWITCH", 4);
-  A.cost_switch = (u32)(cost_switch < 0 ? 0 : (cost_switch > 64 ? 64 : cost_switch));
+  A.cost_switch = kCostUnit * (u32)(cost_switch < 0 ? 0 : (cost_switch > 64 ? 64 : cost_switch));
+  static const int cost_straddle = tune_int("RN_PAIR_COST_STRADDLE", 12);
+  static const int cost_levels = tune_int("RN_PAIR_COST_LEVELS", 4);
+  A.cost_straddle = kCostUnit * (u32)(cost_straddle < 0 ? 0 : (cost_straddle > 64 ? 64 : cost_straddle));
+  A.cost_levels = (u32)(cost_levels < 0 ? 0 : (cost_levels > 64 ? 64 : cost_levels));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
   A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
