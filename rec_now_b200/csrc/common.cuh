@@ -180,6 +180,9 @@ __device__ __forceinline__ void grid_sync(u32* bar, u32& epoch, u32* err) {
 // Wait for the previous kernel of the stream (programmatic dependent launch, see launch_coop); a no-op when the kernel
 // was launched without the attribute.
 __device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Programmatic dependent launch, primary side: the next kernel of the stream / graph may be scheduled from now on (its
+// CTAs start on SMs as they become free and block in grid_dep_wait until this grid has completed and flushed).
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ u64 globaltimer() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // phase timestamp i (CTA 0, thread 0 only)

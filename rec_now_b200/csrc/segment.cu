@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4
                                               GatherArgs G) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
+  grid_dep_launch();
   const uint4 z = make_uint4(0, 0, 0, 0), f = make_uint4(~0u, ~0u, ~0u, ~0u);
   if (G.world) {
     // global mode: the all-gather -- every rank's packed row block, read over NVLink from its peer mapping (4 loads
@@ -83,7 +84,8 @@ static cudaError_t emit(const void* f, dim3 grid, dim3 block, size_t smem, void*
     // programmatic dependent launch: the launch is processed while the previous kernel of the stream still runs; the
     // kernel itself waits for that kernel's completion and memory flush with griddepcontrol.wait (grid_dep_wait)
     static const char* nopdl = getenv("RN_NO_PDL");
-    if (!tl_capturing && !(nopdl && *nopdl == '1')) {
+    static const char* graphpdl = getenv("RN_GRAPH_PDL");       // (RN_GRAPH_PDL=0: no programmatic edges inside the captured graph)
+    if ((!tl_capturing || !(graphpdl && *graphpdl == '0')) && !(nopdl && *nopdl == '1')) {
       attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[na].val.programmaticStreamSerializationAllowed = 1; ++na;
     }

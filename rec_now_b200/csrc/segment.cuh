@@ -400,6 +400,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   u32 epoch = 0;
   Ctl* ctl = S.ctl;
   grid_dep_wait();
+  grid_dep_launch();
   stamp(ctl, 0);
   Plan pl;
   if (S.merged) {
