@@ -59,6 +59,7 @@ static thread_local int tl_nslots = 0;
 static thread_local GraphSlot* tl_update = nullptr;      // slot whose nodes receive the launches of this thread
 static thread_local int tl_next = 0;
 static thread_local bool tl_capturing = false;           // launches go to the private capture stream (graph build)
+static thread_local bool tl_capture_timed = false;       // ... of a timed graph (event-record nodes between the kernels: no programmatic edges)
 static thread_local bool tl_graph_broken = false;        // a graph API call failed: direct launches from now on
 static thread_local cudaStream_t tl_cap_stream = nullptr;
 static thread_local long long tl_graph_launches = 0;   // calls of this thread that went out as one graph launch
@@ -85,7 +86,7 @@ static cudaError_t emit(const void* f, dim3 grid, dim3 block, size_t smem, void*
     // kernel itself waits for that kernel's completion and memory flush with griddepcontrol.wait (grid_dep_wait)
     static const char* nopdl = getenv("RN_NO_PDL");
     static const char* graphpdl = getenv("RN_GRAPH_PDL");       // (RN_GRAPH_PDL=0: no programmatic edges inside the captured graph)
-    if ((!tl_capturing || !(graphpdl && *graphpdl == '0')) && !(nopdl && *nopdl == '1')) {
+    if ((!tl_capturing || (!tl_capture_timed && !(graphpdl && *graphpdl == '0'))) && !(nopdl && *nopdl == '1')) {
       attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[na].val.programmaticStreamSerializationAllowed = 1; ++na;
     }
@@ -127,7 +128,7 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (cudaStreamBeginCapture(tl_cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { tl_graph_broken = true; cudaGetLastError(); return; }
   slot = &tl_slots[tl_nslots];
   slot->dev = dev; slot->f[0] = f_init; slot->f[1] = f_seg; slot->f[2] = f_pair; slot->timed = timed;
-  run_stream = tl_cap_stream; tl_capturing = true; mode = 2;
+  run_stream = tl_cap_stream; tl_capturing = true; tl_capture_timed = timed; mode = 2;
 }
 
 cudaError_t GraphCall::finish(bool ok) {

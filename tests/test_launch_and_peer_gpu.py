@@ -141,4 +141,5 @@ def test_pair_kernel_timing_aid(in_graph):
         lib.rn_profile_disable()
     assert n.value == 4
     assert all(0.002 < t < 5.0 for t in ms), list(ms)
+    assert lib.rn_debug_graph_launches() >= 0, "a graph API call failed: the thread fell back to plain launches"
     check_pairwise(out, ref, ctx=f"timing aid in_graph={in_graph}")
