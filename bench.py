@@ -264,7 +264,17 @@ def ours(args):
     barrier()
     if sampler:
         sampler.timed[1] = time.perf_counter()
-    t_ms = sum(a.elapsed_time(b) for a, b in evs)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    t_ms = sum(step_ms)
+    # the same K steps back to back, no L2 flush between them (what a training loop sees; reported beside `value`)
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    b0.record()
+    for k in range(K):
+        out = step()
+    b1.record()
+    barrier()
+    b2b_ms = b0.elapsed_time(b1) / K
     graph_calls = int(lib.rn_debug_graph_launches()) - g0       # steps that went out as one CUDA-graph launch
     # ---- the dominant kernel alone: the same steps again with CUDA events around the k_pair launch (the events sit
     #      between the kernels of a call, so this pass uses plain launches instead of the cached graph) -----------
@@ -444,6 +454,10 @@ def ours(args):
             "metric": "pairwise_loss_fwd_bwd_pairs_per_s", "value": value, "unit": "pairs/s",
             "samples_per_s": rows_total * K / (t_ms * 1e-3), "n_pair_per_step": n_pair,
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+            "step_us": {"median": float(np.median(step_ms)) * 1e3, "p10": float(np.percentile(step_ms, 10)) * 1e3,
+                        "p90": float(np.percentile(step_ms, 90)) * 1e3, "back_to_back_no_flush": b2b_ms * 1e3,
+                        "note": "rank 0's per-step CUDA events (single-call latency, cold L2); back to back = the K "
+                                "steps enqueued without the flush, one event pair around all of them"},
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded Zipf groups)",
             "config": {"workload": name, "rows_per_gpu": ROWS_PER_GPU, "seed": 0,
                        "l2": "flushed between timed steps (256 MiB write); inputs ~1.6 MB/GPU",

@@ -13,7 +13,6 @@ dense_ref.py    op-for-op float32 NumPy restatement of the reference's dense
                 row-major pair order.  Usable to B ~ 8K.
 seg_ref.py      float64 segmented restatement (truth for loss / gradient at
                 any B), NumPy.
-seg_oracle.c    the same segmented algorithm in plain C (gcc), for B = 65536+.
 generators.py   the seeded synthetic generators of SURVEY.md section 8d.
 torch_dense.py  op-for-op torch-CPU float32 restatement with autograd backward:
                 the timed "reference restatement (torch CPU), not TensorFlow"
