@@ -154,6 +154,13 @@ def pick_cpu_rows(d, budget_s, steps):
 
 def run_cpu_dense(d, steps, warmup, budget_s):
     import torch
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers: undo that here)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if ncpu > torch.get_num_threads():
+        torch.set_num_threads(ncpu)
     rows = pick_cpu_rows(d, budget_s, steps + warmup)
     step = cpu_dense_step_fn(d, rows)
     for _ in range(warmup):
