@@ -96,3 +96,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dp, f)
+
+
+def test_host_front_end_validation_without_gpu(lib):
+    """rn_host_pairwise_*: bad arguments are rejected before any CUDA call; without a device create fails with a
+    status code (no fallback, no abort)."""
+    h = C.c_void_p()
+    assert lib.rn_host_pairwise_create(0, 1, 2, C.byref(h)) == 1          # RN_ERR_ARG
+    assert lib.rn_host_pairwise_create(1024, 0, 2, C.byref(h)) == 1
+    assert lib.rn_host_pairwise_create(1024, 1, 0, C.byref(h)) == 1
+    assert lib.rn_host_pairwise_create(1024, 1, 2, None) == 1
+    t = C.c_int32(0)
+    assert lib.rn_host_pairwise_submit(None, None, C.byref(t)) == 1
+    assert lib.rn_host_pairwise_wait(None, 0) == 1
+    assert lib.rn_host_pairwise_destroy(None) == 0
+    import torch
+    if not torch.cuda.is_available():
+        rc = lib.rn_host_pairwise_create(1024, 1, 2, C.byref(h))
+        assert rc in (4, 6) and not h.value                               # RN_ERR_LAUNCH / RN_ERR_NO_DEVICE
