@@ -2,7 +2,7 @@
  * recnow_b200.h — C ABI of librecnow_b200.so: the B200 (sm_100a) implementation of rec_now's in-batch
  * ranking-loss hot path.  This header is the drop-in boundary: plain C, plain pointers and sizes, no
  * TensorFlow / torch / C++ types.  A TensorFlow custom op (rec_now_b200/tf_ops/recnow_tf_ops.cc), the torch
- * front end (rec_now_b200/rec_block/*.py via ctypes) and the tests all bind exactly these symbols.
+ * front end (the rec_now_b200/rec_block modules via ctypes) and the tests all bind exactly these symbols.
  *
  * Reference interfaces replaced (all under /root/reference/rec_now/rec_block/):
  *   pairwise_loss_from_batch.py:228-279  pairwise_loss(...)            -> rn_pairwise_fwd_bwd

@@ -114,3 +114,23 @@ def test_host_front_end_validation_without_gpu(lib):
     if not torch.cuda.is_available():
         rc = lib.rn_host_pairwise_create(1024, 1, 2, C.byref(h))
         assert rc in (4, 6) and not h.value                               # RN_ERR_LAUNCH / RN_ERR_NO_DEVICE
+
+
+def test_header_is_plain_c_and_example_links(lib, tmp_path):
+    """include/recnow_b200.h compiles as strict C99 (no C++ types cross the boundary) and the C example links against
+    the shared library; without a GPU it reports the missing device through the status code and exits 0."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = str(tmp_path / "host_pairwise")
+    libdir = os.path.join(ROOT, "rec_now_b200")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "host_pairwise.c"), "-o", exe, "-L", libdir, "-lrecnow_b200",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "librecnow_b200 version 102" in r.stdout
