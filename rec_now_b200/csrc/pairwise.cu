@@ -368,6 +368,14 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   bool st_done = true;
   u32 U = 0;
   const u32 lv_cost = DIFF ? A.cost_levels : 0u;     // (label levels only split blocks under label-gain weights)
+  // Occurrence weight of every row for the final pass: the chain cnt -> cprim -> pow is two dependent round trips, on
+  // the critical path if the last warp to leave the pair loop has to walk it in front of the grid barrier.  It is
+  // walked here instead, its loads spread over the prologue, and the weight parked in the (otherwise unused) lossrow
+  // column: each thread reads back what it wrote itself.
+  const u32 gtid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool park = !DYN && fold_power != 0.f;
+  u32 park_pg = kEmpty; u64 park_ch = 0;
+  if (park && gtid0 < B) park_pg = A.cnt[gtid0];
   if (own_list) {
     u32 msum = 0;
     for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     __syncthreads();
     stamp(ctl, 11);
+    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
     block_excl_scan(s_pi, nvb, s_scan);
     stamp(ctl, 12);
     const u32 tot = s_pi[nvb];
@@ -413,7 +422,15 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   } else {
     U = ld_relaxed(&ctl->n_units);
+    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
     __syncthreads();
+  }
+  if (park) {
+    if (gtid0 < B) A.lossrow[gtid0] = occ_pow(park_ch, fold_power);
+    for (u32 p = gtid0 + gridDim.x * blockDim.x; p < B; p += gridDim.x * blockDim.x) {
+      const u32 pg = A.cnt[p];
+      A.lossrow[p] = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
+    }
   }
   stamp(ctl, 16);
   double lsum = 0.0;
@@ -654,25 +671,18 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
       if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
-    // the row permutation, the pair count and the occurrence counts are final before this kernel starts: fetch them
-    // ahead of the barrier
-    const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
-    const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
-    const float gscale = P.factor / denom;
-    auto row_scale = [&](u32 p) -> float {
-      if (fold_power == 0.f) return gscale;
-      const u32 pg = A.cnt[p];
-      return pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) * gscale : 0.f;
-    };
-    const u32 row0 = gtid < B ? A.perm[gtid] : 0u;
-    const float sc0 = gtid < B ? row_scale(gtid) : 0.f;
+    // nothing else in front of the barrier: the last warp to leave the pair loop sets the pace
     stamp(ctl, 21);
     grid_sync(&ctl->bar2, epoch, &ctl->err);
     stamp(ctl, 22);
+    // one round trip of independent loads (pair count, permutation, parked occurrence weight, gradient sum), then the store
+    const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
+    const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
+    const float gscale = P.factor / denom;
+    auto row_scale = [&](u32 p) -> float { return fold_power == 0.f ? gscale : A.lossrow[p] * gscale; };
     // output index: plain, or chunked for a following reduce-scatter (row i -> (i / Bl) * out_chunk + i % Bl)
     auto out_at = [&](u32 row) -> size_t { return P.out_chunk ? (size_t)(row / P.rm.Bl) * P.out_chunk + (row % P.rm.Bl) : row; };
-    if (gtid < B) P.dlogits[out_at(row0)] = A.gacc[gtid] * sc0;
-    for (u32 p = gtid + gthreads; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
+    for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
       const float lossv = (float)(tot / (double)denom);
