@@ -18,8 +18,11 @@
  * Conventions
  *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
  *     including the scratch arena (size from rn_*_scratch_bytes).  The library never allocates, never
- *     synchronises the stream (except the _host count read-backs, which say so) and keeps no state between
- *     calls: calls on different streams with different scratch arenas are independent.
+ *     synchronises the stream (except the _host count read-backs, which say so).  Calls on different
+ *     streams with different scratch arenas are independent.  State the library does keep, per host thread: a small
+ *     cache of instantiated CUDA graphs (one per device and kernel variant, never freed), read-once getenv() tuning
+ *     knobs, and the process-global measurement aid rn_profile_*.  State the CALLER may let it keep: a scratch arena
+ *     declared persistent (rn_pairwise_args.scratch_persistent) carries its clean regions from call to call.
  *   - All work is enqueued on `stream` (a cudaStream_t passed as void*); calls are CUDA-graph capturable.
  *   - Return value: RN_OK or an RN_ERR_* code; rn_strerror() names it.  No exceptions, no abort().
  *   - Device pointers must be 16-byte aligned (RN_ERR_ALIGN otherwise).
@@ -102,6 +105,17 @@ typedef struct rn_pairwise_args {
    * ranks have written their blocks (a device-side barrier on the stream) before the call is enqueued. */
   const void* peer_blocks[8];
   void* gather_dst;
+  /* Persistent scratch arena (0 = off: the arena may hold anything, the call starts with an initialisation kernel).
+   * scratch_persistent != 0 promises that the arena was zeroed once (rn_pairwise_scratch_init) and has since been
+   * written by nothing but rn_pairwise_fwd_bwd calls with the same K and the same scratch_rows: every call leaves the
+   * regions the next one needs clean, so the initialisation kernel is dropped, and (one key column, contiguous rows,
+   * part_count == 1) group segmentation takes the sort-free counting path.  After a device-side error
+   * (rn_last_device_error != 0) zero the arena again.
+   * scratch_rows: the row capacity the arena was sized for (rn_pairwise_scratch_bytes(scratch_rows, K)); 0 = B.  A
+   * persistent arena keeps ONE layout, so batches of different sizes B <= scratch_rows may share it. */
+  int32_t scratch_persistent;
+  int32_t reserved0;
+  int64_t scratch_rows;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {
@@ -131,6 +145,9 @@ int rn_canon_keys_f64(const double* ids, int64_t B, int64_t* keys_out, uint8_t* 
 
 /* ---- pairwise --------------------------------------------------------------------------------------- */
 size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K);
+/* Zero a scratch arena (one cudaMemsetAsync on `stream`): required once before the first call that declares the arena
+ * persistent (rn_pairwise_args.scratch_persistent), and again after anything else wrote into it. */
+int rn_pairwise_scratch_init(void* scratch, size_t scratch_bytes, void* stream);
 int rn_pairwise_fwd_bwd(const rn_pairwise_args* args, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Global mode (one process per GPU): pack this rank's row block for ONE all-gather -- [keys K x int64[B_loc]]

@@ -20,7 +20,7 @@ ERR_NAMES = {1: "RN_ERR_ARG", 2: "RN_ERR_ALIGN", 3: "RN_ERR_SCRATCH", 4: "RN_ERR
 # every symbol include/recnow_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
     "rn_version", "rn_strerror", "rn_canon_keys_f32", "rn_canon_keys_f64",
-    "rn_pairwise_scratch_bytes", "rn_pairwise_fwd_bwd",
+    "rn_pairwise_scratch_bytes", "rn_pairwise_scratch_init", "rn_pairwise_fwd_bwd",
     "rn_pair_indices_scratch_bytes", "rn_pair_indices_count", "rn_pair_indices_fill",
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
@@ -49,6 +49,7 @@ class PairwiseArgs(C.Structure):
         ("dlogits", C.c_void_p), ("row_pairs", C.c_void_p),
         ("block_rows", C.c_int64), ("block_stride", C.c_int64), ("out_chunk", C.c_int64),
         ("peer_blocks", C.c_void_p * 8), ("gather_dst", C.c_void_p),
+        ("scratch_persistent", C.c_int32), ("reserved0", C.c_int32), ("scratch_rows", C.c_int64),
     ]
 
 
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
         getattr(L, name).argtypes = [vp, i64, vp, vp, C.c_int, vp]
     L.rn_pairwise_scratch_bytes.restype = sz
     L.rn_pairwise_scratch_bytes.argtypes = [i64, i32]
+    L.rn_pairwise_scratch_init.argtypes = [vp, sz, vp]
     L.rn_pairwise_fwd_bwd.argtypes = [C.POINTER(PairwiseArgs), vp, sz, vp]
     L.rn_pairwise_fwd_bwd.restype = C.c_int
     L.rn_pair_indices_scratch_bytes.restype = sz

@@ -150,7 +150,7 @@ extern "C" int rn_last_device_error(void* scratch, int32_t* err_host, void* stre
   Ctl h;
   if (cudaMemcpyAsync(&h, scratch, sizeof(Ctl), cudaMemcpyDeviceToHost, (cudaStream_t)stream) != cudaSuccess) return RN_ERR_LAUNCH;
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return RN_ERR_LAUNCH;
-  *err_host = (int32_t)h.err;
+  *err_host = (int32_t)(h.err | h.rep_err);      // (rep_err: filed by the last CTA of a finished pairwise call)
   return RN_OK;
 }
 
@@ -161,8 +161,9 @@ extern "C" int rn_debug_timestamps(void* scratch, uint64_t* ts_host, int32_t cap
   if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) return RN_ERR_LAUNCH;
   for (int i = 0; i < capacity && i < 24; ++i) ts_host[i] = h.ts[i];
   for (int i = 24; i < capacity && i < 32; ++i) ts_host[i] = h.dbg[i - 24];
-  if (capacity > 32) ts_host[32] = ((uint64_t)h.unit_c << 32) | h.n_units;
-  if (capacity > 33) ts_host[33] = h.n_tiles;
+  if (capacity > 32) ts_host[32] = ((uint64_t)(h.unit_c | h.rep_unit_c) << 32) | (h.n_units | h.rep_n_units);
+  if (capacity > 33) ts_host[33] = h.n_tiles | h.rep_n_tiles;
+  if (capacity > 35) ts_host[35] = h.path | h.rep_path;          // segmentation path of the call: 1 counting, 2 radix
   if (capacity > 34) ts_host[34] = (uint64_t)make_layout(1, 1).gstat;   // (layout probe for debug tools: see scripts/)
   return RN_OK;
 }

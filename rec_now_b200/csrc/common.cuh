@@ -29,22 +29,29 @@ struct RowMap {
   __host__ __device__ __forceinline__ size_t i1(u32 i) const { return Bl ? (size_t)(i / Bl) * s1 + (i % Bl) : i; }
 };
 
-// Device-side control block (zero-initialised by k_init at the start of every call).
+// Device-side control block.  Zeroed by k_init on the launch paths that have one; on the PERSISTENT path (see
+// rn_pairwise_args.scratch_persistent) the arena is zeroed once by the caller and the last CTA of every call puts the
+// block back into its clean state (all zero except the barrier generations and the report of the finished call).
 struct Ctl {
   u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range
-  u32 bar;                      // grid barrier arrivals, segmentation kernel
-  u32 bar2;                     // grid barrier arrivals, pair kernel
+  u32 bar_cnt, bar_gen;         // grid barrier of the segmentation kernel: arrivals (self-resetting), generation
+  u32 bar2_cnt, bar2_gen;       // grid barrier of the pair kernel
   u32 k2_ticket;                // dynamic work-unit ticket of the pair kernel
-  u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars)
+  u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars / cleans up)
   u32 n_units, unit_c;          // work list: number of units, J-blocks per unit
   u32 n_groups;                 // distinct groups (listwise)
   u32 n_valid;                  // valid lists (listwise)
-  u32 err;                      // device-side error flags (0 ok; 1 barrier timeout, 2 pair capacity)
+  u32 err;                      // device-side error flags (0 ok; 1 barrier timeout, 2 pair capacity, 4 hash table full)
+  u32 fallback;                 // counting path: a label outside the level menu / a non-positive row weight was seen -> radix path
+  u32 cursor;                   // counting path: next free sorted position (group base allocation)
+  u32 path;                     // which segmentation ran (1 counting, 2 radix); report only
   u64 n_pair;                   // exact kept-pair count
   u64 n_tiles;                  // total 32x32 micro-tiles in the work list
   double loss_sum;              // sum_p wocc * lossrow[p]   (log2 units)
   u64 ts[24];                   // phase timestamps (%globaltimer, ns) written by CTA 0: measurement aid
   u64 dbg[8];                   // pair-kernel debug tallies (RN_PAIR_DEBUG=1): see k_pair
+  // report of the last finished call (copied here before the working fields are reset; read by the rn_debug_* calls)
+  u32 rep_err, rep_path, rep_n_units, rep_unit_c; u64 rep_n_tiles;
 };
 
 // Sort plan.  Compact sort key = (gid << labbits) | ((enc_label >> labshift) & mask): only the varying bit
@@ -83,7 +90,23 @@ struct Layout {
   size_t table, table1;
   // plain
   size_t labpart, slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
+  // counting path (group_count.cuh): group records (clean = zero between calls), created-group lists per 512-row tile,
+  // sorted group index column
+  size_t rec, glist, gcount, sgrp;
+  int64_t Bcap;
 };
+
+// Group record of the counting segmentation path (64 bytes, one per hash slot + one for the rows that cannot pair).
+// The first 16 bytes are claimed with ONE 128-bit compare-and-swap (key + creator row), so a probe never needs a second
+// dependent load to compare keys.  All zero = free.
+struct __align__(16) GRec {
+  u64 key; u32 rep1; u32 base;  // key, creator row + 1 (0 = free), first sorted position of the group
+  u32 cnt[8];                   // rows per label level; rewritten by the offsets phase to the level starts relative to base
+  float wocc; u32 pad0;         // occurrence weight c_h ^ power of the group (non-dynamic pair sets)
+  u64 npair;                    // kept pairs of the group (PW:286-289)
+};
+constexpr int kLevels = 8;       // label levels of the counting path: integer-valued labels -1 .. 6
+constexpr int kGTile = 512;      // rows per tile of the counting path (= kSegThreads)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -95,48 +118,61 @@ inline u32 target_units() {
   return n;
 }
 
-inline Layout make_layout(int64_t B, int K) {
-  Layout L; L.B = B; L.K = K;
+// Offsets depend on the CAPACITY Bcap the arena was sized for (rn_pairwise_args.scratch_rows; = B when 0), the loop
+// bounds (tiles, I-blocks, id bits) on the rows B of the call: a persistent arena keeps one layout for every B <= Bcap.
+inline Layout make_layout(int64_t Bcap, int K, int64_t B = 0) {
+  if (B <= 0) B = Bcap;
+  Layout L; L.B = B; L.K = K; L.Bcap = Bcap;
   L.gbits = B > 1 ? bit_width_u64((uint64_t)(B - 1)) : 1;
-  u32 cap = 1024; while ((int64_t)cap < 2 * B) cap <<= 1;
+  u32 cap = 1024; while ((int64_t)cap < 2 * Bcap) cap <<= 1;
   L.cap = cap;
   L.ipt = (B <= 148 * 1024) ? 2 : 8;                 // sort tile = 1024 rows (<= 148 tiles) or 4096 rows
   L.tile = (u32)(kSegThreads * L.ipt);
   L.ntiles = (u32)((B + L.tile - 1) / L.tile);
   L.nib = (u32)((B + kIB - 1) / kIB);
+  const size_t ipt_cap = (Bcap <= 148 * 1024) ? 2 : 8;
+  const size_t ntiles_cap = (size_t)((Bcap + 1023) / 1024);       // upper bound for either tile size
+  (void)ipt_cap;
+  const size_t nib_cap = (size_t)((Bcap + kIB - 1) / kIB);
+  const size_t Bc = (size_t)Bcap;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
   L.zero_begin = o;
   L.ctl = take(sizeof(Ctl));
   L.hist = take(sizeof(u32) * kMaxPass * kBins);
   L.cprim = take(sizeof(u64) * cap);                   // pair totals per group id (first-occurrence row < B, or table slot < cap)
-  L.th0 = take(sizeof(u32) * (size_t)L.ntiles * kBins);  // tile histograms, buffer 0 (accumulated with atomics in the merged first phase)
+  L.th0 = take(sizeof(u32) * ntiles_cap * kBins);      // tile histograms, buffer 0 (accumulated with atomics in the merged first phase)
   L.zero_end = o;
   L.ones_begin = o;
   L.table = take(sizeof(u32) * cap);
   L.table1 = K > 1 ? take(sizeof(u32) * cap) : L.table;
   L.ones_end = o;
   L.labpart = take(sizeof(u32) * 2 * kInitMaxCtas);
-  L.slot = take(sizeof(u32) * B);
-  L.slot1 = take(sizeof(u32) * B);
-  L.keyA = take(sizeof(u64) * B);
-  L.keyB = take(sizeof(u64) * B);
-  L.valA = take(sizeof(u32) * B);
-  L.valB = take(sizeof(u32) * B);
-  L.tilehist = take(sizeof(u32) * 2 * (size_t)L.ntiles * kBins);    // buffers 1 and 2 (buffer 0 is L.th0)
-  L.aj = take(sizeof(uint2) * B);
-  L.ss = take(sizeof(float) * B);
-  L.sy = take(sizeof(float) * B);
-  L.swp = take(sizeof(float) * B);
-  L.swn = take(sizeof(float) * B);
-  L.gacc = take(sizeof(float) * B);
-  L.lossrow = take(sizeof(float) * B);
-  L.cnt = take(sizeof(u32) * B);
-  L.perm = take(sizeof(u32) * B);
-  L.blk = take(sizeof(uint2) * 2 * (size_t)L.nib);     // two J ranges per I-block
-  L.units = take(sizeof(uint2) * (2 * (size_t)L.nib + target_units() + 1));
-  L.misc = take(sizeof(u64) * (B + 1));
-  L.gstat = take(sizeof(float) * 8 * B);   // listwise per-list records
+  L.slot = take(sizeof(u32) * Bc);
+  L.slot1 = take(sizeof(u32) * Bc);
+  L.keyA = take(sizeof(u64) * Bc);
+  L.keyB = take(sizeof(u64) * Bc);
+  L.valA = take(sizeof(u32) * Bc);
+  L.valB = take(sizeof(u32) * Bc);
+  L.tilehist = take(sizeof(u32) * 2 * ntiles_cap * kBins);    // buffers 1 and 2 (buffer 0 is L.th0)
+  L.aj = take(sizeof(uint2) * Bc);
+  L.ss = take(sizeof(float) * Bc);
+  L.sy = take(sizeof(float) * Bc);
+  L.swp = take(sizeof(float) * Bc);
+  L.swn = take(sizeof(float) * Bc);
+  L.gacc = take(sizeof(float) * Bc);
+  L.lossrow = take(sizeof(float) * Bc);
+  L.cnt = take(sizeof(u32) * Bc);
+  L.perm = take(sizeof(u32) * Bc);
+  L.blk = take(sizeof(uint2) * 2 * nib_cap);           // two J ranges per I-block
+  L.units = take(sizeof(uint2) * (2 * nib_cap + target_units() + 1));
+  L.misc = take(sizeof(u64) * (Bc + 1));
+  L.gstat = take(sizeof(float) * 8 * Bc);   // listwise per-list records
+  const size_t ngt = (Bc + kGTile - 1) / kGTile;
+  L.rec = take(sizeof(GRec) * ((size_t)cap + 1));
+  L.glist = take(sizeof(u32) * ngt * kGTile);
+  L.gcount = take(sizeof(u32) * ngt);
+  L.sgrp = take(sizeof(u32) * Bc);
   L.total = o;
   return L;
 }
@@ -158,19 +194,26 @@ __device__ __forceinline__ u32 ld_acquire(const u32* p) {
   u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
-// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  `epoch` is a per-thread running
-// arrival target (starts at 0; the counter is zeroed by k_init).  The fences publish this CTA's writes and
-// invalidate its L1 so that plain loads after the barrier see other CTAs' data.  A bounded spin turns a
-// scheduling failure into ctl->err instead of a hung GPU.
-__device__ __forceinline__ void grid_sync(u32* bar, u32& epoch, u32* err) {
-  epoch += gridDim.x;
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  bar[0] counts arrivals and is reset by
+// the last arriver, bar[1] is the generation the waiters watch: the pair needs no initialisation beyond "count = 0" and
+// carries nothing from call to call.  The fences publish this CTA's writes and invalidate its L1 so that plain loads
+// after the barrier see other CTAs' data.  A bounded spin turns a scheduling failure (or an arena that was not in its
+// clean state) into ctl->err instead of a hung GPU.
+__device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void grid_sync(u32* bar, u32* err) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    const u32 gen = ld_relaxed(bar + 1);          // (read before arriving: the generation cannot move until this CTA arrives)
     __threadfence();
-    atomicAdd(bar, 1u);
-    u32 spins = 0;
-    while (ld_acquire(bar) < epoch) {
-      if (++spins > (1u << 26)) { atomicOr(err, 1u); break; }
+    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
+      st_relaxed(bar, 0u);
+      st_release(bar + 1, gen + 1u);
+    } else {
+      u32 spins = 0;
+      while (ld_acquire(bar + 1) == gen) {
+        if (++spins > (1u << 23)) { atomicOr(err, 1u); break; }
+      }
     }
     __threadfence();
   }

@@ -77,6 +77,8 @@ extern "C" int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, 
   for (int q = 0; ok && q < depth; ++q) {
     Slot& s = p->slots[q];
     ok = ok && cudaMalloc(reinterpret_cast<void**>(&s.dev), p->slot_bytes) == cudaSuccess;
+    // the slot's scratch arena is persistent (rn_pairwise_args.scratch_persistent): zeroed once, here
+    ok = ok && cudaMemset(s.dev + p->o_scr, 0, p->scratch_bytes) == cudaSuccess;
     ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&s.outs_host), 32, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.cmp_done, cudaEventDisableTiming) == cudaSuccess;
@@ -134,6 +136,7 @@ extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_ar
   a.loss = outs; a.n_pair_f32 = outs + 1; a.n_pair = reinterpret_cast<int64_t*>(outs + 2);
   a.dlogits = reinterpret_cast<float*>(d + p->o_dl);
   a.row_pairs = h->row_pairs ? reinterpret_cast<int64_t*>(d + p->o_rp) : nullptr;
+  a.scratch_persistent = 1; a.scratch_rows = p->B_max;     // (one layout for every batch size this object accepts)
   rc = rn_pairwise_fwd_bwd(&a, d + p->o_scr, p->scratch_bytes, p->s_cmp);
   if (rc) return rc;
   ok = ok && cudaEventRecord(s.cmp_done, p->s_cmp) == cudaSuccess;

@@ -27,6 +27,7 @@ __device__ __forceinline__ float warp_maxf(float v) {
 // Listwise tail of k_seg: bounds -> per-list statistics -> ranks of the valid lists + weighted losses -> gradient,
 // separated by grid barriers (one launch instead of five).
 struct ListwiseTail {
+  static constexpr bool kFast = false;
   BoundsTail bounds;            // astart / gend / perm + gathers of logits (ss) and labels (sy)
   LwParams P;
   const float* ss; const float* sy; float* rec; u32* chunkcnt;
@@ -68,14 +69,13 @@ struct ListwiseTail {
     return nv;
   }
 
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
-                                      u32& epoch) const {
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
     Ctl* ctl = S.ctl;
     const u32 B = P.B, ln = lane_id(), w = threadIdx.x >> 5;
     const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
     const u32* astart = bounds.astart;
-    bounds.run(S, pl, key, val, smem, epoch);
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    bounds.run(S, pl, key, val, smem);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     // ---- per-list statistics; valid lists per 512-position chunk -------------------------------------------
     u32* sm_cnt = smem;                    // [kSegWarps]
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -90,7 +90,7 @@ struct ListwiseTail {
       }
       __syncthreads();
     }
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     // ---- rank of every valid list (exclusive scan of the valid flags over head positions = first-occurrence
     //      order, LW:109), per-list weighted losses, their sum ------------------------------------------------
     u32* sm_scan = smem;                   // [kSegWarps]
@@ -134,7 +134,7 @@ struct ListwiseTail {
       for (int q = 0; q < kSegWarps; ++q) t += sm_d[q];
       if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     // ---- gradient + scalars -------------------------------------------------------------------------------
     const u32 V = ld_relaxed(&ctl->n_valid);
     const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;

@@ -47,11 +47,12 @@ struct PairParams {
 
 // J-block range of virtual block v (2b = range R1 of I-block b, 2b + 1 = range R2, see HeadsTail): first J-block and
 // J-block count; R2 is trimmed so that no (I-block, J-block) tile is listed twice.
+// (a range is stored as (~lo, hi): the counting path builds it with atomicMax from an all-zero = empty record)
 __device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst) {
   const uint2 r = blk[v];
   u32 lo = 0, hi = 0;
-  if (r.y > r.x) { lo = r.x >> 5; hi = (r.y + 31) >> 5; }
-  if (v & 1) { const uint2 r1 = blk[v - 1]; if (r1.y > r1.x) lo = max(lo, (r1.y + 31) >> 5); }
+  if (r.y > ~r.x) { lo = ~r.x >> 5; hi = (r.y + 31) >> 5; }
+  if (v & 1) { const uint2 r1 = blk[v - 1]; if (r1.y > ~r1.x) lo = max(lo, (r1.y + 31) >> 5); }
   jfirst = lo;
   return hi > lo ? hi - lo : 0u;
 }
@@ -60,13 +61,206 @@ __device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst
 // Work units: an I-block (64 sorted rows) x up to C consecutive J-blocks (32 sorted rows each) of its J range.
 // Record = (I-block, first J-block | J-block count << 24).
 struct HeadsTail {
+  static constexpr bool kFast = true;
   PairParams P;
-  uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32 *cnt, *perm;
+  uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32 *cnt, *perm, *sgrp;
   uint2* blk; uint2* units; u32 nib; u64* cprim; const u32* pgid;
   u32 target_units;          // work-list granularity target (units of <= C J-blocks)
 
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
-                                      u32& epoch) const {
+  // ---- counting path (group_count.cuh): count -> offsets -> scatter; false = outside its menu (radix path instead) ----
+  // One row's scatter: its sorted position from the group record, its sorted columns, its negative range and the
+  // J ranges of its I-block.
+  __device__ __forceinline__ void scatter_row(const SegParams& S, u32 i, u32 slot, u32 meta, float s, float y, float wp,
+                                              float wn) const {
+    const GRec* r = S.rec + slot;
+    const u32 li = meta >> 29, rank = meta & 0x1FFFFFFFu;
+    const u32 a = r->base, pre = r->cnt[li];
+    const float wocc = r->wocc;
+    const u32 pos = a + pre + rank;
+    const u32 n = pre;                                       // rows of the group below this row's level
+    aj[pos] = make_uint2(a, n);
+    ss[pos] = s; sy[pos] = y;
+    if (P.rw_pos) swp[pos] = wp;
+    if (P.rw_neg) swn[pos] = wn;
+    gacc[pos] = 0.f; perm[pos] = i; sgrp[pos] = slot;
+    lossrow[pos] = P.dyn_count ? 0.f : wocc;                 // (non-dynamic: the row's occurrence weight, read by k_pair)
+    if (P.dyn_count) cnt[pos] = 0;
+    else if (P.row_pairs) P.row_pairs[i] = (int64_t)n;
+    if (n) {
+      const u32 v = 2u * (pos / kIB) + ((a < (pos & ~(u32)(kIB - 1))) ? 0u : 1u);     // R1: the group began before the I-block
+      atomicMax(&blk[v].x, ~a);
+      atomicMax(&blk[v].y, a + n);
+    }
+  }
+
+  __device__ __forceinline__ bool count_run(const SegParams& S, u32* smem) const {
+    constexpr u32 kLoc = 2 * kGTile;
+    u32* sm_tab = smem;                                           // [kLoc] representative thread of the key hashed here
+    u64* sm_key = reinterpret_cast<u64*>(smem + kLoc);            // [kGTile] keys of the tile
+    u32* sm_gslot = smem + kLoc + 2 * kGTile;                     // [kGTile] record of the representative's key
+    u32* sm_cnt = sm_gslot + kGTile;                              // [kGTile][kLevels] rows per (representative, level) -> rank base
+    u32* sm_misc = sm_cnt + kGTile * kLevels;                     // [0] created records, [1] rows that cannot pair, [2] their rank base
+    u64* sm_red = reinterpret_cast<u64*>(sm_misc + 4);            // [kSegWarps]
+    Ctl* ctl = S.ctl;
+    GRec* rec = S.rec;
+    const u32 B = S.B, tid = threadIdx.x, ln = lane_id(), w = tid >> 5;
+    const u32 ntile = (B + kGTile - 1) / kGTile;
+    const bool single = ntile <= gridDim.x;                       // one tile per CTA: the rows stay in registers
+    const u32 trash = S.capmask + 1u;
+    const bool dyn = P.dyn_count != 0;
+    u32 k_slot = 0, k_meta = 0; float k_s = 0.f, k_y = 0.f, k_wp = 1.f, k_wn = 1.f;
+    bool bad = false;
+    // ---- count --------------------------------------------------------------------------------------------------
+    for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+      const u32 i = t * kGTile + tid;
+      const bool in = i < B;
+      // all loads of the row first (independent, one round trip)
+      const u64 key = in ? (u64)S.keys[i] : 0ull;
+      const float y = in ? S.labels[i] : 0.f;
+      const bool okb = in && (S.row_ok ? S.row_ok[i] != 0 : true);
+      if (single) {
+        k_s = in ? P.logits[i] : 0.f;
+        if (P.rw_pos) k_wp = in ? P.rw_pos[i] : 1.f;
+        if (P.rw_neg) k_wn = in ? P.rw_neg[i] : 1.f;
+        k_y = y;
+      }
+      float wp = 1.f;
+      if (!single && P.rw_pos) wp = in ? P.rw_pos[i] : 1.f; else wp = k_wp;
+      sm_tab[tid] = kEmpty; sm_tab[tid + kGTile] = kEmpty;
+#pragma unroll
+      for (int q = 0; q < kLevels; q += 4) *reinterpret_cast<uint4*>(sm_cnt + tid * kLevels + q) = make_uint4(0, 0, 0, 0);
+      if (tid < 4) sm_misc[tid] = 0;
+      sm_key[tid] = key;
+      const bool ok = okb && !(y != y);
+      int li = 0;
+      if (ok) {
+        if (!label_level(y, li)) { bad = true; li = 0; }
+        if (P.rw_pos && !(wp > 0.f)) bad = true;              // PW:193 C = W > 0 removes the row's pairs: counts are no longer position arithmetic
+      }
+      __syncthreads();
+      // tile-local grouping: the first thread to claim a key's cell represents it
+      const u64 h = mix64(0x9E3779B97F4A7C15ull ^ key);
+      u32 rep = tid;
+      if (ok) {
+        u32 ls = (u32)(h >> 40) & (kLoc - 1);
+        for (;;) {
+          u32 cur = sm_tab[ls];
+          if (cur == kEmpty) {
+            const u32 prev = atomicCAS(&sm_tab[ls], kEmpty, tid);
+            if (prev == kEmpty) { rep = tid; break; }
+            cur = prev;
+          }
+          if (sm_key[cur] == key) { rep = cur; break; }
+          ls = (ls + 1) & (kLoc - 1);
+        }
+      }
+      // rank inside (representative, level) of the tile
+      u32 lr = 0;
+      if (ok) lr = atomicAdd(&sm_cnt[rep * kLevels + li], 1u);
+      else if (in) lr = atomicAdd(&sm_misc[1], 1u);
+      // representatives: find / create the group's record
+      bool created = false; u32 slot = 0;
+      const bool isrep = ok && rep == tid;
+      if (isrep) { slot = grec_insert(rec, S.capmask, h, key, i, created, &ctl->err); sm_gslot[tid] = slot; }
+      if (created) S.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = slot;
+      __syncthreads();
+      // reserve the tile's ranks inside every (group, level): one atomicAdd each, all in flight together
+      if (isrep) {
+        u32 c[kLevels];
+#pragma unroll
+        for (int q = 0; q < kLevels; ++q) c[q] = sm_cnt[tid * kLevels + q];
+#pragma unroll
+        for (int q = 0; q < kLevels; ++q) if (c[q]) c[q] = atomicAdd(&rec[slot].cnt[q], c[q]);
+#pragma unroll
+        for (int q = 0; q < kLevels; ++q) sm_cnt[tid * kLevels + q] = c[q];
+      }
+      if (tid == 0 && sm_misc[1]) {
+        // rows that cannot pair (row_ok = 0, NaN label): one group of one level behind the table
+        if (atomicCAS(&rec[trash].rep1, 0u, 1u) == 0u) S.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = trash;
+        sm_misc[2] = atomicAdd(&rec[trash].cnt[0], sm_misc[1]);
+      }
+      __syncthreads();
+      if (tid == 0) S.gcount[t] = sm_misc[0];
+      if (in) {
+        const u32 rslot = ok ? sm_gslot[rep] : trash;
+        const u32 rank = (ok ? sm_cnt[rep * kLevels + li] : sm_misc[2]) + lr;
+        const u32 meta = ((u32)li << 29) | rank;
+        if (single) { k_slot = rslot; k_meta = meta; }
+        else { S.rslot[i] = rslot; S.rmeta[i] = meta; }
+      }
+      __syncthreads();
+    }
+    if (__syncthreads_or(bad) && tid == 0) st_relaxed(&ctl->fallback, 1u);
+    stamp(ctl, 1);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
+    stamp(ctl, 2);
+    if (ld_relaxed(&ctl->fallback)) return false;
+    // ---- offsets: one thread per record created by this CTA's tiles -------------------------------------------------
+    u64 npsum = 0;
+    for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+      const u32 ncr = S.gcount[t];
+      for (u32 k0 = 0; k0 < ncr; k0 += kSegThreads) {             // (uniform trip count: the body uses warp collectives)
+        const u32 k = k0 + tid;
+        const bool act = k < ncr;
+        u32 slot = 0, tot = 0; u32 pre[kLevels]; u64 pairs = 0;
+        if (act) {
+          slot = S.glist[(size_t)t * kGTile + k];
+          const uint4 c0 = *reinterpret_cast<const uint4*>(rec[slot].cnt), c1 = *reinterpret_cast<const uint4*>(rec[slot].cnt + 4);
+          const u32 c[kLevels] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+          for (int q = 0; q < kLevels; ++q) { pre[q] = tot; pairs += (u64)c[q] * tot; tot += c[q]; }   // pairs of a row = rows below its level
+        }
+        u32 inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+        const u32 wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        u32 wbase = 0;
+        if (ln == 0 && wtot) wbase = atomicAdd(&ctl->cursor, wtot);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (act) {
+          GRec* r = rec + slot;
+          r->base = wbase + inc - tot;
+          *reinterpret_cast<uint4*>(r->cnt) = make_uint4(pre[0], pre[1], pre[2], pre[3]);
+          *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(pre[4], pre[5], pre[6], pre[7]);
+          if (!dyn) {
+            r->npair = pairs;
+            r->wocc = (P.power != 0.f && pairs) ? ((P.power == 1.0f) ? (float)pairs : powf((float)pairs, P.power)) : 0.f;   // PW:147-149
+            npsum += pairs;
+          }
+        }
+      }
+    }
+    if (!dyn) {
+      npsum = warp_sum(npsum);
+      if (ln == 0) sm_red[w] = npsum;
+      __syncthreads();
+      if (tid == 0) {
+        u64 tsum = 0;
+        for (int q = 0; q < kSegWarps; ++q) tsum += sm_red[q];
+        if (tsum) atomicAdd(&ctl->n_pair, tsum);
+      }
+    }
+    if (blockIdx.x == 0 && tid == 0) ctl->path = 1;
+    stamp(ctl, 3);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
+    stamp(ctl, 4);
+    // ---- scatter ------------------------------------------------------------------------------------------------------
+    if (single) {
+      const u32 i = blockIdx.x * kGTile + tid;
+      if (i < B) scatter_row(S, i, k_slot, k_meta, k_s, k_y, k_wp, k_wn);
+    } else {
+      for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const u32 i = t * kGTile + tid;
+        if (i < B)
+          scatter_row(S, i, S.rslot[i], S.rmeta[i], P.logits[i], S.labels[i], P.rw_pos ? P.rw_pos[i] : 1.f,
+                      P.rw_neg ? P.rw_neg[i] : 1.f);
+      }
+    }
+    stamp(ctl, 17);
+    return true;
+  }
+
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
     u32* sm_scan = smem;                       // [kSegWarps][2]
     u32* sm_carry = smem + 2 * kSegWarps;      // [2]
     u32* sm_wj = smem + 36;                    // [kSegWarps][4]
@@ -94,7 +288,9 @@ struct HeadsTail {
       if (in) {
         float wp = 1.f, wn = 1.f;
         const size_t ro = P.rm.i4(row);
-        if (P.rw_pos) { wp = P.rw_pos[ro]; if (!(wp > 0.f)) n = 0; }      // PW:193  C = W > 0
+        // PW:193  C = W > 0: a non-positive positive-side weight removes the row's pairs -- unless a negative-side
+        // weight may flip the sign back (then the tile decides pair by pair)
+        if (P.rw_pos) { wp = P.rw_pos[ro]; if (!P.rw_neg && !(wp > 0.f)) n = 0; }
         if (P.rw_neg) wn = P.rw_neg[ro];
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[ro];
@@ -118,12 +314,12 @@ struct HeadsTail {
       }
       // exact counts (position arithmetic): per row, per PRIMARY group (PW:286-289), total
       u32 cn = 0;
+      // (merged first phase: ids are table slots; the id `cap` collects the rows that cannot pair)
+      const u32 pgi = (in && !(S.merged && gid > S.capmask)) ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
+      if (in) sgrp[p] = pgi;                    // index of the row's occurrence count: k_pair weights the row by c_h^power
       if (count_now) {
         cn = n;
         if (in && P.row_pairs) P.row_pairs[row] = (int64_t)cn;
-        // (merged first phase: ids are table slots; the id `cap` collects the rows that cannot pair)
-        const u32 pgi = (in && !(S.merged && gid > S.capmask)) ? (S.K > 1 ? pgid[row] : gid) : kEmpty;
-        if (in) cnt[p] = pgi;                   // index of the row's occurrence count: k_pair weights the row by c_h^power
         const u32 pg = cn ? pgi : kEmpty;
         const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
         const u32 tot = __reduce_add_sync(m, cn);
@@ -135,8 +331,8 @@ struct HeadsTail {
       if (!(w & 1) && ln == 0) {
         const u32 ib = (t0 + w * 32) / kIB;
         if (ib < nib) {
-          blk[2 * ib] = make_uint2(min(sm_wj[4 * w], sm_wj[4 * w + 4]), max(sm_wj[4 * w + 1], sm_wj[4 * w + 5]));
-          blk[2 * ib + 1] = make_uint2(min(sm_wj[4 * w + 2], sm_wj[4 * w + 6]), max(sm_wj[4 * w + 3], sm_wj[4 * w + 7]));
+          blk[2 * ib] = make_uint2(~min(sm_wj[4 * w], sm_wj[4 * w + 4]), max(sm_wj[4 * w + 1], sm_wj[4 * w + 5]));
+          blk[2 * ib + 1] = make_uint2(~min(sm_wj[4 * w + 2], sm_wj[4 * w + 6]), max(sm_wj[4 * w + 3], sm_wj[4 * w + 7]));
         }
       }
       if (threadIdx.x == 0 && count_now) {
@@ -150,7 +346,7 @@ struct HeadsTail {
     // Batches up to 524288 rows: k_pair partitions the work itself (cost prefixes in shared memory), the kernel ends here
     // without another grid barrier.  Larger batches: explicit unit records.
     if (nib <= kMaxNibS) return;
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     stamp(ctl, 18);
     // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
     //      the unit records of its own I-blocks ------------------------------------------------------------------
@@ -202,8 +398,12 @@ struct KpArgs {
   u32 cost_switch;           // fixed cost of a virtual block (row loads, flush of the row accumulators), same unit
   u32 cost_straddle, cost_levels;   // extra cost of a block that holds a label-level boundary; boundaries per range (see vcost)
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
-  // finalisation
-  const u64 *keyA, *keyB; const u32 *valA, *valB; const u32* pgid; u64* cprim;
+  const u32* sgrp;           // per sorted row: index of its (primary) group's pair total -- cprim[] or, counting path, rec[]
+  u64* cprim;
+  // counting path (group_count.cuh): the call ran without k_init; the records its count phase created are listed per
+  // 512-row tile and zeroed again by the last phase of this kernel
+  int fast; GRec* rec; const u32* glist; const u32* gcount; u32 ngt;
+  uint2* blk_w;              // (the J ranges are zeroed again as well)
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
 };
 
@@ -212,6 +412,25 @@ struct KpArgs {
 // final pass.  The counts are final before k_pair starts.
 __device__ __forceinline__ float occ_pow(u64 ch, float power) {
   return ch ? ((power == 1.0f) ? (float)ch : powf((float)ch, power)) : 0.f;
+}
+
+// ---- end of a call: leave the arena clean for the next one (persistent arenas run without k_init) --------------------
+// Zero the group records created by the count phase of tiles t0, t0 + tstep, ... (four threads per 64-byte record).
+__device__ __forceinline__ void clean_records(const KpArgs& A, u32 t0, u32 tstep) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (u32 t = t0; t < A.ngt; t += tstep) {
+    const u32 n = A.gcount[t];
+    for (u32 k = threadIdx.x; k < 4 * n; k += blockDim.x)
+      reinterpret_cast<uint4*>(A.rec + A.glist[(size_t)t * kGTile + (k >> 2)])[k & 3u] = z;
+  }
+}
+// The CTA that finishes last files the report of the call and resets the working fields of the control block.
+__device__ __forceinline__ void ctl_finish(Ctl* ctl) {
+  ctl->rep_err = ctl->err; ctl->rep_path = ctl->path; ctl->rep_n_units = ctl->n_units; ctl->rep_unit_c = ctl->unit_c;
+  ctl->rep_n_tiles = ctl->n_tiles;
+  ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
+  ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
+  ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;
 }
 
 // In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
@@ -372,10 +591,15 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // the critical path if the last warp to leave the pair loop has to walk it in front of the grid barrier.  It is
   // walked here instead, its loads spread over the prologue, and the weight parked in the (otherwise unused) lossrow
   // column: each thread reads back what it wrote itself.
+  // (Counting path: the offsets phase of k_seg knows every group's total and the scatter phase has already parked the
+  // weights; the pair totals then live in the group records.)
   const u32 gtid0 = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool park = !DYN && fold_power != 0.f;
+  const bool counted = A.fast && ld_relaxed(&ctl->fallback) == 0u;
+  const u64* cprim = counted ? &A.rec->npair : A.cprim;
+  const u32 cstride = counted ? (u32)(sizeof(GRec) / sizeof(u64)) : 1u;
+  const bool park = !DYN && fold_power != 0.f && !counted;
   u32 park_pg = kEmpty; u64 park_ch = 0;
-  if (park && gtid0 < B) park_pg = A.cnt[gtid0];
+  if (park && gtid0 < B) park_pg = A.sgrp[gtid0];
   if (own_list) {
     u32 msum = 0;
     for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
@@ -387,7 +611,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     __syncthreads();
     stamp(ctl, 11);
-    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
+    if (park_pg != kEmpty) park_ch = cprim[(size_t)park_pg * cstride];
     block_excl_scan(s_pi, nvb, s_scan);
     stamp(ctl, 12);
     const u32 tot = s_pi[nvb];
@@ -422,14 +646,14 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   } else {
     U = ld_relaxed(&ctl->n_units);
-    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
+    if (park_pg != kEmpty) park_ch = cprim[(size_t)park_pg * cstride];
     __syncthreads();
   }
   if (park) {
     if (gtid0 < B) A.lossrow[gtid0] = occ_pow(park_ch, fold_power);
     for (u32 p = gtid0 + gridDim.x * blockDim.x; p < B; p += gridDim.x * blockDim.x) {
-      const u32 pg = A.cnt[p];
-      A.lossrow[p] = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
+      const u32 pg = A.sgrp[p];
+      A.lossrow[p] = pg != kEmpty ? occ_pow(cprim[(size_t)pg * cstride], fold_power) : 0.f;
     }
   }
   stamp(ctl, 16);
@@ -626,15 +850,22 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           const u32 qmax = __reduce_max_sync(0xFFFFFFFFu, max(act0 ? lo0 : 0u, act1 ? lo1 : 0u));
           if (qmin == qmax) {
             if (qmin != occ_a) {
-              const u32 pg = A.cnt[qmin];
-              occ_w = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
+              if (counted) occ_w = A.lossrow[qmin];                 // (parked by k_seg's scatter phase)
+              else {
+                const u32 pg = A.sgrp[qmin];
+                occ_w = pg != kEmpty ? occ_pow(cprim[(size_t)pg * cstride], fold_power) : 0.f;
+              }
               occ_a = qmin;
             }
             li0 *= occ_w; li1 *= occ_w;
           } else if (qmin != 0xFFFFFFFFu) {
-            const u32 pg0 = act0 ? A.cnt[pi0] : kEmpty, pg1 = act1 ? A.cnt[pi1] : kEmpty;
-            const u64 ch0 = pg0 != kEmpty ? A.cprim[pg0] : 0ull, ch1 = pg1 != kEmpty ? A.cprim[pg1] : 0ull;
-            li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
+            if (counted) {
+              li0 *= act0 ? A.lossrow[pi0] : 0.f; li1 *= act1 ? A.lossrow[pi1] : 0.f;
+            } else {
+              const u32 pg0 = act0 ? A.sgrp[pi0] : kEmpty, pg1 = act1 ? A.sgrp[pi1] : kEmpty;
+              const u64 ch0 = pg0 != kEmpty ? cprim[(size_t)pg0 * cstride] : 0ull, ch1 = pg1 != kEmpty ? cprim[(size_t)pg1 * cstride] : 0ull;
+              li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
+            }
           }
         }
         lsum += (double)li0 + (double)li1;
@@ -660,7 +891,6 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   }
   const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  u32 epoch = 0;
   if (!DYN) {
     // ---- this CTA's share of sum w * loss, then (after the grid barrier) un-permute and scale the gradient ----
     lsum = warp_sum(lsum);
@@ -673,7 +903,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     // nothing else in front of the barrier: the last warp to leave the pair loop sets the pace
     stamp(ctl, 21);
-    grid_sync(&ctl->bar2, epoch, &ctl->err);
+    grid_sync(&ctl->bar2_cnt, &ctl->err);
     stamp(ctl, 22);
     // one round trip of independent loads (pair count, permutation, parked occurrence weight, gradient sum), then the store
     const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
@@ -697,15 +927,23 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         }
       ctl->ts[23] = globaltimer();
     }
+    // leave the arena clean: J ranges, the group records of the counting path, the control block (last CTA out)
+    {
+      const uint2 z2 = make_uint2(0, 0);
+      for (u32 v = gtid; v < nvb; v += gthreads) A.blk_w[v] = z2;
+      if (A.fast) clean_records(A, blockIdx.x, gridDim.x);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) { __threadfence(); ctl_finish(ctl); }
+      }
+    }
     return;
   }
   // ---- finalisation when the pair set depends on scores / negative-side weights (all CTAs, after a grid barrier) ----
   stamp(ctl, 21);
-  grid_sync(&ctl->bar2, epoch, &ctl->err);
+  grid_sync(&ctl->bar2_cnt, &ctl->err);
   stamp(ctl, 22);
-  const Plan pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), P.gbits, true);
-  const u64* key = (pl.npass & 1) ? A.keyB : A.keyA;
-  const u32* val = (pl.npass & 1) ? A.valB : A.valA;
   {
     // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
     u64 tot_c = 0;
@@ -713,14 +951,13 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 p = p0 + gtid;
       u32 cn = 0, pg = kEmpty;
       if (p < B) {
-        const u32 row = val[p];
         cn = A.cnt[p];
-        if (cn) pg = P.K > 1 ? A.pgid[row] : (u32)(key[p] >> pl.labbits);
-        if (P.row_pairs) P.row_pairs[row] = (int64_t)cn;
+        if (cn) pg = A.sgrp[p];
+        if (P.row_pairs) P.row_pairs[A.perm[p]] = (int64_t)cn;
       }
       const u32 m = __match_any_sync(0xFFFFFFFFu, pg);
       const u32 tot = __reduce_add_sync(m, cn);
-      if (pg != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(A.cprim + pg, (u64)tot);
+      if (pg != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(const_cast<u64*>(cprim) + (size_t)pg * cstride, (u64)tot);
       tot_c += cn;
     }
     tot_c = warp_sum(tot_c);
@@ -731,7 +968,9 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       for (int q = 0; q < kPairWarps; ++q) t += red_u[q];
       if (t) atomicAdd(&ctl->n_pair, t);
     }
-    grid_sync(&ctl->bar2, epoch, &ctl->err);
+    const uint2 z2 = make_uint2(0, 0);
+    for (u32 v = gtid; v < nvb; v += gthreads) A.blk_w[v] = z2;        // (the J ranges were last read in the prologue)
+    grid_sync(&ctl->bar2_cnt, &ctl->err);
   }
   // F_b: scale, apply the occurrence weight, un-permute the gradient, reduce the loss
   const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
@@ -739,58 +978,68 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   const float gscale = P.factor / denom;
   double lp = 0.0;
   for (u32 p = gtid; p < B; p += gthreads) {
-    const u32 row = val[p];
     const float g = A.gacc[p], l = A.lossrow[p];
     float wocc = 1.f;
     if (P.power != 0.f && (g != 0.f || l != 0.f)) {
-      const u32 pg = P.K > 1 ? A.pgid[row] : (u32)(key[p] >> pl.labbits);
-      const u64 ch = A.cprim[pg];
+      const u64 ch = cprim[(size_t)A.sgrp[p] * cstride];
       wocc = ch ? ((P.power == 1.0f) ? (float)ch : powf((float)ch, P.power)) : 0.f;   // PW:147-149
     }
-    P.dlogits[row] = g * wocc * gscale;
+    P.dlogits[A.perm[p]] = g * wocc * gscale;
     lp += (double)l * (double)wocc;
   }
   lp = warp_sum(lp);
   if (ln == 0) red_d[threadIdx.x >> 5] = lp;
   __syncthreads();
+  __shared__ u32 s_last;
   if (threadIdx.x == 0) {
     double t = 0;
     for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
     if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     __threadfence();
-    if (atomicAdd(&ctl->fin_done, 1u) != gridDim.x - 1) return;       // the last CTA writes the scalars
-    __threadfence();
-    ctl->ts[23] = globaltimer();
-    const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
-    *P.loss = (float)(tot / (double)denom);
-    *P.n_pair_f32 = (float)n;                  // PW:276
-    *P.n_pair = (int64_t)n;
+    s_last = (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) ? 1u : 0u;       // the last CTA writes the scalars
+    if (s_last) {
+      __threadfence();
+      ctl->ts[23] = globaltimer();
+      const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+      *P.loss = (float)(tot / (double)denom);
+      *P.n_pair_f32 = (float)n;                  // PW:276
+      *P.n_pair = (int64_t)n;
+    }
   }
+  __syncthreads();
+  if (!s_last) return;
+  // ... and, now that nobody reads the group records any more, leaves the arena clean
+  if (A.fast) clean_records(A, 0, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { __threadfence(); ctl_finish(ctl); }
 }
 
 template <int MODE>
 static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_t st) {
-  static int blocks_per_sm = 0;
-  if (!blocks_per_sm) {
+  // per-device launch state (the opt-in to large dynamic shared memory is a per-device function attribute)
+  static int blocks_per_sm[64] = {0};
+  static size_t smem_set[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!blocks_per_sm[dev]) {
     int nb = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair<MODE>, kPairThreads, 0);
     if (e != cudaSuccess) return e;
     if (nb < 1) nb = 1;
     int want = tune_int("RN_PAIR_BPS", 1);           // CTAs per SM (all co-resident: cooperative launch)
-    blocks_per_sm = want < nb ? (want < 1 ? 1 : want) : nb;
+    blocks_per_sm[dev] = want < nb ? (want < 1 ? 1 : want) : nb;
   }
   PairParams p = P; KpArgs a = A;
   void* args[] = {&p, &a};
   // cost prefix of the static partition: s_pi[2 nib + 1], s_jn[2 nib]
   const size_t smem = A.nib <= kMaxNibS ? sizeof(u32) * (4 * (size_t)A.nib + 2) : 0;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  if (smem > smem_set[dev]) {
     const size_t want = sizeof(u32) * (4 * (size_t)kMaxNibS + 2);
     cudaError_t e = cudaFuncSetAttribute(k_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     if (e != cudaSuccess) return e;
-    smem_set = want;
+    smem_set[dev] = want;
   }
-  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm, kPairThreads, args, st, smem);
+  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm[dev], kPairThreads, args, st, smem);
 }
 
 static const void* pair_func(int mode) {
@@ -867,9 +1116,22 @@ extern "C" size_t rn_pairwise_scratch_bytes(int64_t B, int32_t K) {
   return make_layout(B, K).total;
 }
 
+extern "C" int rn_pairwise_scratch_init(void* scratch, size_t scratch_bytes, void* stream) {
+  if (!scratch || !scratch_bytes) return RN_ERR_ARG;
+  return cudaMemsetAsync(scratch, 0, scratch_bytes, static_cast<cudaStream_t>(stream)) == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+// the counting path runs without k_init (persistent arena, one key column, contiguous rows, the whole pair space)
+static bool counting_eligible(const rn_pairwise_args* a) {
+  static const int off = tune_int("RN_SEG_COUNT", 1);
+  // (batches beyond kMaxNibS I-blocks need the explicit unit records only the radix tail builds)
+  return off && a->scratch_persistent && a->K == 1 && !a->block_rows && a->part_count == 1 &&
+         (a->B + kIB - 1) / kIB <= (int64_t)kMaxNibS;
+}
+
 extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
   if (B <= 0 || K <= 0) return 0;
-  return 3;        // k_init, k_seg<HeadsTail>, k_pair
+  return 3;        // k_init, k_seg<HeadsTail>, k_pair (2 with a persistent arena and one key column: no k_init)
 }
 
 static int validate_pairwise(const rn_pairwise_args* a) {
@@ -877,6 +1139,7 @@ static int validate_pairwise(const rn_pairwise_args* a) {
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
   if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF) return RN_ERR_UNSUPPORTED;
   if (a->part_count < 1 || a->part_rank < 0 || a->part_rank >= a->part_count) return RN_ERR_ARG;
+  if (a->scratch_rows && a->scratch_rows < a->B) return RN_ERR_ARG;
   if (a->block_rows) {
     if (a->block_rows < 0 || a->B % a->block_rows || a->block_stride <= 0 || (a->block_stride & 15) ||
         a->block_stride / 4 > 0xFFFFFFFFll) return RN_ERR_ARG;
@@ -901,10 +1164,11 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   // score- / weight-dependent filters do not (they would need an all-reduce between counting and weighting)
   if (a->part_count > 1 && dyn) return RN_ERR_UNSUPPORTED;
   if (!scratch || check_align(scratch)) return scratch ? RN_ERR_ALIGN : RN_ERR_ARG;
-  const Layout L = make_layout(a->B, a->K);
+  const Layout L = make_layout(a->scratch_rows ? a->scratch_rows : a->B, a->K, a->B);
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
+  const bool fast = counting_eligible(a);
   PairParams P{};
   P.B = (u32)a->B; P.K = a->K; P.gbits = L.gbits;
   P.logits = a->logits; P.labels = a->labels; P.rw_pos = a->rw_pos; P.rw_neg = a->rw_neg;
@@ -926,7 +1190,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   H.aj = at<uint2>(base, L.aj); H.ss = at<float>(base, L.ss); H.sy = at<float>(base, L.sy);
   H.swp = at<float>(base, L.swp); H.swn = at<float>(base, L.swn);
   H.gacc = at<float>(base, L.gacc); H.lossrow = at<float>(base, L.lossrow); H.cnt = at<u32>(base, L.cnt);
-  H.perm = at<u32>(base, L.perm);
+  H.perm = at<u32>(base, L.perm); H.sgrp = at<u32>(base, L.sgrp);
   H.blk = at<uint2>(base, L.blk); H.units = at<uint2>(base, L.units); H.nib = L.nib;
   H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
   H.target_units = target_units();
@@ -938,7 +1202,8 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
     for (u32 r = 0; r < in.gather.world; ++r) in.gather.src[r] = static_cast<const uint4*>(a->peer_blocks[r]);
   }
   static const int allow_merged = tune_int("RN_SEG_MERGED", 1);
-  in.allow_merged = allow_merged && a->part_count == 1;      // ranks of the global mode need identical ids
+  in.fast = fast;
+  in.allow_merged = allow_merged && a->part_count == 1 && !fast;      // ranks of the global mode need identical ids
   if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
@@ -952,9 +1217,9 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.cost_straddle = kCostUnit * (u32)(cost_straddle < 0 ? 0 : (cost_straddle > 64 ? 64 : cost_straddle));
   A.cost_levels = (u32)(cost_levels < 0 ? 0 : (cost_levels > 64 ? 64 : cost_levels));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
-  A.keyA = at<u64>(base, L.keyA); A.keyB = at<u64>(base, L.keyB);
-  A.valA = at<u32>(base, L.valA); A.valB = at<u32>(base, L.valB);
-  A.pgid = H.pgid; A.cprim = H.cprim;
+  A.sgrp = H.sgrp; A.cprim = H.cprim;
+  A.fast = fast ? 1 : 0; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
+  A.ngt = (u32)((a->B + kGTile - 1) / kGTile); A.blk_w = H.blk;
   A.dbgbuf = at<u64>(base, L.gstat);
   int mode = 0;
   if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
@@ -966,7 +1231,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;
   // one launch of a cached CUDA graph; while the pair kernel is being timed: the timed variant of the graph (two
   // event-record nodes around the pair kernel), or plain launches with stream events (RN_PROFILE_GRAPH=0)
-  GraphCall gc(seg_init_func(), f_seg, pair_func(mode), st, !prof || tev != nullptr, tev != nullptr);
+  GraphCall gc(fast ? nullptr : seg_init_func(), f_seg, pair_func(mode), st, !prof || tev != nullptr, tev != nullptr);
   const bool in_graph = gc.capturing() || gc.updating();
   // the three launches of the call (k_init, k_seg, k_pair) on stream s
   auto enqueue = [&](cudaStream_t s, bool graph) -> bool {

@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4
 // each, so the gaps between them count.  When a GraphCall is active on this thread the launches below do not go to
 // the stream: they set the parameters of the three kernel nodes of a cached, instantiated CUDA graph, which the
 // caller then launches once (smaller inter-kernel gaps, one driver call instead of three).
-struct GraphSlot { int dev; const void* f[3]; bool timed; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
-static thread_local GraphSlot tl_slots[24];
+// (f[0] == nullptr: a call without k_init -- the counting path on a persistent arena -- is a graph of two kernel nodes)
+struct GraphSlot { int dev; const void* f[3]; int nf; bool timed; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
+static thread_local GraphSlot tl_slots[48];
 static thread_local int tl_nslots = 0;
 static thread_local GraphSlot* tl_update = nullptr;      // slot whose nodes receive the launches of this thread
 static thread_local int tl_next = 0;
@@ -68,7 +69,7 @@ long long graph_launch_count() { return tl_graph_broken ? -tl_graph_launches - 1
 static cudaError_t emit(const void* f, dim3 grid, dim3 block, size_t smem, void** args, bool coop, cudaStream_t st) {
   if (tl_update) {
     const int i = tl_next++;
-    if (i >= 3 || tl_update->f[i] != f) { if (getenv("RN_GRAPH_DEBUG")) fprintf(stderr, "[recnow] graph node %d: unexpected kernel\n", i); return cudaErrorInvalidValue; }
+    if (i >= tl_update->nf || tl_update->f[i] != f) { if (getenv("RN_GRAPH_DEBUG")) fprintf(stderr, "[recnow] graph node %d: unexpected kernel\n", i); return cudaErrorInvalidValue; }
     cudaKernelNodeParams p{};
     p.func = const_cast<void*>(f); p.gridDim = grid; p.blockDim = block; p.sharedMemBytes = (unsigned)smem;
     p.kernelParams = args; p.extra = nullptr;
@@ -116,9 +117,13 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (cudaStreamIsCapturing(user_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return; }
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return;
+  const void* fl[3]; int nf = 0;
+  if (f_init) fl[nf++] = f_init;
+  fl[nf++] = f_seg; fl[nf++] = f_pair;
+  if (nf == 2) fl[2] = nullptr;
   for (int i = 0; i < tl_nslots; ++i) {
     GraphSlot& g = tl_slots[i];
-    if (g.dev == dev && g.f[0] == f_init && g.f[1] == f_seg && g.f[2] == f_pair && g.timed == timed) {
+    if (g.dev == dev && g.nf == nf && g.f[0] == fl[0] && g.f[1] == fl[1] && g.f[2] == fl[2] && g.timed == timed) {
       slot = &g; tl_update = slot; tl_next = 0; mode = 1;
       return;
     }
@@ -127,14 +132,14 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (!tl_cap_stream && cudaStreamCreateWithFlags(&tl_cap_stream, cudaStreamNonBlocking) != cudaSuccess) { tl_graph_broken = true; return; }
   if (cudaStreamBeginCapture(tl_cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { tl_graph_broken = true; cudaGetLastError(); return; }
   slot = &tl_slots[tl_nslots];
-  slot->dev = dev; slot->f[0] = f_init; slot->f[1] = f_seg; slot->f[2] = f_pair; slot->timed = timed;
+  slot->dev = dev; slot->f[0] = fl[0]; slot->f[1] = fl[1]; slot->f[2] = fl[2]; slot->nf = nf; slot->timed = timed;
   run_stream = tl_cap_stream; tl_capturing = true; tl_capture_timed = timed; mode = 2;
 }
 
 cudaError_t GraphCall::finish(bool ok) {
   if (mode == 0) return ok ? cudaSuccess : cudaErrorUnknown;
   if (mode == 1) {
-    const bool all = tl_next == 3;
+    const bool all = tl_next == slot->nf;
     tl_update = nullptr;
     if (!ok || !all) { tl_graph_broken = true; return cudaErrorUnknown; }
     ++tl_graph_launches;
@@ -147,15 +152,16 @@ cudaError_t GraphCall::finish(bool ok) {
   if (e != cudaSuccess || !ok || !graph) { tl_graph_broken = true; if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return ok ? e : cudaErrorUnknown; }
   cudaGraphNode_t nodes[8]; size_t n = 8;
   bool found[3] = {false, false, false};
-  if (cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess && n == (slot->timed ? 5u : 3u)) {
+  if (cudaGraphGetNodes(graph, nodes, &n) == cudaSuccess && n == (size_t)slot->nf + (slot->timed ? 2u : 0u)) {
     for (size_t i = 0; i < n; ++i) {
       cudaGraphNodeType ty;
       if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
       cudaKernelNodeParams p{};
       if (cudaGraphKernelNodeGetParams(nodes[i], &p) != cudaSuccess) continue;
-      for (int k = 0; k < 3; ++k) if (!found[k] && p.func == slot->f[k]) { slot->node[k] = nodes[i]; found[k] = true; break; }
+      for (int k = 0; k < slot->nf; ++k) if (!found[k] && p.func == slot->f[k]) { slot->node[k] = nodes[i]; found[k] = true; break; }
     }
   }
+  if (slot->nf == 2) found[2] = true;
   if (!(found[0] && found[1] && found[2]) || cudaGraphInstantiate(&slot->exec, graph, 0) != cudaSuccess) {
     // (still run this call: the captured work was not executed)
     tl_graph_broken = true; cudaGetLastError();

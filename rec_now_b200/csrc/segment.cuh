@@ -20,6 +20,7 @@
 //           gathers (listwise, pair materialisation).
 #pragma once
 #include "common.cuh"
+#include "group_count.cuh"
 
 namespace rn {
 
@@ -38,6 +39,10 @@ struct SegParams {
   // get the id `cap` (one group, one label level: no pairs), which sorts last.
   int merged; const u32* labpart; int npart;
   u64* dbgts;                     // RN_SEG_DEBUG=1: per-CTA arrival stamps [phase][cta] (dev tool), else nullptr
+  // counting path (group_count.cuh; fast != 0: no k_init ran, the arena is in its clean state)
+  int fast;
+  GRec* rec; u32 *glist, *gcount, *rslot, *rmeta;
+  uint4 *init_zero, *init_ones; u32 init_zero16, init_ones16;    // regions the radix path needs initialised (fallback)
   __device__ __forceinline__ u32* th_buf(u32 k) const { return k ? tilehist + (size_t)(k - 1) * ntiles * kBins : th0; }
 };
 
@@ -361,9 +366,9 @@ __device__ __forceinline__ void block_maxscan2(u32& x, u32& y, u32* sm) {
 struct GatherCols { const float* src[4]; float* dst[4]; };
 
 struct BoundsTail {
+  static constexpr bool kFast = false;
   u32 *astart, *gend, *perm; GatherCols gc;
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem,
-                                      u32& epoch) const {
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
     u32* sm_scan = smem;            // [kSegWarps][2]
     u32* sm_carry = smem + 2 * kSegWarps;
     const u32 ln = lane_id(), w = threadIdx.x >> 5;
@@ -397,11 +402,22 @@ struct BoundsTail {
 template <int IPT, class Tail>
 __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   __shared__ __align__(16) u32 smem[kSegSmemWords];
-  u32 epoch = 0;
   Ctl* ctl = S.ctl;
   grid_dep_wait();
   grid_dep_launch();
   stamp(ctl, 0);
+  if constexpr (Tail::kFast) {
+    if (S.fast) {
+      // counting path; false = something outside its menu was seen: initialise what the radix path needs and go on
+      if (T.count_run(S, smem)) { stamp(ctl, 19); return; }
+      const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;
+      const uint4 z = make_uint4(0, 0, 0, 0), f = make_uint4(~0u, ~0u, ~0u, ~0u);
+      for (u32 k = gtid; k < S.init_zero16; k += gthreads) S.init_zero[k] = z;
+      for (u32 k = gtid; k < S.init_ones16; k += gthreads) S.init_ones[k] = f;
+      grid_sync(&ctl->bar_cnt, &ctl->err);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->path = 2;
   Plan pl;
   if (S.merged) {
     // label bit range from k_init's partials
@@ -418,28 +434,28 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
     seg_hash_keys<IPT>(S, pl, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[blockIdx.x] = globaltimer();
     stamp(ctl, 3);
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
   } else {
     seg_hash(S, smem);
     stamp(ctl, 1);
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     stamp(ctl, 2);
     pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), S.gbits, S.use_label != 0);
     seg_vkey<IPT>(S, pl, smem);
     stamp(ctl, 3);
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
   }
   stamp(ctl, 4);
   for (int p = 0; p < pl.npass; ++p) {
     seg_sort_pass<IPT>(S, pl, p, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)(1 + p) * gridDim.x + blockIdx.x] = globaltimer();
     stamp(ctl, 5 + 2 * p);
-    grid_sync(&ctl->bar, epoch, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->err);
     stamp(ctl, 6 + 2 * p);
   }
   const u64* key = (pl.npass & 1) ? S.keyB : S.keyA;
   const u32* val = (pl.npass & 1) ? S.valB : S.valA;
-  T.run(S, pl, key, val, smem, epoch);
+  T.run(S, pl, key, val, smem);
   stamp(ctl, 19);
 }
 
@@ -451,6 +467,7 @@ struct SegInputs {
   RowMap rm = RowMap{0, 0, 0, 0};
   bool allow_merged = false;   // the caller accepts table-slot group ids (not deterministic across calls / ranks)
   GatherArgs gather = GatherArgs{};   // peer-memory gather of the blocked input rows by k_init (world = 0: off)
+  bool fast = false;                  // counting path (the tail supports it, the arena is persistent and clean): no k_init
 };
 
 inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs& in) {
@@ -470,22 +487,31 @@ inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs
   static const char* segdbg = getenv("RN_SEG_DEBUG");
   S.dbgts = (segdbg && *segdbg == '1') ? at<u64>(base, L.gstat) : nullptr;
   S.ctl = at<Ctl>(base, L.ctl);
+  S.fast = 0;
+  S.rec = at<GRec>(base, L.rec); S.glist = at<u32>(base, L.glist); S.gcount = at<u32>(base, L.gcount);
+  S.rslot = S.slot; S.rmeta = S.slot1;
+  S.init_zero = at<uint4>(base, L.hist); S.init_zero16 = (u32)((L.zero_end - L.hist) / 16);
+  S.init_ones = at<uint4>(base, L.ones_begin); S.init_ones16 = (u32)((L.ones_end - L.ones_begin) / 16);
   return S;
 }
 
 // group-id bits of the merged first phase: table slots < cap plus the id `cap` of the rows that cannot pair
 inline int seg_merged_gbits(const Layout& L) { return bit_width_u64((uint64_t)L.cap); }
 
-// Enqueue init + the segmentation kernel with the given tail (2 launches).
+// Enqueue init + the segmentation kernel with the given tail (2 launches; 1 on the counting path).
 template <class Tail>
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const Tail& tail, cudaStream_t st) {
-  const bool merged = in.allow_merged && in.K == 1 && in.use_label && in.labels && !in.rm.Bl;
+  const bool fast = Tail::kFast && in.fast && in.K == 1 && in.use_label && in.labels && !in.rm.Bl && !in.gather.world;
+  const bool merged = !fast && in.allow_merged && in.K == 1 && in.use_label && in.labels && !in.rm.Bl;
   int npart = 0;
-  cudaError_t e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart)
-                         : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr);
+  cudaError_t e = cudaSuccess;
+  if (!fast)
+    e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart)
+               : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr);
   if (e != cudaSuccess) return e;
   SegParams S = make_seg_params(L, scratch, in);
   if (merged) { S.merged = 1; S.npart = npart; S.gbits = seg_merged_gbits(L); }
+  S.fast = fast ? 1 : 0;
   Tail T = tail;
   int grid = (int)((in.B + kSegThreads - 1) / kSegThreads);
   const int sms = device_sm_count();

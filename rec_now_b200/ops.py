@@ -40,15 +40,17 @@ REUSE_SCRATCH = True
 _scratch_cache: dict = {}
 
 
-def _scratch(nbytes: int, dev: torch.device, stream_ptr: int) -> torch.Tensor:
+def _scratch(nbytes: int, dev: torch.device, stream_ptr: int, tag=None) -> torch.Tensor:
+    """The arena of (device, stream, size[, tag]).  Arenas are created ZEROED and then written by nothing but the
+    library's calls of one kind (tag), which is what rn_pairwise_args.scratch_persistent promises."""
     if not REUSE_SCRATCH:
-        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    key = (dev.index, stream_ptr, nbytes)
+        return torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    key = (dev.index, stream_ptr, nbytes, tag)
     t = _scratch_cache.get(key)
     if t is None:
         if len(_scratch_cache) > 64:
             _scratch_cache.clear()
-        t = _scratch_cache[key] = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        t = _scratch_cache[key] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
     return t
 
 
@@ -115,7 +117,9 @@ class _PairCall:
         self.fn = lib().rn_pairwise_fwd_bwd
 
 
-_pair_call = None
+import threading
+
+_tls = threading.local()             # (ctypes releases the GIL during the call: the argument struct is per thread)
 _pair_scratch_bytes: dict = {}
 
 
@@ -123,7 +127,6 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
                      factor=1.0, power=0.0, only_wrong=False, reduce_mean=True, part=(0, 1),
                      want_row_pairs=False):
     """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors."""
-    global _pair_call
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()
@@ -140,11 +143,11 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     if nbytes is None:
         nbytes = _pair_scratch_bytes[(b, kk)] = lib().rn_pairwise_scratch_bytes(b, kk)
     st = torch.cuda.current_stream(dev).cuda_stream
-    scratch = _scratch(nbytes, dev, st)
+    scratch = _scratch(nbytes, dev, st, ("pair", kk))
     po = out.data_ptr()
-    pc = _pair_call
+    pc = getattr(_tls, "pair_call", None)
     if pc is None:
-        pc = _pair_call = _PairCall()
+        pc = _tls.pair_call = _PairCall()
     a = pc.args
     a.B = b; a.K = kk; a.label_func = _lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP
     a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
@@ -154,6 +157,7 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     a.loss = po; a.n_pair_f32 = po + 4; a.n_pair = po + 8
     a.dlogits = dlogits.data_ptr(); a.row_pairs = _ptr(row_pairs)
     a.block_rows = 0; a.block_stride = 0; a.out_chunk = 0
+    a.scratch_persistent = 1; a.scratch_rows = 0
     with _on_device(dev):
         rc = pc.fn(pc.ref, scratch.data_ptr(), nbytes, st)
     if rc:
@@ -254,7 +258,7 @@ def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int
     assert out.numel() == world * chunk and out.dtype is torch.float32
     nbytes = lib().rn_pairwise_scratch_bytes(b, kk)
     st = torch.cuda.current_stream(dev).cuda_stream
-    scratch = _scratch(nbytes, dev, st)
+    scratch = _scratch(nbytes, dev, st, ("blocked", kk))
     base, po = gbuf.data_ptr(), scal.data_ptr()
     a = PairwiseArgs(
         B=b, K=kk, label_func=_lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP,
@@ -278,6 +282,13 @@ def device_error(scratch: torch.Tensor) -> int:
     err = C.c_int32(0)
     check(lib().rn_last_device_error(scratch.data_ptr(), C.byref(err), _stream()), "rn_last_device_error")
     return err.value
+
+
+def last_segmentation_path(scratch: torch.Tensor) -> int:
+    """Which segmentation the last finished pairwise call on `scratch` ran: 1 = counting (sort-free), 2 = radix sort."""
+    ts = (C.c_uint64 * 36)()
+    check(lib().rn_debug_timestamps(scratch.data_ptr(), ts, 36, _stream()), "rn_debug_timestamps")
+    return int(ts[35])
 
 
 def _pair_args(s, y, keys, ok, rwp, rwn, label_func, only_wrong, factor=1.0, power=0.0, reduce_mean=True):
