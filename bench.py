@@ -52,15 +52,19 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def kpair_traffic(world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_pair launch from the committed `ncu --set full` capture
-    of this round (profiles/kpair_traffic.json, written by scripts/ncu_summary.py); None if there is none."""
+def kpair_capture(world):
+    """Figures of one k_pair launch from the committed `ncu --set full` capture (profiles/kpair_traffic.json, written
+    from scripts/ncu_summary.py's output): DRAM bytes, MUFU operations actually issued per pair, pipe utilisations."""
     p = os.path.join(ROOT, "profiles", "kpair_traffic.json")
     if world != 1 or not os.path.exists(p):
-        return None
+        return {}
     with open(p) as f:
-        d = json.load(f)
-    return d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)
+        return json.load(f)
+
+
+def kpair_traffic(world):
+    d = kpair_capture(world)
+    return (d.get("dram_bytes_read", 0) + d.get("dram_bytes_write", 0)) if d else None
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -197,6 +201,159 @@ def reference_arm(args):
     emit_line(line)
 
 
+
+# ----------------------------------------------------------------------------------------------------------
+# parity gates (run with every benchmark, outside the timed region) and the other BASELINE configs
+# ----------------------------------------------------------------------------------------------------------
+def parity_pairwise(out, d, spec_kw):
+    """Exact pair count, 1e-5 loss, gradient within 1e-5 of the per-row scale A_i -- against the float64 segmented
+    restatement of the reference (oracle/seg_ref.py: the checker, never the thing measured)."""
+    from oracle import seg_ref as S
+    ref = S.pairwise(d["s"], d["y"], d["g"], S.PairSpec(**spec_kw))
+    n = int(out["n_pair"].item())
+    loss = float(out["loss"].item())
+    g = out["dlogits"].cpu().numpy().astype(np.float64)
+    err = np.abs(g - ref["grad"])
+    scale = ref["grad_abs"]
+    loss_rel = abs(loss - ref["loss"]) / max(abs(ref["loss"]), 1e-30)
+    grad_rel = float((err / np.maximum(scale, 1e-30))[scale > 0].max()) if (scale > 0).any() else 0.0
+    rec = {"oracle": "oracle/seg_ref.py (float64, segmented)", "n_pair": n, "n_pair_exact": n == ref["n_pair"],
+           "n_pair_f32_exact": float(out["n_pair_f32"].item()) == float(np.float32(ref["n_pair"])),
+           "loss_rel": loss_rel, "grad_max_abs_err_over_A": grad_rel,
+           "grad_max_abs_err_over_max_abs_grad": float(err.max() / max(np.abs(ref["grad"]).max(), 1e-30)),
+           "tolerance": 1e-5}
+    rec["ok"] = bool(rec["n_pair_exact"] and rec["n_pair_f32_exact"] and loss_rel <= 1e-5 and
+                     bool((err <= 1e-5 * scale + 1e-12).all()))
+    return rec
+
+
+def parity_listwise(out, d):
+    from oracle import seg_ref as S
+    ref = S.listwise(d["g"], d["y"], d["s"])
+    v = int(out["n_valid"].item())
+    loss = float(out["loss"].item())
+    g = out["dlogits"].cpu().numpy().astype(np.float64)
+    loss_rel = abs(loss - ref["loss"]) / max(abs(ref["loss"]), 1e-30)
+    grad_rel = float(np.abs(g - ref["grad"]).max() / max(np.abs(ref["grad"]).max(), 1e-30))
+    return {"oracle": "oracle/seg_ref.py (float64, segmented)", "n_valid": v, "n_valid_exact": v == ref["n_valid"],
+            "loss_rel": loss_rel, "grad_max_abs_err_over_max_abs_grad": grad_rel, "tolerance": 1e-5,
+            "ok": bool(v == ref["n_valid"] and loss_rel <= 1e-5 and grad_rel <= 1e-5)}
+
+
+def time_device(step, steps, warmup, flush):
+    """Per-step CUDA events with the L2 flushed before every step (single-call latency), then the same steps back to
+    back without the flush (streamed: what a training loop sees)."""
+    import torch
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.fill_(k & 0xFF)
+        evs[k][0].record(); step(); evs[k][1].record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in evs]
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record()
+    for _ in range(steps):
+        step()
+    b1.record(); torch.cuda.synchronize()
+    return {"single_call_us": float(np.mean(ms)) * 1e3, "single_call_median_us": float(np.median(ms)) * 1e3,
+            "streamed_us": b0.elapsed_time(b1) / steps * 1e3}
+
+
+def cpu_dense_full(d, kind, budget_s=60.0):
+    """The reference's dense algorithm (torch-CPU port) at the FULL size of a config, all host threads: the one
+    like-for-like CPU comparison (cfg1, cfg2 pairwise; cfg4 listwise).  None if the host lacks the memory."""
+    import torch
+    from oracle import torch_dense as T
+    b = d["s"].size
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    need = (60 if kind == "pairwise" else 0) * b * b + (0 if kind == "pairwise" else 40 * b * d.get("n_lists", 1))
+    if avail and need > 0.6 * avail:
+        return {"skipped": f"needs ~{need / 2**30:.0f} GiB of host memory, {avail / 2**30:.0f} GiB available"}
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    if ncpu > torch.get_num_threads():
+        torch.set_num_threads(ncpu)
+    s, y = torch.tensor(d["s"]), torch.tensor(d["y"])
+    g = torch.tensor(d["g"]).to(torch.float64)
+    if kind == "pairwise":
+        fn = lambda: T.pairwise_fwd_bwd(s, y, g, power=d["power"])
+    else:
+        fn = lambda: T.listwise_fwd_bwd(g, y, s)
+    t = time.perf_counter(); r = fn(); first = time.perf_counter() - t           # (warm-up; also sizes the run)
+    reps = int(max(1, min(5, budget_s / max(first, 1e-3) - 1)))
+    t = time.perf_counter()
+    for _ in range(reps):
+        r = fn()
+    dt = (time.perf_counter() - t) / reps
+    return {"sec_per_step": dt, "steps": reps, "cores": torch.get_num_threads(), "same_config": True,
+            "kind": "port", "implementation": "oracle/torch_dense.py (op-for-op dense torch-CPU port of the reference)",
+            "result": {"loss": r[0], "count": r[1]}}
+
+
+def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
+    """cfg1, cfg2 (pairwise, binary labels) and cfg4 (listwise): single-call and streamed step time, roofline
+    fraction, parity record, and the dense CPU port at the full size of the config."""
+    import torch
+    from oracle import generators as G
+    from rec_now_b200 import ops
+    recs = {}
+    for name in ("cfg1", "cfg2"):
+        d = getattr(G, name)(0)
+        s, y = torch.tensor(d["s"], device=dev), torch.tensor(d["y"], device=dev)
+        keys = torch.tensor(d["g"], device=dev).reshape(1, -1)
+        step = lambda: ops.pairwise_fwd_bwd(s, y, keys, label_func="step", power=0.0)
+        t = time_device(step, steps, 5, flush)
+        out = step()
+        n = int(out["n_pair"].item())
+        rec = {"workload": f"{name}: pairwise B={s.numel()}, binary labels", "rows": s.numel(), "n_pair": n, **t,
+               "pairs_per_s": n / (t["single_call_us"] * 1e-6), "samples_per_s": s.numel() / (t["single_call_us"] * 1e-6),
+               "sfu_roofline_frac_step": MUFU_PER_PAIR * n / (t["single_call_us"] * 1e-6) / mufu_peak,
+               "hbm_roofline_frac_step": 20 * s.numel() / (t["single_call_us"] * 1e-6) / 1e9 / hbm_gbs,
+               "segmentation_path": {1: "counting", 2: "radix"}.get(ops.last_segmentation_path(out["_scratch"]), "?"),
+               "parity": parity_pairwise(out, d, dict(power=0.0))}
+        if with_cpu:
+            c = cpu_dense_full(d, "pairwise")
+            if "sec_per_step" in c:
+                c["pairs_per_s"] = n / c["sec_per_step"]
+                c["n_pair_matches"] = c["result"]["count"] == n
+                c["speedup_single_call"] = c["sec_per_step"] / (t["single_call_us"] * 1e-6)
+            rec["cpu_full_size"] = c
+        recs[name] = rec
+    d = G.cfg4(0)
+    s, y = torch.tensor(d["s"], device=dev), torch.tensor(d["y"], device=dev)
+    keys = torch.tensor(d["g"], device=dev)
+    step = lambda: ops.listwise_fwd_bwd(keys, y, s)
+    t = time_device(step, steps, 5, flush)
+    out = step()
+    rec = {"workload": f"cfg4: listwise segmented softmax-CE B={s.numel()}, {d['n_lists']} Zipf-size lists (cap 512)",
+           "rows": s.numel(), "n_valid_lists": int(out["n_valid"].item()), **t,
+           "samples_per_s": s.numel() / (t["single_call_us"] * 1e-6),
+           "hbm_roofline": {"bound": "hbm", "algorithmic_bytes_per_sample": 20, "peak_gbs": hbm_gbs,
+                            "achieved_gbs_single_call": 20 * s.numel() / (t["single_call_us"] * 1e-6) / 1e9,
+                            "frac_single_call": 20 * s.numel() / (t["single_call_us"] * 1e-6) / 1e9 / hbm_gbs,
+                            "achieved_gbs_streamed": 20 * s.numel() / (t["streamed_us"] * 1e-6) / 1e9,
+                            "frac_streamed": 20 * s.numel() / (t["streamed_us"] * 1e-6) / 1e9 / hbm_gbs,
+                            "note": "1.3 MB of algorithmic traffic = 0.2 us of HBM time: the path is launch / latency "
+                                    "bound at this size, the fraction says how far"},
+           "parity": parity_listwise(out, d)}
+    if with_cpu:
+        c = cpu_dense_full(d, "listwise")
+        if "sec_per_step" in c:
+            c["samples_per_s"] = s.numel() / c["sec_per_step"]
+            c["speedup_single_call"] = c["sec_per_step"] / (t["single_call_us"] * 1e-6)
+        rec["cpu_full_size"] = c
+    recs["cfg4"] = rec
+    return recs
+
 # ----------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------
@@ -304,6 +461,36 @@ def ours(args):
     pair_ms_plain, out = time_pair_kernel(0)
     n_pair = int(out["n_pair"].item())
     err = ops.device_error(out["_scratch"]) if world == 1 else 0
+
+    # ---- parity gate of the benchmarked workload (outside every timed region) ---------------------------
+    spec_kw = dict(power=-0.5, label_func="diff")
+    strong = None
+    if world == 1:
+        parity = parity_pairwise(out, d, dict(spec_kw, rw_pos=d["w"]))
+        seg_path = {1: "counting (sort-free)", 2: "radix sort"}.get(ops.last_segmentation_path(out["_scratch"]), "?")
+    else:
+        # N > 1: the same global batch on ONE GPU (rank 0), through the single-GPU product path: exact pair count, loss,
+        # this rank's gradient rows; the time of that run is the strong-scaling reference of the global mode
+        seg_path = "radix sort (replicated on every rank)"
+        parity = None
+        if rank == 0:
+            gs, gy, gw = (torch.tensor(d[k], device=dev) for k in ("s", "y", "w"))
+            gk = torch.tensor(d["g"], device=dev).reshape(1, -1)
+            one = lambda: ops.pairwise_fwd_bwd(gs, gy, gk, rw_pos=gw, label_func="diff", power=-0.5)
+            t1 = time_device(one, min(K, 20), 3, flush)
+            ref = one()
+            torch.cuda.synchronize()
+            n1 = int(ref["n_pair"].item())
+            l1, lN = float(ref["loss"].item()), float(out["loss"].item())
+            g1 = ref["dlogits"][lo:hi].double().cpu().numpy(); gN = out["dlogits"].double().cpu().numpy()
+            gerr = float(np.abs(g1 - gN).max() / max(np.abs(g1).max(), 1e-30))
+            parity = {"against": "the same global batch on one GPU through rn_pairwise_fwd_bwd (rank 0)",
+                      "n_pair": n_pair, "n_pair_exact": n1 == n_pair, "loss_rel": abs(l1 - lN) / max(abs(l1), 1e-30),
+                      "grad_max_abs_err_over_max_abs_grad": gerr, "tolerance": 1e-5}
+            parity["ok"] = bool(parity["n_pair_exact"] and parity["loss_rel"] <= 1e-5 and gerr <= 1e-5)
+            strong = {"one_gpu_same_global_batch_us": t1["single_call_us"],
+                      "segmentation_path_one_gpu": {1: "counting", 2: "radix"}.get(ops.last_segmentation_path(ref["_scratch"]), "?")}
+            del gs, gy, gw, gk, ref
 
     # ---- e2e through the public API: pinned host buffers, H2D + loss.backward() + D2H every step -------
     # the step's inputs arrive as ONE pinned host buffer [g int64 | s f32 | y f32 | w f32] (what a data loader hands
@@ -451,6 +638,13 @@ def ours(args):
     if rank == 0:
         peaks, peak_src = measured_peaks()
         clocks = sampler.summary()
+        if world == 1:
+            kernels_per_step, kernel_names = 2, ["k_seg<HeadsTail> (count / offsets / scatter)", "k_pair"]
+            if not seg_path.startswith("counting"):
+                kernels_per_step, kernel_names = 3, ["k_init", "k_seg<HeadsTail>", "k_pair"]
+        else:
+            kernels_per_step = 5
+            kernel_names = ["k_pack", "k_init (+ peer gather)", "k_seg<HeadsTail>", "k_pair", "k_reduce_chunks"]
         value = n_pair * K / (t_ms * 1e-3)
         rows_total = ROWS_PER_GPU * world
         # roofline of the dominant kernel (k_pair): SFU-bound -- 3 MUFU per kept pair; this rank scored 1/world
@@ -489,6 +683,14 @@ def ours(args):
                          "frac_plain_launches": MUFU_PER_PAIR * pairs_per_launch / (pair_ms_plain * 1e-3) / mufu_peak,
                          "algorithmic_mufu_per_pair": MUFU_PER_PAIR, "pairs_per_launch": pairs_per_launch,
                          "traffic": kpair_traffic(world),
+                         # what the kernel really issues (ncu capture): the product-form tiles need ~1.5 MUFU per pair, so
+                         # the XU pipe itself is far from full and the kernel is bound by issue slots (FP32x2, SHFL, MUFU
+                         # sharing the schedulers); `frac` above is the 3-MUFU algorithmic convention of SURVEY 8d
+                         "issued": {k: kpair_capture(world).get(k) for k in
+                                    ("mufu_lane_ops_per_pair_issued", "xu_pipe_pct_of_peak_active", "issue_active_pct",
+                                     "fma_pipe_pct_of_peak_active", "alu_pipe_pct_of_peak_active",
+                                     "thread_instructions_per_pair", "source")},
+                         "binding_resource_measured": "issue slots (see `issued`); the SFU roofline is the algorithmic yardstick",
                          "hbm_view": {"bound": "hbm", "achieved": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9,
                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peak_src,
                                       "frac": HBM_BYTES_PER_SAMPLE * rows_total / (pair_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
@@ -501,9 +703,13 @@ def ours(args):
                                    "api": "rec_block.pairwise_loss_from_batch.pairwise_loss + backward on torch tensors "
                                           "(H2D / D2H every step, Python + autograd-engine host time included)"}
                                   if world == 1 else None},
-            "gpu_launches": int(lib.rn_pairwise_launch_count(rows_total, 1)) * K,
-            "launch_mode": {"kernels_per_step": int(lib.rn_pairwise_launch_count(rows_total, 1)),
+            "gpu_launches": kernels_per_step * K,
+            "launch_mode": {"kernels_per_step": kernels_per_step, "kernels": kernel_names,
                             "steps_enqueued_as_one_cuda_graph_launch": graph_calls},
+            "segmentation_path": seg_path,
+            "parity": parity,
+            "step_breakdown_us": {"step": t_ms / K * 1e3, "k_pair": pair_ms * 1e3, "non_pair": (t_ms / K - pair_ms) * 1e3,
+                                  "step_sfu_roofline_frac": MUFU_PER_PAIR * pairs_per_launch / (t_ms / K * 1e-3) / mufu_peak},
             "clocks": clocks, "device_error": err,
         }
         if world == 1 and not args.no_cpu:
@@ -514,6 +720,27 @@ def ours(args):
                 "sample": f"first {r['rows']} rows of the cfg3 batch through the dense (B,B) torch-CPU restatement of "
                           f"the reference (fwd+bwd, {r['n_pair']} pairs/step, {r['sec_per_step']:.2f} s/step); the "
                           "full B=65536 needs >= 155 GB of dense temporaries"}
+        if world == 1 and not args.no_configs:
+            # the other BASELINE.json configurations (cfg1, cfg2 binary pairwise; cfg4 listwise) + this one, one record each
+            cfgs = other_configs(lib, dev, flush, mufu_peak, peaks["hbm_gbs"], min(K, 100), not args.no_cpu)
+            cfgs["cfg3"] = {"workload": name, "rows": ROWS_PER_GPU, "n_pair": n_pair,
+                            "single_call_us": t_ms / K * 1e3, "streamed_us": b2b_ms * 1e3,
+                            "pairs_per_s": value, "samples_per_s": line["samples_per_s"],
+                            "sfu_roofline_frac_step": line["step_breakdown_us"]["step_sfu_roofline_frac"],
+                            "sfu_roofline_frac_k_pair": line["roofline"]["frac"], "segmentation_path": seg_path,
+                            "parity": parity, "cpu_full_size": {"skipped": "the dense reference algorithm needs >= 155 GB at "
+                                                                "B=65536 (see cpu_baseline for the bounded sample)"}}
+            line["configs"] = cfgs
+        if world > 1:
+            # what the pairs/s figure hides (pairs grow with the square of the group sizes): samples/s, the share of the
+            # step that is not pair scoring, and the strong-scaling view -- the same global batch on one GPU
+            gm = {"rows_total": rows_total, "samples_per_s": line["samples_per_s"],
+                  "k_pair_us": pair_ms * 1e3, "non_pair_us": (t_ms / K - pair_ms) * 1e3}
+            if strong:
+                gm.update(strong)
+                gm["speedup_over_one_gpu_same_batch"] = strong["one_gpu_same_global_batch_us"] / (t_ms / K * 1e3)
+                gm["parallel_efficiency_same_batch"] = gm["speedup_over_one_gpu_same_batch"] / world
+            line["global_mode"] = gm
         emit_line(line)
     if world > 1:
         dist.destroy_process_group()
@@ -537,6 +764,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-configs", action="store_true", help="skip the per-config records (cfg1, cfg2, cfg4)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

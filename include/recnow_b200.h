@@ -231,6 +231,9 @@ int rn_listwise_launch_count(int64_t B);
  * unless RN_GRAPH=0, the stream is under capture, or rn_profile_enable is active); negative (-count - 1) after a graph
  * API failure switched the thread back to plain launches. */
 int64_t rn_debug_graph_launches(void);
+/* Byte offset of a region of the pairwise arena of (B, K) for the developer tools under scripts/ (which: 0 per-CTA
+ * debug stamps, 1 group records, 2 J ranges, 3 piece boundaries); -1 if unknown. */
+int64_t rn_debug_arena_offset(int64_t B, int32_t K, int32_t which);
 
 #ifdef __cplusplus
 }

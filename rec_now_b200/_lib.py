@@ -25,7 +25,7 @@ EXPORTS = [
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
     "rn_bench_mufu", "rn_profile_enable", "rn_profile_enable_ex", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
-    "rn_debug_graph_launches", "rn_pack_row_block", "rn_reduce_peer_chunks",
+    "rn_debug_graph_launches", "rn_debug_arena_offset", "rn_pack_row_block", "rn_reduce_peer_chunks",
     "rn_host_pairwise_create", "rn_host_pairwise_submit", "rn_host_pairwise_wait", "rn_host_pairwise_destroy",
 ]
 
@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
     L.rn_host_pairwise_submit.argtypes = [vp, C.POINTER(PairwiseArgs), C.POINTER(i32)]
     L.rn_host_pairwise_wait.argtypes = [vp, i32]
     L.rn_host_pairwise_destroy.argtypes = [vp]
+    L.rn_debug_arena_offset.restype = i64
+    L.rn_debug_arena_offset.argtypes = [i64, i32, i32]
     L.rn_debug_graph_launches.restype = i64
     L.rn_debug_graph_launches.argtypes = []
     _lib = L

@@ -168,4 +168,11 @@ extern "C" int rn_debug_timestamps(void* scratch, uint64_t* ts_host, int32_t cap
   return RN_OK;
 }
 
+extern "C" int64_t rn_debug_arena_offset(int64_t B, int32_t K, int32_t which) {
+  if (B <= 0 || K <= 0) return -1;
+  const Layout L = make_layout(B, K);
+  switch (which) { case 0: return (int64_t)L.gstat; case 1: return (int64_t)L.rec; case 2: return (int64_t)L.blk; case 3: return (int64_t)L.bnd; }
+  return -1;
+}
+
 extern "C" int64_t rn_debug_graph_launches(void) { return (int64_t)graph_launch_count(); }

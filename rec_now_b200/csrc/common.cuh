@@ -34,8 +34,8 @@ struct RowMap {
 // block back into its clean state (all zero except the barrier generations and the report of the finished call).
 struct Ctl {
   u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range
-  u32 bar_cnt, bar_gen;         // grid barrier of the segmentation kernel: arrivals (self-resetting), generation
-  u32 bar2_cnt, bar2_gen;       // grid barrier of the pair kernel
+  u32 bar_cnt, bar2_cnt;        // grid barriers of the segmentation / pair kernel: arrivals (reset by the last arriver)
+  u32 pad_a[2];
   u32 k2_ticket;                // dynamic work-unit ticket of the pair kernel
   u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars / cleans up)
   u32 n_units, unit_c;          // work list: number of units, J-blocks per unit
@@ -52,6 +52,9 @@ struct Ctl {
   u64 dbg[8];                   // pair-kernel debug tallies (RN_PAIR_DEBUG=1): see k_pair
   // report of the last finished call (copied here before the working fields are reset; read by the rn_debug_* calls)
   u32 rep_err, rep_path, rep_n_units, rep_unit_c; u64 rep_n_tiles;
+  // barrier generations, each in a line of its own: the waiters poll these, the arrivals go to bar_cnt / bar2_cnt
+  __align__(128) u32 bar_gen; u32 pad_g[31];
+  __align__(128) u32 bar2_gen; u32 pad_h[31];
 };
 
 // Sort plan.  Compact sort key = (gid << labbits) | ((enc_label >> labshift) & mask): only the varying bit
@@ -92,7 +95,7 @@ struct Layout {
   size_t labpart, slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
   // counting path (group_count.cuh): group records (clean = zero between calls), created-group lists per 512-row tile,
   // sorted group index column
-  size_t rec, glist, gcount, sgrp;
+  size_t rec, glist, gcount, sgrp, bnd, jn;
   int64_t Bcap;
 };
 
@@ -107,6 +110,7 @@ struct __align__(16) GRec {
 };
 constexpr int kLevels = 8;       // label levels of the counting path: integer-valued labels -1 .. 6
 constexpr int kGTile = 512;      // rows per tile of the counting path (= kSegThreads)
+constexpr u32 kBndCap = 16384;   // piece boundaries of the pair kernel's partition the arena holds (warps of its grid + 1)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -173,6 +177,8 @@ inline Layout make_layout(int64_t Bcap, int K, int64_t B = 0) {
   L.glist = take(sizeof(u32) * ngt * kGTile);
   L.gcount = take(sizeof(u32) * ngt);
   L.sgrp = take(sizeof(u32) * Bc);
+  L.bnd = take(sizeof(uint4) * kBndCap);               // piece boundaries of the pair kernel's partition (PrePart)
+  L.jn = take(sizeof(u32) * 2 * nib_cap);
   L.total = o;
   return L;
 }
@@ -194,24 +200,24 @@ __device__ __forceinline__ u32 ld_acquire(const u32* p) {
   u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
-// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  bar[0] counts arrivals and is reset by
-// the last arriver, bar[1] is the generation the waiters watch: the pair needs no initialisation beyond "count = 0" and
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  *cnt counts arrivals and is reset by
+// the last arriver, *genp is the generation the waiters watch (a line of its own): the pair needs no initialisation beyond "count = 0" and
 // carries nothing from call to call.  The fences publish this CTA's writes and invalidate its L1 so that plain loads
 // after the barrier see other CTAs' data.  A bounded spin turns a scheduling failure (or an arena that was not in its
 // clean state) into ctl->err instead of a hung GPU.
 __device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void grid_sync(u32* bar, u32* err) {
+__device__ __forceinline__ void grid_sync(u32* cnt, u32* genp, u32* err) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    const u32 gen = ld_relaxed(bar + 1);          // (read before arriving: the generation cannot move until this CTA arrives)
+    const u32 gen = ld_relaxed(genp);             // (read before arriving: the generation cannot move until this CTA arrives)
     __threadfence();
-    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-      st_relaxed(bar, 0u);
-      st_release(bar + 1, gen + 1u);
+    if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+      st_relaxed(cnt, 0u);
+      st_release(genp, gen + 1u);
     } else {
       u32 spins = 0;
-      while (ld_acquire(bar + 1) == gen) {
+      while (ld_acquire(genp) == gen) {
         if (++spins > (1u << 23)) { atomicOr(err, 1u); break; }
       }
     }

@@ -75,7 +75,7 @@ struct ListwiseTail {
     const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
     const u32* astart = bounds.astart;
     bounds.run(S, pl, key, val, smem);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     // ---- per-list statistics; valid lists per 512-position chunk -------------------------------------------
     u32* sm_cnt = smem;                    // [kSegWarps]
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -90,7 +90,7 @@ struct ListwiseTail {
       }
       __syncthreads();
     }
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     // ---- rank of every valid list (exclusive scan of the valid flags over head positions = first-occurrence
     //      order, LW:109), per-list weighted losses, their sum ------------------------------------------------
     u32* sm_scan = smem;                   // [kSegWarps]
@@ -134,7 +134,7 @@ struct ListwiseTail {
       for (int q = 0; q < kSegWarps; ++q) t += sm_d[q];
       if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     // ---- gradient + scalars -------------------------------------------------------------------------------
     const u32 V = ld_relaxed(&ctl->n_valid);
     const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;

@@ -57,6 +57,77 @@ __device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst
   return hi > lo ? hi - lo : 0u;
 }
 
+// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
+// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
+// a[n] receives the total (sc: kPairWarps + 2 words).  All threads of the CTA must call it.
+constexpr u32 kScanThreads = 256;
+__device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
+  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
+  const bool act = threadIdx.x < kScanThreads;
+  const u32 per = (n + kScanThreads - 1) / kScanThreads;
+  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
+  u32 sum = 0, inc = 0;
+  if (act) {
+    for (u32 i = i0; i < i1; ++i) sum += a[i];
+    inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+    if (ln == 31) sc[wq] = inc;
+  }
+  __syncthreads();
+  if (act) {
+    u32 off = inc - sum;
+    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
+    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
+    if (threadIdx.x == kScanThreads - 1) a[n] = off;
+  }
+  __syncthreads();
+}
+
+// Largest idx in [lo, hi) with arr[idx] <= key (arr nondecreasing, arr[lo] <= key); one thread, binary search.
+__device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) {
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (arr[mid] <= key) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// Cost of one J-block (32 negatives) of a virtual block; a fast tile costs 8 * kCostUnit.  Range R1 of an I-block (the
+// rows of the group that began before the block) is fast tiles plus the blocks that hold a label-level boundary; range
+// R2 (groups that begin inside the block) is general tiles (a warp that finishes early costs little -- its SMSP
+// neighbours speed up -- while a late one runs alone and cannot fill the SFU pipe, so the estimates lean to the
+// pessimistic side).
+constexpr u32 kCostUnit = 4;                 // cost units per eighth of a fast tile (sub-eighth resolution for the averages below)
+constexpr u32 kCostFast = 8 * kCostUnit;
+// A range R1 of nt J-blocks crosses up to `lv` label-level boundaries of its group; a block that holds one is scored in
+// 2-3 passes (runs_tile) or as a general tile.  Short ranges (medium-sized groups) consist mostly of such blocks, long
+// ones hardly notice: cost per block = 8 + cstr * min(nt, lv) / nt (rounded up).  lv = 0: label levels play no role.
+__device__ __forceinline__ u32 vcost(u32 v, u32 nt, u32 cgen, u32 cstr, u32 lv) {
+  if (v & 1u) return cgen;
+  return kCostFast + (cstr * min(nt, lv) + nt - 1u) / max(nt, 1u);
+}
+
+// Position `pos` of the cost line -> (virtual block, J-block, eighth).  s_pi: cost prefix over the virtual blocks,
+// s_jn: first J-block | J-block count << 16 of every virtual block.
+__device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32 csw,
+                                            u32 cstr, u32 lv, u32& v, u32& jb, u32& e) {
+  if (pos >= tot) { v = nvb; jb = 0; e = 0; return; }
+  v = last_le(s_pi, 0, nvb, pos);
+  u32 o = pos - s_pi[v];
+  o = o > csw ? o - csw : 0u;                      // (the first csw units of a block stand for its row loads / flush)
+  const u32 c = vcost(v, s_jn[v] >> 16, cgen, cstr, lv), q = o / c;
+  jb = (s_jn[v] & 0xFFFFu) + q;
+  e = ((o - q * c) * 8u) / c;
+}
+
+// Partition of the pair kernel's cost line, computed ahead of it (see HeadsTail::partition): boundary r of the
+// wpr = (pair-kernel warps of the grid) equal pieces as (virtual block, J-block, eighth), and per virtual block its first
+// J-block | J-block count << 16.
+struct PrePart {
+  uint4* bnd; u32* jn;        // [wpr + 1] (v, jb, e, -), [nvb]
+  u32 wpr, pair_grid;         // pieces = warps of the pair kernel's grid; its CTAs
+  u32 cost_gen, cost_switch, cost_straddle, lv_cost;
+  int on;                     // the arrays exist and the batch's cost prefix fits k_seg's shared memory
+};
+
 // ---- heads tail of k_seg ---------------------------------------------------------------------------------
 // Work units: an I-block (64 sorted rows) x up to C consecutive J-blocks (32 sorted rows each) of its J range.
 // Record = (I-block, first J-block | J-block count << 24).
@@ -66,6 +137,7 @@ struct HeadsTail {
   uint2* aj; float *ss, *sy, *swp, *swn, *gacc, *lossrow; u32 *cnt, *perm, *sgrp;
   uint2* blk; uint2* units; u32 nib; u64* cprim; const u32* pgid;
   u32 target_units;          // work-list granularity target (units of <= C J-blocks)
+  PrePart pp;
 
   // ---- counting path (group_count.cuh): count -> offsets -> scatter; false = outside its menu (radix path instead) ----
   // One row's scatter: its sorted position from the group record, its sorted columns, its negative range and the
@@ -86,10 +158,74 @@ struct HeadsTail {
     lossrow[pos] = P.dyn_count ? 0.f : wocc;                 // (non-dynamic: the row's occurrence weight, read by k_pair)
     if (P.dyn_count) cnt[pos] = 0;
     else if (P.row_pairs) P.row_pairs[i] = (int64_t)n;
-    if (n) {
-      const u32 v = 2u * (pos / kIB) + ((a < (pos & ~(u32)(kIB - 1))) ? 0u : 1u);     // R1: the group began before the I-block
-      atomicMax(&blk[v].x, ~a);
-      atomicMax(&blk[v].y, a + n);
+  }
+
+  // J ranges of the I-blocks a group touches, from its geometry alone (offsets phase: base, level starts `pre`, level
+  // counts `c`, rows `tot`).  Range = (group start, level start of the group's LAST row inside the block): the levels
+  // ascend along the positions, so that row has the longest negative range.  The block in which the group begins gets
+  // it as R2 (hull with the other groups that begin there: atomicMax on (~lo, hi), zero = empty), every later block
+  // as R1 (exactly one group can reach into a block from the left: plain store).
+  static __device__ __forceinline__ u32 level_start_at(const u32* pre, const u32* c, u32 x) {
+    u32 r = 0;
+#pragma unroll
+    for (int q = 0; q < kLevels; ++q) if (c[q] && pre[q] <= x) r = pre[q];
+    return r;
+  }
+  __device__ __forceinline__ void block_range(u32 b, u32 b0, u32 base, u32 tot, const u32* pre, const u32* c) const {
+    const u32 xlast = min(tot, (b + 1u) * kIB - base) - 1u;
+    const u32 hi = level_start_at(pre, c, xlast);
+    if (!hi) return;
+    if (b == b0) { atomicMax(&blk[2 * b + 1].x, ~base); atomicMax(&blk[2 * b + 1].y, base + hi); }
+    else blk[2 * b] = make_uint2(~base, base + hi);
+  }
+
+  // Cost prefix of the pair kernel's work line and the boundaries of its equal pieces (what k_pair's prologue
+  // otherwise computes in every CTA), by helper h of H: every helper scans the costs, resolves a slice of the boundaries.
+  __device__ __forceinline__ void partition(const SegParams& S, u32* smem, u32 h, u32 H) const {
+    const u32 nvb = 2 * nib;
+    u32* s_pi = smem;                          // [nvb + 1] cost prefix
+    u32* s_jn = smem + nvb + 1;                // [nvb] first J-block | J-block count << 16
+    u32* s_sc = s_jn + nvb;                    // scan partials
+    u32 msum = 0;
+    // (four virtual blocks per round: their range loads are all in flight together)
+    for (u32 v0 = 0; v0 < nvb; v0 += 4 * kSegThreads) {
+      uint2 r[4], rl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u32 v = v0 + k * kSegThreads + threadIdx.x;
+        r[k] = make_uint2(0, 0); rl[k] = make_uint2(0, 0);
+        if (v < nvb) { r[k] = blk[v]; if (v & 1u) rl[k] = blk[v - 1]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u32 v = v0 + k * kSegThreads + threadIdx.x;
+        if (v < nvb) {
+          u32 lo = 0, hi = 0;
+          if (r[k].y > ~r[k].x) { lo = ~r[k].x >> 5; hi = (r[k].y + 31) >> 5; }
+          if ((v & 1u) && rl[k].y > ~rl[k].x) lo = max(lo, (rl[k].y + 31) >> 5);      // (as vblock_tiles)
+          const u32 nt = hi > lo ? hi - lo : 0u;
+          const u32 jn = nt ? (lo | (nt << 16)) : 0u;
+          s_jn[v] = jn;
+          if (h == 0) pp.jn[v] = jn;
+          s_pi[v] = nt ? nt * vcost(v, nt, pp.cost_gen, pp.cost_straddle, pp.lv_cost) + pp.cost_switch : 0u;
+          msum += nt;
+        }
+      }
+    }
+    __syncthreads();
+    block_excl_scan(s_pi, nvb, s_sc);
+    const u32 tot = s_pi[nvb];
+    const u32 q = tot / pp.wpr, rem = tot - q * pp.wpr;
+    for (u32 r = h * kSegThreads + threadIdx.x; r <= pp.wpr; r += H * kSegThreads) {
+      const u32 pos = q * r + (u32)(((u64)rem * r) / pp.wpr);
+      u32 v, jb, e;
+      resolve_pos(pos, tot, nvb, s_pi, s_jn, pp.cost_gen, pp.cost_switch, pp.cost_straddle, pp.lv_cost, v, jb, e);
+      pp.bnd[r] = make_uint4(v, jb, e, 0u);
+    }
+    if (h == 0) {
+      msum = warp_sum(msum);
+      if (lane_id() == 0 && msum) atomicAdd((u64*)&S.ctl->n_tiles, (u64)msum);
+      if (threadIdx.x == 0) { S.ctl->n_units = tot; S.ctl->unit_c = 0; }
     }
   }
 
@@ -191,9 +327,10 @@ struct HeadsTail {
       __syncthreads();
     }
     if (__syncthreads_or(bad) && tid == 0) st_relaxed(&ctl->fallback, 1u);
-    stamp(ctl, 1);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
-    stamp(ctl, 2);
+    auto dbg = [&](u32 ph) { if (S.dbgts && tid == 0) S.dbgts[(size_t)ph * gridDim.x + blockIdx.x] = globaltimer(); };
+    stamp(ctl, 1); dbg(0);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    stamp(ctl, 2); dbg(1);
     if (ld_relaxed(&ctl->fallback)) return false;
     // ---- offsets: one thread per record created by this CTA's tiles -------------------------------------------------
     u64 npsum = 0;
@@ -202,11 +339,13 @@ struct HeadsTail {
       for (u32 k0 = 0; k0 < ncr; k0 += kSegThreads) {             // (uniform trip count: the body uses warp collectives)
         const u32 k = k0 + tid;
         const bool act = k < ncr;
-        u32 slot = 0, tot = 0; u32 pre[kLevels]; u64 pairs = 0;
+        u32 slot = 0, tot = 0; u32 pre[kLevels], c[kLevels]; u64 pairs = 0;
+#pragma unroll
+        for (int q = 0; q < kLevels; ++q) { pre[q] = 0; c[q] = 0; }
         if (act) {
           slot = S.glist[(size_t)t * kGTile + k];
           const uint4 c0 = *reinterpret_cast<const uint4*>(rec[slot].cnt), c1 = *reinterpret_cast<const uint4*>(rec[slot].cnt + 4);
-          const u32 c[kLevels] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
 #pragma unroll
           for (int q = 0; q < kLevels; ++q) { pre[q] = tot; pairs += (u64)c[q] * tot; tot += c[q]; }   // pairs of a row = rows below its level
         }
@@ -217,9 +356,26 @@ struct HeadsTail {
         u32 wbase = 0;
         if (ln == 0 && wtot) wbase = atomicAdd(&ctl->cursor, wtot);
         wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        const u32 base = wbase + inc - tot;
+        // J ranges of the I-blocks the group touches: up to three blocks by its own thread, longer groups by the warp
+        u32 b0 = 0, nblk = 0;
+        if (act && tot) {
+          b0 = base / kIB; nblk = (base + tot - 1u) / kIB - b0 + 1u;
+          for (u32 b = b0; b < b0 + min(nblk, 3u); ++b) block_range(b, b0, base, tot, pre, c);
+        }
+        u32 big = __ballot_sync(0xFFFFFFFFu, nblk > 3u);
+        while (big) {
+          const int src = __ffs(big) - 1; big &= big - 1;
+          u32 gp[kLevels], gc[kLevels];
+#pragma unroll
+          for (int q = 0; q < kLevels; ++q) { gp[q] = __shfl_sync(0xFFFFFFFFu, pre[q], src); gc[q] = __shfl_sync(0xFFFFFFFFu, c[q], src); }
+          const u32 gbase = __shfl_sync(0xFFFFFFFFu, base, src), gtot = __shfl_sync(0xFFFFFFFFu, tot, src);
+          const u32 gb0 = __shfl_sync(0xFFFFFFFFu, b0, src), gnb = __shfl_sync(0xFFFFFFFFu, nblk, src);
+          for (u32 b = gb0 + 3u + ln; b < gb0 + gnb; b += 32) block_range(b, gb0, gbase, gtot, gp, gc);
+        }
         if (act) {
           GRec* r = rec + slot;
-          r->base = wbase + inc - tot;
+          r->base = base;
           *reinterpret_cast<uint4*>(r->cnt) = make_uint4(pre[0], pre[1], pre[2], pre[3]);
           *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(pre[4], pre[5], pre[6], pre[7]);
           if (!dyn) {
@@ -241,10 +397,14 @@ struct HeadsTail {
       }
     }
     if (blockIdx.x == 0 && tid == 0) ctl->path = 1;
-    stamp(ctl, 3);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
-    stamp(ctl, 4);
-    // ---- scatter ------------------------------------------------------------------------------------------------------
+    stamp(ctl, 3); dbg(2);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    stamp(ctl, 4); dbg(3);
+    // ---- scatter (+ the pair kernel's partition, beside it) ----------------------------------------------------------
+    // The J ranges are complete: CTAs without rows (the grid is always full) work out the partition of the pair kernel's
+    // cost line while the others scatter; without enough spare CTAs everybody takes a slice after its rows.
+    const u32 spare = gridDim.x > ntile ? gridDim.x - ntile : 0u;
+    if (pp.on && spare >= 4u && blockIdx.x >= ntile) { partition(S, smem, blockIdx.x - ntile, spare); dbg(4); return true; }
     if (single) {
       const u32 i = blockIdx.x * kGTile + tid;
       if (i < B) scatter_row(S, i, k_slot, k_meta, k_s, k_y, k_wp, k_wn);
@@ -256,7 +416,8 @@ struct HeadsTail {
                       P.rw_neg ? P.rw_neg[i] : 1.f);
       }
     }
-    stamp(ctl, 17);
+    if (pp.on && spare < 4u) { __syncthreads(); partition(S, smem, blockIdx.x, gridDim.x); }
+    stamp(ctl, 17); dbg(4);
     return true;
   }
 
@@ -346,7 +507,7 @@ struct HeadsTail {
     // Batches up to 524288 rows: k_pair partitions the work itself (cost prefixes in shared memory), the kernel ends here
     // without another grid barrier.  Larger batches: explicit unit records.
     if (nib <= kMaxNibS) return;
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     stamp(ctl, 18);
     // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
     //      the unit records of its own I-blocks ------------------------------------------------------------------
@@ -404,6 +565,7 @@ struct KpArgs {
   // 512-row tile and zeroed again by the last phase of this kernel
   int fast; GRec* rec; const u32* glist; const u32* gcount; u32 ngt;
   uint2* blk_w;              // (the J ranges are zeroed again as well)
+  const uint4* bnd; const u32* jn; int pre_on;     // partition computed by k_seg's helper CTAs (PrePart)
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
 };
 
@@ -431,67 +593,6 @@ __device__ __forceinline__ void ctl_finish(Ctl* ctl) {
   ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
   ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
   ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;
-}
-
-// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
-// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
-// a[n] receives the total (sc: kPairWarps + 2 words).  All threads of the CTA must call it.
-constexpr u32 kScanThreads = 256;
-__device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
-  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
-  const bool act = threadIdx.x < kScanThreads;
-  const u32 per = (n + kScanThreads - 1) / kScanThreads;
-  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
-  u32 sum = 0, inc = 0;
-  if (act) {
-    for (u32 i = i0; i < i1; ++i) sum += a[i];
-    inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
-    if (ln == 31) sc[wq] = inc;
-  }
-  __syncthreads();
-  if (act) {
-    u32 off = inc - sum;
-    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
-    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
-    if (threadIdx.x == kScanThreads - 1) a[n] = off;
-  }
-  __syncthreads();
-}
-
-// Largest idx in [lo, hi) with arr[idx] <= key (arr nondecreasing, arr[lo] <= key); one thread, binary search.
-__device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) {
-  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (arr[mid] <= key) lo = mid; else hi = mid; }
-  return lo;
-}
-
-// Cost of one J-block (32 negatives) of a virtual block; a fast tile costs 8 * kCostUnit.  Range R1 of an I-block (the
-// rows of the group that began before the block) is fast tiles plus the blocks that hold a label-level boundary; range
-// R2 (groups that begin inside the block) is general tiles (a warp that finishes early costs little -- its SMSP
-// neighbours speed up -- while a late one runs alone and cannot fill the SFU pipe, so the estimates lean to the
-// pessimistic side).
-constexpr u32 kCostUnit = 4;                 // cost units per eighth of a fast tile (sub-eighth resolution for the averages below)
-constexpr u32 kCostFast = 8 * kCostUnit;
-// A range R1 of nt J-blocks crosses up to `lv` label-level boundaries of its group; a block that holds one is scored in
-// 2-3 passes (runs_tile) or as a general tile.  Short ranges (medium-sized groups) consist mostly of such blocks, long
-// ones hardly notice: cost per block = 8 + cstr * min(nt, lv) / nt (rounded up).  lv = 0: label levels play no role.
-__device__ __forceinline__ u32 vcost(u32 v, u32 nt, u32 cgen, u32 cstr, u32 lv) {
-  if (v & 1u) return cgen;
-  return kCostFast + (cstr * min(nt, lv) + nt - 1u) / max(nt, 1u);
-}
-
-// Position `pos` of the cost line -> (virtual block, J-block, eighth).  s_pi: cost prefix over the virtual blocks,
-// s_jn: first J-block | J-block count << 16 of every virtual block.
-__device__ __forceinline__ void resolve_pos(u32 pos, u32 tot, u32 nvb, const u32* s_pi, const u32* s_jn, u32 cgen, u32 csw,
-                                            u32 cstr, u32 lv, u32& v, u32& jb, u32& e) {
-  if (pos >= tot) { v = nvb; jb = 0; e = 0; return; }
-  v = last_le(s_pi, 0, nvb, pos);
-  u32 o = pos - s_pi[v];
-  o = o > csw ? o - csw : 0u;                      // (the first csw units of a block stand for its row loads / flush)
-  const u32 c = vcost(v, s_jn[v] >> 16, cgen, cstr, lv), q = o / c;
-  jb = (s_jn[v] & 0xFFFFu) + q;
-  e = ((o - q * c) * 8u) / c;
 }
 
 // Positive-side rows of an I-block (two per lane) and the first J block of a segment: loaded one segment ahead.
@@ -600,7 +701,15 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   const bool park = !DYN && fold_power != 0.f && !counted;
   u32 park_pg = kEmpty; u64 park_ch = 0;
   if (park && gtid0 < B) park_pg = A.sgrp[gtid0];
-  if (own_list) {
+  const bool pre = counted && A.pre_on && own_list;     // the partition was worked out by k_seg's helper CTAs
+  const u32* jn_ = pre ? A.jn : s_jn;
+  if (pre) {
+    const u32 wq = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
+    const u32 r = wq * gridDim.x + blockIdx.x;
+    const uint4 ba = A.bnd[r], bz = A.bnd[r + 1];
+    cb = ba.x; cj = ba.y; ce = ba.z; zb = bz.x; zj = bz.y; ze = bz.z;
+    st_done = !(cb < zb || (cb == zb && (cj < zj || (cj == zj && ce < ze))));
+  } else if (own_list) {
     u32 msum = 0;
     for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
       u32 jf;
@@ -682,14 +791,14 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         for (;;) {
           if (st_done || cb >= nvb) return false;
           if (cb > zb || (cb == zb && (cj > zj || (cj == zj && ce >= ze)))) { st_done = true; return false; }
-          const u32 jn = s_jn[cb], jend = (jn & 0xFFFFu) + (jn >> 16);
+          const u32 jn = jn_[cb], jend = (jn & 0xFFFFu) + (jn >> 16);
           if (cj >= jend) {                       // (also skips virtual blocks without tiles)
-            ++cb; cj = cb < nvb ? (s_jn[cb] & 0xFFFFu) : 0u; ce = 0;
+            ++cb; cj = cb < nvb ? (jn_[cb] & 0xFFFFu) : 0u; ce = 0;
             continue;
           }
           sg.b = cb >> 1; sg.jb0 = cj; sg.ea = ce;
           if (cb == zb) { sg.jb1 = ze ? zj + 1 : zj; sg.eb = ze ? ze : 8u; st_done = true; }
-          else { sg.jb1 = jend; sg.eb = 8u; ++cb; cj = cb < nvb ? (s_jn[cb] & 0xFFFFu) : 0u; ce = 0; }
+          else { sg.jb1 = jend; sg.eb = 8u; ++cb; cj = cb < nvb ? (jn_[cb] & 0xFFFFu) : 0u; ce = 0; }
           sg.b = __shfl_sync(0xFFFFFFFFu, sg.b, 0); sg.jb0 = __shfl_sync(0xFFFFFFFFu, sg.jb0, 0);
           sg.jb1 = __shfl_sync(0xFFFFFFFFu, sg.jb1, 0);
           const u32 ee = __shfl_sync(0xFFFFFFFFu, sg.ea | (sg.eb << 4), 0);
@@ -903,7 +1012,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     // nothing else in front of the barrier: the last warp to leave the pair loop sets the pace
     stamp(ctl, 21);
-    grid_sync(&ctl->bar2_cnt, &ctl->err);
+    grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
     stamp(ctl, 22);
     // one round trip of independent loads (pair count, permutation, parked occurrence weight, gradient sum), then the store
     const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
@@ -942,7 +1051,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   }
   // ---- finalisation when the pair set depends on scores / negative-side weights (all CTAs, after a grid barrier) ----
   stamp(ctl, 21);
-  grid_sync(&ctl->bar2_cnt, &ctl->err);
+  grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
   stamp(ctl, 22);
   {
     // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
@@ -970,7 +1079,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     const uint2 z2 = make_uint2(0, 0);
     for (u32 v = gtid; v < nvb; v += gthreads) A.blk_w[v] = z2;        // (the J ranges were last read in the prologue)
-    grid_sync(&ctl->bar2_cnt, &ctl->err);
+    grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
   }
   // F_b: scale, apply the occurrence weight, un-permute the gradient, reduce the loss
   const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
@@ -1014,21 +1123,29 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   if (threadIdx.x == 0) { __threadfence(); ctl_finish(ctl); }
 }
 
+// CTAs per SM of the pair kernel's cooperative grid on the current device (all co-resident), cached per thread.
+static int pair_blocks_per_sm(const void* func, int dev) {
+  struct E { const void* f; int dev; int bps; };
+  static thread_local E cache[32];
+  static thread_local int n = 0;
+  for (int i = 0; i < n; ++i) if (cache[i].f == func && cache[i].dev == dev) return cache[i].bps;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, func, kPairThreads, 0) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (nb < 1) nb = 1;
+  static const int want = tune_int("RN_PAIR_BPS", 1);
+  const int bps = want < nb ? (want < 1 ? 1 : want) : nb;
+  if (n < 32) cache[n++] = E{func, dev, bps};
+  return bps;
+}
+
 template <int MODE>
 static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_t st) {
-  // per-device launch state (the opt-in to large dynamic shared memory is a per-device function attribute)
-  static int blocks_per_sm[64] = {0};
+  // (the opt-in to large dynamic shared memory is a per-device function attribute)
   static size_t smem_set[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!blocks_per_sm[dev]) {
-    int nb = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_pair<MODE>, kPairThreads, 0);
-    if (e != cudaSuccess) return e;
-    if (nb < 1) nb = 1;
-    int want = tune_int("RN_PAIR_BPS", 1);           // CTAs per SM (all co-resident: cooperative launch)
-    blocks_per_sm[dev] = want < nb ? (want < 1 ? 1 : want) : nb;
-  }
+  const int bps = pair_blocks_per_sm((const void*)k_pair<MODE>, dev);
+  if (bps < 1) return cudaErrorUnknown;
   PairParams p = P; KpArgs a = A;
   void* args[] = {&p, &a};
   // cost prefix of the static partition: s_pi[2 nib + 1], s_jn[2 nib]
@@ -1039,7 +1156,7 @@ static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_
     if (e != cudaSuccess) return e;
     smem_set[dev] = want;
   }
-  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * blocks_per_sm[dev], kPairThreads, args, st, smem);
+  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * bps, kPairThreads, args, st, smem);
 }
 
 static const void* pair_func(int mode) {
@@ -1194,6 +1311,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   H.blk = at<uint2>(base, L.blk); H.units = at<uint2>(base, L.units); H.nib = L.nib;
   H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
   H.target_units = target_units();
+  H.pp = PrePart{};
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   in.rm = P.rm;
   if (a->gather_dst) {
@@ -1226,6 +1344,21 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
+  if (fast) {
+    // the pair kernel's partition is worked out by spare CTAs of k_seg beside the scatter phase (HeadsTail::partition)
+    static const int pre_on = tune_int("RN_PAIR_PREPART", 1);
+    int dev = 0; cudaGetDevice(&dev);
+    const int bps = pair_blocks_per_sm(pair_func(mode), dev);
+    const u32 pgrid = (u32)(device_sm_count() * (bps > 0 ? bps : 1));
+    PrePart pp{};
+    pp.bnd = at<uint4>(base, L.bnd); pp.jn = at<u32>(base, L.jn);
+    pp.pair_grid = pgrid; pp.wpr = pgrid * kPairWarps;
+    pp.cost_gen = A.cost_gen; pp.cost_switch = A.cost_switch; pp.cost_straddle = A.cost_straddle;
+    pp.lv_cost = (mode & M_DIFF) ? A.cost_levels : 0u;
+    pp.on = (pre_on && bps > 0 && pp.wpr + 1 <= kBndCap && 4 * (size_t)L.nib + 1 + kPairWarps + 2 <= (size_t)kSegSmemWords) ? 1 : 0;
+    H.pp = pp;
+    A.bnd = pp.bnd; A.jn = pp.jn; A.pre_on = pp.on;
+  }
   const bool prof = g_prof.on && g_prof.n < g_prof.cap;
   cudaEvent_t* tev = (prof && g_prof.graph) ? timed_events() : nullptr;
   const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;

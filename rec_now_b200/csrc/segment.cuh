@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
       const uint4 z = make_uint4(0, 0, 0, 0), f = make_uint4(~0u, ~0u, ~0u, ~0u);
       for (u32 k = gtid; k < S.init_zero16; k += gthreads) S.init_zero[k] = z;
       for (u32 k = gtid; k < S.init_ones16; k += gthreads) S.init_ones[k] = f;
-      grid_sync(&ctl->bar_cnt, &ctl->err);
+      grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->path = 2;
@@ -434,23 +434,23 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
     seg_hash_keys<IPT>(S, pl, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[blockIdx.x] = globaltimer();
     stamp(ctl, 3);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
   } else {
     seg_hash(S, smem);
     stamp(ctl, 1);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     stamp(ctl, 2);
     pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), S.gbits, S.use_label != 0);
     seg_vkey<IPT>(S, pl, smem);
     stamp(ctl, 3);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
   }
   stamp(ctl, 4);
   for (int p = 0; p < pl.npass; ++p) {
     seg_sort_pass<IPT>(S, pl, p, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)(1 + p) * gridDim.x + blockIdx.x] = globaltimer();
     stamp(ctl, 5 + 2 * p);
-    grid_sync(&ctl->bar_cnt, &ctl->err);
+    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
     stamp(ctl, 6 + 2 * p);
   }
   const u64* key = (pl.npass & 1) ? S.keyB : S.keyA;
@@ -517,6 +517,7 @@ cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const T
   const int sms = device_sm_count();
   if (grid > sms) grid = sms;
   if (grid < 1) grid = 1;
+  if (fast) grid = sms;          // (CTAs without rows work out the pair kernel's partition beside the scatter phase)
   void* args[] = {&S, &T};
   const void* fn = (L.ipt == 2) ? (const void*)k_seg<2, Tail> : (const void*)k_seg<8, Tail>;
   return launch_coop(fn, grid, kSegThreads, args, st);
