@@ -133,13 +133,21 @@ typedef struct rn_listwise_args {
   int32_t* n_valid;        /* [1] V */
   int32_t* n_group;        /* [1] G (number of distinct ids) */
   float* dlogits;          /* [B] d mean-loss / d logits (d sum of list_loss if !do_reduce) */
+  /* Persistent scratch arena, as rn_pairwise_args.scratch_persistent (zeroed once with rn_pairwise_scratch_init, then
+   * written by nothing but rn_listwise_fwd_bwd calls with the same B): with do_reduce and neither list_w nor
+   * list_loss the call is ONE kernel without a sort (per-list statistics accumulated on hash records, gradient
+   * written in row order).  rn_listwise_dense needs the sorted form: call it after a non-persistent call only. */
+  int32_t scratch_persistent;
+  int32_t reserved0;
 } rn_listwise_args;
 
 int rn_version(void);
 const char* rn_strerror(int code);
 
-/* Float group ids -> canonical int64 keys; row_ok[i] = 0 where the id is NaN/+-inf.  If and_into != 0 the
- * flag is ANDed into the existing row_ok (used to merge the sample mask and several key columns). */
+/* Float group ids -> canonical int64 keys; row_ok[i] = 0 where the id is NaN/+-inf.  and_into is a bit set: bit 0 =
+ * AND the flag into the existing row_ok (used to merge the sample mask and several key columns); bit 1 = +-inf are
+ * ordinary ids (the listwise path: tf.unique compares with ==, listwise_loss_from_batch.py:109, and inf == inf; the
+ * pairwise path tests g_i - g_j == 0, pairwise_loss_from_batch.py:33-35, where inf - inf is NaN). */
 int rn_canon_keys_f32(const float* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into, void* stream);
 int rn_canon_keys_f64(const double* ids, int64_t B, int64_t* keys_out, uint8_t* row_ok, int and_into, void* stream);
 

@@ -36,16 +36,17 @@ class PairSpec:
     rw_neg: Optional[np.ndarray] = None  # per-sample weight applied on the negative (column) side
 
 
-def canonical_keys(groups) -> tuple[np.ndarray, np.ndarray]:
+def canonical_keys(groups, inf_is_id: bool = False) -> tuple[np.ndarray, np.ndarray]:
     """Composite-key canonicalisation: value equality per key (PW:33-35), -0.0 == +0.0,
-    NaN/+-inf match nothing.  Returns (int64 keys [K,B], row_ok bool[B])."""
+    NaN/+-inf match nothing (inf_is_id: +-inf equal themselves -- tf.unique of the listwise path, LW:109).
+    Returns (int64 keys [K,B], row_ok bool[B])."""
     cols = groups if isinstance(groups, (list, tuple)) else [groups]
     out, ok = [], None
     for g in cols:
         g = np.asarray(g).reshape(-1)
         fin = np.ones(g.size, bool)
         if g.dtype.kind == "f":
-            fin = np.isfinite(g)
+            fin = ~np.isnan(g) if inf_is_id else np.isfinite(g)
             gz = np.where(fin, g, 0) + g.dtype.type(0)          # -0.0 -> +0.0
             k = gz.astype(np.float64).view(np.int64) if g.dtype != np.float64 else gz.view(np.int64)
         else:
@@ -195,9 +196,10 @@ def listwise(group_ids, labels, logits, weights=None, pos_neg_th=0.5):
     """
     s32 = np.asarray(logits, F32).reshape(-1)
     y32 = np.asarray(labels, F32).reshape(-1)
-    keys, ok = canonical_keys(group_ids)
-    # tf.unique puts every row in some list; a NaN/inf id equals nothing, i.e. is a singleton list, and a
-    # singleton is never valid (needs a positive AND a negative) -> dropping those rows gives the same result
+    keys, ok = canonical_keys(group_ids, inf_is_id=True)
+    # tf.unique puts every row in some list (values compared with ==: +-inf ids equal themselves); a NaN id equals
+    # nothing, i.e. is a singleton list, and a singleton is never valid (needs a positive AND a negative) -> dropping
+    # those rows gives the same result
     segs = _group_members(keys, ok)
     th = F32(pos_neg_th)
     losses, firsts, sizes, members = [], [], [], []

@@ -10,10 +10,13 @@ __global__ void __launch_bounds__(256) k_canon(const F* __restrict__ ids, int64_
   if (i >= B) return;
   F v = ids[i];
   bool fin = (v - v) == (F)0;          // false for NaN and +-inf
+  // (and_into bit 1: +-inf are ids like any other -- tf.unique, LW:109, compares with ==, and inf == inf; the pairwise
+  //  path compares g_i - g_j with 0, PW:33-35, and inf - inf is NaN)
+  if ((and_into & 2) && v == v) fin = true;
   v = fin ? v + (F)0 : (F)0;           // -0.0 -> +0.0
   double dv = (double)v;               // float32 ids widen exactly; equality is preserved
   out[i] = __double_as_longlong(dv);
-  if (ok) ok[i] = and_into ? (uint8_t)(ok[i] && fin) : (uint8_t)fin;
+  if (ok) ok[i] = (and_into & 1) ? (uint8_t)(ok[i] && fin) : (uint8_t)fin;
 }
 
 __global__ void __launch_bounds__(256) k_mufu(int iters, float* sink) {

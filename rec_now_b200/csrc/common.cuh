@@ -34,8 +34,7 @@ struct RowMap {
 // block back into its clean state (all zero except the barrier generations and the report of the finished call).
 struct Ctl {
   u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range
-  u32 bar_cnt, bar2_cnt;        // grid barriers of the segmentation / pair kernel: arrivals (reset by the last arriver)
-  u32 pad_a[2];
+  u32 pad_a[4];
   u32 k2_ticket;                // dynamic work-unit ticket of the pair kernel
   u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars / cleans up)
   u32 n_units, unit_c;          // work list: number of units, J-blocks per unit
@@ -52,9 +51,10 @@ struct Ctl {
   u64 dbg[8];                   // pair-kernel debug tallies (RN_PAIR_DEBUG=1): see k_pair
   // report of the last finished call (copied here before the working fields are reset; read by the rn_debug_* calls)
   u32 rep_err, rep_path, rep_n_units, rep_unit_c; u64 rep_n_tiles;
-  // barrier generations, each in a line of its own: the waiters poll these, the arrivals go to bar_cnt / bar2_cnt
-  __align__(128) u32 bar_gen; u32 pad_g[31];
-  __align__(128) u32 bar2_gen; u32 pad_h[31];
+  // arrival counters of the grid barriers of the segmentation / pair kernel, each in a line of its own (they are
+  // polled); zero at the start of a call, counting up across the barriers of the kernel
+  __align__(128) u32 bar_cnt; u32 pad_g[31];
+  __align__(128) u32 bar2_cnt; u32 pad_h[31];
 };
 
 // Sort plan.  Compact sort key = (gid << labbits) | ((enc_label >> labshift) & mask): only the varying bit
@@ -200,26 +200,22 @@ __device__ __forceinline__ u32 ld_acquire(const u32* p) {
   u32 v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
 
-// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  *cnt counts arrivals and is reset by
-// the last arriver, *genp is the generation the waiters watch (a line of its own): the pair needs no initialisation beyond "count = 0" and
-// carries nothing from call to call.  The fences publish this CTA's writes and invalidate its L1 so that plain loads
-// after the barrier see other CTAs' data.  A bounded spin turns a scheduling failure (or an arena that was not in its
-// clean state) into ctl->err instead of a hung GPU.
+// Grid-wide barrier of a cooperatively launched kernel (all CTAs co-resident).  The counter starts a call at zero
+// (k_init, or the clean state the previous call left) and counts up across the barriers of the kernel: `epoch` is the
+// per-thread running arrival target.  The waiters see the last arrival as soon as it lands in L2 -- no second store to
+// wait for.  The fences publish this CTA's writes and invalidate its L1 so that plain loads after the barrier see other
+// CTAs' data.  A bounded spin turns a scheduling failure (or an arena that was not clean) into ctl->err instead of a
+// hung GPU.
 __device__ __forceinline__ void st_relaxed(u32* p, u32 v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void st_release(u32* p, u32 v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void grid_sync(u32* cnt, u32* genp, u32* err) {
+__device__ __forceinline__ void grid_sync(u32* cnt, u32& epoch, u32* err) {
+  epoch += gridDim.x;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const u32 gen = ld_relaxed(genp);             // (read before arriving: the generation cannot move until this CTA arrives)
     __threadfence();
-    if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
-      st_relaxed(cnt, 0u);
-      st_release(genp, gen + 1u);
-    } else {
-      u32 spins = 0;
-      while (ld_acquire(genp) == gen) {
-        if (++spins > (1u << 23)) { atomicOr(err, 1u); break; }
-      }
+    atomicAdd(cnt, 1u);
+    u32 spins = 0;
+    while (ld_relaxed(cnt) < epoch) {
+      if (++spins > (1u << 23)) { atomicOr(err, 1u); break; }
     }
     __threadfence();
   }
@@ -265,6 +261,16 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
   return v;
+}
+
+// The CTA that finishes last files the report of the call and resets the working fields of the control block.
+__device__ __forceinline__ void ctl_finish(Ctl* ctl) {
+  ctl->rep_err = ctl->err; ctl->rep_path = ctl->path; ctl->rep_n_units = ctl->n_units; ctl->rep_unit_c = ctl->unit_c;
+  ctl->rep_n_tiles = ctl->n_tiles;
+  ctl->bar_cnt = 0; ctl->bar2_cnt = 0;
+  ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
+  ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
+  ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;
 }
 
 // Peer-memory gather done by k_init (see rn_pairwise_args.peer_blocks): `world` blocks of n16 16-byte words.

@@ -5,6 +5,7 @@
 // After K1 (sort by (first-occurrence id, row)) a list is a contiguous run of sorted positions and the runs
 // appear in first-occurrence order, so valid-list ranks (the row order of the reference's dense outputs) are
 // an exclusive scan over run heads.  HBM-bound: 20 algorithmic bytes per sample.
+#include <stdlib.h>
 #include "segment.cuh"
 
 namespace rn {
@@ -69,13 +70,13 @@ struct ListwiseTail {
     return nv;
   }
 
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem, u32& epoch) const {
     Ctl* ctl = S.ctl;
     const u32 B = P.B, ln = lane_id(), w = threadIdx.x >> 5;
     const u32 nchunks = (B + kSegThreads - 1) / kSegThreads;
     const u32* astart = bounds.astart;
-    bounds.run(S, pl, key, val, smem);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    bounds.run(S, pl, key, val, smem, epoch);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     // ---- per-list statistics; valid lists per 512-position chunk -------------------------------------------
     u32* sm_cnt = smem;                    // [kSegWarps]
     for (u32 c = blockIdx.x; c < nchunks; c += gridDim.x) {
@@ -90,7 +91,7 @@ struct ListwiseTail {
       }
       __syncthreads();
     }
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     // ---- rank of every valid list (exclusive scan of the valid flags over head positions = first-occurrence
     //      order, LW:109), per-list weighted losses, their sum ------------------------------------------------
     u32* sm_scan = smem;                   // [kSegWarps]
@@ -134,14 +135,17 @@ struct ListwiseTail {
       for (int q = 0; q < kSegWarps; ++q) t += sm_d[q];
       if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     // ---- gradient + scalars -------------------------------------------------------------------------------
     const u32 V = ld_relaxed(&ctl->n_valid);
     const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;
+    // LW:172 nan_to_zero on the reduced loss: tf.cond takes the constant branch, so no gradient flows either
+    const double tsum = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
+    const bool nanloss = P.do_reduce && V && (tsum != tsum);
     for (u32 p = gtid; p < B; p += gthreads) {
       const u32 a = astart[p];
       float g = 0.f;
-      if (rec[(size_t)R_VALID * B + a] != 0.f) {
+      if (!nanloss && rec[(size_t)R_VALID * B + a] != 0.f) {
         const float m = rec[(size_t)R_MAX * B + a], lse = rec[(size_t)R_LSE * B + a], sumy = rec[(size_t)R_SY * B + a];
         float wr = 1.f;
         if (P.list_w) wr = P.list_w[__float_as_uint(rec[(size_t)R_RANK * B + a])];
@@ -152,12 +156,201 @@ struct ListwiseTail {
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       const double t = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
-      if (P.do_reduce) *P.loss = V ? (float)(t / (double)V) : 0.f;   // LW:171-172 (mean; NaN -> 0)
+      if (P.do_reduce) *P.loss = (V && !nanloss) ? (float)(t / (double)V) : 0.f;   // LW:171-172 (mean; NaN -> 0)
       *P.n_valid = (int32_t)V;
       *P.n_group = (int32_t)ld_relaxed(&ctl->n_groups);
     }
   }
 };
+
+
+// ---- K5, counting form: the whole listwise loss in ONE cooperative kernel without a sort or a scatter ---------------
+// (same reference lines: LW:107-148, 166-172).  The loss and its gradient only need PER-LIST statistics -- max logit,
+// sum exp, label sum, sum y (s - max), has-positive / has-negative -- and every row's own (s, y): rows never have to
+// move.  The lists live in the record table of group_count.cuh (one 128-bit compare-and-swap per distinct id and
+// 512-row tile); the statistics are accumulated with atomics on the records:
+//   phase 1  find / create the list's record; max logit (atomicMax on the order-preserving encoding), label sum,
+//            validity flags -- aggregated per tile in shared memory first
+//   phase 2  sum exp(s - max), sum y (s - max) per list; the records' creators count the valid lists (LW:135-137)
+//   phase 3  gradient (softmax - p) / V written in ROW order (coalesced), per-list losses summed; the last CTA out
+//            writes the scalars (mean, NaN -> 0 as LW:172) and leaves the arena clean.
+// Two grid barriers.  Taken when the valid lists' RANKS are not needed (do_reduce, no per-list weights, no per-list
+// output) and the arena is persistent; everything else runs the sorted path above.
+struct __align__(16) LRec { u64 key; u32 rep1; u32 flags; u32 maxenc; float sumy; float Z; float dotm; u32 pad[8]; };
+static_assert(sizeof(LRec) == sizeof(GRec), "the listwise records share the group record table");
+
+__device__ __forceinline__ float dec_label(u32 e) {     // inverse of enc_label
+  const u32 u = (e & 0x80000000u) ? (e ^ 0x80000000u) : ~e;
+  return __uint_as_float(u);
+}
+
+struct LwCountArgs {
+  u32 B; u32 capmask;
+  const int64_t* keys; const uint8_t* row_ok; const float* labels; const float* logits;
+  float th;
+  float* loss; int32_t* n_valid; int32_t* n_group; float* dlogits;
+  GRec* rec; u32 *glist, *gcount, *rslot; Ctl* ctl;
+};
+
+__global__ void __launch_bounds__(kSegThreads, 1) k_lw_count(LwCountArgs A) {
+  constexpr u32 kLoc = 2 * kGTile;
+  __shared__ __align__(16) u32 smem[kLoc + 2 * kGTile + 5 * kGTile + 64];
+  u32* sm_tab = smem;                                           // [kLoc]
+  u64* sm_key = reinterpret_cast<u64*>(smem + kLoc);            // [kGTile]
+  u32* sm_max = smem + kLoc + 2 * kGTile;                       // [kGTile] per representative
+  float* sm_sumy = reinterpret_cast<float*>(sm_max + kGTile);   // [kGTile]
+  u32* sm_flags = sm_max + 2 * kGTile;                          // [kGTile]
+  u32* sm_gslot = sm_max + 3 * kGTile;                          // [kGTile]
+  u32* sm_misc = sm_max + 4 * kGTile;                           // [0] created, [1] singleton rows, [2] valid lists, [3] lists
+  double* sm_d = reinterpret_cast<double*>(sm_max + 4 * kGTile + 16);   // [kSegWarps]
+  Ctl* ctl = A.ctl;
+  LRec* rec = reinterpret_cast<LRec*>(A.rec);
+  const u32 B = A.B, tid = threadIdx.x, ln = lane_id(), w = tid >> 5;
+  const u32 ntile = (B + kGTile - 1) / kGTile;
+  const bool single = ntile <= gridDim.x;
+  u32 epoch = 0;
+  grid_dep_wait();
+  stamp(ctl, 0);
+  if (tid < 4) sm_misc[tid] = 0;              // (CTAs without rows still take part in the reductions below)
+  __syncthreads();
+  u32 k_slot = kEmpty; float k_s = 0.f, k_y = 0.f;
+  // ---- phase 1 ----------------------------------------------------------------------------------------------------
+  for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const u32 i = t * kGTile + tid;
+    const bool in = i < B;
+    const u64 key = in ? (u64)A.keys[i] : 0ull;
+    const float y = in ? A.labels[i] : 0.f, s = in ? A.logits[i] : 0.f;
+    const bool ok = in && (A.row_ok ? A.row_ok[i] != 0 : true);       // (0: the id was NaN / inf -- a singleton list, never valid)
+    sm_tab[tid] = kEmpty; sm_tab[tid + kGTile] = kEmpty;
+    sm_max[tid] = 0u; sm_sumy[tid] = 0.f; sm_flags[tid] = 0u;
+    if (tid < 2) sm_misc[tid] = 0;
+    sm_key[tid] = key;
+    __syncthreads();
+    const u64 h = mix64(0x9E3779B97F4A7C15ull ^ key);
+    u32 rep = tid;
+    if (ok) {
+      u32 ls = (u32)(h >> 40) & (kLoc - 1);
+      for (;;) {
+        u32 cur = sm_tab[ls];
+        if (cur == kEmpty) {
+          const u32 prev = atomicCAS(&sm_tab[ls], kEmpty, tid);
+          if (prev == kEmpty) { rep = tid; break; }
+          cur = prev;
+        }
+        if (sm_key[cur] == key) { rep = cur; break; }
+        ls = (ls + 1) & (kLoc - 1);
+      }
+      atomicMax(&sm_max[rep], enc_label(s));
+      atomicAdd(&sm_sumy[rep], y);
+      const u32 f = ((y > A.th) ? 1u : 0u) | (((y - A.th) < 0.f) ? 2u : 0u);          // LW:135-136
+      if (f) atomicOr(&sm_flags[rep], f);
+    } else if (in) {
+      atomicAdd(&sm_misc[1], 1u);
+    }
+    bool created = false; u32 slot = 0;
+    const bool isrep = ok && rep == tid;
+    if (isrep) { slot = grec_insert(A.rec, A.capmask, h, key, i, created, &ctl->err); sm_gslot[tid] = slot; }
+    if (created) A.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = slot;
+    __syncthreads();
+    if (isrep) {
+      atomicMax(&rec[slot].maxenc, sm_max[tid]);
+      atomicAdd(&rec[slot].sumy, sm_sumy[tid]);
+      if (sm_flags[tid]) atomicOr(&rec[slot].flags, sm_flags[tid]);
+    }
+    if (tid == 0) { A.gcount[t] = sm_misc[0]; if (sm_misc[1]) atomicAdd(&ctl->n_groups, sm_misc[1]); }
+    if (in) {
+      const u32 rslot = ok ? sm_gslot[rep] : kEmpty;
+      if (single) { k_slot = rslot; k_s = s; k_y = y; } else A.rslot[i] = rslot;
+    }
+    __syncthreads();
+  }
+  stamp(ctl, 1);
+  grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
+  stamp(ctl, 2);
+  // ---- phase 2: sum exp and label-weighted logit sum per list; the creators count the valid lists ----------------------
+  float k_e = 0.f;
+  auto accumulate = [&](u32 slot, float s, float y) -> float {
+    if (slot == kEmpty) return 0.f;
+    const float m = dec_label(rec[slot].maxenc);
+    const float e = expf(s - m);
+    atomicAdd(&rec[slot].Z, e);
+    if (y != 0.f) atomicAdd(&rec[slot].dotm, y * (s - m));
+    return e;
+  };
+  u32 nval = 0, nlist = 0;
+  for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const u32 i = t * kGTile + tid;
+    if (single) { if (i < B) k_e = accumulate(k_slot, k_s, k_y); }
+    else if (i < B) accumulate(A.rslot[i], A.logits[i], A.labels[i]);
+    const u32 ncr = A.gcount[t];
+    for (u32 k = tid; k < ncr; k += kSegThreads) {
+      ++nlist;
+      if (rec[A.glist[(size_t)t * kGTile + k]].flags == 3u) ++nval;                   // LW:137
+    }
+  }
+  nval = __reduce_add_sync(0xFFFFFFFFu, nval); nlist = __reduce_add_sync(0xFFFFFFFFu, nlist);
+  if (ln == 0) { if (nval) atomicAdd(&sm_misc[2], nval); if (nlist) atomicAdd(&sm_misc[3], nlist); }
+  __syncthreads();
+  if (tid == 0) { if (sm_misc[2]) atomicAdd(&ctl->n_valid, sm_misc[2]); if (sm_misc[3]) atomicAdd(&ctl->n_groups, sm_misc[3]); }
+  stamp(ctl, 3);
+  grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
+  stamp(ctl, 4);
+  // ---- phase 3: gradient in row order, per-list losses ------------------------------------------------------------------
+  const u32 V = ld_relaxed(&ctl->n_valid);
+  const float invV = V ? 1.0f / (float)V : 0.f;
+  auto grad = [&](u32 slot, float s, float y, float e, bool have_e) -> float {
+    if (slot == kEmpty) return 0.f;
+    const LRec r = rec[slot];
+    if (r.flags != 3u) return 0.f;
+    if (!have_e) e = expf(s - dec_label(r.maxenc));
+    return invV * (e / r.Z - y / r.sumy);                       // xent backprop: softmax - labels (LW:144, LW:167); mean over V
+  };
+  double lsum = 0.0;
+  for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const u32 i = t * kGTile + tid;
+    if (i < B) A.dlogits[i] = single ? grad(k_slot, k_s, k_y, k_e, true) : grad(A.rslot[i], A.logits[i], A.labels[i], 0.f, false);
+    const u32 ncr = A.gcount[t];
+    for (u32 k = tid; k < ncr; k += kSegThreads) {
+      const LRec r = rec[A.glist[(size_t)t * kGTile + k]];
+      // lse - sum p s, max-subtracted.  A valid list whose labels sum to zero holds labels of both signs: p = y / 0 is
+      // +inf and -inf (and 0 / 0), the reference's sum p (lse - z) is inf - inf = NaN (-> 0 by LW:172)
+      if (r.flags == 3u) lsum += (r.sumy == 0.f) ? (double)NAN : (double)(logf(r.Z) - r.dotm / r.sumy);
+    }
+  }
+  lsum = warp_sum(lsum);
+  if (ln == 0) sm_d[w] = lsum;
+  __syncthreads();
+  __shared__ u32 s_last;
+  if (tid == 0) {
+    double tsum = 0;
+    for (int q = 0; q < kSegWarps; ++q) tsum += sm_d[q];
+    if (tsum != 0.0) atomicAdd(&ctl->loss_sum, tsum);           // (a NaN sum compares unequal to 0: it is added, and stays NaN)
+    __threadfence();
+    s_last = (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the last CTA out: scalars, NaN -> 0 (LW:172, value and gradient), clean arena ----------------------------------------
+  __threadfence();
+  const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
+  const float lossv = V ? (float)(tot / (double)V) : 0.f;
+  const bool isnan_ = lossv != lossv;
+  if (tid == 0) {
+    *A.loss = isnan_ ? 0.f : lossv;
+    *A.n_valid = (int32_t)V;
+    *A.n_group = (int32_t)ld_relaxed(&ctl->n_groups);
+    ctl->ts[23] = globaltimer();
+  }
+  if (isnan_) for (u32 i = tid; i < B; i += kSegThreads) A.dlogits[i] = 0.f;      // tf.cond takes the constant branch: no gradient
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (u32 t = 0; t < ntile; ++t) {
+    const u32 n = A.gcount[t];
+    for (u32 k = tid; k < 4 * n; k += kSegThreads)
+      reinterpret_cast<uint4*>(A.rec + A.glist[(size_t)t * kGTile + (k >> 2)])[k & 3u] = z;
+  }
+  __syncthreads();
+  if (tid == 0) { __threadfence(); ctl->path = 1; ctl_finish(ctl); }
+}
 
 __global__ void __launch_bounds__(256) k_lw_dense_fill(size_t n, uint8_t* __restrict__ dm, float* __restrict__ dl,
                                                        float* __restrict__ dz, float pad) {
@@ -214,6 +407,16 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
+  static const char* lwc = getenv("RN_LW_COUNT");
+  if (a->scratch_persistent && a->do_reduce && !a->list_w && !a->list_loss && !(lwc && *lwc == '0')) {
+    // counting form: one cooperative kernel, no sort, no scatter (the ranks of the valid lists are not needed)
+    LwCountArgs A{(u32)a->B, L.cap - 1, a->keys, a->row_ok, a->labels, a->logits, a->pos_neg_th, a->loss, a->n_valid,
+                  a->n_group, a->dlogits, at<GRec>(base, L.rec), at<u32>(base, L.glist), at<u32>(base, L.gcount),
+                  at<u32>(base, L.slot), at<Ctl>(base, L.ctl)};
+    void* args[] = {&A};
+    if (launch_coop((const void*)k_lw_count, device_sm_count(), kSegThreads, args, st) != cudaSuccess) return RN_ERR_LAUNCH;
+    return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+  }
   SegInputs in{a->B, 1, a->keys, nullptr, a->row_ok, false, false};
   u32* astart = at<u32>(base, L.aj);
   u32* gend = at<u32>(base, L.cnt);

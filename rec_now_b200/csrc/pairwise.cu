@@ -151,7 +151,9 @@ struct HeadsTail {
     const u32 pos = a + pre + rank;
     const u32 n = pre;                                       // rows of the group below this row's level
     aj[pos] = make_uint2(a, n);
-    ss[pos] = s; sy[pos] = y;
+    // (a NaN label pairs with nothing, but its row shares I-blocks with rows that do: under label-gain weights the tile
+    // multiplies a zero row weight by (y_i - y_ref), and 0 * NaN would poison the block's sums)
+    ss[pos] = s; sy[pos] = (y != y) ? 0.f : y;
     if (P.rw_pos) swp[pos] = wp;
     if (P.rw_neg) swn[pos] = wn;
     gacc[pos] = 0.f; perm[pos] = i; sgrp[pos] = slot;
@@ -213,7 +215,9 @@ struct HeadsTail {
       }
     }
     __syncthreads();
+    if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)5 * gridDim.x + blockIdx.x] = globaltimer();
     block_excl_scan(s_pi, nvb, s_sc);
+    if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)6 * gridDim.x + blockIdx.x] = globaltimer();
     const u32 tot = s_pi[nvb];
     const u32 q = tot / pp.wpr, rem = tot - q * pp.wpr;
     for (u32 r = h * kSegThreads + threadIdx.x; r <= pp.wpr; r += H * kSegThreads) {
@@ -229,7 +233,7 @@ struct HeadsTail {
     }
   }
 
-  __device__ __forceinline__ bool count_run(const SegParams& S, u32* smem) const {
+  __device__ __forceinline__ bool count_run(const SegParams& S, u32* smem, u32& epoch) const {
     constexpr u32 kLoc = 2 * kGTile;
     u32* sm_tab = smem;                                           // [kLoc] representative thread of the key hashed here
     u64* sm_key = reinterpret_cast<u64*>(smem + kLoc);            // [kGTile] keys of the tile
@@ -329,7 +333,7 @@ struct HeadsTail {
     if (__syncthreads_or(bad) && tid == 0) st_relaxed(&ctl->fallback, 1u);
     auto dbg = [&](u32 ph) { if (S.dbgts && tid == 0) S.dbgts[(size_t)ph * gridDim.x + blockIdx.x] = globaltimer(); };
     stamp(ctl, 1); dbg(0);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 2); dbg(1);
     if (ld_relaxed(&ctl->fallback)) return false;
     // ---- offsets: one thread per record created by this CTA's tiles -------------------------------------------------
@@ -398,7 +402,7 @@ struct HeadsTail {
     }
     if (blockIdx.x == 0 && tid == 0) ctl->path = 1;
     stamp(ctl, 3); dbg(2);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 4); dbg(3);
     // ---- scatter (+ the pair kernel's partition, beside it) ----------------------------------------------------------
     // The J ranges are complete: CTAs without rows (the grid is always full) work out the partition of the pair kernel's
@@ -421,7 +425,7 @@ struct HeadsTail {
     return true;
   }
 
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem, u32& epoch) const {
     u32* sm_scan = smem;                       // [kSegWarps][2]
     u32* sm_carry = smem + 2 * kSegWarps;      // [2]
     u32* sm_wj = smem + 36;                    // [kSegWarps][4]
@@ -455,7 +459,7 @@ struct HeadsTail {
         if (P.rw_neg) wn = P.rw_neg[ro];
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[ro];
-        sy[p] = P.labels[ro];
+        { const float yv = P.labels[ro]; sy[p] = (yv != yv) ? 0.f : yv; }     // (NaN labels pair with nothing; see scatter_row)
         if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
@@ -507,7 +511,7 @@ struct HeadsTail {
     // Batches up to 524288 rows: k_pair partitions the work itself (cost prefixes in shared memory), the kernel ends here
     // without another grid barrier.  Larger batches: explicit unit records.
     if (nib <= kMaxNibS) return;
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 18);
     // ---- work list: every CTA scans the per-I-block tile counts (redundantly, it is ~nib/512 block scans) and emits
     //      the unit records of its own I-blocks ------------------------------------------------------------------
@@ -585,14 +589,6 @@ __device__ __forceinline__ void clean_records(const KpArgs& A, u32 t0, u32 tstep
     for (u32 k = threadIdx.x; k < 4 * n; k += blockDim.x)
       reinterpret_cast<uint4*>(A.rec + A.glist[(size_t)t * kGTile + (k >> 2)])[k & 3u] = z;
   }
-}
-// The CTA that finishes last files the report of the call and resets the working fields of the control block.
-__device__ __forceinline__ void ctl_finish(Ctl* ctl) {
-  ctl->rep_err = ctl->err; ctl->rep_path = ctl->path; ctl->rep_n_units = ctl->n_units; ctl->rep_unit_c = ctl->unit_c;
-  ctl->rep_n_tiles = ctl->n_tiles;
-  ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
-  ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
-  ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;
 }
 
 // Positive-side rows of an I-block (two per lane) and the first J block of a segment: loaded one segment ahead.
@@ -1000,6 +996,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   }
   const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  u32 epoch2 = 0;
   if (!DYN) {
     // ---- this CTA's share of sum w * loss, then (after the grid barrier) un-permute and scale the gradient ----
     lsum = warp_sum(lsum);
@@ -1012,7 +1009,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     // nothing else in front of the barrier: the last warp to leave the pair loop sets the pace
     stamp(ctl, 21);
-    grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
+    grid_sync(&ctl->bar2_cnt, epoch2, &ctl->err);
     stamp(ctl, 22);
     // one round trip of independent loads (pair count, permutation, parked occurrence weight, gradient sum), then the store
     const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
@@ -1051,7 +1048,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   }
   // ---- finalisation when the pair set depends on scores / negative-side weights (all CTAs, after a grid barrier) ----
   stamp(ctl, 21);
-  grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
+  grid_sync(&ctl->bar2_cnt, epoch2, &ctl->err);
   stamp(ctl, 22);
   {
     // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
@@ -1079,7 +1076,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     const uint2 z2 = make_uint2(0, 0);
     for (u32 v = gtid; v < nvb; v += gthreads) A.blk_w[v] = z2;        // (the J ranges were last read in the prologue)
-    grid_sync(&ctl->bar2_cnt, &ctl->bar2_gen, &ctl->err);
+    grid_sync(&ctl->bar2_cnt, epoch2, &ctl->err);
   }
   // F_b: scale, apply the occurrence weight, un-permute the gradient, reduce the loss
   const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);

@@ -368,7 +368,7 @@ struct GatherCols { const float* src[4]; float* dst[4]; };
 struct BoundsTail {
   static constexpr bool kFast = false;
   u32 *astart, *gend, *perm; GatherCols gc;
-  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem) const {
+  __device__ __forceinline__ void run(const SegParams& S, const Plan& pl, const u64* key, const u32* val, u32* smem, u32& epoch) const {
     u32* sm_scan = smem;            // [kSegWarps][2]
     u32* sm_carry = smem + 2 * kSegWarps;
     const u32 ln = lane_id(), w = threadIdx.x >> 5;
@@ -403,18 +403,19 @@ template <int IPT, class Tail>
 __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
   __shared__ __align__(16) u32 smem[kSegSmemWords];
   Ctl* ctl = S.ctl;
+  u32 epoch = 0;
   grid_dep_wait();
   grid_dep_launch();
   stamp(ctl, 0);
   if constexpr (Tail::kFast) {
     if (S.fast) {
       // counting path; false = something outside its menu was seen: initialise what the radix path needs and go on
-      if (T.count_run(S, smem)) { stamp(ctl, 19); return; }
+      if (T.count_run(S, smem, epoch)) { stamp(ctl, 19); return; }
       const u32 gtid = blockIdx.x * kSegThreads + threadIdx.x, gthreads = gridDim.x * kSegThreads;
       const uint4 z = make_uint4(0, 0, 0, 0), f = make_uint4(~0u, ~0u, ~0u, ~0u);
       for (u32 k = gtid; k < S.init_zero16; k += gthreads) S.init_zero[k] = z;
       for (u32 k = gtid; k < S.init_ones16; k += gthreads) S.init_ones[k] = f;
-      grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+      grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->path = 2;
@@ -434,28 +435,28 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_seg(SegParams S, Tail T) {
     seg_hash_keys<IPT>(S, pl, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[blockIdx.x] = globaltimer();
     stamp(ctl, 3);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
   } else {
     seg_hash(S, smem);
     stamp(ctl, 1);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 2);
     pl = make_plan(ld_relaxed(&ctl->lab_or), ld_relaxed(&ctl->lab_nor), S.gbits, S.use_label != 0);
     seg_vkey<IPT>(S, pl, smem);
     stamp(ctl, 3);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
   }
   stamp(ctl, 4);
   for (int p = 0; p < pl.npass; ++p) {
     seg_sort_pass<IPT>(S, pl, p, smem);
     if (S.dbgts && threadIdx.x == 0) S.dbgts[(size_t)(1 + p) * gridDim.x + blockIdx.x] = globaltimer();
     stamp(ctl, 5 + 2 * p);
-    grid_sync(&ctl->bar_cnt, &ctl->bar_gen, &ctl->err);
+    grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 6 + 2 * p);
   }
   const u64* key = (pl.npass & 1) ? S.keyB : S.keyA;
   const u32* val = (pl.npass & 1) ? S.valB : S.valA;
-  T.run(S, pl, key, val, smem);
+  T.run(S, pl, key, val, smem, epoch);
   stamp(ctl, 19);
 }
 

@@ -72,8 +72,9 @@ def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t.detach().reshape(-1).to(torch.float32).contiguous()
 
 
-def canon_keys(groups, row_ok: Optional[torch.Tensor] = None):
-    """Group id tensor(s) -> (int64 keys [K,B], row_ok uint8[B] or None).
+def canon_keys(groups, row_ok: Optional[torch.Tensor] = None, inf_is_id: bool = False):
+    """Group id tensor(s) -> (int64 keys [K,B], row_ok uint8[B] or None).  inf_is_id: +-inf ids equal themselves (the
+    listwise path's tf.unique semantics) instead of matching nothing (the pairwise path's g_i - g_j == 0).
 
     Float ids (what the reference passes, pairwise_loss_from_batch.py:33-35) are canonicalised on the device:
     value equality, -0.0 == +0.0, NaN/inf match nothing.  Integer ids are used as they are.
@@ -100,7 +101,9 @@ def canon_keys(groups, row_ok: Optional[torch.Tensor] = None):
                 ok = torch.empty(b, dtype=torch.uint8, device=dev)
                 and_into = 0
             fn = lib().rn_canon_keys_f32 if g.dtype == torch.float32 else lib().rn_canon_keys_f64
-            check(fn(g.data_ptr(), b, keys[k].data_ptr(), ok.data_ptr(), and_into, _stream()), "rn_canon_keys")
+            with _on_device(dev):
+                check(fn(g.data_ptr(), b, keys[k].data_ptr(), ok.data_ptr(), and_into | (2 if inf_is_id else 0),
+                         _stream(dev)), "rn_canon_keys")
         else:
             keys[k].copy_(g.to(torch.int64))
     return keys, ok
@@ -346,35 +349,92 @@ def occurrence_power_weight(ids: torch.Tensor, power: float) -> torch.Tensor:
     return out
 
 
+class _LwCall:
+    """Per-thread reusable argument struct of rn_listwise_fwd_bwd (see _PairCall)."""
+    __slots__ = ("args", "ref", "fn")
+
+    def __init__(self):
+        self.args = ListwiseArgs()
+        self.ref = C.byref(self.args)
+        self.fn = lib().rn_listwise_fwd_bwd
+
+
+class _LwOut(dict):
+    """Result of listwise_fwd_bwd: scalar views (loss, n_valid, n_group) are made on first use."""
+
+    def __missing__(self, key):
+        out = dict.__getitem__(self, "_out")
+        if key == "loss":
+            v = out[0]
+        elif key == "n_valid":
+            v = out[1:2].view(torch.int32)[0]
+        elif key == "n_group":
+            v = out[2:3].view(torch.int32)[0]
+        else:
+            raise KeyError(key)
+        self[key] = v
+        return v
+
+    def get(self, key, default=None):
+        try:
+            return self[key]
+        except KeyError:
+            return default
+
+
+_lw_scratch_bytes: dict = {}
+
+
 def listwise_fwd_bwd(keys, labels, logits, row_ok=None, list_w=None, pos_neg_th=0.5, do_reduce=True,
-                     want_list_loss=False):
+                     want_list_loss=False, sorted_form=False):
     """rn_listwise_fwd_bwd.  keys: canonical int64 [B].  Returns dict of device tensors (+ the scratch arena
-    and args needed by listwise_dense)."""
+    and args needed by listwise_dense).  sorted_form=True asks for the sorted (radix) form of the call, whose arena
+    listwise_dense can read; otherwise a reduced loss without per-list weights / outputs runs as ONE sort-free kernel
+    on a persistent arena."""
     _need_cuda(keys, labels, logits, row_ok, list_w)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()
-    keys = keys.reshape(-1).to(torch.int64).contiguous()
+    if keys.dtype is not torch.int64 or not keys.is_contiguous() or keys.dim() != 1:
+        keys = keys.reshape(-1).to(torch.int64).contiguous()
     dev = s.device
     ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
     lw = _f32(list_w)
-    loss = torch.zeros(1, dtype=torch.float32, device=dev)
-    counts = torch.empty(8, dtype=torch.int32, device=dev)          # [0] n_valid, [4] n_group (16 B apart)
+    out = torch.empty(4, dtype=torch.float32, device=dev)           # loss f32, n_valid i32, n_group i32
     dlogits = torch.empty(b, dtype=torch.float32, device=dev)
     list_loss = torch.empty(b, dtype=torch.float32, device=dev) if (want_list_loss or not do_reduce) else None
-    nbytes = lib().rn_listwise_scratch_bytes(b)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    a = ListwiseArgs(B=b, keys=keys.data_ptr(), row_ok=_ptr(ok), labels=y.data_ptr(), logits=s.data_ptr(),
-                     list_w=_ptr(lw), pos_neg_th=float(pos_neg_th), do_reduce=int(bool(do_reduce)),
-                     loss=loss.data_ptr(), list_loss=_ptr(list_loss), n_valid=counts.data_ptr(),
-                     n_group=counts.data_ptr() + 16, dlogits=dlogits.data_ptr())
-    with torch.cuda.device(dev):
-        check(lib().rn_listwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, _stream()), "rn_listwise_fwd_bwd")
-    return dict(loss=loss[0], n_valid=counts[0], n_group=counts[4], dlogits=dlogits, list_loss=list_loss,
-                _scratch=scratch, _args=a, _keep=(keys, ok, lw, y, s))
+    nbytes = _lw_scratch_bytes.get(b)
+    if nbytes is None:
+        nbytes = _lw_scratch_bytes[b] = lib().rn_listwise_scratch_bytes(b)
+    counting = do_reduce and lw is None and list_loss is None and not sorted_form
+    st = torch.cuda.current_stream(dev).cuda_stream
+    scratch = _scratch(nbytes, dev, st, "lw") if counting else torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    pc = getattr(_tls, "lw_call", None)
+    if pc is None:
+        pc = _tls.lw_call = _LwCall()
+    a = pc.args
+    po = out.data_ptr()
+    a.B = b; a.keys = keys.data_ptr(); a.row_ok = _ptr(ok); a.labels = y.data_ptr(); a.logits = s.data_ptr()
+    a.list_w = _ptr(lw); a.pos_neg_th = pos_neg_th; a.do_reduce = 1 if do_reduce else 0
+    a.loss = po; a.n_valid = po + 4; a.n_group = po + 8
+    a.list_loss = _ptr(list_loss); a.dlogits = dlogits.data_ptr(); a.scratch_persistent = 1 if counting else 0
+    with _on_device(dev):
+        rc = pc.fn(pc.ref, scratch.data_ptr(), nbytes, st)
+    if rc:
+        check(rc, "rn_listwise_fwd_bwd")
+    res = _LwOut(dlogits=dlogits, list_loss=list_loss, _scratch=scratch, _out=out, _keep=(keys, ok, lw, y, s),
+                 _sorted=not counting)
+    if not counting:
+        if not do_reduce:
+            out[0:1].zero_()                                         # (the kernel only writes a reduced loss)
+        # listwise_dense re-reads the argument struct: give the sorted form its own copy
+        res["_args"] = ListwiseArgs.from_buffer_copy(a)
+    return res
 
 
 def listwise_dense(fwd: dict, n_valid: int, do_mask_logits=True, value_of_masked_logit=-1e9):
     """rn_listwise_dense: the (V,B) dense_mask / dense_labels / dense_logits of to_listwise_sample (LW:142-145)."""
+    if not fwd.get("_sorted", True):
+        raise RuntimeError("listwise_dense needs the sorted form of the call (listwise_fwd_bwd(..., sorted_form=True))")
     a = fwd["_args"]
     b = int(a.B)
     dev = fwd["dlogits"].device

@@ -53,26 +53,29 @@ class _ListwiseBatch:
         self.logits_in = _as_cuda(logits)
         self.labels_in = _as_cuda(labels)
         g = _as_cuda(group_ids)
-        self.keys, self.row_ok = ops.canon_keys(g.reshape(-1))
+        self.keys, self.row_ok = ops.canon_keys(g.reshape(-1), inf_is_id=True)
         self.do_mask_logits, self.value_of_masked_logit = bool(do_mask_logits), float(value_of_masked_logit)
         self.th = float(pos_neg_th)
         self._fwd = {}
         self._dense = None
 
-    def fwd(self, weights=None, do_reduce=True):
-        key = (None if weights is None else weights.data_ptr(), bool(do_reduce))
+    def fwd(self, weights=None, do_reduce=True, sorted_form=False):
+        key = (None if weights is None else weights.data_ptr(), bool(do_reduce), bool(sorted_form))
         if key not in self._fwd:
             self._fwd[key] = ops.listwise_fwd_bwd(self.keys[0], self.labels_in, self.logits_in, row_ok=self.row_ok,
-                                                  list_w=weights, pos_neg_th=self.th, do_reduce=do_reduce)
+                                                  list_w=weights, pos_neg_th=self.th, do_reduce=do_reduce,
+                                                  sorted_form=sorted_form)
         return self._fwd[key]
 
     def n_valid(self) -> int:
-        return int(self.fwd()["n_valid"].item())          # synchronises (V is data dependent)
+        f = next(iter(self._fwd.values())) if self._fwd else self.fwd()
+        return int(f["n_valid"].item())                   # synchronises (V is data dependent)
 
     def dense(self):
         if self._dense is None:
-            v = self.n_valid()
-            dm, dl, dz = ops.listwise_dense(self.fwd(), v, self.do_mask_logits, self.value_of_masked_logit)
+            f = self.fwd(sorted_form=True)                # (the dense layout is filled from the sorted form's arena)
+            v = int(f["n_valid"].item())
+            dm, dl, dz = ops.listwise_dense(f, v, self.do_mask_logits, self.value_of_masked_logit)
             dz = _DenseLogits.apply(self.logits_in, dz, dm)
             self._dense = (dm, dl, dz)
         return self._dense
@@ -166,7 +169,11 @@ def listwise_loss_via_softmax_cross_entropy_with_logits(labels_for_softmax,
     lazy = (isinstance(labels_for_softmax, LazyDense) and isinstance(logits_for_softmax, LazyDense)
             and labels_for_softmax._batch is logits_for_softmax._batch
             and labels_for_softmax._which == 1 and logits_for_softmax._which == 2)
-    if lazy and logits_for_softmax._batch.do_mask_logits and logits_for_softmax._batch.th >= 0:
+    # (the segmented kernels drop the non-member columns, which is what the reference computes when their logit is
+    # value_of_masked_logit = -1e9: exp underflows to 0; a mild value such as -10 keeps (B - n) exp(value) in every
+    # denominator, LW:139-140, 167 -- that case takes the dense formula below)
+    if (lazy and logits_for_softmax._batch.do_mask_logits and logits_for_softmax._batch.th >= 0
+            and logits_for_softmax._batch.value_of_masked_logit <= -1.0e4):
         batch = logits_for_softmax._batch
         w = None if weights is None else _f32(weights).reshape(-1).contiguous()
         return _FusedListwiseLoss.apply(batch.logits_in, batch, w, bool(do_reduce))

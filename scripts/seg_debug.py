@@ -20,11 +20,13 @@ _lib.lib().rn_debug_timestamps(scr.data_ptr(), ts, 34, None)
 B = s.numel()
 gstat_off = _lib.lib().rn_debug_arena_offset(B, 1, 0)
 grid = torch.cuda.get_device_properties(0).multi_processor_count
-NPH = 5
+NPH = 7
 a = scr[gstat_off:gstat_off + 8 * NPH * grid].view(torch.int64).cpu().numpy().reshape(NPH, grid)
 t0 = ts[0]
-print("phases of the counting path: 0 count done, 1 past barrier 1, 2 offsets done, 3 past barrier 2, 4 scatter / partition done")
+print("phases of the counting path: 0 count done, 1 past barrier 1, 2 offsets done, 3 past barrier 2, 4 scatter / partition done; helper CTAs only: 5 costs in shared memory, 6 scanned")
 for ph in range(NPH):
+    if ph >= 5:
+        a[ph] = np.where(a[ph] < t0, t0, a[ph])
     t = (a[ph] - t0) / 1e3
     print(f"phase {ph}: arrival min {t.min():.1f} med {np.median(t):.1f} max {t.max():.1f} us; slowest CTAs {np.argsort(-t)[:6]} ; by CTA/8: " + " ".join(f"{t[k:k+8].max():.1f}" for k in range(0, grid, 8)))
 print("stamps", " ".join(f"{i}:{(x - t0) / 1e3:.1f}" for i, x in enumerate(list(ts)[:24]) if x))

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def run_listwise(g, y, s, list_w=None, th=0.5, do_reduce=True):
     from rec_now_b200 import ops
-    keys, ok = ops.canon_keys(dev(g))
+    keys, ok = ops.canon_keys(dev(g), inf_is_id=True)
     return ops.listwise_fwd_bwd(keys[0], dev(y), dev(s), row_ok=ok, list_w=None if list_w is None else dev(list_w),
                                 pos_neg_th=th, do_reduce=do_reduce, want_list_loss=True)
 

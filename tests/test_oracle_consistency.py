@@ -85,3 +85,17 @@ def test_generators_shapes_and_estimates():
     assert d4["g"].shape == (65536,) and 1500 < d4["n_lists"] < 2600
     d5 = G.cfg5(2, rows_per_rank=1024, groups_per_rank=64)
     assert d5["g"].shape == (2048,)
+
+
+def test_listwise_inf_ids_form_one_list():
+    """tf.unique (LW:109) compares ids with ==: +inf ids equal each other (one list), NaN ids equal nothing.  The dense
+    op-for-op restatement and the segmented one must agree on that."""
+    from oracle import dense_ref as D
+    from oracle import seg_ref as S
+    g = np.array([1, np.inf, 1, np.inf, np.nan, np.nan, -np.inf, np.inf], np.float32)
+    y = np.array([1, 1, 0, 0, 1, 0, 1, 0], np.float32)
+    s = np.linspace(-1, 1, 8).astype(np.float32)
+    d, r = D.listwise_full(g, y, s), S.listwise(g, y, s)
+    assert d["n_valid"] == r["n_valid"] == 2                 # {0, 2} and the three +inf rows
+    assert abs(float(d["loss"]) - r["loss"]) < 1e-6
+    assert np.abs(d["grad"] - r["grad"]).max() < 1e-6
