@@ -471,7 +471,9 @@ def ours(args):
     else:
         # N > 1: the same global batch on ONE GPU (rank 0), through the single-GPU product path: exact pair count, loss,
         # this rank's gradient rows; the time of that run is the strong-scaling reference of the global mode
-        seg_path = "radix sort (replicated on every rank)"
+        seg_path = {1: "counting (sort-free), replicated on every rank; each rank scores the pairs whose negative row it owns",
+                    2: "radix sort, replicated on every rank; the cost line is split across the ranks"}.get(
+                        global_mode.last_segmentation_path(), "?")
         parity = None
         if rank == 0:
             gs, gy, gw = (torch.tensor(d[k], device=dev) for k in ("s", "y", "w"))
@@ -643,8 +645,8 @@ def ours(args):
             if not seg_path.startswith("counting"):
                 kernels_per_step, kernel_names = 3, ["k_init", "k_seg<HeadsTail>", "k_pair"]
         else:
-            kernels_per_step = 5
-            kernel_names = ["k_pack", "k_init (+ peer gather)", "k_seg<HeadsTail>", "k_pair", "k_reduce_chunks"]
+            kernels_per_step = 7
+            kernel_names = ["k_pack", "k_xbar", "k_init (+ peer gather)", "k_seg<HeadsTail>", "k_pair", "k_xbar", "k_reduce_out"]
         value = n_pair * K / (t_ms * 1e-3)
         rows_total = ROWS_PER_GPU * world
         # roofline of the dominant kernel (k_pair): SFU-bound -- 3 MUFU per kept pair; this rank scored 1/world
@@ -664,10 +666,11 @@ def ours(args):
                        "l2": "flushed between timed steps (256 MiB write); inputs ~1.6 MB/GPU",
                        "timing": "CUDA events per step on the launch stream, summed over steps, max over ranks",
                        "multi_gpu": None if world == 1 else (
-                           "peer memory over NVLink (torch symmetric memory), no collective calls: pack kernel -> device "
-                           "barrier -> ONE graph launch whose first kernel gathers every rank's row block with peer loads "
-                           "-> replicated segmentation -> even split of the pair work -> barrier -> one kernel sums this "
-                           "rank's gradient chunk from the peers' buffers"
+                           "ONE C-ABI call per step (rn_global_pairwise_fwd_bwd) over NVLink peer mappings, no collective "
+                           "calls: pack kernel -> device-side flag barrier -> ONE graph launch whose first kernel gathers every "
+                           "rank's row block with peer loads -> replicated sort-free segmentation -> each rank scores the "
+                           "pairs whose negative row it owns -> flag barrier -> one kernel sums this rank's gradient chunk "
+                           "from the peers' buffers"
                            if global_mode.exchange_path() == "peer" else
                            "ONE NCCL all-gather of packed per-rank row blocks -> replicated segmentation on the blocked "
                            "rows -> even work-unit split -> ONE NCCL reduce-scatter (gradient chunks, partial loss in a "

@@ -171,6 +171,31 @@ int rn_pack_row_block(const int64_t* keys, int32_t K, const float* logits, const
 int rn_reduce_peer_chunks(const void* const* peer_out, int32_t world, int32_t my_rank, int64_t chunk, float* dst,
                           void* stream);
 
+/* ---- global in-batch mode: ONE call per step and rank --------------------------------------------------------
+ * pairwise_loss over the concatenation of all ranks' rows (rank order = row order; SURVEY.md 8e -- the reference has
+ * no multi-GPU mode, these are the semantics BASELINE.json's north_star defines).  One process per GPU.  Every rank
+ * owns one symmetric buffer of rn_global_buffer_bytes(...) bytes, zeroed once, and mapped into every process of the
+ * box (cudaIpc*, CUDA VMM, torch symmetric memory: the caller's plumbing); peer_buf[r] is rank r's buffer as mapped
+ * into THIS process (peer_buf[rank] = the own one).  gather_buf: local device memory of rn_global_gather_bytes(...)
+ * bytes (the gathered global rows).  `local` describes THIS rank's rows exactly as for rn_pairwise_fwd_bwd (B = rows per
+ * rank, a multiple of 16 and the same on every rank; device pointers; dlogits[B]; loss / n_pair are the GLOBAL values,
+ * identical on all ranks; the multi-GPU fields of `local` stay 0 / {0, 1}).  step: 0, 1, 2, ... -- the same on every
+ * rank, incremented by the caller after every call on this set of buffers.  The call enqueues on `stream`: pack ->
+ * device-side barrier over NVLink (flag words in the peers' buffers) -> the kernels (the first one gathers every
+ * rank's packed rows with peer loads; every rank segments the same rows and scores its share of the pair space) ->
+ * barrier -> one kernel that sums this rank's gradient chunk over the peers' buffers.  No collective library, no host
+ * synchronisation.  Score- / weight-dependent pair sets (only_wrong, rw_neg): RN_ERR_UNSUPPORTED. */
+typedef struct rn_global_args {
+  rn_pairwise_args local;
+  int32_t world, rank;
+  void* peer_buf[8];
+  void* gather_buf;
+  int64_t step;
+} rn_global_args;
+size_t rn_global_buffer_bytes(int64_t B_loc, int32_t K, int32_t world, int32_t has_rw_pos, int32_t has_row_ok);
+size_t rn_global_gather_bytes(int64_t B_loc, int32_t K, int32_t world, int32_t has_rw_pos, int32_t has_row_ok);
+int rn_global_pairwise_fwd_bwd(const rn_global_args* args, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- pairwise, HOST buffers ------------------------------------------------------------------------------
  * Front end for callers whose tensors live in host memory (a CPU-placed TF2 op, a data loader): the same call as
  * rn_pairwise_fwd_bwd, but EVERY pointer of rn_pairwise_args is a HOST pointer (pinned memory, or the copies are

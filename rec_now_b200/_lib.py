@@ -26,6 +26,7 @@ EXPORTS = [
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
     "rn_bench_mufu", "rn_profile_enable", "rn_profile_enable_ex", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
     "rn_debug_graph_launches", "rn_debug_arena_offset", "rn_pack_row_block", "rn_reduce_peer_chunks",
+    "rn_global_buffer_bytes", "rn_global_gather_bytes", "rn_global_pairwise_fwd_bwd",
     "rn_host_pairwise_create", "rn_host_pairwise_submit", "rn_host_pairwise_wait", "rn_host_pairwise_destroy",
 ]
 
@@ -51,6 +52,11 @@ class PairwiseArgs(C.Structure):
         ("peer_blocks", C.c_void_p * 8), ("gather_dst", C.c_void_p),
         ("scratch_persistent", C.c_int32), ("reserved0", C.c_int32), ("scratch_rows", C.c_int64),
     ]
+
+
+class GlobalArgs(C.Structure):
+    _fields_ = [("local", PairwiseArgs), ("world", C.c_int32), ("rank", C.c_int32),
+                ("peer_buf", C.c_void_p * 8), ("gather_buf", C.c_void_p), ("step", C.c_int64)]
 
 
 class ListwiseArgs(C.Structure):
@@ -108,6 +114,11 @@ def lib() -> C.CDLL:
     L.rn_listwise_launch_count.argtypes = [i64]
     L.rn_pack_row_block.argtypes = [vp, i32, vp, vp, vp, vp, i64, vp, i64, vp]
     L.rn_reduce_peer_chunks.argtypes = [C.POINTER(C.c_void_p), i32, i32, i64, vp, vp]
+    L.rn_global_buffer_bytes.restype = sz
+    L.rn_global_buffer_bytes.argtypes = [i64, i32, i32, i32, i32]
+    L.rn_global_gather_bytes.restype = sz
+    L.rn_global_gather_bytes.argtypes = [i64, i32, i32, i32, i32]
+    L.rn_global_pairwise_fwd_bwd.argtypes = [C.POINTER(GlobalArgs), vp, sz, vp]
     L.rn_host_pairwise_create.argtypes = [i64, i32, i32, C.POINTER(vp)]
     L.rn_host_pairwise_submit.argtypes = [vp, C.POINTER(PairwiseArgs), C.POINTER(i32)]
     L.rn_host_pairwise_wait.argtypes = [vp, i32]

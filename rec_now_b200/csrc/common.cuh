@@ -95,7 +95,7 @@ struct Layout {
   size_t labpart, slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
   // counting path (group_count.cuh): group records (clean = zero between calls), created-group lists per 512-row tile,
   // sorted group index column
-  size_t rec, glist, gcount, sgrp, bnd, jn;
+  size_t rec, rec2, glist, gcount, sgrp, bnd, jn;
   int64_t Bcap;
 };
 
@@ -108,6 +108,9 @@ struct __align__(16) GRec {
   float wocc; u32 pad0;         // occurrence weight c_h ^ power of the group (non-dynamic pair sets)
   u64 npair;                    // kept pairs of the group (PW:286-289)
 };
+// Second record of a group, global mode only: rows per label level among THIS rank's rows (cl) and among the other
+// ranks' rows (cr); cr is rewritten by the offsets phase to the level starts of the remote part.  All zero = clean.
+struct __align__(16) GRec2 { u32 cl[8]; u32 cr[8]; };
 constexpr int kLevels = 8;       // label levels of the counting path: integer-valued labels -1 .. 6
 constexpr int kGTile = 512;      // rows per tile of the counting path (= kSegThreads)
 constexpr u32 kBndCap = 16384;   // piece boundaries of the pair kernel's partition the arena holds (warps of its grid + 1)
@@ -174,6 +177,7 @@ inline Layout make_layout(int64_t Bcap, int K, int64_t B = 0) {
   L.gstat = take(sizeof(float) * 8 * Bc);   // listwise per-list records
   const size_t ngt = (Bc + kGTile - 1) / kGTile;
   L.rec = take(sizeof(GRec) * ((size_t)cap + 1));
+  L.rec2 = take(sizeof(GRec2) * ((size_t)cap + 1));
   L.glist = take(sizeof(u32) * ngt * kGTile);
   L.gcount = take(sizeof(u32) * ngt);
   L.sgrp = take(sizeof(u32) * Bc);

@@ -148,8 +148,11 @@ struct HeadsTail {
     const u32 li = meta >> 29, rank = meta & 0x1FFFFFFFu;
     const u32 a = r->base, pre = r->cnt[li];
     const float wocc = r->wocc;
-    const u32 pos = a + pre + rank;
-    const u32 n = pre;                                       // rows of the group below this row's level
+    // global mode: the group is laid out [local rows by level][remote rows by level]; a row of either part pairs with
+    // the LOCAL rows below its level (every pair is scored by the rank that owns its negative)
+    const bool remote = S.rm.Bl && (i / S.rm.Bl != (u32)P.part_rank) && slot <= S.capmask;
+    const u32 pos = a + (remote ? S.rec2[slot].cr[li] : pre) + rank;
+    const u32 n = pre;                                       // (local) rows of the group below this row's level
     aj[pos] = make_uint2(a, n);
     // (a NaN label pairs with nothing, but its row shares I-blocks with rows that do: under label-gain weights the tile
     // multiplies a zero row weight by (y_i - y_ref), and 0 * NaN would poison the block's sums)
@@ -167,18 +170,32 @@ struct HeadsTail {
   // ascend along the positions, so that row has the longest negative range.  The block in which the group begins gets
   // it as R2 (hull with the other groups that begin there: atomicMax on (~lo, hi), zero = empty), every later block
   // as R1 (exactly one group can reach into a block from the left: plain store).
-  static __device__ __forceinline__ u32 level_start_at(const u32* pre, const u32* c, u32 x) {
+  // Geometry of one group as the offsets phase knows it.  Layout of the group's rows: the LOCAL rows by level, then (global
+  // mode) the remote rows by level.  pl[q] / pr[q]: start of level q inside the local / remote part, relative to the
+  // group's base (pr includes nl); ml / mr: bit q set = the level holds rows of that part.  The negative range of a row of
+  // level q is [base, base + pl[q]) in either part.
+  struct Geo { u32 base, tot, nl, ml, mr; u32 pl[kLevels], pr[kLevels]; };
+  static __device__ __forceinline__ u32 range_len_at(const Geo& g, u32 x) {        // pl[level of the row at relative position x]
     u32 r = 0;
+    if (x < g.nl) {
 #pragma unroll
-    for (int q = 0; q < kLevels; ++q) if (c[q] && pre[q] <= x) r = pre[q];
+      for (int q = 0; q < kLevels; ++q) if (((g.ml >> q) & 1u) && g.pl[q] <= x) r = g.pl[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < kLevels; ++q) if (((g.mr >> q) & 1u) && g.pr[q] <= x) r = g.pl[q];
+    }
     return r;
   }
-  __device__ __forceinline__ void block_range(u32 b, u32 b0, u32 base, u32 tot, const u32* pre, const u32* c) const {
-    const u32 xlast = min(tot, (b + 1u) * kIB - base) - 1u;
-    const u32 hi = level_start_at(pre, c, xlast);
+  __device__ __forceinline__ void block_range(u32 b, u32 b0, const Geo& g) const {
+    // rows of the group inside I-block b: relative positions [x0, x1]; the range length grows with the position inside
+    // each part, so the longest one belongs to the last local row or to the last row
+    const u32 x0 = b == b0 ? 0u : b * kIB - g.base, x1 = min(g.tot, (b + 1u) * kIB - g.base) - 1u;
+    u32 hi = 0;
+    if (x0 < g.nl) hi = range_len_at(g, min(x1, g.nl - 1u));
+    if (x1 >= g.nl) hi = max(hi, range_len_at(g, x1));
     if (!hi) return;
-    if (b == b0) { atomicMax(&blk[2 * b + 1].x, ~base); atomicMax(&blk[2 * b + 1].y, base + hi); }
-    else blk[2 * b] = make_uint2(~base, base + hi);
+    if (b == b0) { atomicMax(&blk[2 * b + 1].x, ~g.base); atomicMax(&blk[2 * b + 1].y, g.base + hi); }
+    else blk[2 * b] = make_uint2(~g.base, g.base + hi);
   }
 
   // Cost prefix of the pair kernel's work line and the boundaries of its equal pieces (what k_pair's prologue
@@ -248,24 +265,30 @@ struct HeadsTail {
     const bool single = ntile <= gridDim.x;                       // one tile per CTA: the rows stay in registers
     const u32 trash = S.capmask + 1u;
     const bool dyn = P.dyn_count != 0;
+    // global mode (blocked rows): tiles never straddle two ranks' blocks (block_rows is a multiple of the tile); a tile
+    // of another rank's rows counts into the REMOTE half of the groups' second records
+    const bool glob = S.rm.Bl != 0;
+    GRec2* rec2 = S.rec2;
     u32 k_slot = 0, k_meta = 0; float k_s = 0.f, k_y = 0.f, k_wp = 1.f, k_wn = 1.f;
     bool bad = false;
     // ---- count --------------------------------------------------------------------------------------------------
     for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
       const u32 i = t * kGTile + tid;
       const bool in = i < B;
+      const bool tile_remote = glob && (t * kGTile / S.rm.Bl != (u32)P.part_rank);
+      const size_t i8 = S.rm.i8(i), i4 = S.rm.i4(i), i1 = S.rm.i1(i);
       // all loads of the row first (independent, one round trip)
-      const u64 key = in ? (u64)S.keys[i] : 0ull;
-      const float y = in ? S.labels[i] : 0.f;
-      const bool okb = in && (S.row_ok ? S.row_ok[i] != 0 : true);
+      const u64 key = in ? (u64)S.keys[i8] : 0ull;
+      const float y = in ? S.labels[i4] : 0.f;
+      const bool okb = in && (S.row_ok ? S.row_ok[i1] != 0 : true);
       if (single) {
-        k_s = in ? P.logits[i] : 0.f;
-        if (P.rw_pos) k_wp = in ? P.rw_pos[i] : 1.f;
-        if (P.rw_neg) k_wn = in ? P.rw_neg[i] : 1.f;
+        k_s = in ? P.logits[i4] : 0.f;
+        if (P.rw_pos) k_wp = in ? P.rw_pos[i4] : 1.f;
+        if (P.rw_neg) k_wn = in ? P.rw_neg[i4] : 1.f;
         k_y = y;
       }
       float wp = 1.f;
-      if (!single && P.rw_pos) wp = in ? P.rw_pos[i] : 1.f; else wp = k_wp;
+      if (!single && P.rw_pos) wp = in ? P.rw_pos[i4] : 1.f; else wp = k_wp;
       sm_tab[tid] = kEmpty; sm_tab[tid + kGTile] = kEmpty;
 #pragma unroll
       for (int q = 0; q < kLevels; q += 4) *reinterpret_cast<uint4*>(sm_cnt + tid * kLevels + q) = make_uint4(0, 0, 0, 0);
@@ -309,8 +332,9 @@ struct HeadsTail {
         u32 c[kLevels];
 #pragma unroll
         for (int q = 0; q < kLevels; ++q) c[q] = sm_cnt[tid * kLevels + q];
+        u32* tgt = glob ? (tile_remote ? rec2[slot].cr : rec2[slot].cl) : rec[slot].cnt;
 #pragma unroll
-        for (int q = 0; q < kLevels; ++q) if (c[q]) c[q] = atomicAdd(&rec[slot].cnt[q], c[q]);
+        for (int q = 0; q < kLevels; ++q) if (c[q]) c[q] = atomicAdd(tgt + q, c[q]);
 #pragma unroll
         for (int q = 0; q < kLevels; ++q) sm_cnt[tid * kLevels + q] = c[q];
       }
@@ -343,45 +367,66 @@ struct HeadsTail {
       for (u32 k0 = 0; k0 < ncr; k0 += kSegThreads) {             // (uniform trip count: the body uses warp collectives)
         const u32 k = k0 + tid;
         const bool act = k < ncr;
-        u32 slot = 0, tot = 0; u32 pre[kLevels], c[kLevels]; u64 pairs = 0;
-#pragma unroll
-        for (int q = 0; q < kLevels; ++q) { pre[q] = 0; c[q] = 0; }
+        u32 slot = 0; u64 pairs = 0;
+        Geo g{};                    // (inactive lanes: an empty group)
         if (act) {
           slot = S.glist[(size_t)t * kGTile + k];
-          const uint4 c0 = *reinterpret_cast<const uint4*>(rec[slot].cnt), c1 = *reinterpret_cast<const uint4*>(rec[slot].cnt + 4);
-          c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+          u32 cl[kLevels], cr[kLevels];
+          if (glob && slot <= S.capmask) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(rec2[slot].cl), a1 = *reinterpret_cast<const uint4*>(rec2[slot].cl + 4);
+            const uint4 b0 = *reinterpret_cast<const uint4*>(rec2[slot].cr), b1 = *reinterpret_cast<const uint4*>(rec2[slot].cr + 4);
+            cl[0] = a0.x; cl[1] = a0.y; cl[2] = a0.z; cl[3] = a0.w; cl[4] = a1.x; cl[5] = a1.y; cl[6] = a1.z; cl[7] = a1.w;
+            cr[0] = b0.x; cr[1] = b0.y; cr[2] = b0.z; cr[3] = b0.w; cr[4] = b1.x; cr[5] = b1.y; cr[6] = b1.z; cr[7] = b1.w;
+          } else {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(rec[slot].cnt), a1 = *reinterpret_cast<const uint4*>(rec[slot].cnt + 4);
+            cl[0] = a0.x; cl[1] = a0.y; cl[2] = a0.z; cl[3] = a0.w; cl[4] = a1.x; cl[5] = a1.y; cl[6] = a1.z; cl[7] = a1.w;
 #pragma unroll
-          for (int q = 0; q < kLevels; ++q) { pre[q] = tot; pairs += (u64)c[q] * tot; tot += c[q]; }   // pairs of a row = rows below its level
+            for (int q = 0; q < kLevels; ++q) cr[q] = 0;
+          }
+          u32 below = 0;
+#pragma unroll
+          for (int q = 0; q < kLevels; ++q) {
+            g.pl[q] = g.nl; g.nl += cl[q]; if (cl[q]) g.ml |= 1u << q;
+            pairs += (u64)(cl[q] + cr[q]) * below; below += cl[q] + cr[q];        // pairs of a row = ALL rows of the group below its level
+          }
+          g.tot = g.nl;
+#pragma unroll
+          for (int q = 0; q < kLevels; ++q) { g.pr[q] = g.tot; g.tot += cr[q]; if (cr[q]) g.mr |= 1u << q; }
         }
-        u32 inc = tot;
+        u32 inc = g.tot;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
         const u32 wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
         u32 wbase = 0;
         if (ln == 0 && wtot) wbase = atomicAdd(&ctl->cursor, wtot);
         wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        const u32 base = wbase + inc - tot;
+        g.base = wbase + inc - g.tot;
         // J ranges of the I-blocks the group touches: up to three blocks by its own thread, longer groups by the warp
         u32 b0 = 0, nblk = 0;
-        if (act && tot) {
-          b0 = base / kIB; nblk = (base + tot - 1u) / kIB - b0 + 1u;
-          for (u32 b = b0; b < b0 + min(nblk, 3u); ++b) block_range(b, b0, base, tot, pre, c);
+        if (act && g.tot) {
+          b0 = g.base / kIB; nblk = (g.base + g.tot - 1u) / kIB - b0 + 1u;
+          for (u32 b = b0; b < b0 + min(nblk, 3u); ++b) block_range(b, b0, g);
         }
         u32 big = __ballot_sync(0xFFFFFFFFu, nblk > 3u);
         while (big) {
           const int src = __ffs(big) - 1; big &= big - 1;
-          u32 gp[kLevels], gc[kLevels];
+          Geo h;
+          h.base = __shfl_sync(0xFFFFFFFFu, g.base, src); h.tot = __shfl_sync(0xFFFFFFFFu, g.tot, src);
+          h.nl = __shfl_sync(0xFFFFFFFFu, g.nl, src); h.ml = __shfl_sync(0xFFFFFFFFu, g.ml, src); h.mr = __shfl_sync(0xFFFFFFFFu, g.mr, src);
 #pragma unroll
-          for (int q = 0; q < kLevels; ++q) { gp[q] = __shfl_sync(0xFFFFFFFFu, pre[q], src); gc[q] = __shfl_sync(0xFFFFFFFFu, c[q], src); }
-          const u32 gbase = __shfl_sync(0xFFFFFFFFu, base, src), gtot = __shfl_sync(0xFFFFFFFFu, tot, src);
+          for (int q = 0; q < kLevels; ++q) { h.pl[q] = __shfl_sync(0xFFFFFFFFu, g.pl[q], src); h.pr[q] = __shfl_sync(0xFFFFFFFFu, g.pr[q], src); }
           const u32 gb0 = __shfl_sync(0xFFFFFFFFu, b0, src), gnb = __shfl_sync(0xFFFFFFFFu, nblk, src);
-          for (u32 b = gb0 + 3u + ln; b < gb0 + gnb; b += 32) block_range(b, gb0, gbase, gtot, gp, gc);
+          for (u32 b = gb0 + 3u + ln; b < gb0 + gnb; b += 32) block_range(b, gb0, h);
         }
         if (act) {
           GRec* r = rec + slot;
-          r->base = base;
-          *reinterpret_cast<uint4*>(r->cnt) = make_uint4(pre[0], pre[1], pre[2], pre[3]);
-          *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(pre[4], pre[5], pre[6], pre[7]);
+          r->base = g.base;
+          *reinterpret_cast<uint4*>(r->cnt) = make_uint4(g.pl[0], g.pl[1], g.pl[2], g.pl[3]);
+          *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(g.pl[4], g.pl[5], g.pl[6], g.pl[7]);
+          if (glob && slot <= S.capmask) {
+            *reinterpret_cast<uint4*>(rec2[slot].cr) = make_uint4(g.pr[0], g.pr[1], g.pr[2], g.pr[3]);
+            *reinterpret_cast<uint4*>(rec2[slot].cr + 4) = make_uint4(g.pr[4], g.pr[5], g.pr[6], g.pr[7]);
+          }
           if (!dyn) {
             r->npair = pairs;
             r->wocc = (P.power != 0.f && pairs) ? ((P.power == 1.0f) ? (float)pairs : powf((float)pairs, P.power)) : 0.f;   // PW:147-149
@@ -415,9 +460,11 @@ struct HeadsTail {
     } else {
       for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
         const u32 i = t * kGTile + tid;
-        if (i < B)
-          scatter_row(S, i, S.rslot[i], S.rmeta[i], P.logits[i], S.labels[i], P.rw_pos ? P.rw_pos[i] : 1.f,
-                      P.rw_neg ? P.rw_neg[i] : 1.f);
+        if (i < B) {
+          const size_t i4 = S.rm.i4(i);
+          scatter_row(S, i, S.rslot[i], S.rmeta[i], P.logits[i4], S.labels[i4], P.rw_pos ? P.rw_pos[i4] : 1.f,
+                      P.rw_neg ? P.rw_neg[i4] : 1.f);
+        }
       }
     }
     if (pp.on && spare < 4u) { __syncthreads(); partition(S, smem, blockIdx.x, gridDim.x); }
@@ -567,7 +614,7 @@ struct KpArgs {
   u64* cprim;
   // counting path (group_count.cuh): the call ran without k_init; the records its count phase created are listed per
   // 512-row tile and zeroed again by the last phase of this kernel
-  int fast; GRec* rec; const u32* glist; const u32* gcount; u32 ngt;
+  int fast; GRec* rec; GRec2* rec2; const u32* glist; const u32* gcount; u32 ngt;     // (rec2: global mode only, else nullptr)
   uint2* blk_w;              // (the J ranges are zeroed again as well)
   const uint4* bnd; const u32* jn; int pre_on;     // partition computed by k_seg's helper CTAs (PrePart)
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
@@ -586,8 +633,11 @@ __device__ __forceinline__ void clean_records(const KpArgs& A, u32 t0, u32 tstep
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (u32 t = t0; t < A.ngt; t += tstep) {
     const u32 n = A.gcount[t];
-    for (u32 k = threadIdx.x; k < 4 * n; k += blockDim.x)
-      reinterpret_cast<uint4*>(A.rec + A.glist[(size_t)t * kGTile + (k >> 2)])[k & 3u] = z;
+    for (u32 k = threadIdx.x; k < 4 * n; k += blockDim.x) {
+      const u32 slot = A.glist[(size_t)t * kGTile + (k >> 2)];
+      reinterpret_cast<uint4*>(A.rec + slot)[k & 3u] = z;
+      if (A.rec2) reinterpret_cast<uint4*>(A.rec2 + slot)[k & 3u] = z;
+    }
   }
 }
 
@@ -723,7 +773,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     // this rank's share [r0, r1) of the cost line, one equal piece per warp; the 2 x 32 piece boundaries of this CTA's
     // warps are resolved by 64 threads at once (s_bnd: [64][v, jb, e])
     u32 r0 = 0, r1 = tot;
-    if (P.part_count > 1) {
+    if (P.part_count > 1 && !counted) {      // (counting path: the ranks split the pairs by the owner of the negative row instead)
       r0 = (u32)(((u64)tot * (u32)P.part_rank) / (u32)P.part_count);
       r1 = (u32)(((u64)tot * ((u32)P.part_rank + 1)) / (u32)P.part_count);
     }
@@ -1239,8 +1289,9 @@ extern "C" int rn_pairwise_scratch_init(void* scratch, size_t scratch_bytes, voi
 static bool counting_eligible(const rn_pairwise_args* a) {
   static const int off = tune_int("RN_SEG_COUNT", 1);
   // (batches beyond kMaxNibS I-blocks need the explicit unit records only the radix tail builds)
-  return off && a->scratch_persistent && a->K == 1 && !a->block_rows && a->part_count == 1 &&
-         (a->B + kIB - 1) / kIB <= (int64_t)kMaxNibS;
+  // global mode (blocked rows): the rank blocks must be whole tiles of the count phase
+  return off && a->scratch_persistent && a->K == 1 && (a->block_rows % kGTile) == 0 && (a->part_count == 1 || a->block_rows) &&
+         !(a->block_rows && a->row_pairs) && (a->B + kIB - 1) / kIB <= (int64_t)kMaxNibS;
 }
 
 extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
@@ -1333,7 +1384,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.cost_levels = (u32)(cost_levels < 0 ? 0 : (cost_levels > 64 ? 64 : cost_levels));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.sgrp = H.sgrp; A.cprim = H.cprim;
-  A.fast = fast ? 1 : 0; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
+  A.fast = fast ? 1 : 0; A.rec2 = (fast && a->block_rows) ? at<GRec2>(base, L.rec2) : nullptr; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
   A.ngt = (u32)((a->B + kGTile - 1) / kGTile); A.blk_w = H.blk;
   A.dbgbuf = at<u64>(base, L.gstat);
   int mode = 0;
@@ -1361,7 +1412,7 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;
   // one launch of a cached CUDA graph; while the pair kernel is being timed: the timed variant of the graph (two
   // event-record nodes around the pair kernel), or plain launches with stream events (RN_PROFILE_GRAPH=0)
-  GraphCall gc(fast ? nullptr : seg_init_func(), f_seg, pair_func(mode), st, !prof || tev != nullptr, tev != nullptr);
+  GraphCall gc((fast && !a->gather_dst) ? nullptr : seg_init_func(), f_seg, pair_func(mode), st, !prof || tev != nullptr, tev != nullptr);
   const bool in_graph = gc.capturing() || gc.updating();
   // the three launches of the call (k_init, k_seg, k_pair) on stream s
   auto enqueue = [&](cudaStream_t s, bool graph) -> bool {

@@ -41,7 +41,7 @@ struct SegParams {
   u64* dbgts;                     // RN_SEG_DEBUG=1: per-CTA arrival stamps [phase][cta] (dev tool), else nullptr
   // counting path (group_count.cuh; fast != 0: no k_init ran, the arena is in its clean state)
   int fast;
-  GRec* rec; u32 *glist, *gcount, *rslot, *rmeta;
+  GRec* rec; GRec2* rec2; u32 *glist, *gcount, *rslot, *rmeta;
   uint4 *init_zero, *init_ones; u32 init_zero16, init_ones16;    // regions the radix path needs initialised (fallback)
   __device__ __forceinline__ u32* th_buf(u32 k) const { return k ? tilehist + (size_t)(k - 1) * ntiles * kBins : th0; }
 };
@@ -489,7 +489,7 @@ inline SegParams make_seg_params(const Layout& L, void* scratch, const SegInputs
   S.dbgts = (segdbg && *segdbg == '1') ? at<u64>(base, L.gstat) : nullptr;
   S.ctl = at<Ctl>(base, L.ctl);
   S.fast = 0;
-  S.rec = at<GRec>(base, L.rec); S.glist = at<u32>(base, L.glist); S.gcount = at<u32>(base, L.gcount);
+  S.rec = at<GRec>(base, L.rec); S.rec2 = at<GRec2>(base, L.rec2); S.glist = at<u32>(base, L.glist); S.gcount = at<u32>(base, L.gcount);
   S.rslot = S.slot; S.rmeta = S.slot1;
   S.init_zero = at<uint4>(base, L.hist); S.init_zero16 = (u32)((L.zero_end - L.hist) / 16);
   S.init_ones = at<uint4>(base, L.ones_begin); S.init_ones16 = (u32)((L.ones_end - L.ones_begin) / 16);
@@ -502,11 +502,12 @@ inline int seg_merged_gbits(const Layout& L) { return bit_width_u64((uint64_t)L.
 // Enqueue init + the segmentation kernel with the given tail (2 launches; 1 on the counting path).
 template <class Tail>
 cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const Tail& tail, cudaStream_t st) {
-  const bool fast = Tail::kFast && in.fast && in.K == 1 && in.use_label && in.labels && !in.rm.Bl && !in.gather.world;
+  const bool fast = Tail::kFast && in.fast && in.K == 1 && in.use_label && in.labels;
   const bool merged = !fast && in.allow_merged && in.K == 1 && in.use_label && in.labels && !in.rm.Bl;
   int npart = 0;
   cudaError_t e = cudaSuccess;
-  if (!fast)
+  // (counting path: no initialisation kernel -- except in the global mode, whose first kernel is also the peer gather)
+  if (!fast || in.gather.world)
     e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart)
                : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr);
   if (e != cudaSuccess) return e;

@@ -46,50 +46,69 @@ def _all_gather_cols(cols, group):
 
 
 class _PeerState:
-    """Peer-mapped (symmetric) buffers of one (group, block layout): two input blocks and two chunked gradient buffers
-    per rank, alternating between consecutive steps, so that a rank that runs ahead never overwrites what a peer
-    still reads (every step passes two device-side barriers; see _peer_global)."""
+    """The symmetric buffer of one (group, shape) -- rn_global_buffer_bytes: flag words, two packed input blocks, two
+    chunked gradient buffers -- allocated with torch symmetric memory (the plumbing that maps every rank's buffer into
+    every process), zeroed once; plus this rank's local buffers of the one-call global step (rn_global_pairwise_fwd_bwd)."""
 
-    def __init__(self, group, dev, stride: int, out_floats: int):
+    def __init__(self, group, dev, b_loc: int, kk: int, has_w: bool, has_ok: bool):
+        import ctypes as C
         import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
         g = dist.group.WORLD if group is None else group
-        self.in_off = [0, stride]
-        self.out_off = [2 * stride, 2 * stride + 4 * out_floats]
-        total = 2 * stride + 8 * out_floats
+        world = dist.get_world_size(group)
+        lib = _lib.lib()
+        total = lib.rn_global_buffer_bytes(b_loc, kk, world, int(has_w), int(has_ok))
         self.buf = symm_mem.empty(total, dtype=torch.uint8, device=dev)
+        self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, g.group_name)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.stride, self.out_floats, self.step = stride, out_floats, 0
-
-    def in_block(self, p):
-        return self.buf[self.in_off[p]:self.in_off[p] + self.stride]
-
-    def out_buf(self, p):
-        return self.buf[self.out_off[p]:self.out_off[p] + 4 * self.out_floats].view(torch.float32)
+        self.gather = torch.empty(lib.rn_global_gather_bytes(b_loc, kk, world, int(has_w), int(has_ok)),
+                                  dtype=torch.uint8, device=dev)
+        self.scratch_bytes = lib.rn_pairwise_scratch_bytes(world * b_loc, kk)
+        self.scratch = torch.zeros(self.scratch_bytes, dtype=torch.uint8, device=dev)
+        self.args = _lib.GlobalArgs()
+        self.args.world, self.args.rank = world, dist.get_rank(group)
+        for r in range(world):
+            self.args.peer_buf[r] = self.ptrs[r]
+        self.args.gather_buf = self.gather.data_ptr()
+        self.ref = C.byref(self.args)
+        self.fn = lib.rn_global_pairwise_fwd_bwd
+        self.step = 0
+        torch.cuda.synchronize(dev)
+        self.hdl.barrier(channel=0)              # every rank's buffer is zeroed before anyone's first step
+        torch.cuda.synchronize(dev)
 
 
 _peer_states: dict = {}
 _peer_broken = False
 
 
-def _peer_state(group, dev, stride, out_floats) -> Optional[_PeerState]:
+def _peer_state(group, dev, b_loc, kk, has_w, has_ok) -> Optional[_PeerState]:
     """The cached peer-memory state, or None when it is switched off (RN_GLOBAL_P2P=0) or symmetric memory is not
     available on this box (then the NCCL collectives are used)."""
     global _peer_broken
     import os
     if _peer_broken or os.environ.get("RN_GLOBAL_P2P", "1") == "0" or dist.get_world_size(group) > 8:
         return None
-    key = (id(group), dev.index, stride, out_floats)
+    key = (id(group), dev.index, b_loc, kk, has_w, has_ok)
     st = _peer_states.get(key)
     if st is None:
         try:
-            st = _peer_states[key] = _PeerState(group, dev, stride, out_floats)
+            st = _peer_states[key] = _PeerState(group, dev, b_loc, kk, has_w, has_ok)
         except Exception as e:               # no peer access / no symmetric memory: fall back to the collectives
             import warnings
             warnings.warn(f"rec_now_b200 global mode: peer memory unavailable ({e!r}); using NCCL collectives")
             _peer_broken = True
             return None
     return st
+
+
+def last_segmentation_path() -> int:
+    """Segmentation path of the last finished peer-memory step (1 counting, 2 radix sort, 0 unknown)."""
+    from . import ops
+    for st in _peer_states.values():
+        return ops.last_segmentation_path(st.scratch)
+    return 0
 
 
 def exchange_path() -> str:
@@ -101,27 +120,33 @@ def exchange_path() -> str:
 
 
 def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
-    """Global step over NVLink peer mappings, no collective calls: pack this rank's block into its symmetric buffer ->
-    device-side barrier -> ONE graph launch whose first kernel gathers all ranks' blocks with peer loads and whose
-    last kernel leaves the chunked partial gradients in the symmetric buffer -> barrier -> one kernel sums this
-    rank's chunk over the peers' buffers."""
-    from . import ops
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    b_loc = logits.numel()
-    kk = keys.shape[0]
-    lay = ops.packed_block_layout(b_loc, kk, rw_pos is not None, row_ok is not None)
-    p = st.step & 1
+    """Global step over NVLink peer mappings: ONE C-ABI call (rn_global_pairwise_fwd_bwd) enqueues pack -> device-side
+    barrier -> the kernels (the first gathers all ranks' blocks with peer loads, the last leaves the chunked partial
+    gradients in the symmetric buffer) -> barrier -> the peer-read reduction.  No collective calls, no torch ops."""
+    from . import _lib, ops
+    s, y, rwp = ops._f32(logits), ops._f32(labels), ops._f32(rw_pos)
+    b_loc = s.numel()
+    dev = s.device
+    ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    out = torch.empty(4, dtype=torch.float32, device=dev)            # loss, n_pair_f32, n_pair (int64 in [2:4])
+    dlogits = torch.empty(b_loc, dtype=torch.float32, device=dev)
+    a = st.args.local
+    a.B = b_loc; a.K = keys.shape[0]
+    a.label_func = _lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP
+    a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
+    a.row_ok = ops._ptr(ok); a.rw_pos = ops._ptr(rwp); a.rw_neg = None
+    a.factor = factor; a.power = power; a.only_wrong = 0; a.reduce_mean = 1 if reduce_mean else 0
+    a.part_rank, a.part_count = 0, 1
+    a.scratch_persistent = 1                    # (st.scratch was zeroed at creation and is only ever used by this call)
+    po = out.data_ptr()
+    a.loss = po; a.n_pair_f32 = po + 4; a.n_pair = po + 8; a.dlogits = dlogits.data_ptr(); a.row_pairs = None
+    st.args.step = st.step
     st.step += 1
-    ops.pack_row_block(keys, logits, labels, rw_pos, row_ok, lay["stride"], out=st.in_block(p))
-    st.hdl.barrier(channel=0)                                   # every rank's block of this step is written
-    gbuf = torch.empty(world * lay["stride"], dtype=torch.uint8, device=logits.device)
-    res = ops.pairwise_fwd_bwd_blocked(gbuf, world, b_loc, kk, rw_pos is not None, row_ok is not None,
-                                       label_func=label_func, factor=factor, power=power, reduce_mean=reduce_mean,
-                                       part=(rank, world), peer_blocks=[b + st.in_off[p] for b in st.ptrs],
-                                       out=st.out_buf(p))
-    st.hdl.barrier(channel=1)                                   # every rank's partial gradients are written
-    mine = ops.reduce_peer_chunks([b + st.out_off[p] for b in st.ptrs], rank, res["chunk"], logits.device)
-    return dict(loss=mine[b_loc], n_pair=res["n_pair"], dlogits=mine[:b_loc])
+    with ops._on_device(dev):
+        rc = st.fn(st.ref, st.scratch.data_ptr(), st.scratch_bytes, torch.cuda.current_stream(dev).cuda_stream)
+    if rc:
+        _lib.check(rc, "rn_global_pairwise_fwd_bwd")
+    return dict(loss=out[0], n_pair=out[2:4].view(torch.int64)[0], dlogits=dlogits, _keep=(s, y, rwp, ok, keys))
 
 
 def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
@@ -134,7 +159,7 @@ def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, pow
     kk = keys.shape[0]
     lay = ops.packed_block_layout(b_loc, kk, rw_pos is not None, row_ok is not None)
     if _compute_blocked is None:
-        st = _peer_state(group, logits.device, lay["stride"], world * (b_loc + 4))
+        st = _peer_state(group, logits.device, b_loc, kk, rw_pos is not None, row_ok is not None)
         if st is not None:
             return _peer_global(st, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group)
     if _compute_blocked is None:

@@ -68,6 +68,8 @@ def _f32(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
     if t.dtype is torch.float32 and t.is_contiguous():
+        if t.data_ptr() & 15:          # (a legal view with an offset, e.g. logits[1:]: the ABI wants 16-byte aligned columns)
+            return t.detach().clone()
         return t                       # only the data pointer and numel() are used: no detach / view (each costs ~1.5 us)
     return t.detach().reshape(-1).to(torch.float32).contiguous()
 
