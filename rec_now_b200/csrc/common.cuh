@@ -308,6 +308,11 @@ struct GraphCall {
 // The two events recorded by the timed graphs of this thread (created on first use; nullptr on failure).
 cudaEvent_t* timed_events();
 
+// Global mode with a score- / weight-dependent pair set: where stage 1 publishes this rank's partial per-row pair counts
+// (by original row) and where stage 2 finds every rank's (peer-mapped), see pairwise_call.
+struct DynSplit { u32* xcnt_out; const u32* xcnt_peer[8]; int world; };
+int pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, void* stream, const DynSplit* split, int stage);
+
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 
 }  // namespace rn

@@ -96,7 +96,7 @@ extern "C" int rn_global_pairwise_fwd_bwd(const rn_global_args* g, void* scratch
   const rn_pairwise_args& l = g->local;
   if (l.B <= 0 || (l.B & 15) || l.K <= 0 || l.K > 8) return RN_ERR_ARG;
   if (!l.keys || !l.logits || !l.labels || !l.loss || !l.n_pair_f32 || !l.n_pair || !l.dlogits) return RN_ERR_ARG;
-  if (l.rw_neg || l.only_wrong) return RN_ERR_UNSUPPORTED;       // (score- / weight-dependent pair sets: rn_global_pairwise_dyn, not built yet)
+  const bool dyn = l.rw_neg || l.only_wrong;        // score- / weight-dependent pair set: two stages with the ranks' counts summed between
   if (l.block_rows || l.out_chunk || l.gather_dst || l.part_count > 1) return RN_ERR_ARG;
   for (int r = 0; r < g->world; ++r) if (!g->peer_buf[r] || check_align(g->peer_buf[r])) return RN_ERR_ARG;
   const bool has_w = l.rw_pos != nullptr, has_ok = l.row_ok != nullptr;
@@ -127,7 +127,8 @@ extern "C" int rn_global_pairwise_fwd_bwd(const rn_global_args* g, void* scratch
   a.B = l.B * g->world;
   a.keys = reinterpret_cast<const int64_t*>(gb + koff); a.logits = reinterpret_cast<const float*>(gb + soff);
   a.labels = reinterpret_cast<const float*>(gb + yoff);
-  a.rw_pos = has_w ? reinterpret_cast<const float*>(gb + woff) : nullptr; a.rw_neg = nullptr;
+  a.rw_pos = has_w ? reinterpret_cast<const float*>(gb + woff) : nullptr;
+  if (l.rw_neg) return RN_ERR_UNSUPPORTED;          // (a negative-side weight column is not part of the packed row block)
   a.row_ok = has_ok ? reinterpret_cast<const uint8_t*>(gb + okoff) : nullptr;
   a.part_rank = g->rank; a.part_count = g->world;
   a.block_rows = l.B; a.block_stride = (int64_t)L.stride; a.out_chunk = (int64_t)L.chunk;
@@ -140,8 +141,22 @@ extern "C" int rn_global_pairwise_fwd_bwd(const rn_global_args* g, void* scratch
   // (the arena is persistent: the caller zeroed it once, every call leaves it clean -- the sort-free counting
   //  segmentation then runs on the gathered rows, each rank scoring the pairs whose negative row it owns)
   a.scratch_persistent = g->local.scratch_persistent; a.scratch_rows = 0;
-  rc = rn_pairwise_fwd_bwd(&a, scratch, scratch_bytes, stream);
-  if (rc) return rc;
+  if (!dyn) {
+    rc = rn_pairwise_fwd_bwd(&a, scratch, scratch_bytes, stream);
+    if (rc) return rc;
+  } else {
+    // stage 1: the kernels up to this rank's partial per-row pair counts, published by original row in its buffer;
+    // barrier; stage 2: sum of the ranks' counts -> exact n and c_h -> weights -> partial gradients (PW:197-203, 282-291)
+    DynSplit sp{};
+    sp.world = g->world;
+    sp.xcnt_out = reinterpret_cast<u32*>(mine + L.cnt[p]);
+    for (int r = 0; r < g->world; ++r) sp.xcnt_peer[r] = reinterpret_cast<const u32*>(static_cast<char*>(g->peer_buf[r]) + L.cnt[p]);
+    rc = pairwise_call(&a, scratch, scratch_bytes, stream, &sp, 1);
+    if (rc) return rc;
+    xbar(2);
+    rc = pairwise_call(&a, scratch, scratch_bytes, stream, &sp, 2);
+    if (rc) return rc;
+  }
   // 4. barrier: every rank's partial gradients are written
   xbar(1);
   // 5. this rank's chunk, summed over the peers' buffers

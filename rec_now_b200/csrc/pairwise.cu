@@ -617,6 +617,10 @@ struct KpArgs {
   int fast; GRec* rec; GRec2* rec2; const u32* glist; const u32* gcount; u32 ngt;     // (rec2: global mode only, else nullptr)
   uint2* blk_w;              // (the J ranges are zeroed again as well)
   const uint4* bnd; const u32* jn; int pre_on;     // partition computed by k_seg's helper CTAs (PrePart)
+  // global mode with a score- / weight-dependent pair set: the per-row pair counts are partial (this rank's negatives).
+  // k_pair publishes them by ORIGINAL row (xcnt_out) and stops; after a cross-rank barrier k_fin_dyn sums the ranks'
+  // arrays (xcnt_peer, peer-mapped) and finishes: counts -> occurrence weights -> gradient (PW:197-203, 282-291)
+  u32* xcnt_out; const u32* xcnt_peer[8]; int xworld; u32* xsum;      // xsum: local [B] scratch for the summed counts
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
 };
 
@@ -698,6 +702,9 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
   }
   return true;
 }
+
+__device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
+                                             u32& epoch2, u64* red_u, double* red_d);
 
 template <int MODE>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
@@ -1100,6 +1107,28 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   stamp(ctl, 21);
   grid_sync(&ctl->bar2_cnt, epoch2, &ctl->err);
   stamp(ctl, 22);
+  if (A.xcnt_out) {
+    // global mode: publish this rank's partial per-row counts by original row and stop; k_fin_dyn finishes the call
+    for (u32 p = gtid; p < B; p += gthreads) A.xcnt_out[A.perm[p]] = A.cnt[p];
+    const uint2 z2 = make_uint2(0, 0);
+    for (u32 v = gtid; v < nvb; v += gthreads) A.blk_w[v] = z2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) { ctl->bar2_cnt = 0; ctl->fin_done = 0; }     // (everybody is past the barrier)
+    }
+    return;
+  }
+  dyn_finalize(P, A, cprim, cstride, nvb, epoch2, red_u, red_d);
+}
+
+// Counts -> occurrence weights -> gradient and loss for a score- / weight-dependent pair set (the tail of k_pair, or
+// k_fin_dyn in the global mode).  All CTAs of a cooperative grid; one grid barrier inside.
+__device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
+                                             u32& epoch2, u64* red_u, double* red_d) {
+  Ctl* ctl = A.ctl;
+  const u32 B = P.B, ln = lane_id();
+  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
   {
     // F_a: exact counts from the kernel's per-row tallies: per row, per PRIMARY group (PW:286-289), total
     u64 tot_c = 0;
@@ -1107,7 +1136,12 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 p = p0 + gtid;
       u32 cn = 0, pg = kEmpty;
       if (p < B) {
-        cn = A.cnt[p];
+        if (A.xworld) {                                    // global mode: the ranks' partial counts of this row
+          const u32 row = A.perm[p];
+          for (int r = 0; r < A.xworld; ++r) cn += A.xcnt_peer[r][row];
+        } else {
+          cn = A.cnt[p];
+        }
         if (cn) pg = A.sgrp[p];
         if (P.row_pairs) P.row_pairs[A.perm[p]] = (int64_t)cn;
       }
@@ -1132,6 +1166,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   const u64 n = *reinterpret_cast<volatile u64*>(&ctl->n_pair);
   const float denom = P.reduce_mean ? ((float)n + 1.0e-10f) : 1.0f;       // PW:125-126, PW:13
   const float gscale = P.factor / denom;
+  auto out_at = [&](u32 row) -> size_t { return P.out_chunk ? (size_t)(row / P.rm.Bl) * P.out_chunk + (row % P.rm.Bl) : row; };
   double lp = 0.0;
   for (u32 p = gtid; p < B; p += gthreads) {
     const float g = A.gacc[p], l = A.lossrow[p];
@@ -1140,7 +1175,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u64 ch = cprim[(size_t)A.sgrp[p] * cstride];
       wocc = ch ? ((P.power == 1.0f) ? (float)ch : powf((float)ch, P.power)) : 0.f;   // PW:147-149
     }
-    P.dlogits[A.perm[p]] = g * wocc * gscale;
+    P.dlogits[out_at(A.perm[p])] = g * wocc * gscale;
     lp += (double)l * (double)wocc;
   }
   lp = warp_sum(lp);
@@ -1157,9 +1192,16 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       __threadfence();
       ctl->ts[23] = globaltimer();
       const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
-      *P.loss = (float)(tot / (double)denom);
+      const float lossv = (float)(tot / (double)denom);
+      *P.loss = lossv;
       *P.n_pair_f32 = (float)n;                  // PW:276
       *P.n_pair = (int64_t)n;
+      if (P.out_chunk)                           // the (partial) loss rides in every chunk of the reduce-scatter
+        for (u32 r = 0; r * P.rm.Bl < B; ++r) {
+          float* tl = P.dlogits + (size_t)r * P.out_chunk + P.rm.Bl;
+          tl[0] = lossv;
+          for (u32 q = 1; P.rm.Bl + q < P.out_chunk; ++q) tl[q] = 0.f;
+        }
     }
   }
   __syncthreads();
@@ -1168,6 +1210,32 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   if (A.fast) clean_records(A, 0, 1);
   __syncthreads();
   if (threadIdx.x == 0) { __threadfence(); ctl_finish(ctl); }
+}
+
+// Second stage of a global-mode call whose pair set depends on scores / weights (see KpArgs::xcnt_out).
+__global__ void __launch_bounds__(kPairThreads) k_fin_dyn(PairParams P, KpArgs A) {
+  __shared__ u64 red_u[kPairWarps];
+  __shared__ double red_d[kPairWarps];
+  grid_dep_wait();
+  const bool counted = A.fast && ld_relaxed(&A.ctl->fallback) == 0u;
+  const u64* cprim = counted ? &A.rec->npair : A.cprim;
+  const u32 cstride = counted ? (u32)(sizeof(GRec) / sizeof(u64)) : 1u;
+  u32 epoch2 = 0;
+  // the ranks' partial counts summed in ROW order first (coalesced 16-byte peer loads), then gathered locally
+  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  const u32 n4 = P.B / 4;                                    // (the rows per rank are a multiple of 16)
+  for (u32 i = gtid; i < n4; i += gthreads) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int r = 0; r < A.xworld; ++r) {
+      const uint4 v = reinterpret_cast<const uint4*>(A.xcnt_peer[r])[i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<uint4*>(A.xsum)[i] = acc;
+  }
+  grid_sync(&A.ctl->bar2_cnt, epoch2, &A.ctl->err);
+  KpArgs A1 = A;
+  A1.xworld = 1; A1.xcnt_peer[0] = A.xsum;
+  dyn_finalize(P, A1, cprim, cstride, 2 * A.nib, epoch2, red_u, red_d);
 }
 
 // CTAs per SM of the pair kernel's cooperative grid on the current device (all co-resident), cached per thread.
@@ -1299,7 +1367,7 @@ extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
   return 3;        // k_init, k_seg<HeadsTail>, k_pair (2 with a persistent arena and one key column: no k_init)
 }
 
-static int validate_pairwise(const rn_pairwise_args* a) {
+static int validate_pairwise(const rn_pairwise_args* a, bool split = false) {
   if (!a || a->B <= 0 || a->B > (1ll << 28) || a->K <= 0 || a->K > 8) return RN_ERR_ARG;
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
   if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF) return RN_ERR_UNSUPPORTED;
@@ -1309,7 +1377,7 @@ static int validate_pairwise(const rn_pairwise_args* a) {
     if (a->block_rows < 0 || a->B % a->block_rows || a->block_stride <= 0 || (a->block_stride & 15) ||
         a->block_stride / 4 > 0xFFFFFFFFll) return RN_ERR_ARG;
     if (a->out_chunk && (a->out_chunk <= a->block_rows || a->out_chunk > 0x7FFFFFFFll)) return RN_ERR_ARG;
-    if (a->only_wrong || a->rw_neg) return RN_ERR_UNSUPPORTED;
+    if ((a->only_wrong || a->rw_neg) && !split) return RN_ERR_UNSUPPORTED;
     if (a->gather_dst) {
       const int64_t world = a->B / a->block_rows;
       if (world > 8 || check_align(a->gather_dst)) return RN_ERR_ARG;
@@ -1322,12 +1390,21 @@ static int validate_pairwise(const rn_pairwise_args* a) {
 }
 
 extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, void* stream) {
-  int rc = validate_pairwise(a);
+  return rn::pairwise_call(a, scratch, scratch_bytes, stream, nullptr, 0);
+}
+
+// The call behind rn_pairwise_fwd_bwd.  split != nullptr (global mode, score- / weight-dependent pair set): stage 1 runs
+// the kernels up to the per-row partial counts (published by original row in split->xcnt_out), stage 2 -- after the
+// caller's cross-rank barrier -- launches k_fin_dyn, which sums the ranks' counts and finishes the call.
+int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, void* stream, const DynSplit* split,
+                      int stage) {
+  int rc = validate_pairwise(a, split != nullptr);
   if (rc) return rc;
   const bool dyn = a->only_wrong || a->rw_neg;
   // partial (multi-GPU) evaluation needs globally consistent counts: position arithmetic gives them, the
-  // score- / weight-dependent filters do not (they would need an all-reduce between counting and weighting)
-  if (a->part_count > 1 && dyn) return RN_ERR_UNSUPPORTED;
+  // score- / weight-dependent filters need the ranks' counts summed between counting and weighting (split)
+  if ((a->part_count > 1 || a->block_rows) && dyn && !split) return RN_ERR_UNSUPPORTED;
+  if (split && !dyn) return RN_ERR_ARG;
   if (!scratch || check_align(scratch)) return scratch ? RN_ERR_ALIGN : RN_ERR_ARG;
   const Layout L = make_layout(a->scratch_rows ? a->scratch_rows : a->B, a->K, a->B);
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
@@ -1387,6 +1464,11 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
   A.fast = fast ? 1 : 0; A.rec2 = (fast && a->block_rows) ? at<GRec2>(base, L.rec2) : nullptr; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
   A.ngt = (u32)((a->B + kGTile - 1) / kGTile); A.blk_w = H.blk;
   A.dbgbuf = at<u64>(base, L.gstat);
+  if (split) {
+    A.xcnt_out = split->xcnt_out; A.xworld = split->world;
+    for (int r = 0; r < split->world; ++r) A.xcnt_peer[r] = split->xcnt_peer[r];
+    A.xsum = at<u32>(base, L.misc);
+  }
   int mode = 0;
   if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
@@ -1407,6 +1489,17 @@ extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, siz
     H.pp = pp;
     A.bnd = pp.bnd; A.jn = pp.jn; A.pre_on = pp.on;
   }
+  if (split && stage == 2) {
+    // second stage: the finishing kernel alone (cooperative, the pair kernel's grid)
+    int dev = 0; cudaGetDevice(&dev);
+    const int bps = pair_blocks_per_sm((const void*)k_fin_dyn, dev);
+    if (bps < 1) return RN_ERR_LAUNCH;
+    KpArgs A2 = A; A2.xcnt_out = nullptr;
+    void* args[] = {&P, &A2};
+    if (launch_coop((const void*)k_fin_dyn, device_sm_count() * bps, kPairThreads, args, st) != cudaSuccess) return RN_ERR_LAUNCH;
+    return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+  }
+  if (split) A.xworld = 0;          // (stage 1 tallies its own pairs; the ranks' sums are stage 2's)
   const bool prof = g_prof.on && g_prof.n < g_prof.cap;
   cudaEvent_t* tev = (prof && g_prof.graph) ? timed_events() : nullptr;
   const void* f_seg = (L.ipt == 2) ? (const void*)k_seg<2, HeadsTail> : (const void*)k_seg<8, HeadsTail>;

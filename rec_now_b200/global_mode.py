@@ -19,8 +19,9 @@ all-reduce.)
 The even tile split (instead of "positive side is local") keeps the ranks balanced for any row placement,
 e.g. a loader that shards by user.
 
-``only_use_wrong_order_pair`` / negative-side weights make the pair set depend on scores / weights, i.e. the
-counts would need an extra all-reduce between counting and weighting: not supported here (RN_ERR_UNSUPPORTED).
+``only_use_wrong_order_pair`` makes the pair set depend on the scores, so the pair counts n and c_h (PW:197-203,
+282-291) are only known once every rank has counted: over peer memory the call runs in two stages -- the kernels up to
+this rank's per-row counts, a barrier, then one kernel that sums the ranks' counts and finishes (weights, gradient).
 """
 from __future__ import annotations
 
@@ -119,7 +120,8 @@ def exchange_path() -> str:
     return "nccl" if _peer_broken or __import__("os").environ.get("RN_GLOBAL_P2P", "1") == "0" else "unused"
 
 
-def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
+def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
+                 only_wrong=False):
     """Global step over NVLink peer mappings: ONE C-ABI call (rn_global_pairwise_fwd_bwd) enqueues pack -> device-side
     barrier -> the kernels (the first gathers all ranks' blocks with peer loads, the last leaves the chunked partial
     gradients in the symmetric buffer) -> barrier -> the peer-read reduction.  No collective calls, no torch ops."""
@@ -135,7 +137,7 @@ def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_fun
     a.label_func = _lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP
     a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
     a.row_ok = ops._ptr(ok); a.rw_pos = ops._ptr(rwp); a.rw_neg = None
-    a.factor = factor; a.power = power; a.only_wrong = 0; a.reduce_mean = 1 if reduce_mean else 0
+    a.factor = factor; a.power = power; a.only_wrong = 1 if only_wrong else 0; a.reduce_mean = 1 if reduce_mean else 0
     a.part_rank, a.part_count = 0, 1
     a.scratch_persistent = 1                    # (st.scratch was zeroed at creation and is only ever used by this call)
     po = out.data_ptr()
@@ -150,7 +152,7 @@ def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_fun
 
 
 def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
-                   _compute_blocked=None):
+                   _compute_blocked=None, only_wrong=False):
     """The two-collective path: pack this rank's columns into one block -> ONE all-gather -> the kernels read the
     blocked rows in place and write gradient chunks with the partial loss riding in each -> ONE reduce-scatter."""
     from . import ops
@@ -161,7 +163,11 @@ def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, pow
     if _compute_blocked is None:
         st = _peer_state(group, logits.device, b_loc, kk, rw_pos is not None, row_ok is not None)
         if st is not None:
-            return _peer_global(st, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group)
+            return _peer_global(st, logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
+                                only_wrong)
+    if only_wrong:
+        raise NotImplementedError("only_use_wrong_order_pair in the global mode needs the peer-memory path "
+                                  "(the ranks' pair counts are summed between counting and weighting)")
     if _compute_blocked is None:
         block = ops.pack_row_block(keys, logits, labels, rw_pos, row_ok, lay["stride"])        # one launch
     else:                                   # (CPU/gloo test of the collective plumbing: same layout with torch ops)
@@ -188,7 +194,8 @@ def _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, pow
 def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: torch.Tensor,
                             rw_pos: Optional[torch.Tensor] = None, row_ok: Optional[torch.Tensor] = None,
                             label_func: str = "step", factor: float = 1.0, power: float = 0.0,
-                            reduce_mean: bool = True, group=None, _compute: Optional[Callable] = None):
+                            reduce_mean: bool = True, group=None, _compute: Optional[Callable] = None,
+                            only_wrong: bool = False):
     """Global in-batch pairwise loss, forward + backward, for this rank's rows.
 
     logits/labels/rw_pos/row_ok: [B_loc]; keys: canonical int64 [K, B_loc].  Every rank must pass the same
@@ -200,7 +207,10 @@ def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: to
     keys = keys.reshape(-1, b_loc)
     kk = keys.shape[0]
     if _compute is None and b_loc % 16 == 0 and keys.dtype is torch.int64 and keys.is_contiguous():
-        return _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group)
+        return _packed_global(logits, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group,
+                              only_wrong=only_wrong)
+    if only_wrong:
+        raise NotImplementedError("only_use_wrong_order_pair in the global mode needs rows per rank in multiples of 16")
     cols = [keys[k] for k in range(kk)] + [logits.reshape(-1).to(torch.float32), labels.reshape(-1).to(torch.float32),
                                            None if rw_pos is None else rw_pos.reshape(-1).to(torch.float32),
                                            None if row_ok is None else row_ok.reshape(-1).to(torch.uint8)]
@@ -221,9 +231,9 @@ def global_pairwise_fwd_bwd(logits: torch.Tensor, labels: torch.Tensor, keys: to
 
 class _GlobalPairwiseLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, outputs, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group):
+    def forward(ctx, outputs, labels, keys, rw_pos, row_ok, label_func, factor, power, reduce_mean, group, only_wrong):
         out = global_pairwise_fwd_bwd(outputs.detach(), labels, keys, rw_pos, row_ok, label_func, factor, power,
-                                      reduce_mean, group)
+                                      reduce_mean, group, only_wrong=only_wrong)
         ctx.save_for_backward(out["dlogits"])
         ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
         n = out["n_pair"].to(torch.float32)
@@ -233,12 +243,12 @@ class _GlobalPairwiseLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_loss, _g_n):
         (d,) = ctx.saved_tensors
-        return ((g_loss * d).reshape(ctx.out_shape).to(ctx.out_dtype),) + (None,) * 9
+        return ((g_loss * d).reshape(ctx.out_shape).to(ctx.out_dtype),) + (None,) * 10
 
 
 def global_pairwise_loss(outputs, labels, groups, click_occurance_power=0.0, mask=None, factor=1.0,
                          reduce_mean=True, label_pair_to_weight_func=None, return_num_pair=False, group=None,
-                         **kwargs):
+                         only_use_wrong_order_pair=False, **kwargs):
     """pairwise_loss over the union of all ranks' batches (BPR loss, fused weight menu).  Differentiable
     w.r.t. ``outputs``; the returned loss is the GLOBAL loss, so gradients are those of the global objective
     (no further averaging across ranks is needed for the logits)."""
@@ -255,5 +265,6 @@ def global_pairwise_loss(outputs, labels, groups, click_occurance_power=0.0, mas
         if label_pair_to_weight_func.pos_kw is not None:
             rw_pos = _as_cuda(kwargs[label_pair_to_weight_func.pos_kw])
     loss, n = _GlobalPairwiseLoss.apply(outputs, labels, keys, rw_pos, row_ok, label_func, float(factor),
-                                        float(click_occurance_power), bool(reduce_mean), group)
+                                        float(click_occurance_power), bool(reduce_mean), group,
+                                        bool(only_use_wrong_order_pair))
     return (loss, n) if return_num_pair else loss
