@@ -114,7 +114,12 @@ typedef struct rn_pairwise_args {
    * scratch_rows: the row capacity the arena was sized for (rn_pairwise_scratch_bytes(scratch_rows, K)); 0 = B.  A
    * persistent arena keeps ONE layout, so batches of different sizes B <= scratch_rows may share it. */
   int32_t scratch_persistent;
-  int32_t reserved0;
+  /* Deterministic mode (0 = off).  The default path accumulates d loss / d logits with floating-point atomics and places
+   * groups in arrival order: results jitter from run to run at the 1e-7 level.  deterministic != 0 gives bit-identical
+   * loss and dlogits for identical inputs (same device, same library): radix segmentation with first-occurrence group
+   * ids, gradient sums in 64-bit fixed point (resolution: the largest pair weight x 2^-(61 - log2 2B)), loss partials
+   * summed in a fixed order.  Slower (the sort), single GPU, not with only_wrong / rw_neg (RN_ERR_UNSUPPORTED). */
+  int32_t deterministic;
   int64_t scratch_rows;
 } rn_pairwise_args;
 

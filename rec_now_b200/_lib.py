@@ -50,7 +50,7 @@ class PairwiseArgs(C.Structure):
         ("dlogits", C.c_void_p), ("row_pairs", C.c_void_p),
         ("block_rows", C.c_int64), ("block_stride", C.c_int64), ("out_chunk", C.c_int64),
         ("peer_blocks", C.c_void_p * 8), ("gather_dst", C.c_void_p),
-        ("scratch_persistent", C.c_int32), ("reserved0", C.c_int32), ("scratch_rows", C.c_int64),
+        ("scratch_persistent", C.c_int32), ("deterministic", C.c_int32), ("scratch_rows", C.c_int64),
     ]
 
 

@@ -34,7 +34,8 @@ struct RowMap {
 // block back into its clean state (all zero except the barrier generations and the report of the finished call).
 struct Ctl {
   u32 lab_or, lab_nor;          // OR of label bits / OR of ~label bits over pairable rows -> varying bit range
-  u32 pad_a[4];
+  u32 det_w, det_y;             // deterministic mode: max |row weight| and max |label| (float bits), bound of a pair weight
+  u32 pad_a[2];
   u32 k2_ticket;                // dynamic work-unit ticket of the pair kernel
   u32 fin_done;                 // CTAs that finished the final reduction (the last one writes the scalars / cleans up)
   u32 n_units, unit_c;          // work list: number of units, J-blocks per unit
@@ -95,7 +96,7 @@ struct Layout {
   size_t labpart, slot, slot1, keyA, keyB, valA, valB, tilehist, aj, ss, sy, swp, swn, gacc, lossrow, cnt, perm, blk, units, misc, gstat;
   // counting path (group_count.cuh): group records (clean = zero between calls), created-group lists per 512-row tile,
   // sorted group index column
-  size_t rec, rec2, glist, gcount, sgrp, bnd, jn;
+  size_t rec, rec2, glist, gcount, sgrp, bnd, jn, lpart;
   int64_t Bcap;
 };
 
@@ -111,6 +112,7 @@ struct __align__(16) GRec {
 // Second record of a group, global mode only: rows per label level among THIS rank's rows (cl) and among the other
 // ranks' rows (cr); cr is rewritten by the offsets phase to the level starts of the remote part.  All zero = clean.
 struct __align__(16) GRec2 { u32 cl[8]; u32 cr[8]; };
+static_assert(sizeof(GRec2) == sizeof(GRec), "the second records are addressed through the first table's base pointer");
 constexpr int kLevels = 8;       // label levels of the counting path: integer-valued labels -1 .. 6
 constexpr int kGTile = 512;      // rows per tile of the counting path (= kSegThreads)
 constexpr u32 kBndCap = 16384;   // piece boundaries of the pair kernel's partition the arena holds (warps of its grid + 1)
@@ -183,6 +185,7 @@ inline Layout make_layout(int64_t Bcap, int K, int64_t B = 0) {
   L.sgrp = take(sizeof(u32) * Bc);
   L.bnd = take(sizeof(uint4) * kBndCap);               // piece boundaries of the pair kernel's partition (PrePart)
   L.jn = take(sizeof(u32) * 2 * nib_cap);
+  L.lpart = take(sizeof(double) * 1024);                // per-CTA loss partials (deterministic mode)
   L.total = o;
   return L;
 }
@@ -271,7 +274,7 @@ __device__ __forceinline__ u32 warp_min(u32 v) {
 __device__ __forceinline__ void ctl_finish(Ctl* ctl) {
   ctl->rep_err = ctl->err; ctl->rep_path = ctl->path; ctl->rep_n_units = ctl->n_units; ctl->rep_unit_c = ctl->unit_c;
   ctl->rep_n_tiles = ctl->n_tiles;
-  ctl->bar_cnt = 0; ctl->bar2_cnt = 0;
+  ctl->bar_cnt = 0; ctl->bar2_cnt = 0; ctl->det_w = 0; ctl->det_y = 0;
   ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
   ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
   ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;

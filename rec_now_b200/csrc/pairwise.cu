@@ -40,6 +40,7 @@ struct PairParams {
   const float* logits; const float* labels; const float* rw_pos; const float* rw_neg;
   float c_log2;          // factor * log2(e)
   float factor, power; int reduce_mean; int dyn_count; int debug;
+  int det;               // deterministic mode: fixed-point gradient accumulators, ordered loss partials
   int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
@@ -138,6 +139,7 @@ struct HeadsTail {
   uint2* blk; uint2* units; u32 nib; u64* cprim; const u32* pgid;
   u32 target_units;          // work-list granularity target (units of <= C J-blocks)
   PrePart pp;
+  unsigned long long* g64;   // deterministic mode: fixed-point gradient accumulators (zeroed here)
 
   // ---- counting path (group_count.cuh): count -> offsets -> scatter; false = outside its menu (radix path instead) ----
   // One row's scatter: its sorted position from the group record, its sorted columns, its negative range and the
@@ -512,6 +514,13 @@ struct HeadsTail {
         gacc[p] = 0.f; perm[p] = row;
         lossrow[p] = 0.f;
         if (P.dyn_count) cnt[p] = 0;
+        if (P.det) {
+          // bound of one pair weight, for the scale of the fixed-point accumulators: max |w_i| and max |y| over the rows
+          g64[p] = 0ull;
+          const u32 wb = __float_as_uint(fabsf(wp)), yb = __float_as_uint(fabsf(sy[p]));
+          const u32 wm = __reduce_max_sync(__activemask(), wb), ym = __reduce_max_sync(__activemask(), yb);
+          if (ln == (u32)(__ffs(__activemask()) - 1)) { atomicMax(&ctl->det_w, wm); atomicMax(&ctl->det_y, ym); }
+        }
       }
       // J ranges needed by this warp's 32 rows (two warps make one I-block): R1 = the range of the rows whose group
       // began before the I-block (one group: it can reach far to the left), R2 = the hull of the ranges of the rows
@@ -614,13 +623,16 @@ struct KpArgs {
   u64* cprim;
   // counting path (group_count.cuh): the call ran without k_init; the records its count phase created are listed per
   // 512-row tile and zeroed again by the last phase of this kernel
-  int fast; GRec* rec; GRec2* rec2; const u32* glist; const u32* gcount; u32 ngt;     // (rec2: global mode only, else nullptr)
+  int fast; GRec* rec; u32 rec2_off; const u32* glist; const u32* gcount; u32 ngt;     // (rec2_off: global mode only, else 0)
   uint2* blk_w;              // (the J ranges are zeroed again as well)
   const uint4* bnd; const u32* jn; int pre_on;     // partition computed by k_seg's helper CTAs (PrePart)
   // global mode with a score- / weight-dependent pair set: the per-row pair counts are partial (this rank's negatives).
   // k_pair publishes them by ORIGINAL row (xcnt_out) and stops; after a cross-rank barrier k_fin_dyn sums the ranks'
   // arrays (xcnt_peer, peer-mapped) and finishes: counts -> occurrence weights -> gradient (PW:197-203, 282-291)
   u32* xcnt_out; const u32* xcnt_peer[8]; int xworld; u32* xsum;      // xsum: local [B] scratch for the summed counts
+  // deterministic mode: per-row gradient sums as 64-bit fixed point (integer adds commute: any arrival order gives the
+  // same bits), one loss partial per CTA summed in CTA order
+  unsigned long long* g64; double* lpart;
   u64* dbgbuf;      // RN_PAIR_DEBUG: per warp {first segment start, loop exit, busy cycles, segments | general tiles << 32}
 };
 
@@ -640,7 +652,9 @@ __device__ __forceinline__ void clean_records(const KpArgs& A, u32 t0, u32 tstep
     for (u32 k = threadIdx.x; k < 4 * n; k += blockDim.x) {
       const u32 slot = A.glist[(size_t)t * kGTile + (k >> 2)];
       reinterpret_cast<uint4*>(A.rec + slot)[k & 3u] = z;
-      if (A.rec2) reinterpret_cast<uint4*>(A.rec2 + slot)[k & 3u] = z;
+      // (the second records sit rec2_off records behind the first ones: one base pointer for both -- the pair kernel
+      // runs at its register limit, and a second pointer kept for this tail costs it hundreds of bytes of spills)
+      if (A.rec2_off) reinterpret_cast<uint4*>(A.rec + A.rec2_off + slot)[k & 3u] = z;
     }
   }
 }
@@ -706,7 +720,9 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
 __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
                                              u32& epoch2, u64* red_u, double* red_d);
 
-template <int MODE>
+// DET: deterministic mode (fixed-point gradient accumulators, ordered loss partials) -- a separate instantiation, so that
+// the default kernel carries none of it through the pair loop.
+template <int MODE, bool DET = false>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // Work = the (I-block x J-block) tiles of the staircase, laid out on a COST LINE: virtual block after virtual block
   // (the two J ranges of every I-block), J-block after J-block, each with the cost vcost() estimates for it (a fast tile
@@ -748,12 +764,28 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // (Counting path: the offsets phase of k_seg knows every group's total and the scatter phase has already parked the
   // weights; the pair totals then live in the group records.)
   const u32 gtid0 = blockIdx.x * blockDim.x + threadIdx.x;
+  // (only `counted` stays live through the pair loop -- the kernel runs at its register limit; the radix path's totals
+  // are A.cprim with stride 1, the counting path needs no totals inside the loop)
   const bool counted = A.fast && ld_relaxed(&ctl->fallback) == 0u;
-  const u64* cprim = counted ? &A.rec->npair : A.cprim;
-  const u32 cstride = counted ? (u32)(sizeof(GRec) / sizeof(u64)) : 1u;
   const bool park = !DYN && fold_power != 0.f && !counted;
   u32 park_pg = kEmpty; u64 park_ch = 0;
   if (park && gtid0 < B) park_pg = A.sgrp[gtid0];
+  // Deterministic mode: the scale of the fixed-point gradient accumulators.  A row's sum is bounded by (pairs it takes part
+  // in <= 2 B) x (largest pair weight W); the scale leaves that bound just inside 62 bits, i.e. a resolution of
+  // W x 2^-(61 - log2 2B) per contribution (W x 2^-44 at B = 65536).
+  // (kept in shared memory: the pair loop has no registers to spare)
+  __shared__ double s_dscale[2];
+  if (DET && threadIdx.x == 0) {
+    float W = fmaxf(__uint_as_float(ld_relaxed(&ctl->det_w)), 1.0e-30f);
+    if (DIFF) W *= 2.0f * fmaxf(__uint_as_float(ld_relaxed(&ctl->det_y)), 1.0e-30f);
+    int ew; frexpf(W, &ew);                                  // W < 2^ew
+    const int e = 61 - (33 - __clz(B)) - ew;                 // (2 B < 2^(33 - clz B))
+    s_dscale[0] = ldexp(1.0, e); s_dscale[1] = ldexp(1.0, -e);
+  }
+  auto gadd = [&](u32 p, float v) {
+    if (DET) atomicAdd(A.g64 + p, (unsigned long long)__double2ll_rn((double)v * s_dscale[0]));
+    else atomicAdd(A.gacc + p, v);
+  };
   const bool pre = counted && A.pre_on && own_list;     // the partition was worked out by k_seg's helper CTAs
   const u32* jn_ = pre ? A.jn : s_jn;
   if (pre) {
@@ -773,7 +805,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     __syncthreads();
     stamp(ctl, 11);
-    if (park_pg != kEmpty) park_ch = cprim[(size_t)park_pg * cstride];
+    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
     block_excl_scan(s_pi, nvb, s_scan);
     stamp(ctl, 12);
     const u32 tot = s_pi[nvb];
@@ -808,14 +840,14 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   } else {
     U = ld_relaxed(&ctl->n_units);
-    if (park_pg != kEmpty) park_ch = cprim[(size_t)park_pg * cstride];
+    if (park_pg != kEmpty) park_ch = A.cprim[park_pg];
     __syncthreads();
   }
   if (park) {
     if (gtid0 < B) A.lossrow[gtid0] = occ_pow(park_ch, fold_power);
     for (u32 p = gtid0 + gridDim.x * blockDim.x; p < B; p += gridDim.x * blockDim.x) {
       const u32 pg = A.sgrp[p];
-      A.lossrow[p] = pg != kEmpty ? occ_pow(cprim[(size_t)pg * cstride], fold_power) : 0.f;
+      A.lossrow[p] = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
     }
   }
   stamp(ctl, 16);
@@ -990,17 +1022,17 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         }
         if (tally) { if (fast) d_fastcyc += (u64)(clock64() - d_g0); else d_gencyc += (u64)(clock64() - d_g0); }
         TR_ADD(tr_tile);
-        if (accj != 0.f && !(P.debug & 4)) atomicAdd(A.gacc + pjm, accj);      // (debug bit 4: timing experiment without the RED)
+        if (accj != 0.f && !(P.debug & 4)) gadd(pjm, accj);      // (debug bit 4: timing experiment without the RED)
         pjm = pjn; sjm = sjn; yjm = yjn; wnjm = wnjn;
         TR_ADD(tr_post);
       }
       if (pi0 < B && an0.y) {
-        if (gi0 != 0.f) atomicAdd(A.gacc + pi0, -gi0);
+        if (gi0 != 0.f) gadd(pi0, -gi0);
         if (DYN && li0 != 0.f) atomicAdd(A.lossrow + pi0, li0);
         if (DYN && cnt0) atomicAdd(A.cnt + pi0, cnt0);
       }
       if (pi1 < B && an1.y) {
-        if (gi1 != 0.f) atomicAdd(A.gacc + pi1, -gi1);
+        if (gi1 != 0.f) gadd(pi1, -gi1);
         if (DYN && li1 != 0.f) atomicAdd(A.lossrow + pi1, li1);
         if (DYN && cnt1) atomicAdd(A.cnt + pi1, cnt1);
       }
@@ -1015,7 +1047,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
               if (counted) occ_w = A.lossrow[qmin];                 // (parked by k_seg's scatter phase)
               else {
                 const u32 pg = A.sgrp[qmin];
-                occ_w = pg != kEmpty ? occ_pow(cprim[(size_t)pg * cstride], fold_power) : 0.f;
+                occ_w = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
               }
               occ_a = qmin;
             }
@@ -1025,7 +1057,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
               li0 *= act0 ? A.lossrow[pi0] : 0.f; li1 *= act1 ? A.lossrow[pi1] : 0.f;
             } else {
               const u32 pg0 = act0 ? A.sgrp[pi0] : kEmpty, pg1 = act1 ? A.sgrp[pi1] : kEmpty;
-              const u64 ch0 = pg0 != kEmpty ? cprim[(size_t)pg0 * cstride] : 0ull, ch1 = pg1 != kEmpty ? cprim[(size_t)pg1 * cstride] : 0ull;
+              const u64 ch0 = pg0 != kEmpty ? A.cprim[pg0] : 0ull, ch1 = pg1 != kEmpty ? A.cprim[pg1] : 0ull;
               li0 *= occ_pow(ch0, fold_power); li1 *= occ_pow(ch1, fold_power);
             }
           }
@@ -1062,7 +1094,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     if (threadIdx.x == 0) {
       double t = 0;
       for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
-      if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
+      if (DET) A.lpart[blockIdx.x] = t;                       // (summed in CTA order behind the barrier)
+      else if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
     }
     // nothing else in front of the barrier: the last warp to leave the pair loop sets the pace
     stamp(ctl, 21);
@@ -1075,9 +1108,12 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     auto row_scale = [&](u32 p) -> float { return fold_power == 0.f ? gscale : A.lossrow[p] * gscale; };
     // output index: plain, or chunked for a following reduce-scatter (row i -> (i / Bl) * out_chunk + i % Bl)
     auto out_at = [&](u32 row) -> size_t { return P.out_chunk ? (size_t)(row / P.rm.Bl) * P.out_chunk + (row % P.rm.Bl) : row; };
-    for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
+    if (DET) for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = (float)((double)(long long)A.g64[p] * s_dscale[1]) * row_scale(p);
+    else for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+      double lsum_all = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
+      if (DET) { lsum_all = 0.0; for (u32 c = 0; c < gridDim.x; ++c) lsum_all += A.lpart[c]; }
+      const double tot = lsum_all * 0.6931471805599453;
       const float lossv = (float)(tot / (double)denom);
       *P.loss = lossv;
       *P.n_pair_f32 = (float)n;                  // PW:276
@@ -1119,7 +1155,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
     return;
   }
-  dyn_finalize(P, A, cprim, cstride, nvb, epoch2, red_u, red_d);
+  dyn_finalize(P, A, counted ? &A.rec->npair : A.cprim, counted ? (u32)(sizeof(GRec) / sizeof(u64)) : 1u, nvb, epoch2, red_u, red_d);
 }
 
 // Counts -> occurrence weights -> gradient and loss for a score- / weight-dependent pair set (the tail of k_pair, or
@@ -1253,13 +1289,14 @@ static int pair_blocks_per_sm(const void* func, int dev) {
   return bps;
 }
 
-template <int MODE>
+template <int MODE, bool DET = false>
 static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_t st) {
   // (the opt-in to large dynamic shared memory is a per-device function attribute)
   static size_t smem_set[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  const int bps = pair_blocks_per_sm((const void*)k_pair<MODE>, dev);
+  const void* fn = (const void*)k_pair<MODE, DET>;
+  const int bps = pair_blocks_per_sm(fn, dev);
   if (bps < 1) return cudaErrorUnknown;
   PairParams p = P; KpArgs a = A;
   void* args[] = {&p, &a};
@@ -1267,15 +1304,19 @@ static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_
   const size_t smem = A.nib <= kMaxNibS ? sizeof(u32) * (4 * (size_t)A.nib + 2) : 0;
   if (smem > smem_set[dev]) {
     const size_t want = sizeof(u32) * (4 * (size_t)kMaxNibS + 2);
-    cudaError_t e = cudaFuncSetAttribute(k_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want);
     if (e != cudaSuccess) return e;
     smem_set[dev] = want;
   }
-  return launch_coop((const void*)k_pair<MODE>, device_sm_count() * bps, kPairThreads, args, st, smem);
+  return launch_coop(fn, device_sm_count() * bps, kPairThreads, args, st, smem);
 }
 
+constexpr int M_DET = 16;          // (dispatch only: deterministic instantiation of a non-dynamic mode)
 static const void* pair_func(int mode) {
   switch (mode) {
+    case M_DET: return (const void*)k_pair<0, true>;
+    case M_DET | M_HASW: return (const void*)k_pair<M_HASW, true>;
+    case M_DET | M_HASW | M_DIFF: return (const void*)k_pair<M_HASW | M_DIFF, true>;
 #define RN_CASE(m) case m: return (const void*)k_pair<m>;
     RN_CASE(0) RN_CASE(M_WRONG)
     RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
@@ -1289,6 +1330,9 @@ static const void* pair_func(int mode) {
 
 static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A, cudaStream_t st) {
   switch (mode) {
+    case M_DET: return launch_pair<0, true>(P, A, st);
+    case M_DET | M_HASW: return launch_pair<M_HASW, true>(P, A, st);
+    case M_DET | M_HASW | M_DIFF: return launch_pair<M_HASW | M_DIFF, true>(P, A, st);
 #define RN_CASE(m) case m: return launch_pair<m>(P, A, st);
     RN_CASE(0) RN_CASE(M_WRONG)
     RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
@@ -1410,8 +1454,11 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
-  const bool fast = counting_eligible(a);
+  const bool det = a->deterministic != 0;
+  if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
+  const bool fast = counting_eligible(a) && !det;       // (the counting path places groups and rows in arrival order)
   PairParams P{};
+  P.det = det ? 1 : 0;
   P.B = (u32)a->B; P.K = a->K; P.gbits = L.gbits;
   P.logits = a->logits; P.labels = a->labels; P.rw_pos = a->rw_pos; P.rw_neg = a->rw_neg;
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;
@@ -1437,6 +1484,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
   H.target_units = target_units();
   H.pp = PrePart{};
+  H.g64 = at<unsigned long long>(base, L.misc);
   SegInputs in{a->B, a->K, a->keys, a->labels, a->row_ok, true, true};
   in.rm = P.rm;
   if (a->gather_dst) {
@@ -1446,7 +1494,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   }
   static const int allow_merged = tune_int("RN_SEG_MERGED", 1);
   in.fast = fast;
-  in.allow_merged = allow_merged && a->part_count == 1 && !fast;      // ranks of the global mode need identical ids
+  in.allow_merged = allow_merged && a->part_count == 1 && !fast && !det;      // ranks of the global mode need identical ids; so does a deterministic call (table slots depend on insertion order)
   if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }
   KpArgs A{};
   A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
@@ -1461,9 +1509,10 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   A.cost_levels = (u32)(cost_levels < 0 ? 0 : (cost_levels > 64 ? 64 : cost_levels));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
   A.sgrp = H.sgrp; A.cprim = H.cprim;
-  A.fast = fast ? 1 : 0; A.rec2 = (fast && a->block_rows) ? at<GRec2>(base, L.rec2) : nullptr; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
+  A.fast = fast ? 1 : 0; A.rec2_off = (fast && a->block_rows) ? (u32)((L.rec2 - L.rec) / sizeof(GRec)) : 0u; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
   A.ngt = (u32)((a->B + kGTile - 1) / kGTile); A.blk_w = H.blk;
   A.dbgbuf = at<u64>(base, L.gstat);
+  A.g64 = H.g64; A.lpart = at<double>(base, L.lpart);
   if (split) {
     A.xcnt_out = split->xcnt_out; A.xworld = split->world;
     for (int r = 0; r < split->world; ++r) A.xcnt_peer[r] = split->xcnt_peer[r];
@@ -1474,6 +1523,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
+  if (det) mode |= M_DET;
   if (fast) {
     // the pair kernel's partition is worked out by spare CTAs of k_seg beside the scatter phase (HeadsTail::partition)
     static const int pre_on = tune_int("RN_PAIR_PREPART", 1);
