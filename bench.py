@@ -352,6 +352,26 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
             c["speedup_single_call"] = c["sec_per_step"] / (t["single_call_us"] * 1e-6)
         rec["cpu_full_size"] = c
     recs["cfg4"] = rec
+    # GAUC: the evaluation metric on the same segmentation, cfg3's batch
+    from oracle import seg_ref as S
+    from rec_now_b200 import metrics
+    d = G.cfg3(0)
+    s, y, g = torch.tensor(d["s"], device=dev), torch.tensor(d["y"], device=dev), torch.tensor(d["g"], device=dev)
+    step = lambda: metrics.gauc(s, y, g, return_details=True)
+    t = time_device(step, steps, 5, flush)
+    out = step()
+    ref = S.gauc(d["s"], d["y"], d["g"])
+    n = int(out["n_pair"].item())
+    recs["gauc_cfg3"] = {"workload": "GAUC (group AUC over label-ordered pairs, ties 1/2, weight = rows of the group) on cfg3's batch",
+                         "rows": s.numel(), "n_pair": n, **t, "pairs_per_s": n / (t["single_call_us"] * 1e-6),
+                         "gauc": float(out["gauc"].item()),
+                         "parity": {"oracle": "oracle/seg_ref.py::gauc (float64, exact integer counts)",
+                                    "n_pair_exact": n == ref["n_pair"],
+                                    "concordant2_exact": int(out["concordant2"].item()) == ref["concordant2"],
+                                    "n_valid_groups_exact": int(out["n_valid_groups"].item()) == ref["n_valid_groups"],
+                                    "gauc_abs_err": abs(float(out["gauc"].item()) - ref["gauc"]),
+                                    "ok": bool(n == ref["n_pair"] and int(out["concordant2"].item()) == ref["concordant2"]
+                                               and abs(float(out["gauc"].item()) - ref["gauc"]) <= 1e-6)}}
     return recs
 
 # ----------------------------------------------------------------------------------------------------------

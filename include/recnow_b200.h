@@ -232,6 +232,29 @@ size_t rn_occurrence_scratch_bytes(int64_t N);
 int rn_occurrence_power_weight(const int64_t* ids, int64_t N, float power, float* out,
                                void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- GAUC: group AUC on the same segmentation --------------------------------------------------------------
+ * The metric the in-batch ranking losses are meant to move (the reference quotes its online GAUC uplift, README.md:5, 8,
+ * and ships no implementation).  Per group (same keys; rows with row_ok != 0 and a non-NaN label):
+ *   pairs_g = {(i, j) : y_i > y_j}  (the pair set of pairwise_loss, pairwise_loss_from_batch.py:189),
+ *   AUC_g = (#{s_i > s_j} + 1/2 #{s_i == s_j}) / |pairs_g|;  GAUC = sum |g| AUC_g / sum |g| over groups with pairs.
+ * Counts are exact integers.  scratch: rn_gauc_scratch_bytes; scratch_persistent as in rn_pairwise_args. */
+typedef struct rn_gauc_args {
+  int64_t B;
+  int32_t K;
+  int32_t scratch_persistent;
+  const int64_t* keys;        /* [K][B] */
+  const float* scores;        /* [B] */
+  const float* labels;        /* [B] */
+  const uint8_t* row_ok;      /* NULL or [B] */
+  float* gauc;                /* [1] */
+  float* auc_mean;            /* NULL or [1]: unweighted mean of AUC_g */
+  int32_t* n_valid_groups;    /* [1] groups with at least one ordered label pair */
+  int64_t* n_pair;            /* NULL or [1]: sum of |pairs_g| (= n_pair of pairwise_loss with default options) */
+  int64_t* concordant2;       /* NULL or [1]: 2 x concordant + ties over all pairs */
+} rn_gauc_args;
+size_t rn_gauc_scratch_bytes(int64_t B, int32_t K);
+int rn_gauc(const rn_gauc_args* args, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- listwise --------------------------------------------------------------------------------------- */
 size_t rn_listwise_scratch_bytes(int64_t B);
 int rn_listwise_fwd_bwd(const rn_listwise_args* args, void* scratch, size_t scratch_bytes, void* stream);

@@ -227,3 +227,31 @@ def listwise(group_ids, labels, logits, weights=None, pos_neg_th=0.5):
         lw, loss = ll, 0.0                                                   # LW:172 nan_to_zero
     return dict(loss=loss, grad=grad, n_valid=v, n_group=len(segs) + int((~ok).sum()), list_loss=lw,
                 list_first_row=np.asarray(firsts, np.int64), list_size=np.asarray(sizes, np.int64))
+
+
+def gauc(scores, labels, groups, mask=None):
+    """float64 truth for the GAUC metric of rec_now_b200.metrics.gauc / rn_gauc (the reference quotes the metric,
+    README.md:5, 8, without implementing it; definition: include/recnow_b200.h).  Per group of rows that can pair (finite
+    key, mask, non-NaN label): pairs = {(i, j): y_i > y_j} (PW:189), AUC = (#{s_i > s_j} + #{s_i == s_j} / 2) / #pairs;
+    GAUC = sum |g| AUC_g / sum |g| over the groups with pairs.  Counts are exact integers.
+    Returns dict(gauc, auc_mean, n_valid_groups, n_pair, concordant2)."""
+    s = np.asarray(scores, F32).reshape(-1)
+    y = np.asarray(labels, F32).reshape(-1)
+    keys, ok = canonical_keys(groups)
+    ok = ok & ~np.isnan(y)
+    if mask is not None:
+        ok = ok & np.asarray(mask, bool).reshape(-1)
+    num = den = asum = 0.0
+    n_pair = conc2 = nv = 0
+    for m in _group_members(keys, ok):
+        ym, sm = y[m], s[m]
+        pm = ym[:, None] > ym[None, :]
+        n = int(pm.sum())
+        if not n:
+            continue
+        c2 = int((2 * (sm[:, None] > sm[None, :])[pm]).sum() + (sm[:, None] == sm[None, :])[pm].sum())
+        auc = c2 / (2.0 * n)
+        num += m.size * auc; den += m.size; asum += auc
+        n_pair += n; conc2 += c2; nv += 1
+    return dict(gauc=num / den if den else 0.0, auc_mean=asum / nv if nv else 0.0, n_valid_groups=nv, n_pair=n_pair,
+                concordant2=conc2)

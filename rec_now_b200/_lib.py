@@ -23,6 +23,7 @@ EXPORTS = [
     "rn_pairwise_scratch_bytes", "rn_pairwise_scratch_init", "rn_pairwise_fwd_bwd",
     "rn_pair_indices_scratch_bytes", "rn_pair_indices_count", "rn_pair_indices_fill",
     "rn_occurrence_scratch_bytes", "rn_occurrence_power_weight",
+    "rn_gauc_scratch_bytes", "rn_gauc",
     "rn_listwise_scratch_bytes", "rn_listwise_fwd_bwd", "rn_listwise_dense",
     "rn_bench_mufu", "rn_profile_enable", "rn_profile_enable_ex", "rn_profile_collect", "rn_profile_disable", "rn_last_device_error", "rn_debug_timestamps", "rn_pairwise_launch_count", "rn_listwise_launch_count",
     "rn_debug_graph_launches", "rn_debug_arena_offset", "rn_pack_row_block", "rn_reduce_peer_chunks",
@@ -57,6 +58,13 @@ class PairwiseArgs(C.Structure):
 class GlobalArgs(C.Structure):
     _fields_ = [("local", PairwiseArgs), ("world", C.c_int32), ("rank", C.c_int32),
                 ("peer_buf", C.c_void_p * 8), ("gather_buf", C.c_void_p), ("step", C.c_int64)]
+
+
+class GaucArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("K", C.c_int32), ("scratch_persistent", C.c_int32),
+                ("keys", C.c_void_p), ("scores", C.c_void_p), ("labels", C.c_void_p), ("row_ok", C.c_void_p),
+                ("gauc", C.c_void_p), ("auc_mean", C.c_void_p), ("n_valid_groups", C.c_void_p),
+                ("n_pair", C.c_void_p), ("concordant2", C.c_void_p)]
 
 
 class ListwiseArgs(C.Structure):
@@ -100,6 +108,9 @@ def lib() -> C.CDLL:
     L.rn_occurrence_scratch_bytes.restype = sz
     L.rn_occurrence_scratch_bytes.argtypes = [i64]
     L.rn_occurrence_power_weight.argtypes = [vp, i64, f32, vp, vp, sz, vp]
+    L.rn_gauc_scratch_bytes.restype = sz
+    L.rn_gauc_scratch_bytes.argtypes = [i64, i32]
+    L.rn_gauc.argtypes = [C.POINTER(GaucArgs), vp, sz, vp]
     L.rn_listwise_scratch_bytes.restype = sz
     L.rn_listwise_scratch_bytes.argtypes = [i64]
     L.rn_listwise_fwd_bwd.argtypes = [C.POINTER(ListwiseArgs), vp, sz, vp]

@@ -48,6 +48,7 @@ struct Ctl {
   u64 n_pair;                   // exact kept-pair count
   u64 n_tiles;                  // total 32x32 micro-tiles in the work list
   double loss_sum;              // sum_p wocc * lossrow[p]   (log2 units)
+  double acc_d[4];              // generic double accumulators (GAUC: weighted AUC sum, weight sum, plain AUC sum)
   u64 ts[24];                   // phase timestamps (%globaltimer, ns) written by CTA 0: measurement aid
   u64 dbg[8];                   // pair-kernel debug tallies (RN_PAIR_DEBUG=1): see k_pair
   // report of the last finished call (copied here before the working fields are reset; read by the rn_debug_* calls)
@@ -278,7 +279,80 @@ __device__ __forceinline__ void ctl_finish(Ctl* ctl) {
   ctl->lab_or = 0; ctl->lab_nor = 0; ctl->k2_ticket = 0; ctl->fin_done = 0; ctl->n_units = 0; ctl->unit_c = 0;
   ctl->n_groups = 0; ctl->n_valid = 0; ctl->err = 0; ctl->fallback = 0; ctl->cursor = 0; ctl->path = 0;
   ctl->n_pair = 0; ctl->n_tiles = 0; ctl->loss_sum = 0.0;
+  ctl->acc_d[0] = 0.0; ctl->acc_d[1] = 0.0; ctl->acc_d[2] = 0.0; ctl->acc_d[3] = 0.0;
 }
+
+// J-block range of virtual block v (2b = range R1 of I-block b, 2b + 1 = range R2, see HeadsTail): first J-block and
+// J-block count; R2 is trimmed so that no (I-block, J-block) tile is listed twice.
+// (a range is stored as (~lo, hi): the counting path builds it with atomicMax from an all-zero = empty record)
+__device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst) {
+  const uint2 r = blk[v];
+  u32 lo = 0, hi = 0;
+  if (r.y > ~r.x) { lo = ~r.x >> 5; hi = (r.y + 31) >> 5; }
+  if (v & 1) { const uint2 r1 = blk[v - 1]; if (r1.y > ~r1.x) lo = max(lo, (r1.y + 31) >> 5); }
+  jfirst = lo;
+  return hi > lo ? hi - lo : 0u;
+}
+
+// Zero every group record the count phase created (listed per 512-row tile): all CTAs of the grid, behind a grid barrier
+// that nobody reads the records after.  A warp per tile, four lanes per 64-byte record.
+__device__ __forceinline__ void clean_records_grid(GRec* rec, u32 rec2_off, const u32* glist, const u32* gcount, u32 ngt) {
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  const u32 ln = threadIdx.x & 31u, nw = blockDim.x >> 5;
+  for (u32 t = blockIdx.x * nw + (threadIdx.x >> 5); t < ngt; t += gridDim.x * nw) {
+    const u32 n = gcount[t];
+    for (u32 k = ln; k < 4 * n; k += 32) {
+      const u32 slot = glist[(size_t)t * kGTile + (k >> 2)];
+      reinterpret_cast<uint4*>(rec + slot)[k & 3u] = z;
+      if (rec2_off) reinterpret_cast<uint4*>(rec + rec2_off + slot)[k & 3u] = z;
+    }
+  }
+}
+
+// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
+// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
+// a[n] receives the total (sc: 34 words).  All threads of the CTA must call it.
+constexpr u32 kScanThreads = 256;
+__device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
+  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
+  const bool act = threadIdx.x < kScanThreads;
+  const u32 per = (n + kScanThreads - 1) / kScanThreads;
+  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
+  u32 sum = 0, inc = 0;
+  if (act) {
+    for (u32 i = i0; i < i1; ++i) sum += a[i];
+    inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+    if (ln == 31) sc[wq] = inc;
+  }
+  __syncthreads();
+  if (act) {
+    u32 off = inc - sum;
+    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
+    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
+    if (threadIdx.x == kScanThreads - 1) a[n] = off;
+  }
+  __syncthreads();
+}
+
+// Largest idx in [lo, hi) with arr[idx] <= key (arr nondecreasing, arr[lo] <= key); one thread, binary search.
+__device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) {
+  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (arr[mid] <= key) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// GAUC kernel (gauc.cu) on the arrays the pairwise segmentation leaves; the host entry lives with the segmentation's
+// instantiation in pairwise.cu.
+struct GaucArgs {
+  u32 B, nib;
+  const uint2* aj; const float* ss; const uint2* blk; uint2* blk_w;
+  u64* acc2; u64* npg; u32* gsz;        // per group (indexed by its first sorted position): 2 x concordant + ties, pairs, rows
+  float* gauc; float* auc_mean; int32_t* n_valid; int64_t* n_pair; int64_t* conc2;
+  int fast; GRec* rec; u32 rec2_off; const u32* glist; const u32* gcount; u32 ngt;
+  Ctl* ctl;
+};
+cudaError_t launch_gauc(const GaucArgs& A, cudaStream_t st);
 
 // Peer-memory gather done by k_init (see rn_pairwise_args.peer_blocks): `world` blocks of n16 16-byte words.
 struct GatherArgs { const uint4* src[8]; uint4* dst; u32 n16; u32 world; };

@@ -320,36 +320,31 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_lw_count(LwCountArgs A) {
   lsum = warp_sum(lsum);
   if (ln == 0) sm_d[w] = lsum;
   __syncthreads();
-  __shared__ u32 s_last;
   if (tid == 0) {
     double tsum = 0;
     for (int q = 0; q < kSegWarps; ++q) tsum += sm_d[q];
     if (tsum != 0.0) atomicAdd(&ctl->loss_sum, tsum);           // (a NaN sum compares unequal to 0: it is added, and stays NaN)
-    __threadfence();
-    s_last = (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) ? 1u : 0u;
   }
-  __syncthreads();
-  if (!s_last) return;
-  // ---- the last CTA out: scalars, NaN -> 0 (LW:172, value and gradient), clean arena ----------------------------------------
-  __threadfence();
+  stamp(ctl, 5);
+  grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
+  stamp(ctl, 6);
+  // ---- behind the last barrier: scalars, NaN -> 0 (LW:172, value and gradient), clean arena (all CTAs) -----------------
   const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
   const float lossv = V ? (float)(tot / (double)V) : 0.f;
   const bool isnan_ = lossv != lossv;
-  if (tid == 0) {
+  if (blockIdx.x == 0 && tid == 0) {
     *A.loss = isnan_ ? 0.f : lossv;
     *A.n_valid = (int32_t)V;
     *A.n_group = (int32_t)ld_relaxed(&ctl->n_groups);
-    ctl->ts[23] = globaltimer();
   }
-  if (isnan_) for (u32 i = tid; i < B; i += kSegThreads) A.dlogits[i] = 0.f;      // tf.cond takes the constant branch: no gradient
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  for (u32 t = 0; t < ntile; ++t) {
-    const u32 n = A.gcount[t];
-    for (u32 k = tid; k < 4 * n; k += kSegThreads)
-      reinterpret_cast<uint4*>(A.rec + A.glist[(size_t)t * kGTile + (k >> 2)])[k & 3u] = z;
-  }
+  if (isnan_)                                                   // tf.cond takes the constant branch: no gradient
+    for (u32 i = blockIdx.x * kSegThreads + tid; i < B; i += gridDim.x * kSegThreads) A.dlogits[i] = 0.f;
+  clean_records_grid(A.rec, 0, A.glist, A.gcount, ntile);
   __syncthreads();
-  if (tid == 0) { __threadfence(); ctl->path = 1; ctl_finish(ctl); }
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) { __threadfence(); ctl->ts[23] = globaltimer(); ctl->path = 1; ctl_finish(ctl); }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_lw_dense_fill(size_t n, uint8_t* __restrict__ dm, float* __restrict__ dl,

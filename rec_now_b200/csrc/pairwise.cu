@@ -46,51 +46,6 @@ struct PairParams {
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
 };
 
-// J-block range of virtual block v (2b = range R1 of I-block b, 2b + 1 = range R2, see HeadsTail): first J-block and
-// J-block count; R2 is trimmed so that no (I-block, J-block) tile is listed twice.
-// (a range is stored as (~lo, hi): the counting path builds it with atomicMax from an all-zero = empty record)
-__device__ __forceinline__ u32 vblock_tiles(const uint2* blk, u32 v, u32& jfirst) {
-  const uint2 r = blk[v];
-  u32 lo = 0, hi = 0;
-  if (r.y > ~r.x) { lo = ~r.x >> 5; hi = (r.y + 31) >> 5; }
-  if (v & 1) { const uint2 r1 = blk[v - 1]; if (r1.y > ~r1.x) lo = max(lo, (r1.y + 31) >> 5); }
-  jfirst = lo;
-  return hi > lo ? hi - lo : 0u;
-}
-
-// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
-// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
-// a[n] receives the total (sc: kPairWarps + 2 words).  All threads of the CTA must call it.
-constexpr u32 kScanThreads = 256;
-__device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
-  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
-  const bool act = threadIdx.x < kScanThreads;
-  const u32 per = (n + kScanThreads - 1) / kScanThreads;
-  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
-  u32 sum = 0, inc = 0;
-  if (act) {
-    for (u32 i = i0; i < i1; ++i) sum += a[i];
-    inc = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
-    if (ln == 31) sc[wq] = inc;
-  }
-  __syncthreads();
-  if (act) {
-    u32 off = inc - sum;
-    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
-    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
-    if (threadIdx.x == kScanThreads - 1) a[n] = off;
-  }
-  __syncthreads();
-}
-
-// Largest idx in [lo, hi) with arr[idx] <= key (arr nondecreasing, arr[lo] <= key); one thread, binary search.
-__device__ __forceinline__ u32 last_le(const u32* arr, u32 lo, u32 hi, u32 key) {
-  while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (arr[mid] <= key) lo = mid; else hi = mid; }
-  return lo;
-}
-
 // Cost of one J-block (32 negatives) of a virtual block; a fast tile costs 8 * kCostUnit.  Range R1 of an I-block (the
 // rows of the group that began before the block) is fast tiles plus the blocks that hold a label-level boundary; range
 // R2 (groups that begin inside the block) is general tiles (a warp that finishes early costs little -- its SMSP
@@ -1217,35 +1172,33 @@ __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& 
   lp = warp_sum(lp);
   if (ln == 0) red_d[threadIdx.x >> 5] = lp;
   __syncthreads();
-  __shared__ u32 s_last;
   if (threadIdx.x == 0) {
     double t = 0;
     for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
     if (t != 0.0) atomicAdd(&ctl->loss_sum, t);
-    __threadfence();
-    s_last = (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) ? 1u : 0u;       // the last CTA writes the scalars
-    if (s_last) {
-      __threadfence();
-      ctl->ts[23] = globaltimer();
-      const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
-      const float lossv = (float)(tot / (double)denom);
-      *P.loss = lossv;
-      *P.n_pair_f32 = (float)n;                  // PW:276
-      *P.n_pair = (int64_t)n;
-      if (P.out_chunk)                           // the (partial) loss rides in every chunk of the reduce-scatter
-        for (u32 r = 0; r * P.rm.Bl < B; ++r) {
-          float* tl = P.dlogits + (size_t)r * P.out_chunk + P.rm.Bl;
-          tl[0] = lossv;
-          for (u32 q = 1; P.rm.Bl + q < P.out_chunk; ++q) tl[q] = 0.f;
-        }
-    }
   }
+  grid_sync(&ctl->bar2_cnt, epoch2, &ctl->err);
+  // behind the last barrier: the scalars (CTA 0) and, now that nobody reads the group records any more, a clean arena
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->ts[23] = globaltimer();
+    const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+    const float lossv = (float)(tot / (double)denom);
+    *P.loss = lossv;
+    *P.n_pair_f32 = (float)n;                  // PW:276
+    *P.n_pair = (int64_t)n;
+    if (P.out_chunk)                           // the (partial) loss rides in every chunk of the reduce-scatter
+      for (u32 r = 0; r * P.rm.Bl < B; ++r) {
+        float* tl = P.dlogits + (size_t)r * P.out_chunk + P.rm.Bl;
+        tl[0] = lossv;
+        for (u32 q = 1; P.rm.Bl + q < P.out_chunk; ++q) tl[q] = 0.f;
+      }
+  }
+  if (A.fast) clean_records_grid(A.rec, A.rec2_off, A.glist, A.gcount, A.ngt);
   __syncthreads();
-  if (!s_last) return;
-  // ... and, now that nobody reads the group records any more, leaves the arena clean
-  if (A.fast) clean_records(A, 0, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) { __threadfence(); ctl_finish(ctl); }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl->fin_done, 1u) == gridDim.x - 1) { __threadfence(); ctl_finish(ctl); }
+  }
 }
 
 // Second stage of a global-mode call whose pair set depends on scores / weights (see KpArgs::xcnt_out).
@@ -1585,5 +1538,54 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
     }
     ++g_prof.n;
   }
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+
+// ---- GAUC (gauc.cu): the pairwise segmentation, then the concordance kernel ---------------------------------------
+extern "C" size_t rn_gauc_scratch_bytes(int64_t B, int32_t K) { return rn_pairwise_scratch_bytes(B, K); }
+
+extern "C" int rn_gauc(const rn_gauc_args* g, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!g || g->B <= 0 || g->B > (1ll << 28) || g->K <= 0 || g->K > 8) return RN_ERR_ARG;
+  if (!g->keys || !g->scores || !g->labels || !g->gauc || !g->n_valid_groups) return RN_ERR_ARG;
+  const void* ptrs[] = {g->keys, g->scores, g->labels, g->row_ok};
+  for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
+  if (!scratch || check_align(scratch)) return scratch ? RN_ERR_ALIGN : RN_ERR_ARG;
+  if ((g->B + kIB - 1) / kIB > (int64_t)kMaxNibS) return RN_ERR_UNSUPPORTED;       // (the explicit work list of very large batches is the pair kernel's)
+  const Layout L = make_layout(g->B, g->K);
+  if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(scratch);
+  static const int count_on = tune_int("RN_SEG_COUNT", 1);
+  const bool fast = count_on && g->scratch_persistent && g->K == 1;
+  PairParams P{};
+  P.B = (u32)g->B; P.K = g->K; P.gbits = L.gbits;
+  P.logits = g->scores; P.labels = g->labels;
+  P.factor = 1.f; P.power = 0.f; P.reduce_mean = 1; P.c_log2 = 1.4426950408889634f;
+  P.part_rank = 0; P.part_count = 1;
+  P.rm = RowMap{0, 0, 0, 0};
+  HeadsTail H{};
+  H.P = P;
+  H.aj = at<uint2>(base, L.aj); H.ss = at<float>(base, L.ss); H.sy = at<float>(base, L.sy);
+  H.swp = at<float>(base, L.swp); H.swn = at<float>(base, L.swn);
+  H.gacc = at<float>(base, L.gacc); H.lossrow = at<float>(base, L.lossrow); H.cnt = at<u32>(base, L.cnt);
+  H.perm = at<u32>(base, L.perm); H.sgrp = at<u32>(base, L.sgrp);
+  H.blk = at<uint2>(base, L.blk); H.units = at<uint2>(base, L.units); H.nib = L.nib;
+  H.cprim = at<u64>(base, L.cprim); H.pgid = at<u32>(base, L.slot1);
+  H.target_units = target_units();
+  H.pp = PrePart{};
+  H.g64 = at<unsigned long long>(base, L.misc);
+  SegInputs in{g->B, g->K, g->keys, g->labels, g->row_ok, true, true};
+  in.fast = fast;
+  if (seg_run(L, scratch, in, H, st) != cudaSuccess) return RN_ERR_LAUNCH;
+  GaucArgs A{};
+  A.B = (u32)g->B; A.nib = L.nib; A.aj = H.aj; A.ss = H.ss; A.blk = H.blk; A.blk_w = H.blk;
+  A.acc2 = at<u64>(base, L.misc); A.npg = at<u64>(base, L.keyA); A.gsz = at<u32>(base, L.cnt);
+  // (the sorted keys may live in keyA after an even number of radix passes: nothing reads them after k_seg)
+  A.gauc = g->gauc; A.auc_mean = g->auc_mean; A.n_valid = g->n_valid_groups; A.n_pair = g->n_pair; A.conc2 = g->concordant2;
+  A.fast = fast ? 1 : 0; A.rec = at<GRec>(base, L.rec); A.rec2_off = 0; A.glist = at<u32>(base, L.glist);
+  A.gcount = at<u32>(base, L.gcount); A.ngt = (u32)((g->B + kGTile - 1) / kGTile);
+  A.ctl = at<Ctl>(base, L.ctl);
+  if (launch_gauc(A, st) != cudaSuccess) return RN_ERR_LAUNCH;
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
 }
