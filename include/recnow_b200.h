@@ -121,6 +121,14 @@ typedef struct rn_pairwise_args {
    * summed in a fixed order.  Slower (the sort), single GPU, not with only_wrong / rw_neg (RN_ERR_UNSUPPORTED). */
   int32_t deterministic;
   int64_t scratch_rows;
+  /* Focal term fused into the same pass (0 = off): the call returns
+   *   loss = pairwise loss + focal_weight * focal_crossentropy_loss(labels, logits, alpha, gamma, stop_weight_gradient)
+   * (rec_block/focal_loss.py:12-66 of the reference, return_mean = True: the mean over ALL B rows, masked or not) and
+   * dlogits holds the gradient of that sum -- the joint pointwise + pairwise objective of a ranking model in one call, the
+   * focal part riding in the pair kernel's first and last pass.  focal_alpha / focal_gamma = 0 switch the respective
+   * factor off (the reference's `if alpha:` / `if gamma:`).  Not with only_wrong / rw_neg / blocked rows. */
+  float focal_weight, focal_alpha, focal_gamma;
+  int32_t focal_stop_weight_gradient;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {

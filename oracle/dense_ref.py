@@ -327,3 +327,23 @@ def listwise_full(group_ids, labels, logits, weights=None, do_mask_logits=True,
         gd = (sm * dl.astype(np.float64).sum(axis=-1, keepdims=True) - dl) * (w / v)[:, None]
         grad = np.where(dm, gd, 0.0).sum(axis=0).astype(F32)
     return dict(loss=F32(loss), n_valid=int(v), list_loss=per_list, dense_mask=dm, grad=grad)
+
+
+# ---- focal loss (rec_now/rec_block/focal_loss.py; fused by the product into the pairwise call as an extra term) ----------
+def focal_crossentropy_loss(labels, logits, alpha=0.25, gamma=2.0, stop_weight_gradient=False, return_mean=True):
+    """focal_loss.py:12-66, op for op in float32 (stop_weight_gradient only matters for the gradient)."""
+    if alpha and (alpha <= 0.0 or alpha >= 1.0):
+        raise ValueError("Value of alpha should be greater than zero and less than one.")           # focal_loss.py:43-44
+    if gamma and gamma < 0:
+        raise ValueError("Value of gamma should be greater than or equal to zero.")                 # focal_loss.py:45-46
+    y = np.asarray(labels, F32)
+    z = np.asarray(logits, F32)
+    loss = sigmoid_cross_entropy_with_logits(y, z)                                                  # focal_loss.py:48
+    if alpha:
+        a = F32(alpha)
+        loss = (y * a + (F32(1) - y) * (F32(1) - a)) * loss                                         # focal_loss.py:50-53
+    if gamma:
+        p = (F32(1) / (F32(1) + np.exp(-z))).astype(F32)                                            # focal_loss.py:56
+        sim = y * p + (F32(1) - y) * (F32(1) - p)                                                   # focal_loss.py:57
+        loss = np.power(F32(1) - sim, F32(gamma)).astype(F32) * loss                                # focal_loss.py:59-62
+    return F32(np.mean(loss, dtype=F32)) if return_mean else loss                                   # focal_loss.py:64-66

@@ -255,3 +255,23 @@ def gauc(scores, labels, groups, mask=None):
         n_pair += n; conc2 += c2; nv += 1
     return dict(gauc=num / den if den else 0.0, auc_mean=asum / nv if nv else 0.0, n_valid_groups=nv, n_pair=n_pair,
                 concordant2=conc2)
+
+
+def focal(labels, logits, alpha=0.25, gamma=2.0, stop_weight_gradient=False):
+    """float64 truth for focal_crossentropy_loss(return_mean=True) (focal_loss.py:12-66) and its gradient with respect
+    to the logits.  Returns dict(loss, grad[B])."""
+    y = np.asarray(labels, F32).reshape(-1).astype(np.float64)
+    z = np.asarray(logits, F32).reshape(-1).astype(np.float64)
+    ce = np.maximum(z, 0) - z * y + np.log1p(np.exp(-np.abs(z)))
+    p = 1.0 / (1.0 + np.exp(-z))
+    af = (y * alpha + (1 - y) * (1 - alpha)) if alpha else np.ones_like(z)
+    mod, dmod = np.ones_like(z), np.zeros_like(z)
+    if gamma:
+        om = 1.0 - (y * p + (1 - y) * (1 - p))
+        mod = om ** gamma
+        if not stop_weight_gradient:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                dmod = -gamma * om ** (gamma - 1.0) * (2 * y - 1) * p * (1 - p)
+    fl = af * mod * ce
+    grad = af * (mod * (p - y) + ce * dmod) / z.size
+    return dict(loss=float(fl.mean()), grad=grad)

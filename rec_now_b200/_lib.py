@@ -52,6 +52,8 @@ class PairwiseArgs(C.Structure):
         ("block_rows", C.c_int64), ("block_stride", C.c_int64), ("out_chunk", C.c_int64),
         ("peer_blocks", C.c_void_p * 8), ("gather_dst", C.c_void_p),
         ("scratch_persistent", C.c_int32), ("deterministic", C.c_int32), ("scratch_rows", C.c_int64),
+        ("focal_weight", C.c_float), ("focal_alpha", C.c_float), ("focal_gamma", C.c_float),
+        ("focal_stop_weight_gradient", C.c_int32),
     ]
 
 

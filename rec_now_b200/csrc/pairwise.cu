@@ -41,6 +41,7 @@ struct PairParams {
   float c_log2;          // factor * log2(e)
   float factor, power; int reduce_mean; int dyn_count; int debug;
   int det;               // deterministic mode: fixed-point gradient accumulators, ordered loss partials
+  float focal_w, focal_alpha, focal_gamma; int focal_stop;      // fused focal term (rn_pairwise_args.focal_*); focal_w = 0: off
   int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
@@ -675,6 +676,25 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
 __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
                                              u32& epoch2, u64* red_u, double* red_d);
 
+// One row of focal_crossentropy_loss (rec_block/focal_loss.py:12-66 of the reference): value and d / d logit.
+//   ce = sigmoid_cross_entropy_with_logits(y, z) = max(z, 0) - z y + log1p(exp(-|z|))                  (focal_loss.py:48)
+//   alpha factor y alpha + (1 - y)(1 - alpha)                                                          (:50-53)
+//   modulating factor (1 - (y p + (1 - y)(1 - p)))^gamma, p = sigmoid(z); optionally without gradient  (:55-62)
+// (not inlined: it runs once per row outside the pair loop, and the pair kernel has no registers to spare)
+__device__ __noinline__ float2 focal_row(float z, float y, float alpha, float gamma, int stop) {
+  const float e = expf(-fabsf(z));
+  const float ce = fmaxf(z, 0.f) - z * y + log1pf(e);
+  const float p = z >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+  const float af = alpha != 0.f ? y * alpha + (1.0f - y) * (1.0f - alpha) : 1.0f;
+  float mod = 1.0f, dmod = 0.f;
+  if (gamma != 0.f) {
+    const float om = 1.0f - (y * p + (1.0f - y) * (1.0f - p));
+    mod = powf(om, gamma);
+    if (!stop) dmod = -gamma * powf(om, gamma - 1.0f) * (2.0f * y - 1.0f) * p * (1.0f - p);
+  }
+  return make_float2(af * mod * ce, af * (mod * (p - y) + ce * dmod));
+}
+
 // DET: deterministic mode (fixed-point gradient accumulators, ordered loss partials) -- a separate instantiation, so that
 // the default kernel carries none of it through the pair loop.
 template <int MODE, bool DET = false>
@@ -804,6 +824,20 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 pg = A.sgrp[p];
       A.lossrow[p] = pg != kEmpty ? occ_pow(A.cprim[pg], fold_power) : 0.f;
     }
+  }
+  if (!DYN && P.focal_w != 0.f) {
+    // fused focal term, value: sum over ALL rows (original order; the mean is over B), one atomic per CTA
+    double fs = 0.0;
+    for (u32 i = gtid0; i < B; i += gridDim.x * blockDim.x) fs += (double)focal_row(P.logits[i], P.labels[i], P.focal_alpha, P.focal_gamma, P.focal_stop).x;
+    fs = warp_sum(fs);
+    if (ln == 0) red_d[threadIdx.x >> 5] = fs;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int q = 0; q < kPairWarps; ++q) t += red_d[q];
+      atomicAdd(&ctl->acc_d[3], t);
+    }
+    __syncthreads();
   }
   stamp(ctl, 16);
   double lsum = 0.0;
@@ -1063,13 +1097,22 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     auto row_scale = [&](u32 p) -> float { return fold_power == 0.f ? gscale : A.lossrow[p] * gscale; };
     // output index: plain, or chunked for a following reduce-scatter (row i -> (i / Bl) * out_chunk + i % Bl)
     auto out_at = [&](u32 row) -> size_t { return P.out_chunk ? (size_t)(row / P.rm.Bl) * P.out_chunk + (row % P.rm.Bl) : row; };
-    if (DET) for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = (float)((double)(long long)A.g64[p] * s_dscale[1]) * row_scale(p);
+    if (P.focal_w != 0.f) {
+      // ... plus the focal term's gradient, focal_w / B * d focal_i / d logit_i (the mean is over all rows)
+      const float fsc = P.focal_w / (float)B;
+      for (u32 p = gtid; p < B; p += gthreads) {
+        const u32 row = A.perm[p];
+        const float gp = DET ? (float)((double)(long long)A.g64[p] * s_dscale[1]) : A.gacc[p];
+        P.dlogits[row] = gp * row_scale(p) + fsc * focal_row(P.logits[row], P.labels[row], P.focal_alpha, P.focal_gamma, P.focal_stop).y;
+      }
+    } else if (DET) for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = (float)((double)(long long)A.g64[p] * s_dscale[1]) * row_scale(p);
     else for (u32 p = gtid; p < B; p += gthreads) P.dlogits[out_at(A.perm[p])] = A.gacc[p] * row_scale(p);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       double lsum_all = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
       if (DET) { lsum_all = 0.0; for (u32 c = 0; c < gridDim.x; ++c) lsum_all += A.lpart[c]; }
       const double tot = lsum_all * 0.6931471805599453;
-      const float lossv = (float)(tot / (double)denom);
+      float lossv = (float)(tot / (double)denom);
+      if (P.focal_w != 0.f) lossv += P.focal_w * (float)(*reinterpret_cast<volatile double*>(&ctl->acc_d[3]) / (double)B);
       *P.loss = lossv;
       *P.n_pair_f32 = (float)n;                  // PW:276
       *P.n_pair = (int64_t)n;
@@ -1407,11 +1450,16 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
+  if (a->focal_weight != 0.f && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
+  if (a->focal_weight != 0.f && ((a->focal_alpha != 0.f && !(a->focal_alpha > 0.f && a->focal_alpha < 1.f)) || a->focal_gamma < 0.f))
+    return RN_ERR_ARG;                                  // (focal_loss.py:43-46)
   const bool det = a->deterministic != 0;
   if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
   const bool fast = counting_eligible(a) && !det;       // (the counting path places groups and rows in arrival order)
   PairParams P{};
   P.det = det ? 1 : 0;
+  P.focal_w = a->focal_weight; P.focal_alpha = a->focal_alpha; P.focal_gamma = a->focal_gamma;
+  P.focal_stop = a->focal_stop_weight_gradient;
   P.B = (u32)a->B; P.K = a->K; P.gbits = L.gbits;
   P.logits = a->logits; P.labels = a->labels; P.rw_pos = a->rw_pos; P.rw_neg = a->rw_neg;
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;

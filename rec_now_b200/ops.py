@@ -130,7 +130,7 @@ _pair_scratch_bytes: dict = {}
 
 def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
                      factor=1.0, power=0.0, only_wrong=False, reduce_mean=True, part=(0, 1),
-                     want_row_pairs=False, deterministic=False):
+                     want_row_pairs=False, deterministic=False, focal=None):
     """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors."""
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
@@ -163,6 +163,11 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     a.dlogits = dlogits.data_ptr(); a.row_pairs = _ptr(row_pairs)
     a.block_rows = 0; a.block_stride = 0; a.out_chunk = 0
     a.scratch_persistent = 1; a.scratch_rows = 0; a.deterministic = 1 if deterministic else 0
+    if focal is None:
+        a.focal_weight = 0.0
+    else:       # (weight, alpha or 0, gamma or 0, stop_weight_gradient): the fused focal term, see rn_pairwise_args
+        a.focal_weight, a.focal_alpha, a.focal_gamma = focal[0], focal[1], focal[2]
+        a.focal_stop_weight_gradient = 1 if focal[3] else 0
     with _on_device(dev):
         rc = pc.fn(pc.ref, scratch.data_ptr(), nbytes, st)
     if rc:

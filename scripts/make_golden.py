@@ -32,10 +32,12 @@ def consts(path):
             except ValueError:
                 pass
         if isinstance(node, ast.Call) and getattr(node.func, "attr", "") in ("assertAlmostEqual", "assertEquals"):
-            try:
-                out[node.lineno] = ast.literal_eval(node.args[1])
-            except (ValueError, IndexError):
-                pass
+            for k in (1, 0):              # (expected value second -- TPW, TLW -- or first -- the focal test)
+                try:
+                    out[node.lineno] = ast.literal_eval(node.args[k])
+                    break
+                except (ValueError, IndexError):
+                    pass
     return out, src.splitlines()
 
 
@@ -68,6 +70,16 @@ def main():
     for name, l, e, nv in (("listwise_loss", l1, exp_lw[0], exp_nv[0]), ("listwise_loss_case2", l2, exp_lw[1], exp_nv[1])):
         g["cases"].append({"name": name, "cite": f"TLW:{l}-{l + 12}", "groups": lw[l][0], "labels": lw[l + 1][0],
                            "logits": lw[l + 2][0], "expected_n_valid_list": nv, "expected_loss": e})
+    # focal loss (fused by the product into the pairwise call): tests/rec_block/test_focal_loss.py
+    fl, fl_src = consts(os.path.join(REF, "test_focal_loss.py"))
+    g["source"]["TFL"] = "tests/rec_block/test_focal_loss.py"
+    l_lab = line_of(fl_src, r"labels = tf.constant")
+    l_log = line_of(fl_src, r"logits = tf.constant")
+    exp_fl = [fl[i + 1] for i, l in enumerate(fl_src) if "assertAlmostEqual(" in l]
+    g["cases"].append({"name": "focal_crossentropy_loss", "cite": f"TFL:{l_lab}-{len(fl_src)}", "labels": fl[l_lab],
+                       "logits": fl[l_log], "expected_alpha_none_gamma_none": exp_fl[0],
+                       "expected_alpha_0.25_gamma_none": exp_fl[1], "expected_alpha_none_gamma_1": exp_fl[2],
+                       "tolerance": 1e-5})
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1)
     print(json.dumps(g, indent=1))

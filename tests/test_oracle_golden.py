@@ -115,3 +115,33 @@ class TestListwiseLoss(unittest.TestCase):
 
 if __name__ == "__main__":
     unittest.main()
+
+
+def test_focal_loss_known_answers():
+    """tests/rec_block/test_focal_loss.py of the reference: the three golden values pin the focal restatements (float32
+    op-for-op and float64) that check the fused joint loss."""
+    import json, os
+    from oracle import dense_ref as D
+    from oracle import seg_ref as S
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = json.load(open(os.path.join(here, "golden", "reference_known_answers.json")))
+    c = [x for x in g["cases"] if x["name"] == "focal_crossentropy_loss"][0]
+    y, z = np.asarray(c["labels"], np.float32), np.asarray(c["logits"], np.float32)
+    for key, kw in (("expected_alpha_none_gamma_none", dict(alpha=None, gamma=None)),
+                    ("expected_alpha_0.25_gamma_none", dict(alpha=0.25, gamma=None)),
+                    ("expected_alpha_none_gamma_1", dict(alpha=None, gamma=1))):
+        assert abs(float(D.focal_crossentropy_loss(y, z, **kw)) - c[key]) < c["tolerance"], key
+        assert abs(S.focal(y, z, alpha=kw["alpha"] or 0, gamma=kw["gamma"] or 0)["loss"] - c[key]) < c["tolerance"], key
+    # the float64 gradient against central differences
+    rng = np.random.default_rng(0)
+    y = (rng.random(50) < 0.4).astype(np.float32); z = rng.standard_normal(50).astype(np.float32)
+    for kw in (dict(alpha=0.25, gamma=2.0), dict(alpha=0, gamma=1.5), dict(alpha=0.7, gamma=0), dict(alpha=0.25, gamma=2.0, stop_weight_gradient=True)):
+        r = S.focal(y, z, **kw)
+        if kw.get("stop_weight_gradient"):
+            continue
+        eps = 1e-3
+        for i in (0, 7, 23):
+            zp, zm = z.astype(np.float64).copy(), z.astype(np.float64).copy()
+            zp[i] += eps; zm[i] -= eps
+            fd = (S.focal(y, zp.astype(np.float32), **kw)["loss"] - S.focal(y, zm.astype(np.float32), **kw)["loss"]) / (2 * eps)
+            assert abs(fd - r["grad"][i]) < 2e-4 * max(1.0, abs(fd)), (kw, i, fd, r["grad"][i])
