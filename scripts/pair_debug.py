@@ -32,7 +32,7 @@ t = list(ts)
 B = s.numel()
 NW = int(__import__('os').environ.get('NW', '16'))
 total = scr.numel()
-gstat_off = total - ((8 * 4 * B + 255) // 256) * 256
+gstat_off = _lib.lib().rn_debug_arena_offset(B, 1, 0)
 rec = scr[gstat_off:gstat_off + 148 * NW * 64].view(torch.int64).cpu().numpy().reshape(-1, 8)
 t20 = t[20]
 start = (rec[:, 0] - t20) / 1e3; end = (rec[:, 1] - t20) / 1e3

@@ -25,7 +25,7 @@ off = scr.numel()
 def back(nbytes):
     global off
     off -= al(nbytes); return off
-o_gstat = back(8 * 4 * B); o_misc = back(8 * (B + 1)); o_units = back(8 * (2 * nib + 16384 + 1)); o_blk = back(16 * nib)
+o_gstat = __import__('rec_now_b200._lib', fromlist=['lib']).lib().rn_debug_arena_offset(B, 1, 0); _ = back(8 * 4 * B); o_misc = back(8 * (B + 1)); o_units = back(8 * (2 * nib + 16384 + 1)); o_blk = back(16 * nib)
 o_perm = back(4 * B); o_cnt = back(4 * B); o_loss = back(4 * B); o_gacc = back(4 * B); o_swn = back(4 * B); o_swp = back(4 * B)
 o_sy = back(4 * B); o_ss = back(4 * B); o_aj = back(8 * B)
 g = lambda o, n, dt: scr[o:o + n].view(dt).cpu().numpy()

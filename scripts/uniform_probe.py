@@ -19,7 +19,7 @@ for _ in range(50):
 torch.cuda.synchronize()
 scr = out["_scratch"]
 ts = (C.c_uint64 * 34)(); _lib.lib().rn_debug_timestamps(scr.data_ptr(), ts, 34, None); t = list(ts)
-total = scr.numel(); gstat_off = total - ((8 * 4 * B + 255) // 256) * 256
+total = scr.numel(); gstat_off = _lib.lib().rn_debug_arena_offset(B, 1, 0)
 rec = scr[gstat_off:gstat_off + 148 * 32 * 64].view(torch.int64).cpu().numpy().reshape(-1, 8)
 t20 = t[20]; start = (rec[:, 0] - t20) / 1e3; end = (rec[:, 1] - t20) / 1e3; eig = rec[:, 7] & 0xFFFFFFFF; gen = rec[:, 3] >> 32
 ok = rec[:, 1] > 0
