@@ -491,7 +491,7 @@ def ours(args):
     else:
         # N > 1: the same global batch on ONE GPU (rank 0), through the single-GPU product path: exact pair count, loss,
         # this rank's gradient rows; the time of that run is the strong-scaling reference of the global mode
-        seg_path = {1: "counting (sort-free), replicated on every rank; each rank scores the pairs whose negative row it owns",
+        seg_path = {1: "counting (sort-free), replicated on every rank; each rank scores the pairs whose positive row it owns",
                     2: "radix sort, replicated on every rank; the cost line is split across the ranks"}.get(
                         global_mode.last_segmentation_path(), "?")
         parity = None
@@ -689,7 +689,7 @@ def ours(args):
                            "ONE C-ABI call per step (rn_global_pairwise_fwd_bwd) over NVLink peer mappings, no collective "
                            "calls: pack kernel -> device-side flag barrier -> ONE graph launch whose first kernel gathers every "
                            "rank's row block with peer loads -> replicated sort-free segmentation -> each rank scores the "
-                           "pairs whose negative row it owns -> flag barrier -> one kernel sums this rank's gradient chunk "
+                           "pairs whose positive row it owns -> flag barrier -> one kernel sums this rank's gradient chunk "
                            "from the peers' buffers"
                            if global_mode.exchange_path() == "peer" else
                            "ONE NCCL all-gather of packed per-rank row blocks -> replicated segmentation on the blocked "

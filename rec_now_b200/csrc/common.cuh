@@ -107,7 +107,8 @@ struct Layout {
 struct __align__(16) GRec {
   u64 key; u32 rep1; u32 base;  // key, creator row + 1 (0 = free), first sorted position of the group
   u32 cnt[8];                   // rows per label level; rewritten by the offsets phase to the level starts relative to base
-  float wocc; u32 pad0;         // occurrence weight c_h ^ power of the group (non-dynamic pair sets)
+  float wocc; u32 own;          // occurrence weight c_h ^ power of the group; global mode: 0 = this rank scores its own rows of
+                                // the group, 1 = ALL rows (it owns the whole small group), 2 = none (another rank does)
   u64 npair;                    // kept pairs of the group (PW:286-289)
 };
 // Second record of a group, global mode only: rows per label level among THIS rank's rows (cl) and among the other
@@ -116,6 +117,7 @@ struct __align__(16) GRec2 { u32 cl[8]; u32 cr[8]; };
 static_assert(sizeof(GRec2) == sizeof(GRec), "the second records are addressed through the first table's base pointer");
 constexpr int kLevels = 8;       // label levels of the counting path: integer-valued labels -1 .. 6
 constexpr int kGTile = 512;      // rows per tile of the counting path (= kSegThreads)
+constexpr u32 kOwnRows = 2048;   // global mode: groups below this many rows are scored whole by ONE rank (hash of the key)
 constexpr u32 kBndCap = 16384;   // piece boundaries of the pair kernel's partition the arena holds (warps of its grid + 1)
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
@@ -309,30 +311,38 @@ __device__ __forceinline__ void clean_records_grid(GRec* rec, u32 rec2_off, cons
   }
 }
 
-// In-place exclusive prefix sum of a[0, n) by the first kScanThreads threads of the CTA (every thread owns a contiguous
-// run; the fixed per-thread cost is what counts at these sizes, so a quarter of the CTA is faster than all of it);
-// a[n] receives the total (sc: 34 words).  All threads of the CTA must call it.
-constexpr u32 kScanThreads = 256;
+// In-place exclusive prefix sum of a[0, n) in shared memory by the whole CTA (blockDim.x a multiple of 32, <= 1024).
+// Every WARP owns a contiguous segment and walks it 32 elements at a time (coalesced, conflict-free accesses, a shuffle
+// scan per step, the running sum in a register) -- no barrier inside the walk; then one scan over the warps' totals and
+// a second walk that adds the warp's offset.  a[n] receives the total (sc: 34 words).  All threads must call it.
 __device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
-  const u32 ln = lane_id(), wq = threadIdx.x >> 5;
-  const bool act = threadIdx.x < kScanThreads;
-  const u32 per = (n + kScanThreads - 1) / kScanThreads;
-  const u32 i0 = min(threadIdx.x * per, n), i1 = act ? min(i0 + per, n) : i0;
-  u32 sum = 0, inc = 0;
-  if (act) {
-    for (u32 i = i0; i < i1; ++i) sum += a[i];
-    inc = sum;
+  const u32 ln = lane_id(), w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const u32 seg = ((n + nw - 1) / nw + 31u) & ~31u;
+  const u32 s0 = min(w * seg, n), s1 = min(s0 + seg, n);
+  u32 carry = 0;
+  for (u32 base = s0; base < s1; base += 32) {
+    const u32 i = base + ln;
+    const u32 v = i < s1 ? a[i] : 0u;
+    u32 inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
-    if (ln == 31) sc[wq] = inc;
+    if (i < s1) a[i] = carry + inc - v;
+    carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+  }
+  if (ln == 0) sc[w] = carry;
+  __syncthreads();
+  if (w == 0) {
+    const u32 x = ln < nw ? sc[ln] : 0u;
+    u32 xi = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, xi, o); if (ln >= (u32)o) xi += y; }
+    sc[ln] = xi - x;
+    if (ln == 31) sc[32] = xi;
   }
   __syncthreads();
-  if (act) {
-    u32 off = inc - sum;
-    for (u32 q = 0; q < wq; ++q) off += sc[q];                 // <= 7 partials
-    for (u32 i = i0; i < i1; ++i) { const u32 v = a[i]; a[i] = off; off += v; }
-    if (threadIdx.x == kScanThreads - 1) a[n] = off;
-  }
+  const u32 off = sc[w];
+  if (off) for (u32 i = s0 + ln; i < s1; i += 32) a[i] += off;
+  if (threadIdx.x == 0) a[n] = sc[32];
   __syncthreads();
 }
 

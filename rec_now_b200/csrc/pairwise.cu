@@ -104,13 +104,16 @@ struct HeadsTail {
                                               float wn) const {
     const GRec* r = S.rec + slot;
     const u32 li = meta >> 29, rank = meta & 0x1FFFFFFFu;
-    const u32 a = r->base, pre = r->cnt[li];
+    const u32 a = r->base, pre = r->cnt[li], own = r->own;
     const float wocc = r->wocc;
-    // global mode: the group is laid out [local rows by level][remote rows by level]; a row of either part pairs with
-    // the LOCAL rows below its level (every pair is scored by the rank that owns its negative)
+    // global mode: inside every label level the rank's OWN rows come first, then the other ranks' rows.  An own row pairs
+    // with all rows below its level, wherever they live; a remote row is only ever a negative here (every pair is scored
+    // by the rank that owns its positive row, so no two ranks need to agree on the order of the rows)
+    // Small groups are not split: ONE rank (a hash of the key picks it) takes all their rows as positives, the others
+    // none -- otherwise every rank would walk every I-block of every small group for a few own rows each.
     const bool remote = S.rm.Bl && (i / S.rm.Bl != (u32)P.part_rank) && slot <= S.capmask;
     const u32 pos = a + (remote ? S.rec2[slot].cr[li] : pre) + rank;
-    const u32 n = pre;                                       // (local) rows of the group below this row's level
+    const u32 n = (own == 2u || (remote && own != 1u)) ? 0u : pre;      // rows of the group below this row's level
     aj[pos] = make_uint2(a, n);
     // (a NaN label pairs with nothing, but its row shares I-blocks with rows that do: under label-gain weights the tile
     // multiplies a zero row weight by (y_i - y_ref), and 0 * NaN would poison the block's sums)
@@ -128,29 +131,18 @@ struct HeadsTail {
   // ascend along the positions, so that row has the longest negative range.  The block in which the group begins gets
   // it as R2 (hull with the other groups that begin there: atomicMax on (~lo, hi), zero = empty), every later block
   // as R1 (exactly one group can reach into a block from the left: plain store).
-  // Geometry of one group as the offsets phase knows it.  Layout of the group's rows: the LOCAL rows by level, then (global
-  // mode) the remote rows by level.  pl[q] / pr[q]: start of level q inside the local / remote part, relative to the
-  // group's base (pr includes nl); ml / mr: bit q set = the level holds rows of that part.  The negative range of a row of
-  // level q is [base, base + pl[q]) in either part.
-  struct Geo { u32 base, tot, nl, ml, mr; u32 pl[kLevels], pr[kLevels]; };
-  static __device__ __forceinline__ u32 range_len_at(const Geo& g, u32 x) {        // pl[level of the row at relative position x]
-    u32 r = 0;
-    if (x < g.nl) {
-#pragma unroll
-      for (int q = 0; q < kLevels; ++q) if (((g.ml >> q) & 1u) && g.pl[q] <= x) r = g.pl[q];
-    } else {
-#pragma unroll
-      for (int q = 0; q < kLevels; ++q) if (((g.mr >> q) & 1u) && g.pr[q] <= x) r = g.pl[q];
-    }
-    return r;
-  }
+  // Geometry of one group as the offsets phase knows it.  The group's rows are laid out level by level; inside a level the
+  // rank's OWN rows come first, then (global mode) the other ranks' rows.  ls[q]: start of level q relative to the group's
+  // base, co[q]: own rows of the level (they sit at [ls[q], ls[q] + co[q])).  The negative range of an own row of level q
+  // is [base, base + ls[q]); remote rows have none.
+  struct Geo { u32 base, tot; u32 ls[kLevels], co[kLevels]; };
   __device__ __forceinline__ void block_range(u32 b, u32 b0, const Geo& g) const {
-    // rows of the group inside I-block b: relative positions [x0, x1]; the range length grows with the position inside
-    // each part, so the longest one belongs to the last local row or to the last row
+    // rows of the group inside I-block b: relative positions [x0, x1]; the longest range belongs to the highest level
+    // that has an own row in there
     const u32 x0 = b == b0 ? 0u : b * kIB - g.base, x1 = min(g.tot, (b + 1u) * kIB - g.base) - 1u;
     u32 hi = 0;
-    if (x0 < g.nl) hi = range_len_at(g, min(x1, g.nl - 1u));
-    if (x1 >= g.nl) hi = max(hi, range_len_at(g, x1));
+#pragma unroll
+    for (int q = 0; q < kLevels; ++q) if (g.co[q] && g.ls[q] <= x1 && g.ls[q] + g.co[q] > x0) hi = g.ls[q];
     if (!hi) return;
     if (b == b0) { atomicMax(&blk[2 * b + 1].x, ~g.base); atomicMax(&blk[2 * b + 1].y, g.base + hi); }
     else blk[2 * b] = make_uint2(~g.base, g.base + hi);
@@ -318,18 +310,44 @@ struct HeadsTail {
     grid_sync(&ctl->bar_cnt, epoch, &ctl->err);
     stamp(ctl, 2); dbg(1);
     if (ld_relaxed(&ctl->fallback)) return false;
-    // ---- offsets: one thread per record created by this CTA's tiles -------------------------------------------------
+    // ---- offsets: one thread per record created by this CTA's tiles (all tiles' lists walked as one) ---------------------
     u64 npsum = 0;
-    for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
-      const u32 ncr = S.gcount[t];
-      for (u32 k0 = 0; k0 < ncr; k0 += kSegThreads) {             // (uniform trip count: the body uses warp collectives)
-        const u32 k = k0 + tid;
-        const bool act = k < ncr;
-        u32 slot = 0; u64 pairs = 0;
+    u32* sm_toff = smem;                     // [tiles of this CTA + 1] prefix of their list lengths (<= 64 tiles; else tile by tile)
+    const u32 my_tiles = blockIdx.x < ntile ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const bool flat = my_tiles <= 64u;
+    u32 total = 0;
+    if (flat) {
+      if (tid == 0) {
+        u32 acc = 0;
+        for (u32 q = 0; q < my_tiles; ++q) { sm_toff[q] = acc; acc += S.gcount[blockIdx.x + q * gridDim.x]; }
+        sm_toff[my_tiles] = acc;
+      }
+      __syncthreads();
+      total = sm_toff[my_tiles];
+    }
+    const u32 nrounds = flat ? (total + kSegThreads - 1) / kSegThreads : my_tiles;
+    for (u32 rd = 0; rd < nrounds; ++rd) {
+      // (flat: round rd handles items [rd * 512, +512) of the concatenated lists; else round rd = tile rd, lists <= 512 long)
+      u32 t = 0, k = 0; bool act = false;
+      if (flat) {
+        const u32 item = rd * kSegThreads + tid;
+        if (item < total) {
+          u32 q = 0;
+          while (sm_toff[q + 1] <= item) ++q;
+          t = blockIdx.x + q * gridDim.x; k = item - sm_toff[q]; act = true;
+        }
+      } else {
+        t = blockIdx.x + rd * gridDim.x; k = tid; act = k < S.gcount[t];
+      }
+      {
+        u32 slot = 0; u64 pairs = 0; u32 own = 0;
         Geo g{};                    // (inactive lanes: an empty group)
+        u32 cl[kLevels];            // own rows per level (the split of every level: own rows first, then the others')
+#pragma unroll
+        for (int q = 0; q < kLevels; ++q) cl[q] = 0;
         if (act) {
           slot = S.glist[(size_t)t * kGTile + k];
-          u32 cl[kLevels], cr[kLevels];
+          u32 cr[kLevels];
           if (glob && slot <= S.capmask) {
             const uint4 a0 = *reinterpret_cast<const uint4*>(rec2[slot].cl), a1 = *reinterpret_cast<const uint4*>(rec2[slot].cl + 4);
             const uint4 b0 = *reinterpret_cast<const uint4*>(rec2[slot].cr), b1 = *reinterpret_cast<const uint4*>(rec2[slot].cr + 4);
@@ -341,15 +359,18 @@ struct HeadsTail {
 #pragma unroll
             for (int q = 0; q < kLevels; ++q) cr[q] = 0;
           }
-          u32 below = 0;
 #pragma unroll
           for (int q = 0; q < kLevels; ++q) {
-            g.pl[q] = g.nl; g.nl += cl[q]; if (cl[q]) g.ml |= 1u << q;
-            pairs += (u64)(cl[q] + cr[q]) * below; below += cl[q] + cr[q];        // pairs of a row = ALL rows of the group below its level
+            g.ls[q] = g.tot; g.co[q] = cl[q];
+            pairs += (u64)(cl[q] + cr[q]) * g.tot;             // pairs of a row = ALL rows of the group below its level
+            g.tot += cl[q] + cr[q];
           }
-          g.tot = g.nl;
+          if (glob && slot <= S.capmask && g.tot < kOwnRows) {
+            // a small group is scored whole by one rank: every rank picks the same one from the key
+            own = ((u32)(mix64(0xD6E8FEB86659FD93ull ^ rec[slot].key) >> 32) % (u32)P.part_count == (u32)P.part_rank) ? 1u : 2u;
 #pragma unroll
-          for (int q = 0; q < kLevels; ++q) { g.pr[q] = g.tot; g.tot += cr[q]; if (cr[q]) g.mr |= 1u << q; }
+            for (int q = 0; q < kLevels; ++q) g.co[q] = own == 1u ? cl[q] + cr[q] : 0u;
+          }
         }
         u32 inc = g.tot;
 #pragma unroll
@@ -370,20 +391,20 @@ struct HeadsTail {
           const int src = __ffs(big) - 1; big &= big - 1;
           Geo h;
           h.base = __shfl_sync(0xFFFFFFFFu, g.base, src); h.tot = __shfl_sync(0xFFFFFFFFu, g.tot, src);
-          h.nl = __shfl_sync(0xFFFFFFFFu, g.nl, src); h.ml = __shfl_sync(0xFFFFFFFFu, g.ml, src); h.mr = __shfl_sync(0xFFFFFFFFu, g.mr, src);
 #pragma unroll
-          for (int q = 0; q < kLevels; ++q) { h.pl[q] = __shfl_sync(0xFFFFFFFFu, g.pl[q], src); h.pr[q] = __shfl_sync(0xFFFFFFFFu, g.pr[q], src); }
+          for (int q = 0; q < kLevels; ++q) { h.ls[q] = __shfl_sync(0xFFFFFFFFu, g.ls[q], src); h.co[q] = __shfl_sync(0xFFFFFFFFu, g.co[q], src); }
           const u32 gb0 = __shfl_sync(0xFFFFFFFFu, b0, src), gnb = __shfl_sync(0xFFFFFFFFu, nblk, src);
           for (u32 b = gb0 + 3u + ln; b < gb0 + gnb; b += 32) block_range(b, gb0, h);
         }
         if (act) {
           GRec* r = rec + slot;
           r->base = g.base;
-          *reinterpret_cast<uint4*>(r->cnt) = make_uint4(g.pl[0], g.pl[1], g.pl[2], g.pl[3]);
-          *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(g.pl[4], g.pl[5], g.pl[6], g.pl[7]);
-          if (glob && slot <= S.capmask) {
-            *reinterpret_cast<uint4*>(rec2[slot].cr) = make_uint4(g.pr[0], g.pr[1], g.pr[2], g.pr[3]);
-            *reinterpret_cast<uint4*>(rec2[slot].cr + 4) = make_uint4(g.pr[4], g.pr[5], g.pr[6], g.pr[7]);
+          *reinterpret_cast<uint4*>(r->cnt) = make_uint4(g.ls[0], g.ls[1], g.ls[2], g.ls[3]);
+          *reinterpret_cast<uint4*>(r->cnt + 4) = make_uint4(g.ls[4], g.ls[5], g.ls[6], g.ls[7]);
+          if (glob && slot <= S.capmask) {       // (start of the remote rows of every level; the split of the group)
+            *reinterpret_cast<uint4*>(rec2[slot].cr) = make_uint4(g.ls[0] + cl[0], g.ls[1] + cl[1], g.ls[2] + cl[2], g.ls[3] + cl[3]);
+            *reinterpret_cast<uint4*>(rec2[slot].cr + 4) = make_uint4(g.ls[4] + cl[4], g.ls[5] + cl[5], g.ls[6] + cl[6], g.ls[7] + cl[7]);
+            r->own = own;
           }
           if (!dyn) {
             r->npair = pairs;
@@ -416,13 +437,22 @@ struct HeadsTail {
       const u32 i = blockIdx.x * kGTile + tid;
       if (i < B) scatter_row(S, i, k_slot, k_meta, k_s, k_y, k_wp, k_wn);
     } else {
-      for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
-        const u32 i = t * kGTile + tid;
-        if (i < B) {
-          const size_t i4 = S.rm.i4(i);
-          scatter_row(S, i, S.rslot[i], S.rmeta[i], P.logits[i4], S.labels[i4], P.rw_pos ? P.rw_pos[i4] : 1.f,
-                      P.rw_neg ? P.rw_neg[i4] : 1.f);
+      // (four tiles per round: the loads of their rows and of the rows' records are all in flight together)
+      for (u32 t0 = blockIdx.x; t0 < ntile; t0 += 4 * gridDim.x) {
+        u32 ri[4], rs[4], rmt[4]; float fs[4], fy[4], fwp[4], fwn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const u32 t = t0 + q * gridDim.x, i = t * kGTile + tid;
+          ri[q] = (t < ntile && i < B) ? i : kEmpty;
+          if (ri[q] != kEmpty) {
+            const size_t i4 = S.rm.i4(i);
+            rs[q] = S.rslot[i]; rmt[q] = S.rmeta[i]; fs[q] = P.logits[i4]; fy[q] = S.labels[i4];
+            fwp[q] = P.rw_pos ? P.rw_pos[i4] : 1.f; fwn[q] = P.rw_neg ? P.rw_neg[i4] : 1.f;
+          }
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (ri[q] != kEmpty) scatter_row(S, ri[q], rs[q], rmt[q], fs[q], fy[q], fwp[q], fwn[q]);
       }
     }
     if (pp.on && spare < 4u) { __syncthreads(); partition(S, smem, blockIdx.x, gridDim.x); }
@@ -771,12 +801,31 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     st_done = !(cb < zb || (cb == zb && (cj < zj || (cj == zj && ce < ze))));
   } else if (own_list) {
     u32 msum = 0;
-    for (u32 v = threadIdx.x; v < nvb; v += kPairThreads) {
-      u32 jf;
-      const u32 nt = vblock_tiles(A.blk, v, jf);
-      s_jn[v] = nt ? (jf | (nt << 16)) : 0u;
-      s_pi[v] = nt ? nt * vcost(v, nt, A.cost_gen, A.cost_straddle, lv_cost) + A.cost_switch : 0u;
-      msum += nt;
+    // (one 16-byte load per I-block = both of its J ranges; four I-blocks per round, their loads in flight together)
+    for (u32 b0 = 0; b0 < A.nib; b0 += 4 * kPairThreads) {
+      uint4 rr[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u32 b = b0 + k * kPairThreads + threadIdx.x;
+        rr[k] = b < A.nib ? reinterpret_cast<const uint4*>(A.blk)[b] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const u32 b = b0 + k * kPairThreads + threadIdx.x;
+        if (b < A.nib) {
+          // (as vblock_tiles: R1 = (x, y), R2 = (z, w) trimmed so that no tile is listed twice)
+          u32 lo1 = 0, hi1 = 0, lo2 = 0, hi2 = 0;
+          if (rr[k].y > ~rr[k].x) { lo1 = ~rr[k].x >> 5; hi1 = (rr[k].y + 31) >> 5; }
+          if (rr[k].w > ~rr[k].z) { lo2 = ~rr[k].z >> 5; hi2 = (rr[k].w + 31) >> 5; }
+          if (hi1 > lo1) lo2 = max(lo2, hi1);
+          const u32 nt1 = hi1 > lo1 ? hi1 - lo1 : 0u, nt2 = hi2 > lo2 ? hi2 - lo2 : 0u;
+          s_jn[2 * b] = nt1 ? (lo1 | (nt1 << 16)) : 0u;
+          s_jn[2 * b + 1] = nt2 ? (lo2 | (nt2 << 16)) : 0u;
+          s_pi[2 * b] = nt1 ? nt1 * vcost(2 * b, nt1, A.cost_gen, A.cost_straddle, lv_cost) + A.cost_switch : 0u;
+          s_pi[2 * b + 1] = nt2 ? nt2 * vcost(2 * b + 1, nt2, A.cost_gen, A.cost_straddle, lv_cost) + A.cost_switch : 0u;
+          msum += nt1 + nt2;
+        }
+      }
     }
     __syncthreads();
     stamp(ctl, 11);

@@ -249,7 +249,8 @@ def reduce_peer_chunks(peer_out_ptrs: Sequence[int], rank: int, chunk: int, dev:
 
 def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int, has_w: bool, has_ok: bool,
                              label_func="step", factor=1.0, power=0.0, reduce_mean=True, part=(0, 1),
-                             peer_blocks: Optional[Sequence[int]] = None, out: Optional[torch.Tensor] = None):
+                             peer_blocks: Optional[Sequence[int]] = None, out: Optional[torch.Tensor] = None,
+                             persistent: bool = False):
     """rn_pairwise_fwd_bwd on `world` packed row blocks (packed_block_layout) as ONE all-gather leaves them (or, with
     `peer_blocks` = the device pointers of every rank's block in peer-mapped memory, as the call's first kernel
     gathers them into `gbuf` itself), with the
@@ -277,7 +278,7 @@ def pairwise_fwd_bwd_blocked(gbuf: torch.Tensor, world: int, b_loc: int, kk: int
         factor=float(factor), power=float(power), only_wrong=0, reduce_mean=int(bool(reduce_mean)),
         part_rank=int(part[0]), part_count=int(part[1]),
         loss=po, n_pair_f32=po + 4, n_pair=po + 8, dlogits=out.data_ptr(), row_pairs=None,
-        block_rows=b_loc, block_stride=lay["stride"], out_chunk=chunk)
+        block_rows=b_loc, block_stride=lay["stride"], out_chunk=chunk, scratch_persistent=1 if persistent else 0)
     if peer_blocks is not None:          # k_init gathers the ranks' blocks into gbuf over NVLink (no all-gather call)
         assert len(peer_blocks) == world
         for r in range(world):

@@ -159,6 +159,12 @@ def to_listwise_sample(group_ids, labels, logits, do_mask_logits=True, value_of_
 def listwise_loss_from_batch(group_ids, labels, logits, weights=None, do_reduce=True, pos_neg_th=0.5):
     """Fused to_listwise_sample + listwise_loss_via_softmax_cross_entropy_with_logits (LW:89-173) without the
     (V,B) tensors: returns (loss or per-list losses[:V], n_valid_list)."""
+    if not do_reduce:
+        # the registered gradient scales the saved d mean-loss / d logits by the upstream of output 0 only; per-list
+        # upstream gradients (output 1) would need the rows' list ranks from the op -- refused until that exists and a
+        # machine with TensorFlow has tested it (the torch drop-in handles this case through the dense mask)
+        raise NotImplementedError("do_reduce=False is not differentiable through the fused TF op; use to_listwise_sample + "
+                                  "listwise_loss_via_softmax_cross_entropy_with_logits(do_reduce=False)")
     keys, ok = _canon(group_ids, None)
     y = tf.reshape(tf.cast(labels, tf.float32), [-1])
     s = tf.reshape(tf.cast(logits, tf.float32), [-1])
