@@ -158,6 +158,95 @@ def _match_bpr(pairloss_func) -> Optional[tuple]:
     return None
 
 
+# --------------------------------------------------------------------------------------------------------
+# arbitrary callables that ARE one of the fused forms
+# --------------------------------------------------------------------------------------------------------
+# The reference's API takes Python callables (PW:229, 234-235) and its own test passes a wrapper around bpr_loss_func and
+# a lambda `float(y_i > y_j)` (TPW:38-39, 51-53).  A callable that depends only on its tensor arguments can be recognised
+# by what it computes: it is evaluated ONCE on a fixed grid of probe values (a 16 x 16 grid of label pairs: negative,
+# fractional, repeated and large values; random pair vectors for a loss function) and compared with the fused forms.  The
+# verdict is cached per callable object (one small device-to-host read the first time, nothing afterwards).  A callable
+# that matches on every probe point and still differs elsewhere would have to be built for the purpose;
+# RN_PROBE_CALLABLES=0 switches the recognition off (everything unknown then takes the materialised-pair path).
+_probe_cache: dict = {}
+_PROBE_LABELS = [-3.0, -1.0, -0.5, 0.0, 0.0, 0.25, 0.5, 1.0, 1.0, 1.1, 2.0, 3.0, 4.0, 7.25, 100.0, 1.0e4]
+
+
+def _probe_enabled() -> bool:
+    import os
+    return os.environ.get("RN_PROBE_CALLABLES", "1") != "0"
+
+
+def _classify_weight_func(f, kwargs: dict, device) -> Optional["FusedPairWeight"]:
+    """FusedPairWeight equivalent of a label-only ``label_pair_to_weight_func`` (no tensor kwargs), or None."""
+    if not _probe_enabled() or any(isinstance(v, torch.Tensor) for v in kwargs.values()):
+        return None
+    try:
+        key = ("w", id(f), tuple(sorted((k, repr(v)) for k, v in kwargs.items())))
+    except Exception:
+        return None
+    hit = _probe_cache.get(key)
+    if hit is not None and hit[0] is f:
+        return hit[1]
+    res = None
+    try:
+        t = torch.tensor(_PROBE_LABELS, dtype=torch.float32, device=device)
+        y, yt = t.reshape(-1, 1).expand(-1, t.numel()).contiguous(), t.reshape(1, -1).expand(t.numel(), -1).contiguous()
+        w = f(y, yt, **kwargs)
+        if isinstance(w, torch.Tensor) and w.shape == y.shape:
+            w = w.to(torch.float32)
+            step = (y > yt).to(torch.float32)
+            cands = (("step", step), ("diff", (y - yt) * step))
+            verdict = [bool(torch.equal(w, c)) or bool(torch.allclose(w, c, rtol=1e-6, atol=0.0)) for _, c in cands]
+            for (name, _), ok in zip(cands, verdict):
+                if ok:
+                    res = FusedPairWeight(name)
+                    break
+    except Exception:
+        res = None
+    if len(_probe_cache) > 256:
+        _probe_cache.clear()
+    _probe_cache[key] = (f, res)
+    return res
+
+
+def _classify_pairloss_func(f, device) -> Optional[tuple]:
+    """(factor, reduce_mean) if ``pairloss_func`` computes what bpr_loss_func(factor=1) computes (mean or sum), else None."""
+    if not _probe_enabled():
+        return None
+    key = ("l", id(f))
+    hit = _probe_cache.get(key)
+    if hit is not None and hit[0] is f:
+        return hit[1]
+    res = None
+    try:
+        g = torch.Generator(device="cpu").manual_seed(1234)
+        verdicts = {(1.0, True): True, (1.0, False): True}
+        for n in (1, 7, 33):
+            pos = (torch.randn(n, generator=g) * 3).to(device)
+            neg = (torch.randn(n, generator=g) * 3).to(device)
+            wts = torch.rand(n, generator=g).to(device) + 0.1
+            for wv in (None, wts):
+                out = f(pos, neg, wv)
+                if not isinstance(out, torch.Tensor) or out.numel() != 1:
+                    verdicts = {}
+                    break
+                for k in list(verdicts):
+                    ref = bpr_loss_func(pos, neg, wv, factor=k[0], reduce_mean=k[1])
+                    if not torch.allclose(out.reshape(()).to(torch.float32), ref, rtol=1e-6, atol=1e-7):
+                        verdicts[k] = False
+        for k in ((1.0, True), (1.0, False)):
+            if verdicts.get(k):
+                res = k
+                break
+    except Exception:
+        res = None
+    if len(_probe_cache) > 256:
+        _probe_cache.clear()
+    _probe_cache[key] = (f, res)
+    return res
+
+
 def _gather_kwargs(kwargs: dict, b: int, pos: torch.Tensor, neg: torch.Tensor) -> dict:
     out = {}
     for k, v in kwargs.items():
@@ -184,6 +273,11 @@ def pairwise_loss(outputs, labels, groups,
     b = outputs.numel()
     mask_t = None if mask is None else _as_cuda(mask).reshape(-1).to(torch.bool)
     keys, row_ok = ops.canon_keys(group_list, mask_t)
+    if label_pair_to_weight_func is not None and not isinstance(label_pair_to_weight_func, FusedPairWeight):
+        # a label-only callable that computes one of the fused forms (e.g. the reference's test lambda, TPW:51-53)
+        recognised = _classify_weight_func(label_pair_to_weight_func, kwargs, outputs.device)
+        if recognised is not None:
+            label_pair_to_weight_func = recognised
     fused_w = label_pair_to_weight_func if isinstance(label_pair_to_weight_func, FusedPairWeight) else None
     rw_pos = rw_neg = None
     label_func = "step"
@@ -195,6 +289,8 @@ def pairwise_loss(outputs, labels, groups,
             # W = [y_i > y_j], C = W > 0: identical to the default; keep the weight-free kernel
             fused_w = None
     bpr = _match_bpr(pairloss_func)
+    if bpr is None and callable(pairloss_func):
+        bpr = _classify_pairloss_func(pairloss_func, outputs.device)      # e.g. a wrapper around bpr_loss_func (TPW:38-39)
     power = float(click_occurance_power)
 
     if bpr is not None and (label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight)):

@@ -141,3 +141,54 @@ def test_cpu_tensors_raise():
     t = torch.zeros(4, 1)
     with pytest.raises(RuntimeError):
         pairwise_loss(t, t, t)
+
+
+def test_reference_test_callables_take_the_fused_path(monkeypatch):
+    """the reference's own test passes a wrapper around bpr_loss_func and a `float(y_i > y_j)` weight
+    function (TPW:38-39, 51-53).  Both are recognised by what they compute (probed once, cached) and must NOT go through
+    pair materialisation; a callable that is none of the fused forms still does."""
+    from rec_now_b200 import ops
+    from rec_now_b200.rec_block import pairwise_loss_from_batch as PW
+    calls = {"n": 0}
+    real = ops.pair_indices
+
+    def counting_pair_indices(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+
+    monkeypatch.setattr(ops, "pair_indices", counting_pair_indices)
+    g, logits, label = colt([1, 1, 2, 2, 2]), colt([0, 1, 2, 3, 4]), colt([1.1, 0, 0, 1, 1])
+
+    def pairwise_loss_func(outputs_pos, outputs_neg, weights):
+        return PW.bpr_loss_func(outputs_pos, outputs_neg, weights, 1.0)
+
+    def step_weights(label_matrix, label_matrix_transpose, **kwargs):
+        return (label_matrix > label_matrix_transpose).to(torch.float32)
+
+    def gain_weights(label_matrix, label_matrix_transpose):
+        return (label_matrix - label_matrix_transpose) * (label_matrix > label_matrix_transpose).to(torch.float32)
+
+    loss = PW.pairwise_loss(logits, label, g, pairwise_loss_func, click_occurance_power=-0.5,
+                            label_pair_to_weight_func=step_weights)
+    assert abs(loss.item() - 0.5415076) < 1e-5 and calls["n"] == 0
+    # label-gain weights, a larger batch: same value as the explicit FusedPairWeight
+    rng = np.random.default_rng(0)
+    b = 3000
+    gg = torch.tensor(rng.integers(0, 40, b).astype(np.float32), device="cuda")
+    s = torch.tensor(rng.standard_normal(b).astype(np.float32), device="cuda")
+    y = torch.tensor(rng.integers(0, 5, b).astype(np.float32), device="cuda")
+    a = PW.pairwise_loss(s, y, gg, pairwise_loss_func, label_pair_to_weight_func=gain_weights)
+    bb = PW.pairwise_loss(s, y, gg, label_pair_to_weight_func=PW.FusedPairWeight("diff"))
+    assert calls["n"] == 0 and abs(a.item() - bb.item()) <= 2e-6 * abs(bb.item())
+    # not one of the fused forms: squared label gain -> materialised pairs, still the right value
+    sq = lambda lm, lmt: ((lm - lmt) ** 2) * (lm > lmt).to(torch.float32)
+    c = PW.pairwise_loss(s, y, gg, label_pair_to_weight_func=sq)
+    assert calls["n"] == 1
+    from oracle import dense_ref as D
+    ref = D.pairwise_loss(s.cpu().numpy(), y.cpu().numpy(), gg.cpu().numpy(),
+                          label_pair_to_weight_func=lambda lm, lmt: ((lm - lmt) ** 2) * (lm > lmt).astype(np.float32))
+    assert abs(c.item() - float(ref)) <= 1e-4 * abs(float(ref))
+    # the recognition can be switched off
+    monkeypatch.setenv("RN_PROBE_CALLABLES", "0")
+    PW.pairwise_loss(logits, label, g, pairwise_loss_func, click_occurance_power=-0.5)
+    assert calls["n"] == 2
