@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define RN_VERSION 102 /* 0.1.2: host-buffer front end (rn_host_pairwise_*) */
+#define RN_VERSION 103 /* 0.1.3: pair_loss / margin (hinge), RN_LABEL_GAIN2, small-batch kernel, segment pooling */
 
 enum {
   RN_OK = 0,
@@ -59,7 +59,14 @@ enum {
  * Optional per-sample factors rw_pos (row/positive side) and rw_neg (column/negative side) multiply W;
  * whenever any weight is present the reference's rule C = (W > 0) applies (a non-positive or NaN factor
  * removes the pairs it touches).  Anything else goes through rn_pair_indices_* + the caller's own code. */
-enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1 };
+enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2 };
+/*   GAIN2: W = (2^y_i - 2^y_j)*[y_i > y_j]   (NDCG-style exponential gains, the usual RankNet / LambdaRank gain; the
+ *          sorted label column then holds 2^y.  Labels whose gains coincide in float32 although y_i > y_j keep their pair
+ *          with weight 0 -- integer labels never do.)
+ * pairloss_func menu (pairwise_loss_from_batch.py:229, 274; the reference ships bpr_loss_func only, :96-127):
+ *   LOGISTIC: l = softplus(-x), x = (s_i - s_j)*factor            (bpr_loss_func)
+ *   HINGE:    l = max(0, margin - x)                               (margin ranking loss; d l / d x = -[margin - x > 0]) */
+enum { RN_LOSS_LOGISTIC = 0, RN_LOSS_HINGE = 1 };
 
 typedef struct rn_pairwise_args {
   int64_t B;               /* rows in the batch */
@@ -129,6 +136,10 @@ typedef struct rn_pairwise_args {
    * factor off (the reference's `if alpha:` / `if gamma:`).  Not with only_wrong / rw_neg / blocked rows. */
   float focal_weight, focal_alpha, focal_gamma;
   int32_t focal_stop_weight_gradient;
+  /* Pair loss (RN_LOSS_*; 0 = the logistic bpr_loss_func) and the hinge margin (>= 0).  Everything else -- pair set,
+   * weights, counts, occurrence weights, 1/n -- is shared.  HINGE: not with deterministic. */
+  int32_t pair_loss;
+  float margin;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {

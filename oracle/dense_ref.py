@@ -100,6 +100,22 @@ def bpr_loss_func(outputs_pos, outputs_neg, weights=None, factor=1.0, reduce_mea
     return F32(loss)
 
 
+def hinge_loss_func(outputs_pos, outputs_neg, weights=None, margin=1.0, factor=1.0, reduce_mean=True):
+    """Margin ranking loss behind the reference's pairloss_func hook (PW:229, called as PW:274: (pos, neg, weights)):
+    max(0, margin - (pos - neg) * factor), weighted and reduced exactly as bpr_loss_func (PW:117-126).  The reference
+    ships only bpr_loss_func; this is SURVEY 8f N2's first "other pair loss"."""
+    logits = (np.asarray(outputs_pos, F32) - np.asarray(outputs_neg, F32)).astype(F32)
+    if factor != 1.0:
+        logits = (logits * F32(factor)).astype(F32)
+    losses = np.maximum(F32(margin) - logits, F32(0)).astype(F32)
+    if weights is not None:
+        losses = (losses * np.asarray(weights, F32)).astype(F32)
+    loss = np.sum(losses, dtype=F32)
+    if reduce_mean:
+        loss = F32(loss / (F32(losses.size) + F32(SMALL_POSITIVE_FLOAT)))
+    return F32(loss)
+
+
 def occurance_power_weight(group_id, power=0.0):
     """PW:130-151."""
     _, idx, count = unique_with_counts(group_id)

@@ -13,6 +13,7 @@ The fused weight menu mirrored here (and in include/recnow_b200.h):
     label_func "step":  C = y_i > y_j,              W = None      (PW:188-190, the default)
     label_func "diff":  W = (y_i - y_j) * [y_i > y_j] [* rw_pos_i] [* rw_neg_j],  C = W > 0   (PW:192-193)
     label_func "step" with row weights:  W = [y_i > y_j] [* rw_pos_i] [* rw_neg_j], C = W > 0
+    label_func "gain2": W = (2^y_i - 2^y_j) * [y_i > y_j] [* rw ...]   (exponential gains; float32 exp2 as the product)
 i.e. what a reference user writes as label_pair_to_weight_func(Y, Yt, sample_weight=w).
 """
 from __future__ import annotations
@@ -34,6 +35,9 @@ class PairSpec:
     label_func: str = "step"            # "step" | "diff"
     rw_pos: Optional[np.ndarray] = None  # per-sample weight applied on the positive (row) side
     rw_neg: Optional[np.ndarray] = None  # per-sample weight applied on the negative (column) side
+    # pairloss_func menu beyond bpr_loss_func (the reference only ships the hook, PW:229, 274):
+    pair_loss: str = "logistic"         # "logistic" = bpr_loss_func | "hinge" = max(0, margin - x), x as PW:117-119
+    margin: float = 1.0
 
 
 def canonical_keys(groups, inf_is_id: bool = False) -> tuple[np.ndarray, np.ndarray]:
@@ -97,7 +101,8 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         ok = ok & np.asarray(mask, bool).reshape(-1)                         # PW:154-172
     rwp = None if spec.rw_pos is None else np.asarray(spec.rw_pos, F32).reshape(-1)
     rwn = None if spec.rw_neg is None else np.asarray(spec.rw_neg, F32).reshape(-1)
-    has_w = spec.label_func == "diff" or rwp is not None or rwn is not None
+    has_w = spec.label_func in ("diff", "gain2") or rwp is not None or rwn is not None
+    g32 = np.exp2(y32).astype(F32) if spec.label_func == "gain2" else y32
     segs = _group_members(keys, ok)
 
     row_pairs = np.zeros(b, np.int64)
@@ -116,8 +121,8 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         if not has_w:
             cond, w = gt, None                                               # PW:188-190
         else:
-            if spec.label_func == "diff":
-                w = ((yi - yj).astype(F32) * gt.astype(F32)).astype(F32)
+            if spec.label_func in ("diff", "gain2"):
+                w = ((g32[mi][:, None] - g32[m][None, :]).astype(F32) * gt.astype(F32)).astype(F32)
             else:
                 w = gt.astype(F32)
             if rwp is not None:
@@ -165,8 +170,13 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
                 c = np.array([prim_count.get(k, 1) for k in prim[mi].tolist()], np.float64)
                 wt = wt * np.power(c, float(spec.power))[:, None]
             wt = np.where(cond, wt, 0.0)
-            loss += float((wt * _softplus_neg(x)).sum())
-            d = wt * _sigma_neg(x) * f
+            if spec.pair_loss == "hinge":
+                v = float(spec.margin) - x
+                loss += float((wt * np.maximum(v, 0.0)).sum())
+                d = wt * (v > 0) * f
+            else:
+                loss += float((wt * _softplus_neg(x)).sum())
+                d = wt * _sigma_neg(x) * f
             grad[mi] -= d.sum(axis=1)
             np.add.at(grad, m, d.sum(axis=0))
             gabs[mi] += np.abs(d).sum(axis=1)

@@ -12,11 +12,13 @@ enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8 };
 // General (masked) 32x32 tile for one positive row per lane, rotation steps [t0, t1) (multiples of 4; the whole tile is
 // [0, 32)).  Lane l meets negative l ^ t at step t, so disjoint step ranges score disjoint pair sets: a tile can be
 // split between warps at a granularity of 4 steps.
-template <int MODE, bool FULL>
+// HINGE: the pair loss is max(0, margin - x) with x = (s_i - s_j) * factor (c = factor, plain units) instead of the
+// logistic softplus(-x): its "sigma" is the step [margin - x > 0], no SFU operation at all.
+template <int MODE, bool FULL, bool HINGE = false>
 __device__ __forceinline__ void tile_general(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
                                              const u32 pjm, const float sjm, const float yjm, const float wnjm,
                                              const float c, const int t0, const int t1, float& li, float& gi, u32& cnt,
-                                             float& accj) {
+                                             float& accj, const float margin = 0.f) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
   float gi_t = 0.f, li_t = 0.f;
 #pragma unroll 2
@@ -27,12 +29,18 @@ __device__ __forceinline__ void tile_general(const float si, const float yi, con
       const float sj = __shfl_xor_sync(0xFFFFFFFFu, sjm, t);
       const float x = si - sj;                           // PW:117 (float32 subtract, as the reference)
       const float xs = x * c;                            // (x * factor) in log2 units
-      const float e = mufu_ex2(-fabsf(xs));              // exp(-|x|)
-      const float t1p = 1.0f + e;
-      const float L = mufu_lg2(t1p);                     // log1p(exp(-|x|)) / ln2
-      const float r = mufu_rcp(t1p);
-      const float lo2 = fmaxf(-xs, 0.f) + L;             // softplus(-x) / ln2        (PW:120-121, TF stable form)
-      float d = (xs >= 0.f ? e : 1.0f) * r;              // sigma(-x)
+      float lo2, d;
+      if (HINGE) {
+        const float v = fmaf(-x, c, margin);             // hinge: max(0, margin - x), d/dx = -[margin - x > 0] (as tile_hinge)
+        lo2 = fmaxf(v, 0.f); d = v > 0.f ? 1.0f : 0.f;
+      } else {
+        const float e = mufu_ex2(-fabsf(xs));            // exp(-|x|)
+        const float t1p = 1.0f + e;
+        const float L = mufu_lg2(t1p);                   // log1p(exp(-|x|)) / ln2
+        const float r = mufu_rcp(t1p);
+        lo2 = fmaxf(-xs, 0.f) + L;                       // softplus(-x) / ln2        (PW:120-121, TF stable form)
+        d = (xs >= 0.f ? e : 1.0f) * r;                  // sigma(-x)
+      }
       bool valid = true;
       if (!FULL) { const u32 pj = pjm ^ (u32)t; valid = (pj >= lo) && (pj < hi); }
       if (WRONG) valid = valid && (x < 0.f);             // PW:200-202  s_i < s_j
@@ -100,6 +108,36 @@ __device__ __forceinline__ void tile_fast(const float si0, const float si1, cons
   const float L0 = m0 + mufu_lg2(p0), L1 = m1 + mufu_lg2(p1);       // sum softplus(-x) / ln2   (PW:120-121)
   li0 += HASW ? wv0 * L0 : L0; li1 += HASW ? wv1 * L1 : L1;
   gi0 += g0; gi1 += g1;
+}
+
+// Fast 64x32 tile of the hinge loss max(0, margin - x): same contract as tile_fast (both rows of a lane pair with all
+// 32 negatives, pair weight constant over the tile, out-of-range negatives carry the sentinel score -3e38 so that x = +huge
+// and the pair is inactive).  No SFU operation: ~7 FP32 / compare operations per pair.
+template <bool PART = false>
+__device__ __forceinline__ void tile_hinge(const float si0, const float si1, const float wv0, const float wv1,
+                                           const float sjm, const float c, const float margin, float& li0, float& li1,
+                                           float& gi0, float& gi1, float& accj, const int ts = 0, const int te = 32) {
+  float l0 = 0.f, l1 = 0.f, g0 = 0.f, g1 = 0.f;
+#pragma unroll (PART ? 1 : 8)
+  for (int tb = (PART ? ts : 0); tb < (PART ? te : 32); tb += 4) {
+    float sj[4], back[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sj[k] = __shfl_xor_sync(0xFFFFFFFFu, sjm, tb + k);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // margin - (s_i - s_j) * c: the difference first, as the reference (PW:117) -- tied scores give exactly `margin`
+      const float v0 = fmaf(sj[k] - si0, c, margin), v1 = fmaf(sj[k] - si1, c, margin);
+      const bool a0 = v0 > 0.f, a1 = v1 > 0.f;
+      l0 += a0 ? v0 : 0.f; l1 += a1 ? v1 : 0.f;
+      g0 += a0 ? 1.0f : 0.f; g1 += a1 ? 1.0f : 0.f;
+      back[k] = (a0 ? wv0 : 0.f) + (a1 ? wv1 : 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) back[k] = __shfl_xor_sync(0xFFFFFFFFu, back[k], tb + k);
+    accj += (back[0] + back[1]) + (back[2] + back[3]);
+  }
+  li0 = fmaf(wv0, l0, li0); li1 = fmaf(wv1, l1, li1);
+  gi0 = fmaf(wv0, g0, gi0); gi1 = fmaf(wv1, g1, gi1);
 }
 
 // ---- product-form fast tile ------------------------------------------------------------------------------------

@@ -42,6 +42,9 @@ struct PairParams {
   float factor, power; int reduce_mean; int dyn_count; int debug;
   int det;               // deterministic mode: fixed-point gradient accumulators, ordered loss partials
   float focal_w, focal_alpha, focal_gamma; int focal_stop;      // fused focal term (rn_pairwise_args.focal_*); focal_w = 0: off
+  float margin;          // hinge pair loss (rn_pairwise_args.pair_loss = RN_LOSS_HINGE): max(0, margin - x); c_log2 is then the plain factor
+  double loss_unit;      // unit of the accumulated pair losses: ln 2 (logistic, log2 units) or 1 (hinge)
+  int gain2;             // label_func RN_LABEL_GAIN2: the sorted label column holds 2^y (W = 2^y_i - 2^y_j)
   int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
@@ -117,7 +120,7 @@ struct HeadsTail {
     aj[pos] = make_uint2(a, n);
     // (a NaN label pairs with nothing, but its row shares I-blocks with rows that do: under label-gain weights the tile
     // multiplies a zero row weight by (y_i - y_ref), and 0 * NaN would poison the block's sums)
-    ss[pos] = s; sy[pos] = (y != y) ? 0.f : y;
+    ss[pos] = s; sy[pos] = (y != y) ? 0.f : (P.gain2 ? exp2f(y) : y);
     if (P.rw_pos) swp[pos] = wp;
     if (P.rw_neg) swn[pos] = wn;
     gacc[pos] = 0.f; perm[pos] = i; sgrp[pos] = slot;
@@ -494,7 +497,7 @@ struct HeadsTail {
         if (P.rw_neg) wn = P.rw_neg[ro];
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[ro];
-        { const float yv = P.labels[ro]; sy[p] = (yv != yv) ? 0.f : yv; }     // (NaN labels pair with nothing; see scatter_row)
+        { const float yv = P.labels[ro]; sy[p] = (yv != yv) ? 0.f : (P.gain2 ? exp2f(yv) : yv); }     // (NaN labels pair with nothing; see scatter_row)
         if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
@@ -727,7 +730,8 @@ __device__ __noinline__ float2 focal_row(float z, float y, float alpha, float ga
 
 // DET: deterministic mode (fixed-point gradient accumulators, ordered loss partials) -- a separate instantiation, so that
 // the default kernel carries none of it through the pair loop.
-template <int MODE, bool DET = false>
+// HINGE: the pair loss is the hinge max(0, margin - x) (tile_hinge / tile_general<.., HINGE>) instead of the logistic loss.
+template <int MODE, bool DET = false, bool HINGE = false>
 __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   // Work = the (I-block x J-block) tiles of the staircase, laid out on a COST LINE: virtual block after virtual block
   // (the two J ranges of every I-block), J-block after J-block, each with the cost vcost() estimates for it (a fast tile
@@ -1005,6 +1009,10 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
           if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
           const float sje = jin ? sjm : -3.0e38f;
+          if (HINGE) {
+            if (part) tile_hinge<true>(si0, si1, wv0, wv1, sje, c, P.margin, li0, li1, gi0, gi1, accj, ts, te);
+            else      tile_hinge<false>(si0, si1, wv0, wv1, sje, c, P.margin, li0, li1, gi0, gi1, accj);
+          } else {
           // product form (one SFU operation per pair) when the scores of the tile lie within 2^+-kProdRange of a
           // reference score -- here the first negative of the overlap; otherwise exp(-|x|) per pair
           const float mref = __shfl_sync(0xFFFFFFFFu, sjm, smin - j0);
@@ -1020,7 +1028,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
             if (part) tile_fast<true, true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj, ts, te);
             else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
           }
-        } else if (any_in && DIFF && !RWN && !WRONG && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
+          }
+        } else if (!HINGE && any_in && DIFF && !RWN && !WRONG && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
                    runs_tile(in0, in1, lo0, lo1, hi0, hi1, si0, si1, yi0, yi1, wp0, wp1, pjm, sjm, yjm, jin, smin, j0, c, ts, te,
                              li0, li1, gi0, gi1, accj)) {
           // (scored as up to three product-form passes, one per label level of the negatives)
@@ -1031,7 +1040,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           const bool any1 = __any_sync(0xFFFFFFFFu, in1);
           // product form of the general tile (two SFU operations per pair) under the same range test as tile_prod
           bool gprod = false; float Fg = 0.f, Eg0 = 0.f, Eg1 = 0.f;
-          if (!WRONG && use_prod && !(P.debug & 128)) {                  // (debug bit 128: general tiles with exp per pair)
+          if (!HINGE && !WRONG && use_prod && !(P.debug & 128)) {                  // (debug bit 128: general tiles with exp per pair)
             const float mref = __shfl_sync(0xFFFFFFFFu, sjm, smin - j0);
             const float aj = (sjm - mref) * c, a0 = (si0 - mref) * c, a1 = (si1 - mref) * c;
             gprod = __all_sync(0xFFFFFFFFu, (!jin || fabsf(aj) <= kProdRange) && (!in0 || fabsf(a0) <= kProdRange) &&
@@ -1049,12 +1058,12 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
             }
           } else {
           if (any0) {
-            if (full0) tile_general<MODE, true>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
-            else       tile_general<MODE, false>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj);
+            if (full0) tile_general<MODE, true, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin);
+            else       tile_general<MODE, false, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin);
           }
           if (any1) {
-            if (full1) tile_general<MODE, true>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
-            else       tile_general<MODE, false>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj);
+            if (full1) tile_general<MODE, true, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin);
+            else       tile_general<MODE, false, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin);
           }
           }
         }
@@ -1159,7 +1168,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       double lsum_all = *reinterpret_cast<volatile double*>(&ctl->loss_sum);
       if (DET) { lsum_all = 0.0; for (u32 c = 0; c < gridDim.x; ++c) lsum_all += A.lpart[c]; }
-      const double tot = lsum_all * 0.6931471805599453;
+      const double tot = lsum_all * P.loss_unit;
       float lossv = (float)(tot / (double)denom);
       if (P.focal_w != 0.f) lossv += P.focal_w * (float)(*reinterpret_cast<volatile double*>(&ctl->acc_d[3]) / (double)B);
       *P.loss = lossv;
@@ -1273,7 +1282,7 @@ __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& 
   // behind the last barrier: the scalars (CTA 0) and, now that nobody reads the group records any more, a clean arena
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->ts[23] = globaltimer();
-    const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * 0.6931471805599453;
+    const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * P.loss_unit;
     const float lossv = (float)(tot / (double)denom);
     *P.loss = lossv;
     *P.n_pair_f32 = (float)n;                  // PW:276
@@ -1334,13 +1343,13 @@ static int pair_blocks_per_sm(const void* func, int dev) {
   return bps;
 }
 
-template <int MODE, bool DET = false>
+template <int MODE, bool DET = false, bool HINGE = false>
 static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_t st) {
   // (the opt-in to large dynamic shared memory is a per-device function attribute)
   static size_t smem_set[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  const void* fn = (const void*)k_pair<MODE, DET>;
+  const void* fn = (const void*)k_pair<MODE, DET, HINGE>;
   const int bps = pair_blocks_per_sm(fn, dev);
   if (bps < 1) return cudaErrorUnknown;
   PairParams p = P; KpArgs a = A;
@@ -1357,8 +1366,16 @@ static cudaError_t launch_pair(const PairParams& P, const KpArgs& A, cudaStream_
 }
 
 constexpr int M_DET = 16;          // (dispatch only: deterministic instantiation of a non-dynamic mode)
+constexpr int M_HINGE = 32;        // (dispatch only: hinge pair loss)
 static const void* pair_func(int mode) {
   switch (mode) {
+#define RN_CASE(m) case M_HINGE | (m): return (const void*)k_pair<m, false, true>;
+    RN_CASE(0) RN_CASE(M_WRONG)
+    RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF) RN_CASE(M_HASW | M_DIFF | M_WRONG)
+    RN_CASE(M_HASW | M_RWN) RN_CASE(M_HASW | M_RWN | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF | M_RWN) RN_CASE(M_HASW | M_DIFF | M_RWN | M_WRONG)
+#undef RN_CASE
     case M_DET: return (const void*)k_pair<0, true>;
     case M_DET | M_HASW: return (const void*)k_pair<M_HASW, true>;
     case M_DET | M_HASW | M_DIFF: return (const void*)k_pair<M_HASW | M_DIFF, true>;
@@ -1375,6 +1392,13 @@ static const void* pair_func(int mode) {
 
 static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A, cudaStream_t st) {
   switch (mode) {
+#define RN_CASE(m) case M_HINGE | (m): return launch_pair<m, false, true>(P, A, st);
+    RN_CASE(0) RN_CASE(M_WRONG)
+    RN_CASE(M_HASW) RN_CASE(M_HASW | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF) RN_CASE(M_HASW | M_DIFF | M_WRONG)
+    RN_CASE(M_HASW | M_RWN) RN_CASE(M_HASW | M_RWN | M_WRONG)
+    RN_CASE(M_HASW | M_DIFF | M_RWN) RN_CASE(M_HASW | M_DIFF | M_RWN | M_WRONG)
+#undef RN_CASE
     case M_DET: return launch_pair<0, true>(P, A, st);
     case M_DET | M_HASW: return launch_pair<M_HASW, true>(P, A, st);
     case M_DET | M_HASW | M_DIFF: return launch_pair<M_HASW | M_DIFF, true>(P, A, st);
@@ -1459,7 +1483,9 @@ extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
 static int validate_pairwise(const rn_pairwise_args* a, bool split = false) {
   if (!a || a->B <= 0 || a->B > (1ll << 28) || a->K <= 0 || a->K > 8) return RN_ERR_ARG;
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
-  if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF) return RN_ERR_UNSUPPORTED;
+  if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF && a->label_func != RN_LABEL_GAIN2) return RN_ERR_UNSUPPORTED;
+  if (a->pair_loss != RN_LOSS_LOGISTIC && a->pair_loss != RN_LOSS_HINGE) return RN_ERR_UNSUPPORTED;
+  if (a->pair_loss == RN_LOSS_HINGE && !(a->margin >= 0.f)) return RN_ERR_ARG;
   if (a->part_count < 1 || a->part_rank < 0 || a->part_rank >= a->part_count) return RN_ERR_ARG;
   if (a->scratch_rows && a->scratch_rows < a->B) return RN_ERR_ARG;
   if (a->block_rows) {
@@ -1504,6 +1530,8 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
     return RN_ERR_ARG;                                  // (focal_loss.py:43-46)
   const bool det = a->deterministic != 0;
   if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
+  const bool hinge = a->pair_loss == RN_LOSS_HINGE;
+  if (det && hinge) return RN_ERR_UNSUPPORTED;
   const bool fast = counting_eligible(a) && !det;       // (the counting path places groups and rows in arrival order)
   PairParams P{};
   P.det = det ? 1 : 0;
@@ -1512,7 +1540,9 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   P.B = (u32)a->B; P.K = a->K; P.gbits = L.gbits;
   P.logits = a->logits; P.labels = a->labels; P.rw_pos = a->rw_pos; P.rw_neg = a->rw_neg;
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;
-  P.c_log2 = a->factor * 1.4426950408889634f;
+  P.c_log2 = hinge ? a->factor : a->factor * 1.4426950408889634f;
+  P.margin = a->margin; P.loss_unit = hinge ? 1.0 : 0.6931471805599453;
+  P.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : 0;
   static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
   P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;
@@ -1569,11 +1599,13 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
     A.xsum = at<u32>(base, L.misc);
   }
   int mode = 0;
-  if (a->label_func == RN_LABEL_DIFF || a->rw_pos || a->rw_neg) mode |= M_HASW;
-  if (a->label_func == RN_LABEL_DIFF) mode |= M_DIFF;
+  const bool diff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
+  if (diff || a->rw_pos || a->rw_neg) mode |= M_HASW;
+  if (diff) mode |= M_DIFF;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
   if (det) mode |= M_DET;
+  if (hinge) mode |= M_HINGE;
   if (fast) {
     // the pair kernel's partition is worked out by spare CTAs of k_seg beside the scatter phase (HeadsTail::partition)
     static const int pre_on = tune_int("RN_PAIR_PREPART", 1);

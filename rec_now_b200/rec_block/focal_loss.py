@@ -65,7 +65,7 @@ def pairwise_loss_with_focal(outputs, labels, groups, focal_weight=1.0, alpha=0.
     if gamma and gamma < 0:
         raise ValueError("Value of gamma should be greater than or equal to zero.")
     bpr = _match_bpr(pairloss_func)
-    if bpr is None:
+    if bpr is None or bpr[2] is not None:
         raise NotImplementedError("the fused joint loss needs bpr_loss_func (or a functools.partial of it)")
     outputs, labels = _as_cuda(outputs), _as_cuda(labels)
     gl = [_as_cuda(g) for g in groups] if isinstance(groups, list) else [_as_cuda(groups)]

@@ -83,6 +83,23 @@ def bpr_loss_func(outputs_pos, outputs_neg, weights=None, factor=1.0, reduce_mea
     return loss
 
 
+def hinge_loss_func(outputs_pos, outputs_neg, weights=None, margin=1.0, factor=1.0, reduce_mean=True):
+    """Margin ranking loss for the ``pairloss_func`` hook (PW:229, called as PW:274): max(0, margin - (pos - neg) *
+    factor), weighted and reduced exactly as bpr_loss_func (PW:122-126).  Not in the reference (which ships only
+    bpr_loss_func); ``pairwise_loss(..., pairloss_func=hinge_loss_func)`` or a keyword partial of it takes the fused
+    kernel."""
+    logits = outputs_pos - outputs_neg
+    if factor != 1.0:
+        logits = logits * factor
+    losses = torch.clamp(margin - logits, min=0)
+    if weights is not None:
+        losses = losses * weights
+    loss = torch.sum(losses)
+    if reduce_mean:
+        loss = loss / (float(losses.numel()) + SMALL_POSIVITE_FLOAT)
+    return loss
+
+
 def occurance_power_weight(group_id, power=0.0):
     """PW:130-151: count(group_id == group_id[i]) ** power, float32."""
     g = _as_cuda(group_id)
@@ -99,19 +116,24 @@ def occurance_power_weight(group_id, power=0.0):
 class FusedPairWeight:
     """A ``label_pair_to_weight_func`` the fused kernel understands.
 
-    ``W[i,j] = phi(y_i, y_j) * kwargs[pos_kw][i] * kwargs[neg_kw][j]`` with ``phi`` = ``[y_i > y_j]`` ("step")
-    or ``(y_i - y_j) * [y_i > y_j]`` ("diff").  It is also a plain callable with the reference's contract
+    ``W[i,j] = phi(y_i, y_j) * kwargs[pos_kw][i] * kwargs[neg_kw][j]`` with ``phi`` = ``[y_i > y_j]`` ("step"),
+    ``(y_i - y_j) * [y_i > y_j]`` ("diff") or ``(2^y_i - 2^y_j) * [y_i > y_j]`` ("gain2": NDCG-style exponential gains).  It is also a plain callable with the reference's contract
     (label_matrix, label_matrix_transpose, **kwargs) -> weights, so the same object works with the reference.
     """
 
     def __init__(self, label_func: str = "step", pos_kw: Optional[str] = None, neg_kw: Optional[str] = None):
-        if label_func not in ("step", "diff"):
-            raise ValueError("label_func must be 'step' or 'diff'")
+        if label_func not in ("step", "diff", "gain2"):
+            raise ValueError("label_func must be 'step', 'diff' or 'gain2'")
         self.label_func, self.pos_kw, self.neg_kw = label_func, pos_kw, neg_kw
 
     def __call__(self, label_matrix, label_matrix_transpose, **kwargs):
         gt = (label_matrix > label_matrix_transpose).to(torch.float32)
-        w = (label_matrix - label_matrix_transpose) * gt if self.label_func == "diff" else gt
+        if self.label_func == "diff":
+            w = (label_matrix - label_matrix_transpose) * gt
+        elif self.label_func == "gain2":
+            w = (torch.exp2(label_matrix) - torch.exp2(label_matrix_transpose)) * gt
+        else:
+            w = gt
         if self.pos_kw is not None:
             w = w * kwargs[self.pos_kw].reshape(-1, 1)
         if self.neg_kw is not None:
@@ -126,10 +148,11 @@ label_gain_times_sample_weight = FusedPairWeight("diff", pos_kw="sample_weight")
 class _FusedPairwiseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor, reduce_mean,
-                only_wrong, power):
+                only_wrong, power, hinge_margin=None):
         out = ops.pairwise_fwd_bwd(outputs, labels, keys, row_ok=row_ok, rw_pos=rw_pos, rw_neg=rw_neg,
                                    label_func=label_func, factor=factor, power=power, only_wrong=only_wrong,
-                                   reduce_mean=reduce_mean)
+                                   reduce_mean=reduce_mean, pair_loss="logistic" if hinge_margin is None else "hinge",
+                                   margin=1.0 if hinge_margin is None else hinge_margin)
         ctx.save_for_backward(out["dlogits"])
         ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
         n_pair = out["n_pair_f32"]
@@ -144,17 +167,23 @@ class _FusedPairwiseLoss(torch.autograd.Function):
             g = g.reshape(ctx.out_shape)
         if g.dtype != ctx.out_dtype:
             g = g.to(ctx.out_dtype)
-        return (g,) + (None,) * 10
+        return (g,) + (None,) * 11
 
 
 def _match_bpr(pairloss_func) -> Optional[tuple]:
-    """(factor, reduce_mean) if pairloss_func is bpr_loss_func or a keyword-only partial of it."""
+    """(factor, reduce_mean, hinge margin or None) if pairloss_func is bpr_loss_func / hinge_loss_func or a keyword-only
+    partial of one of them."""
     if pairloss_func is bpr_loss_func:
-        return 1.0, True
-    if isinstance(pairloss_func, functools.partial) and pairloss_func.func is bpr_loss_func and not pairloss_func.args:
+        return 1.0, True, None
+    if pairloss_func is hinge_loss_func:
+        return 1.0, True, 1.0
+    if isinstance(pairloss_func, functools.partial) and not pairloss_func.args:
         kw = dict(pairloss_func.keywords)
-        if set(kw) <= {"factor", "reduce_mean"}:
-            return float(kw.get("factor", 1.0)), bool(kw.get("reduce_mean", True))
+        if pairloss_func.func is bpr_loss_func and set(kw) <= {"factor", "reduce_mean"}:
+            return float(kw.get("factor", 1.0)), bool(kw.get("reduce_mean", True)), None
+        if pairloss_func.func is hinge_loss_func and set(kw) <= {"factor", "reduce_mean", "margin"} and \
+                float(kw.get("margin", 1.0)) >= 0.0:
+            return float(kw.get("factor", 1.0)), bool(kw.get("reduce_mean", True)), float(kw.get("margin", 1.0))
     return None
 
 
@@ -196,8 +225,9 @@ def _classify_weight_func(f, kwargs: dict, device) -> Optional["FusedPairWeight"
         if isinstance(w, torch.Tensor) and w.shape == y.shape:
             w = w.to(torch.float32)
             step = (y > yt).to(torch.float32)
-            cands = (("step", step), ("diff", (y - yt) * step))
-            verdict = [bool(torch.equal(w, c)) or bool(torch.allclose(w, c, rtol=1e-6, atol=0.0)) for _, c in cands]
+            cands = (("step", step), ("diff", (y - yt) * step), ("gain2", (torch.exp2(y) - torch.exp2(yt)) * step))
+            # (equal_nan: 2^1e4 overflows, inf - inf on the grid's diagonal is NaN in the callable and in the candidate alike)
+            verdict = [bool(torch.equal(w, c)) or bool(torch.allclose(w, c, rtol=1e-6, atol=0.0, equal_nan=True)) for _, c in cands]
             for (name, _), ok in zip(cands, verdict):
                 if ok:
                     res = FusedPairWeight(name)
@@ -211,7 +241,8 @@ def _classify_weight_func(f, kwargs: dict, device) -> Optional["FusedPairWeight"
 
 
 def _classify_pairloss_func(f, device) -> Optional[tuple]:
-    """(factor, reduce_mean) if ``pairloss_func`` computes what bpr_loss_func(factor=1) computes (mean or sum), else None."""
+    """(factor, reduce_mean, hinge margin or None) if ``pairloss_func`` computes what bpr_loss_func(factor=1) or
+    hinge_loss_func(margin=1, factor=1) computes (mean or sum), else None."""
     if not _probe_enabled():
         return None
     key = ("l", id(f))
@@ -221,7 +252,7 @@ def _classify_pairloss_func(f, device) -> Optional[tuple]:
     res = None
     try:
         g = torch.Generator(device="cpu").manual_seed(1234)
-        verdicts = {(1.0, True): True, (1.0, False): True}
+        verdicts = {(1.0, True, None): True, (1.0, False, None): True, (1.0, True, 1.0): True, (1.0, False, 1.0): True}
         for n in (1, 7, 33):
             pos = (torch.randn(n, generator=g) * 3).to(device)
             neg = (torch.randn(n, generator=g) * 3).to(device)
@@ -232,10 +263,11 @@ def _classify_pairloss_func(f, device) -> Optional[tuple]:
                     verdicts = {}
                     break
                 for k in list(verdicts):
-                    ref = bpr_loss_func(pos, neg, wv, factor=k[0], reduce_mean=k[1])
+                    ref = bpr_loss_func(pos, neg, wv, factor=k[0], reduce_mean=k[1]) if k[2] is None else \
+                        hinge_loss_func(pos, neg, wv, margin=k[2], factor=k[0], reduce_mean=k[1])
                     if not torch.allclose(out.reshape(()).to(torch.float32), ref, rtol=1e-6, atol=1e-7):
                         verdicts[k] = False
-        for k in ((1.0, True), (1.0, False)):
+        for k in ((1.0, True, None), (1.0, False, None), (1.0, True, 1.0), (1.0, False, 1.0)):
             if verdicts.get(k):
                 res = k
                 break
@@ -294,9 +326,9 @@ def pairwise_loss(outputs, labels, groups,
     power = float(click_occurance_power)
 
     if bpr is not None and (label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight)):
-        factor, reduce_mean = bpr
+        factor, reduce_mean, hinge_margin = bpr
         loss, n_pair = _FusedPairwiseLoss.apply(outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor,
-                                                reduce_mean, bool(only_use_wrong_order_pair), power)
+                                                reduce_mean, bool(only_use_wrong_order_pair), power, hinge_margin)
         return (loss, n_pair) if return_num_pair else loss
 
     # ---- general path: materialised pairs + the caller's callables ------------------------------------

@@ -99,3 +99,39 @@ def test_listwise_inf_ids_form_one_list():
     assert d["n_valid"] == r["n_valid"] == 2                 # {0, 2} and the three +inf rows
     assert abs(float(d["loss"]) - r["loss"]) < 1e-6
     assert np.abs(d["grad"] - r["grad"]).max() < 1e-6
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(0, 10 ** 6), st.integers(2, 100), st.integers(1, 8), st.sampled_from([0.0, 0.5, 1.0]),
+       st.sampled_from(["step", "gain2"]), st.sampled_from([0.0, -0.5]))
+def test_hinge_and_gain2_dense_vs_segmented(seed, b, ng, margin, label_func, power):
+    """the hinge pair loss behind the pairloss_func hook (PW:229, 274) and exponential label gains behind
+    label_pair_to_weight_func (PW:175-194) -- the dense op-for-op pipeline with those callables plugged in against the
+    segmented float64 form the GPU tests use."""
+    import functools
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    s = (rng.standard_normal(b) * 2).astype(np.float32)
+    y = rng.integers(0, 4, b).astype(np.float32)
+    spec = S.PairSpec(factor=1.3, power=power, label_func=label_func, pair_loss="hinge", margin=margin)
+    r = S.pairwise(s, y, g, spec)
+    wf = None if label_func == "step" else (lambda a, c: ((np.exp2(a) - np.exp2(c)) * (a > c)).astype(np.float32))
+    loss, n = D.pairwise_loss(s, y, g, pairloss_func=functools.partial(D.hinge_loss_func, margin=margin, factor=1.3),
+                              return_num_pair=True, click_occurance_power=power, label_pair_to_weight_func=wf)
+    assert int(n) == r["n_pair"]
+    assert abs(float(loss) - r["loss"]) <= 3e-6 * max(1.0, abs(r["loss"]))
+    # gradient of the float64 form by central differences on the loss (away from the kinks)
+    if r["n_pair"] and b <= 40:
+        eps = 1e-3
+        for i in rng.choice(b, size=min(b, 4), replace=False):
+            sp, sm = s.astype(np.float64).copy(), s.astype(np.float64).copy()
+            sp[i] += eps; sm[i] -= eps
+            # (float32 inputs are part of the contract: skip rows whose +-eps move crosses a hinge kink)
+            lp = S.pairwise(sp.astype(np.float32), y, g, spec)["loss"]
+            lm = S.pairwise(sm.astype(np.float32), y, g, spec)["loss"]
+            fd = (lp - lm) / (float(np.float32(sp[i]) - np.float32(sm[i])))
+            if abs(fd - r["grad"][i]) > 0.05 * max(1.0, abs(r["grad"][i])):
+                # a kink inside [s - eps, s + eps]: the one-sided slopes must bracket the analytic value
+                l0 = r["loss"]
+                f1 = (lp - l0) / float(np.float32(sp[i]) - s[i]); f2 = (l0 - lm) / float(s[i] - np.float32(sm[i]))
+                assert min(f1, f2) - 0.05 <= r["grad"][i] <= max(f1, f2) + 0.05

@@ -45,4 +45,5 @@ def run_pairwise(s, y, groups, spec=S.PairSpec(), mask=None, part=(0, 1), want_r
         rw_pos=None if spec.rw_pos is None else dev(spec.rw_pos),
         rw_neg=None if spec.rw_neg is None else dev(spec.rw_neg),
         label_func=spec.label_func, factor=spec.factor, power=spec.power, only_wrong=spec.only_wrong,
-        reduce_mean=spec.reduce_mean, part=part, want_row_pairs=want_row_pairs)
+        reduce_mean=spec.reduce_mean, part=part, want_row_pairs=want_row_pairs,
+        pair_loss=spec.pair_loss, margin=spec.margin)
