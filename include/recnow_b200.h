@@ -14,6 +14,7 @@
  *                                                                         rn_listwise_dense (compat layout)
  *   listwise_loss_from_batch.py:151-173  listwise_loss_via_softmax_cross_entropy_with_logits
  *                                                                      -> rn_listwise_fwd_bwd
+ *   embedding_util.py:239-324            embedding_using_sparse_batch_segment_ids -> rn_segment_pool_fwd / _bwd
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory,
@@ -273,6 +274,31 @@ typedef struct rn_gauc_args {
 } rn_gauc_args;
 size_t rn_gauc_scratch_bytes(int64_t B, int32_t K);
 int rn_gauc(const rn_gauc_args* args, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- segment pooling of slot embeddings (the step that feeds the model whose logits the losses score) ----------
+ * Replaces rec_block/embedding_util.py:239-324 (embedding_using_sparse_batch_segment_ids; helper
+ * sparse_batch_segment_ids_of_targets :127-198) for an embedding_func that is a table lookup:
+ *   out[b][t][:] = sum over columns c with slots[b][c] == target_slots[t] of  weights[b][c] * table[ids[b][c]][:]
+ * (method 'sum' = unsorted_segment_sum; mean != 0: 'mean' = unsorted_segment_mean, the sum divided by the number of such
+ * columns, empty segments 0), accumulated in column order with the product rounded before the add, i.e. bit-identical
+ * to TF's CPU kernels.  One launch, nothing materialised.  With an arbitrary embedding_func the caller passes
+ * table = embedding_func(unique ids) and ids = the positions' indices into it (what tf.unique returns, :306-311).
+ * An id outside [0, V) contributes nothing and sets bit 3 of *err_flag (a device word, NULL = do not report). */
+typedef struct rn_pool_args {
+  int64_t B, C;                 /* rows and columns of slots / ids / weights */
+  int32_t T, D;                 /* target slots, embedding width */
+  int32_t mean, reserved0;
+  const int32_t* slots;         /* [B][C] */
+  const int64_t* ids;           /* [B][C] row of `table` */
+  const float* weights;         /* NULL or [B][C] */
+  const int32_t* target_slots;  /* [T] (device), distinct */
+  const float* table;           /* [V][D] */
+  int64_t V;
+} rn_pool_args;
+int rn_segment_pool_fwd(const rn_pool_args* args, float* out /* [B][T][D] */, uint32_t* err_flag, void* stream);
+/* Gradients of a scalar through out: d_table[V][D] += (accumulated with atomics: zero it first; NULL = skip) and
+ * d_weights[B][C] += <table[id], d_out[b][t]> (NULL = skip; needs weights). */
+int rn_segment_pool_bwd(const rn_pool_args* args, const float* d_out, float* d_table, float* d_weights, void* stream);
 
 /* ---- listwise --------------------------------------------------------------------------------------- */
 size_t rn_listwise_scratch_bytes(int64_t B);

@@ -30,6 +30,7 @@ EXPORTS = [
     "rn_debug_graph_launches", "rn_debug_arena_offset", "rn_pack_row_block", "rn_reduce_peer_chunks",
     "rn_global_buffer_bytes", "rn_global_gather_bytes", "rn_global_pairwise_fwd_bwd",
     "rn_host_pairwise_create", "rn_host_pairwise_submit", "rn_host_pairwise_wait", "rn_host_pairwise_destroy",
+    "rn_segment_pool_fwd", "rn_segment_pool_bwd",
 ]
 
 
@@ -69,6 +70,12 @@ class GaucArgs(C.Structure):
                 ("keys", C.c_void_p), ("scores", C.c_void_p), ("labels", C.c_void_p), ("row_ok", C.c_void_p),
                 ("gauc", C.c_void_p), ("auc_mean", C.c_void_p), ("n_valid_groups", C.c_void_p),
                 ("n_pair", C.c_void_p), ("concordant2", C.c_void_p)]
+
+
+class PoolArgs(C.Structure):
+    _fields_ = [("B", C.c_int64), ("C", C.c_int64), ("T", C.c_int32), ("D", C.c_int32), ("mean", C.c_int32),
+                ("reserved0", C.c_int32), ("slots", C.c_void_p), ("ids", C.c_void_p), ("weights", C.c_void_p),
+                ("target_slots", C.c_void_p), ("table", C.c_void_p), ("V", C.c_int64)]
 
 
 class ListwiseArgs(C.Structure):
@@ -138,6 +145,8 @@ def lib() -> C.CDLL:
     L.rn_host_pairwise_submit.argtypes = [vp, C.POINTER(PairwiseArgs), C.POINTER(i32)]
     L.rn_host_pairwise_wait.argtypes = [vp, i32]
     L.rn_host_pairwise_destroy.argtypes = [vp]
+    L.rn_segment_pool_fwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp]
+    L.rn_segment_pool_bwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp, vp]
     L.rn_debug_arena_offset.restype = i64
     L.rn_debug_arena_offset.argtypes = [i64, i32, i32]
     L.rn_debug_graph_launches.restype = i64

@@ -400,6 +400,9 @@ cudaEvent_t* timed_events();
 struct DynSplit { u32* xcnt_out; const u32* xcnt_peer[8]; int world; };
 int pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, void* stream, const DynSplit* split, int stage);
 
+// Small batches (small.cu): the whole call as one launch of one CTA; true if it took the call (*rc = its status).
+bool small_pairwise(const rn_pairwise_args* a, void* scratch, cudaStream_t st, int mode, bool hinge, int* rc);
+
 inline int check_align(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ? RN_ERR_ALIGN : RN_OK; }
 
 }  // namespace rn

@@ -242,4 +242,23 @@ __device__ __forceinline__ void tile_general_prod(const float Ei, const float yi
   li += li_t; gi += gi_t;
 }
 
+// One row of focal_crossentropy_loss (rec_block/focal_loss.py:12-66 of the reference): value and d / d logit.
+//   ce = sigmoid_cross_entropy_with_logits(y, z) = max(z, 0) - z y + log1p(exp(-|z|))                  (focal_loss.py:48)
+//   alpha factor y alpha + (1 - y)(1 - alpha)                                                          (:50-53)
+//   modulating factor (1 - (y p + (1 - y)(1 - p)))^gamma, p = sigmoid(z); optionally without gradient  (:55-62)
+// (not inlined: it runs once per row outside the pair loop, and the pair kernel has no registers to spare)
+static __device__ __noinline__ float2 focal_row(float z, float y, float alpha, float gamma, int stop) {
+  const float e = expf(-fabsf(z));
+  const float ce = fmaxf(z, 0.f) - z * y + log1pf(e);
+  const float p = z >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);
+  const float af = alpha != 0.f ? y * alpha + (1.0f - y) * (1.0f - alpha) : 1.0f;
+  float mod = 1.0f, dmod = 0.f;
+  if (gamma != 0.f) {
+    const float om = 1.0f - (y * p + (1.0f - y) * (1.0f - p));
+    mod = powf(om, gamma);
+    if (!stop) dmod = -gamma * powf(om, gamma - 1.0f) * (2.0f * y - 1.0f) * p * (1.0f - p);
+  }
+  return make_float2(af * mod * ce, af * (mod * (p - y) + ce * dmod));
+}
+
 }  // namespace rn

@@ -709,25 +709,6 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
 __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
                                              u32& epoch2, u64* red_u, double* red_d);
 
-// One row of focal_crossentropy_loss (rec_block/focal_loss.py:12-66 of the reference): value and d / d logit.
-//   ce = sigmoid_cross_entropy_with_logits(y, z) = max(z, 0) - z y + log1p(exp(-|z|))                  (focal_loss.py:48)
-//   alpha factor y alpha + (1 - y)(1 - alpha)                                                          (:50-53)
-//   modulating factor (1 - (y p + (1 - y)(1 - p)))^gamma, p = sigmoid(z); optionally without gradient  (:55-62)
-// (not inlined: it runs once per row outside the pair loop, and the pair kernel has no registers to spare)
-__device__ __noinline__ float2 focal_row(float z, float y, float alpha, float gamma, int stop) {
-  const float e = expf(-fabsf(z));
-  const float ce = fmaxf(z, 0.f) - z * y + log1pf(e);
-  const float p = z >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);
-  const float af = alpha != 0.f ? y * alpha + (1.0f - y) * (1.0f - alpha) : 1.0f;
-  float mod = 1.0f, dmod = 0.f;
-  if (gamma != 0.f) {
-    const float om = 1.0f - (y * p + (1.0f - y) * (1.0f - p));
-    mod = powf(om, gamma);
-    if (!stop) dmod = -gamma * powf(om, gamma - 1.0f) * (2.0f * y - 1.0f) * p * (1.0f - p);
-  }
-  return make_float2(af * mod * ce, af * (mod * (p - y) + ce * dmod));
-}
-
 // DET: deterministic mode (fixed-point gradient accumulators, ordered loss partials) -- a separate instantiation, so that
 // the default kernel carries none of it through the pair loop.
 // HINGE: the pair loss is the hinge max(0, margin - x) (tile_hinge / tile_general<.., HINGE>) instead of the logistic loss.
@@ -1532,6 +1513,17 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
   const bool hinge = a->pair_loss == RN_LOSS_HINGE;
   if (det && hinge) return RN_ERR_UNSUPPORTED;
+  if (!split && !(g_prof.on && g_prof.n < g_prof.cap)) {
+    // batches of up to 1024 rows: one launch of one CTA, everything in shared memory (small.cu)
+    int smode = 0;
+    const bool sdiff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
+    if (sdiff || a->rw_pos || a->rw_neg) smode |= M_HASW;
+    if (sdiff) smode |= M_DIFF;
+    if (a->rw_neg) smode |= M_RWN;
+    if (a->only_wrong) smode |= M_WRONG;
+    int src = RN_OK;
+    if (small_pairwise(a, scratch, st, smode, hinge, &src)) return src;
+  }
   const bool fast = counting_eligible(a) && !det;       // (the counting path places groups and rows in arrival order)
   PairParams P{};
   P.det = det ? 1 : 0;

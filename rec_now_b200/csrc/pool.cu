@@ -1,0 +1,147 @@
+// Segment pooling of slot embeddings: the step that feeds the model whose logits the ranking losses score.
+//
+// Replaces rec_block/embedding_util.py:239-324 of the reference (embedding_using_sparse_batch_segment_ids and its helper
+// sparse_batch_segment_ids_of_targets :127-198): a StaticHashTable lookup of every slot, boolean_mask, unique, gather,
+// weight multiply and unsorted_segment_sum / _mean over (row, target slot) segments -- seven stock TF ops and three
+// materialised [kept, D] intermediates -- as ONE gather-accumulate kernel: output segment (b, t) walks the C columns of row
+// b and adds weight * E[id] for the columns whose slot is target_slots[t], in column order (the order of TF's CPU
+// kernel, so sums are bit-identical to it).  HBM bound: D * 4 bytes per kept id in, B * T * D * 4 bytes out, nothing
+// materialised in between.  Backward: d E[id] += w * d out[b, t] (vector atomics: ids repeat), d w = <E[id], d out[b, t]>.
+#include "common.cuh"
+
+namespace rn {
+
+struct PoolParams {
+  u32 B, C, T, D; int mean;
+  const int32_t* slots; const int64_t* ids; const float* weights; const int32_t* tslots;
+  const float* table; int64_t V;
+};
+
+// One thread per VEC consecutive floats of an output segment; the D / VEC threads of a segment are neighbours, so the
+// slot / id / weight loads are warp broadcasts and the table rows are read as contiguous vectors.
+template <int VEC>
+__global__ void __launch_bounds__(256) k_pool_fwd(PoolParams P, float* __restrict__ out, u32* __restrict__ err) {
+  const u32 dv = P.D / VEC;
+  const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 seg = gid / dv;
+  if (seg >= (u64)P.B * P.T) return;
+  const u32 v = (u32)(gid - seg * dv);
+  const u32 b = (u32)(seg / P.T), t = (u32)(seg - (u64)b * P.T);
+  const int32_t target = P.tslots[t];
+  const int32_t* srow = P.slots + (size_t)b * P.C;
+  const int64_t* irow = P.ids + (size_t)b * P.C;
+  const float* wrow = P.weights ? P.weights + (size_t)b * P.C : nullptr;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  u32 cnt = 0;
+  for (u32 c = 0; c < P.C; ++c) {
+    if (srow[c] != target) continue;
+    const int64_t id = irow[c];
+    if (id < 0 || id >= P.V) { if (err) atomicOr(err, 8u); continue; }   // (tf.gather would raise: flagged, skipped)
+    const float w = wrow ? wrow[c] : 1.0f;
+    const float* e = P.table + (size_t)id * P.D + (size_t)v * VEC;
+    float ev[VEC];
+    if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(e); ev[0] = q.x; ev[1] = q.y; ev[2 % VEC] = q.z; ev[3 % VEC] = q.w; }
+    else { for (int k = 0; k < VEC; ++k) ev[k] = e[k]; }
+    // embeddings * weights, then the segment sum: two roundings, as the reference's two ops (:310-317)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = __fadd_rn(acc[k], wrow ? __fmul_rn(ev[k], w) : ev[k]);
+    ++cnt;
+  }
+  if (P.mean && cnt > 1) {                                                // unsorted_segment_mean: sum / max(count, 1)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = __fdiv_rn(acc[k], (float)cnt);
+  }
+  float* o = out + (size_t)seg * P.D + (size_t)v * VEC;
+  if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2 % VEC], acc[3 % VEC]);
+  else { for (int k = 0; k < VEC; ++k) o[k] = acc[k]; }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) k_pool_bwd(PoolParams P, const float* __restrict__ d_out, float* __restrict__ d_table,
+                                                  float* __restrict__ d_weights) {
+  const u32 dv = P.D / VEC;
+  const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 seg = gid / dv;
+  if (seg >= (u64)P.B * P.T) return;
+  const u32 v = (u32)(gid - seg * dv);
+  const u32 b = (u32)(seg / P.T), t = (u32)(seg - (u64)b * P.T);
+  const int32_t target = P.tslots[t];
+  const int32_t* srow = P.slots + (size_t)b * P.C;
+  const int64_t* irow = P.ids + (size_t)b * P.C;
+  const float* wrow = P.weights ? P.weights + (size_t)b * P.C : nullptr;
+  float g[VEC];
+  {
+    const float* go = d_out + (size_t)seg * P.D + (size_t)v * VEC;
+    if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(go); g[0] = q.x; g[1] = q.y; g[2 % VEC] = q.z; g[3 % VEC] = q.w; }
+    else { for (int k = 0; k < VEC; ++k) g[k] = go[k]; }
+  }
+  if (P.mean) {
+    u32 cnt = 0;
+    for (u32 c = 0; c < P.C; ++c) cnt += srow[c] == target ? 1u : 0u;
+    if (cnt > 1) { const float r = 1.0f / (float)cnt; for (int k = 0; k < VEC; ++k) g[k] *= r; }
+  }
+  for (u32 c = 0; c < P.C; ++c) {
+    if (srow[c] != target) continue;
+    const int64_t id = irow[c];
+    if (id < 0 || id >= P.V) continue;
+    const float w = wrow ? wrow[c] : 1.0f;
+    if (d_table) {
+      float* dt = d_table + (size_t)id * P.D + (size_t)v * VEC;
+      if (VEC == 4) atomicAdd(reinterpret_cast<float4*>(dt), make_float4(g[0] * w, g[1] * w, g[2 % VEC] * w, g[3 % VEC] * w));
+      else { for (int k = 0; k < VEC; ++k) atomicAdd(dt + k, g[k] * w); }
+    }
+    if (d_weights) {
+      const float* e = P.table + (size_t)id * P.D + (size_t)v * VEC;
+      float dot = 0.f;
+      for (int k = 0; k < VEC; ++k) dot = fmaf(e[k], g[k], dot);
+      atomicAdd(d_weights + (size_t)b * P.C + c, dot);
+    }
+  }
+}
+
+static int pool_params(const rn_pool_args* a, PoolParams& P) {
+  if (!a || a->B <= 0 || a->C <= 0 || a->T <= 0 || a->D <= 0 || a->V <= 0) return RN_ERR_ARG;
+  if (a->B > 0x7FFFFFFFll || a->C > 0x7FFFFFFFll) return RN_ERR_ARG;
+  if (!a->slots || !a->ids || !a->target_slots || !a->table) return RN_ERR_ARG;
+  P.B = (u32)a->B; P.C = (u32)a->C; P.T = (u32)a->T; P.D = (u32)a->D; P.mean = a->mean;
+  P.slots = a->slots; P.ids = a->ids; P.weights = a->weights; P.tslots = a->target_slots; P.table = a->table; P.V = a->V;
+  return RN_OK;
+}
+
+}  // namespace rn
+
+using namespace rn;
+
+extern "C" int rn_segment_pool_fwd(const rn_pool_args* a, float* out, uint32_t* err_flag, void* stream) {
+  PoolParams P;
+  int rc = pool_params(a, P);
+  if (rc) return rc;
+  if (!out) return RN_ERR_ARG;
+  const bool vec = (P.D % 4) == 0 && check_align(a->table) == RN_OK && check_align(out) == RN_OK;
+  const u64 threads = (u64)P.B * P.T * (vec ? P.D / 4 : P.D);
+  const u64 grid = (threads + 255) / 256;
+  if (grid > 0x7FFFFFFFull) return RN_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) k_pool_fwd<4><<<(unsigned)grid, 256, 0, st>>>(P, out, err_flag);
+  else k_pool_fwd<1><<<(unsigned)grid, 256, 0, st>>>(P, out, err_flag);
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}
+
+extern "C" int rn_segment_pool_bwd(const rn_pool_args* a, const float* d_out, float* d_table, float* d_weights, void* stream) {
+  PoolParams P;
+  int rc = pool_params(a, P);
+  if (rc) return rc;
+  if (!d_out || (!d_table && !d_weights)) return RN_ERR_ARG;
+  if (d_weights && !a->weights) return RN_ERR_ARG;
+  const bool vec = (P.D % 4) == 0 && check_align(a->table) == RN_OK && check_align(d_out) == RN_OK &&
+                   (!d_table || check_align(d_table) == RN_OK);
+  const u64 threads = (u64)P.B * P.T * (vec ? P.D / 4 : P.D);
+  const u64 grid = (threads + 255) / 256;
+  if (grid > 0x7FFFFFFFull) return RN_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec) k_pool_bwd<4><<<(unsigned)grid, 256, 0, st>>>(P, d_out, d_table, d_weights);
+  else k_pool_bwd<1><<<(unsigned)grid, 256, 0, st>>>(P, d_out, d_table, d_weights);
+  return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+}

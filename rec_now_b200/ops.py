@@ -300,7 +300,7 @@ def device_error(scratch: torch.Tensor) -> int:
 
 
 def last_segmentation_path(scratch: torch.Tensor) -> int:
-    """Which segmentation the last finished pairwise call on `scratch` ran: 1 = counting (sort-free), 2 = radix sort."""
+    """Which segmentation the last finished pairwise call on `scratch` ran: 1 = counting (sort-free), 2 = radix sort, 3 = the one-CTA kernel of small batches (no segmentation pass)."""
     ts = (C.c_uint64 * 36)()
     check(lib().rn_debug_timestamps(scratch.data_ptr(), ts, 36, _stream()), "rn_debug_timestamps")
     return int(ts[35])

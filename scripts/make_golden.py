@@ -25,8 +25,11 @@ def consts(path):
     out = {}
     for node in ast.walk(tree):
         if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "constant" and node.args:
-            out[node.lineno] = ast.literal_eval(node.args[0])
-        if isinstance(node, ast.Assign) and isinstance(node.value, ast.List):
+            try:
+                out[node.lineno] = ast.literal_eval(node.args[0])
+            except ValueError:
+                pass
+        if isinstance(node, ast.Assign) and isinstance(node.value, (ast.List, ast.Tuple)):
             try:
                 out[node.lineno] = ast.literal_eval(node.value)
             except ValueError:
@@ -80,6 +83,27 @@ def main():
                        "logits": fl[l_log], "expected_alpha_none_gamma_none": exp_fl[0],
                        "expected_alpha_0.25_gamma_none": exp_fl[1], "expected_alpha_none_gamma_1": exp_fl[2],
                        "tolerance": 1e-5})
+    # slot pooling: tests/rec_block/test_embedding_util.py:55-106
+    eu, eu_src = consts(os.path.join(REF, "test_embedding_util.py"))
+    g["source"]["TEU"] = "tests/rec_block/test_embedding_util.py"
+    l_t = line_of(eu_src, r"def test_sparse_batch_segment_ids_of_targets")
+    l_sl = line_of(eu_src, r"slots = \[\[", l_t)
+    g["cases"].append({"name": "sparse_batch_segment_ids_of_targets", "cite": f"TEU:{l_t}-{l_t + 15}",
+                       "slots": eu[l_sl], "target_slots": eu[line_of(eu_src, r"target_slots = ", l_t)],
+                       "expected_mask": eu[line_of(eu_src, r"expected_mask = ", l_t)],
+                       "expected_sp_segment_ids": eu[line_of(eu_src, r"expected_sp_segment_ids = ", l_t)],
+                       "num_rows": 2, "num_ids": 3, "num_segments": 6})
+    l_p = line_of(eu_src, r"def test_embedding_using_sparse_batch_segment_ids")
+    l_e1 = line_of(eu_src, r"expected_results = ", l_p)
+    l_e2 = line_of(eu_src, r"expected_results = ", l_e1)
+    # (the test derives its inputs in code -- params = [[i, -i]] for 40 keys, slots = int((ids + 0.5) / 10), weights =
+    # ids * 10, TEU:72-91 -- only the ids and the expected values are literals)
+    g["cases"].append({"name": "embedding_using_sparse_batch_segment_ids", "cite": f"TEU:{l_p}-{l_e2 + 6}",
+                       "num_slots": 4, "num_keys_per_slot": 10, "target_slots": eu[line_of(eu_src, r"target_slots = ", l_p)],
+                       "ids": eu[line_of(eu_src, r"ids = \[\[", l_p)],
+                       "expected_with_weights": eu[l_e1],
+                       # (TEU:104-108 ends in a stray comma: a 1-tuple holding the list)
+                       "expected_without_weights": eu[l_e2][0] if isinstance(eu[l_e2], tuple) else eu[l_e2]})
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1)
     print(json.dumps(g, indent=1))

@@ -41,6 +41,17 @@ def run(d, iters=200):
             out = ops.pairwise_fwd_bwd(s, y, keys, **kw)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
+    if os.environ.get("RN_QT_GRAPH"):           # device time without the host: 50 calls captured in one CUDA graph, replayed
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(50):
+                out = ops.pairwise_fwd_bwd(s, y, keys, **kw)
+        g.replay(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        print(f"   graph replay (50 calls per graph): {e0.elapsed_time(e1) / 500 * 1e3:.2f} us/call")
     n = int(out["n_pair"].item())
     print(f"{d['name']}: B={s.numel()} n_pair={n} {ms*1e3:.1f} us/call  {n/ms/1e6:.2f} Gpairs/s  "
           f"SFU-frac(3 MUFU, 4.65e12/s)={3*n/(ms*1e-3)/4.65e12:.3f} loss={out['loss'].item():.6f} err={ops.device_error(out['_scratch'])}")

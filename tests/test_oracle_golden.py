@@ -145,3 +145,37 @@ def test_focal_loss_known_answers():
             zp[i] += eps; zm[i] -= eps
             fd = (S.focal(y, zp.astype(np.float32), **kw)["loss"] - S.focal(y, zm.astype(np.float32), **kw)["loss"]) / (2 * eps)
             assert abs(fd - r["grad"][i]) < 2e-4 * max(1.0, abs(fd)), (kw, i, fd, r["grad"][i])
+
+
+class TestEmbeddingUtil(unittest.TestCase):
+    """tests/rec_block/test_embedding_util.py:55-106 of the reference (TEU), against oracle/pool_ref.py -- the checker of
+    the segment-pooling kernel."""
+
+    def _golden(self, name):
+        import json
+        import os
+        g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_known_answers.json")))
+        return [c for c in g["cases"] if c["name"] == name][0]
+
+    def test_sparse_batch_segment_ids_of_targets(self):         # TEU:55-69
+        from oracle import pool_ref as P
+        c = self._golden("sparse_batch_segment_ids_of_targets")
+        mask, sp, num_rows, num_ids, num_segments = P.sparse_batch_segment_ids_of_targets(c["slots"], c["target_slots"])
+        self.assertEqual(mask.tolist(), c["expected_mask"])
+        self.assertEqual(sp.tolist(), c["expected_sp_segment_ids"])
+        self.assertEqual((num_rows, num_ids, num_segments), (c["num_rows"], c["num_ids"], c["num_segments"]))
+
+    def test_embedding_using_sparse_batch_segment_ids(self):    # TEU:71-109
+        from oracle import pool_ref as P
+        c = self._golden("embedding_using_sparse_batch_segment_ids")
+        params = np.array([[i, -i] for i in range(c["num_slots"] * c["num_keys_per_slot"])], np.float32)   # TEU:77-78
+        ids = np.array(c["ids"])
+        slots = ((ids.astype(np.float64) + 0.5) / 10.0).astype(np.int32)                                  # TEU:88-89
+        weights = ids.astype(np.float32) * 10.0                                                            # TEU:91
+        for uu in (True, False):
+            out = P.embedding_using_sparse_batch_segment_ids(lambda i: params[np.asarray(i)], slots, c["target_slots"], ids,
+                                                             weights=weights, use_unique=uu)
+            self.assertEqual(out.tolist(), c["expected_with_weights"])
+            out = P.embedding_using_sparse_batch_segment_ids(lambda i: params[np.asarray(i)], slots, c["target_slots"], ids,
+                                                             use_unique=uu)
+            self.assertEqual(out.tolist(), c["expected_without_weights"])
