@@ -318,7 +318,8 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
                "pairs_per_s": n / (t["single_call_us"] * 1e-6), "samples_per_s": s.numel() / (t["single_call_us"] * 1e-6),
                "sfu_roofline_frac_step": MUFU_PER_PAIR * n / (t["single_call_us"] * 1e-6) / mufu_peak,
                "hbm_roofline_frac_step": 20 * s.numel() / (t["single_call_us"] * 1e-6) / 1e9 / hbm_gbs,
-               "segmentation_path": {1: "counting", 2: "radix"}.get(ops.last_segmentation_path(out["_scratch"]), "?"),
+               "segmentation_path": {1: "counting", 2: "radix", 3: "one-CTA kernel (small batch, csrc/small.cu)"}.get(
+                   ops.last_segmentation_path(out["_scratch"]), "?"),
                "parity": parity_pairwise(out, d, dict(power=0.0))}
         if with_cpu:
             c = cpu_dense_full(d, "pairwise")
@@ -372,6 +373,57 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
                                     "gauc_abs_err": abs(float(out["gauc"].item()) - ref["gauc"]),
                                     "ok": bool(n == ref["n_pair"] and int(out["concordant2"].item()) == ref["concordant2"]
                                                and abs(float(out["gauc"].item()) - ref["gauc"]) <= 1e-6)}}
+    # hinge (margin) pair loss on cfg3's batch: same pair set / weights, no SFU operation per pair
+    w = torch.tensor(d["w"], device=dev)
+    keys = g.reshape(1, -1)
+    step = lambda: ops.pairwise_fwd_bwd(s, y, keys, rw_pos=w, label_func="diff", power=-0.5, pair_loss="hinge", margin=1.0)
+    t = time_device(step, steps, 5, flush)
+    out = step()
+    spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=d["w"], pair_loss="hinge", margin=1.0)
+    ref = S.pairwise(d["s"], d["y"], d["g"], spec)
+    gerr = np.abs(out["dlogits"].cpu().numpy().astype(np.float64) - ref["grad"])
+    hn = int(out["n_pair"].item())
+    recs["hinge_cfg3"] = {"workload": "hinge pair loss max(0, 1 - x) on cfg3's batch (graded labels, label-gain x sample weights, power -0.5)",
+                          "rows": s.numel(), "n_pair": hn, **t, "pairs_per_s": hn / (t["single_call_us"] * 1e-6),
+                          "parity": {"oracle": "oracle/seg_ref.py (float64, pair_loss='hinge')", "n_pair_exact": hn == ref["n_pair"],
+                                     "loss_rel": abs(float(out["loss"].item()) - ref["loss"]) / max(abs(ref["loss"]), 1e-30),
+                                     "grad_max_abs_err_over_A": float((gerr / np.maximum(ref["grad_abs"], 1e-30))[ref["grad_abs"] > 0].max()),
+                                     "tolerance": 1e-5,
+                                     "ok": bool(hn == ref["n_pair"] and abs(float(out["loss"].item()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+                                                and (gerr <= 1e-5 * ref["grad_abs"] + 1e-12).all())}}
+    # segment pooling of slot embeddings: HBM-bound gather + segment sum, one kernel
+    from oracle import pool_ref as PR
+    from rec_now_b200.rec_block import embedding_util as EU
+    rng = np.random.default_rng(0)
+    pb, pc, pt, pd, pv = 65536, 32, 8, 64, 1 << 20
+    slots_h = rng.integers(0, 16, (pb, pc)).astype(np.int32)
+    ids_h = rng.integers(0, pv, (pb, pc)).astype(np.int64)
+    w_h = rng.uniform(0.5, 1.5, (pb, pc)).astype(np.float32)
+    targets = [1, 3, 4, 7, 8, 10, 13, 15]
+    table = torch.randn((pv, pd), device=dev)
+    slots_t, ids_t, w_t = (torch.tensor(v, device=dev) for v in (slots_h, ids_h, w_h))
+    step = lambda: EU.segment_pool(table, slots_t, targets, ids_t, w_t)
+    t = time_device(step, steps, 5, flush)
+    out = step()
+    kept = int(np.isin(slots_h, targets).sum())
+    bytes_alg = kept * pd * 4 + pb * pt * pd * 4 + pb * pc * 16          # table rows in, pooled rows out, slots + ids + weights
+    nchk = 256
+    th = table.cpu().numpy()
+    refp = PR.embedding_using_sparse_batch_segment_ids(lambda i: th[np.asarray(i)], slots_h[:nchk], targets, ids_h[:nchk],
+                                                       weights=w_h[:nchk], use_unique=False)
+    recs["segment_pool"] = {"workload": f"embedding_using_sparse_batch_segment_ids: B={pb} rows x {pc} columns, {pt} target slots of 16, "
+                                        f"D={pd}, table {pv} x {pd} f32 (256 MiB), weights, method sum",
+                            "rows": pb, "kept_ids": kept, **t,
+                            "hbm_roofline": {"bound": "hbm", "algorithmic_bytes": bytes_alg, "peak_gbs": hbm_gbs,
+                                             "achieved_gbs_single_call": bytes_alg / (t["single_call_us"] * 1e-6) / 1e9,
+                                             "frac_single_call": bytes_alg / (t["single_call_us"] * 1e-6) / 1e9 / hbm_gbs,
+                                             "achieved_gbs_streamed": bytes_alg / (t["streamed_us"] * 1e-6) / 1e9,
+                                             "frac_streamed": bytes_alg / (t["streamed_us"] * 1e-6) / 1e9 / hbm_gbs,
+                                             "note": "random 256-byte table rows (sector-granular gathers), bytes = D*4 per kept id "
+                                                     "+ the pooled output + the slot / id / weight columns"},
+                            "parity": {"oracle": "oracle/pool_ref.py (op-for-op restatement of embedding_util.py:127-324) on the first "
+                                                 f"{nchk} rows", "bit_exact": bool(np.array_equal(out[:nchk].cpu().numpy(), refp)),
+                                       "ok": bool(np.array_equal(out[:nchk].cpu().numpy(), refp))}}
     return recs
 
 # ----------------------------------------------------------------------------------------------------------

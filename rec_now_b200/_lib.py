@@ -145,8 +145,9 @@ def lib() -> C.CDLL:
     L.rn_host_pairwise_submit.argtypes = [vp, C.POINTER(PairwiseArgs), C.POINTER(i32)]
     L.rn_host_pairwise_wait.argtypes = [vp, i32]
     L.rn_host_pairwise_destroy.argtypes = [vp]
-    L.rn_segment_pool_fwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp]
-    L.rn_segment_pool_bwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp, vp]
+    if hasattr(L, "rn_segment_pool_fwd"):       # (absent only from older builds loaded through RN_LIB_PATH for A/B timing)
+        L.rn_segment_pool_fwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp]
+        L.rn_segment_pool_bwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp, vp]
     L.rn_debug_arena_offset.restype = i64
     L.rn_debug_arena_offset.argtypes = [i64, i32, i32]
     L.rn_debug_graph_launches.restype = i64

@@ -58,6 +58,83 @@ __global__ void __launch_bounds__(256) k_pool_fwd(PoolParams P, float* __restric
   else { for (int k = 0; k < VEC; ++k) o[k] = acc[k]; }
 }
 
+// Warp-per-row forward kernel (the bandwidth path): a warp owns row b.  Its lanes load the row's slots / ids / weights
+// 32 columns at a time (coalesced), every target slot's columns are found with ONE ballot, and the warp then streams the
+// kept table rows -- all 32 lanes on one row (D floats contiguous: full sectors), four rows in flight per warp before the
+// first add, added in column order (same sums as k_pool_fwd).  Lane l holds elements l * VEC + k of every 32 * VEC chunk.
+template <int VEC, int CH>
+__global__ void __launch_bounds__(256) k_pool_fwd_rows(PoolParams P, float* __restrict__ out, u32* __restrict__ err) {
+  const u32 ln = threadIdx.x & 31u;
+  const u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  const int32_t* srow = P.slots + (size_t)b * P.C;
+  const int64_t* irow = P.ids + (size_t)b * P.C;
+  const float* wrow = P.weights ? P.weights + (size_t)b * P.C : nullptr;
+  for (u32 t = 0; t < P.T; ++t) {
+    const int32_t target = P.tslots[t];
+    float acc[CH][VEC];
+#pragma unroll
+    for (int h = 0; h < CH; ++h)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[h][k] = 0.f;
+    u32 cnt = 0;
+    for (u32 c0 = 0; c0 < P.C; c0 += 32) {
+      const u32 c = c0 + ln;
+      const bool in = c < P.C;
+      const int32_t sl = in ? srow[c] : 0;
+      int64_t id = 0; float w = 1.f;
+      bool hit = in && sl == target;
+      if (hit) { id = irow[c]; if (wrow) w = wrow[c]; }
+      if (hit && (id < 0 || id >= P.V)) { if (err) atomicOr(err, 8u); hit = false; }     // (tf.gather would raise: flagged, skipped)
+      u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+      cnt += (u32)__popc(m);
+      while (m) {
+        // up to four kept columns per round: their row loads are issued before the first add
+        int src[4]; float wv[4]; float ev[4][CH][VEC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { src[r] = m ? __ffs(m) - 1 : -1; if (m) m &= m - 1; }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int sl_ = src[r] < 0 ? 0 : src[r];
+          const int64_t rid = __shfl_sync(0xFFFFFFFFu, id, sl_);
+          wv[r] = __shfl_sync(0xFFFFFFFFu, w, sl_);
+          if (src[r] >= 0) {
+            const float* e = P.table + (size_t)rid * P.D + (size_t)ln * VEC;
+#pragma unroll
+            for (int h = 0; h < CH; ++h) {
+              if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(e + h * 32 * VEC); ev[r][h][0] = q.x; ev[r][h][1 % VEC] = q.y; ev[r][h][2 % VEC] = q.z; ev[r][h][3 % VEC] = q.w; }
+              else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2*>(e + h * 32 * VEC); ev[r][h][0] = q.x; ev[r][h][1 % VEC] = q.y; }
+              else ev[r][h][0] = e[h * 32 * VEC];
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (src[r] >= 0) {
+#pragma unroll
+            for (int h = 0; h < CH; ++h)
+#pragma unroll
+              for (int k = 0; k < VEC; ++k) acc[h][k] = __fadd_rn(acc[h][k], wrow ? __fmul_rn(ev[r][h][k], wv[r]) : ev[r][h][k]);
+          }
+        }
+      }
+    }
+    if (P.mean && cnt > 1) {
+#pragma unroll
+      for (int h = 0; h < CH; ++h)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[h][k] = __fdiv_rn(acc[h][k], (float)cnt);
+    }
+    float* o = out + ((size_t)b * P.T + t) * P.D + (size_t)ln * VEC;
+#pragma unroll
+    for (int h = 0; h < CH; ++h) {
+      if (VEC == 4) *reinterpret_cast<float4*>(o + h * 32 * VEC) = make_float4(acc[h][0], acc[h][1 % VEC], acc[h][2 % VEC], acc[h][3 % VEC]);
+      else if (VEC == 2) *reinterpret_cast<float2*>(o + h * 32 * VEC) = make_float2(acc[h][0], acc[h][1 % VEC]);
+      else o[h * 32 * VEC] = acc[h][0];
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) k_pool_bwd(PoolParams P, const float* __restrict__ d_out, float* __restrict__ d_table,
                                                   float* __restrict__ d_weights) {
@@ -124,6 +201,21 @@ extern "C" int rn_segment_pool_fwd(const rn_pool_args* a, float* out, uint32_t* 
   const u64 grid = (threads + 255) / 256;
   if (grid > 0x7FFFFFFFull) return RN_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // widths that are whole warps of float / float2 / float4: the warp-per-row kernel (one table row per load instruction)
+  if (check_align(a->table) == RN_OK && check_align(out) == RN_OK) {
+    const u64 rgrid = ((u64)P.B * 32 + 255) / 256;
+    if (rgrid <= 0x7FFFFFFFull) {
+      bool done = true;
+      switch (P.D) {
+        case 32:  k_pool_fwd_rows<1, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, out, err_flag); break;
+        case 64:  k_pool_fwd_rows<2, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, out, err_flag); break;
+        case 128: k_pool_fwd_rows<4, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, out, err_flag); break;
+        case 256: k_pool_fwd_rows<4, 2><<<(unsigned)rgrid, 256, 0, st>>>(P, out, err_flag); break;
+        default: done = false;
+      }
+      if (done) return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+    }
+  }
   if (vec) k_pool_fwd<4><<<(unsigned)grid, 256, 0, st>>>(P, out, err_flag);
   else k_pool_fwd<1><<<(unsigned)grid, 256, 0, st>>>(P, out, err_flag);
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
