@@ -629,16 +629,20 @@ def ours(args):
                                         label_pair_to_weight_func=PW.label_gain_times_sample_weight,
                                         sample_weight=cols["w"])
             else:
-                loss = global_mode.global_pairwise_loss(logits, cols["y"], cols["g"], click_occurance_power=-0.5,
-                                                        label_pair_to_weight_func=PW.label_gain_times_sample_weight,
-                                                        sample_weight=cols["w"])
-            loss.backward()
+                # global mode: the forward + backward entry point (ONE C-ABI call per step and rank,
+                # rn_global_pairwise_fwd_bwd: loss and d loss / d logits of this rank's rows come back together)
+                res = global_mode.global_pairwise_fwd_bwd(cols["s"], cols["y"], cols["g"].reshape(1, -1), rw_pos=cols["w"],
+                                                          label_func="diff", power=-0.5)
+                loss, grad_t = res["loss"], res["dlogits"]
+            if world == 1:
+                loss.backward()
+                grad_t = logits.grad
             if rt is not None:                           # D2H of the step's results on the compute stream
                 rt.cudaMemcpyAsync(h_loss_ptr, loss.data_ptr(), 4, 2, main_ptr)
-                rt.cudaMemcpyAsync(h_grad_ptr, logits.grad.data_ptr(), 4 * ROWS_PER_GPU, 2, main_ptr)
+                rt.cudaMemcpyAsync(h_grad_ptr, grad_t.data_ptr(), 4 * ROWS_PER_GPU, 2, main_ptr)
             else:
                 h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
-                h_grad.copy_(logits.grad, non_blocking=True)
+                h_grad.copy_(grad_t, non_blocking=True)
             consumed[q].record(main)
             logits.grad = None
             cols["s"].requires_grad_(False)
@@ -658,7 +662,8 @@ def ours(args):
     d2h = h_loss.numel() * 4 + h_grad.numel() * 4
     e2e_api_ms = e2e_ms
     e2e_api = ("rec_block.pairwise_loss_from_batch.pairwise_loss + backward" if world == 1
-               else "global_mode.global_pairwise_loss + backward")
+               else "global_mode.global_pairwise_fwd_bwd (torch device tensors in, loss + d loss / d logits out: one "
+                    "rn_global_pairwise_fwd_bwd call per step and rank)")
     e2e_pipeline = ("inputs of step k+1 copied H2D on a copy stream (two device buffers) while step k computes; loss and "
                     "gradient copied D2H every step; autograd engine single-threaded "
                     "(torch.autograd.set_multithreading_enabled(False))")

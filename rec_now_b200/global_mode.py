@@ -134,7 +134,7 @@ def _peer_global(st: _PeerState, logits, labels, keys, rw_pos, row_ok, label_fun
     dlogits = torch.empty(b_loc, dtype=torch.float32, device=dev)
     a = st.args.local
     a.B = b_loc; a.K = keys.shape[0]
-    a.label_func = _lib.RN_LABEL_DIFF if label_func == "diff" else _lib.RN_LABEL_STEP
+    a.label_func = ops._LABEL_FUNCS[label_func]
     a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
     a.row_ok = ops._ptr(ok); a.rw_pos = ops._ptr(rwp); a.rw_neg = None
     a.factor = factor; a.power = power; a.only_wrong = 1 if only_wrong else 0; a.reduce_mean = 1 if reduce_mean else 0

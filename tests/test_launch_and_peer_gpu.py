@@ -38,7 +38,8 @@ def test_graph_launch_across_shapes_and_modes():
             s, y, g, spec = _case(b, groups, seed + 10 * rep, graded, weights)
             check_pairwise(run_pairwise(s, y, g, spec), S.pairwise(s, y, g, spec), ctx=f"B={b} rep={rep}")
     after = int(lib.rn_debug_graph_launches())
-    assert after - before == 2 * len(cases), (before, after)
+    # (batches of up to 1024 rows are one ordinary launch of the one-CTA kernel, not a graph)
+    assert after - before == 2 * sum(1 for c in cases if c[0] > 1024), (before, after)
 
 
 def test_plain_launches_under_callers_graph_capture():
