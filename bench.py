@@ -602,6 +602,9 @@ def ours(args):
     nbytes_in, cs_ptr, pin_ptr = pin_all.numel(), C.c_void_p(cs.cuda_stream), pin_all.data_ptr()
     dev_ptr = [t.data_ptr() for t in dev_all]
     h_loss_ptr, h_grad_ptr, main_ptr = h_loss.data_ptr(), h_grad.data_ptr(), C.c_void_p(main.cuda_stream)
+    outs = torch.cuda.Stream(dev)
+    outs_ptr = C.c_void_p(outs.cuda_stream)
+    done_ev = [torch.cuda.Event(), torch.cuda.Event()]
 
     def enqueue_copy(q):
         cs.wait_event(consumed[q])                       # the step that last read this buffer is done with it
@@ -637,7 +640,15 @@ def ours(args):
             if world == 1:
                 loss.backward()
                 grad_t = logits.grad
-            if rt is not None:                           # D2H of the step's results on the compute stream
+            if rt is not None and world > 1:
+                # D2H of the step's results on a copy-out stream (behind an event of the compute stream), so that the
+                # next step's kernels do not queue behind the copy; the allocator is told the stream uses the tensors
+                done_ev[q].record(main)
+                outs.wait_event(done_ev[q])
+                rt.cudaMemcpyAsync(h_loss_ptr, loss.data_ptr(), 4, 2, outs_ptr)
+                rt.cudaMemcpyAsync(h_grad_ptr, grad_t.data_ptr(), 4 * ROWS_PER_GPU, 2, outs_ptr)
+                loss.record_stream(outs); grad_t.record_stream(outs)
+            elif rt is not None:                         # D2H of the step's results on the compute stream
                 rt.cudaMemcpyAsync(h_loss_ptr, loss.data_ptr(), 4, 2, main_ptr)
                 rt.cudaMemcpyAsync(h_grad_ptr, grad_t.data_ptr(), 4 * ROWS_PER_GPU, 2, main_ptr)
             else:
@@ -655,6 +666,7 @@ def ours(args):
         a.record()
         e2e_steps(K)
         cs.synchronize()
+        main.wait_stream(outs)                           # (the last results are in host memory when the clock stops)
         b.record()
         barrier()
     e2e_ms = a.elapsed_time(b)
@@ -665,8 +677,8 @@ def ours(args):
                else "global_mode.global_pairwise_fwd_bwd (torch device tensors in, loss + d loss / d logits out: one "
                     "rn_global_pairwise_fwd_bwd call per step and rank)")
     e2e_pipeline = ("inputs of step k+1 copied H2D on a copy stream (two device buffers) while step k computes; loss and "
-                    "gradient copied D2H every step; autograd engine single-threaded "
-                    "(torch.autograd.set_multithreading_enabled(False))")
+                    "gradient copied D2H every step" + ("; autograd engine single-threaded "
+                    "(torch.autograd.set_multithreading_enabled(False))" if world == 1 else " on a copy-out stream"))
     e2e_timing = "CUDA events on the compute stream around the K steps"
     if world == 1:
         # ---- e2e through the C ABI with HOST buffers (rn_host_pairwise_*): every step copies its pinned host columns

@@ -135,6 +135,94 @@ __global__ void __launch_bounds__(256) k_pool_fwd_rows(PoolParams P, float* __re
   }
 }
 
+// The same warp-per-row walk with ALL target slots in one pass: the accumulators of the row's T output segments live in
+// shared memory (T * D floats per warp; a lane only ever touches its own columns, so there is nothing to synchronise),
+// every lane classifies its column against the target list once, and the kept columns of the whole row are streamed RIN
+// table rows at a time -- one dependent phase per 32 columns instead of one per target slot.  Column order per segment is
+// unchanged (same sums).  T <= 32 (lane t keeps the segment's column count for the mean).
+template <int VEC, int CH, int RIN>
+__global__ void __launch_bounds__(256) k_pool_fwd_rows_all(PoolParams P, float* __restrict__ out, u32* __restrict__ err) {
+  extern __shared__ __align__(16) float pool_acc[];
+  const u32 ln = threadIdx.x & 31u, wq = threadIdx.x >> 5;
+  const u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  float* acc = pool_acc + (size_t)wq * P.T * P.D;
+  const int32_t* srow = P.slots + (size_t)b * P.C;
+  const int64_t* irow = P.ids + (size_t)b * P.C;
+  const float* wrow = P.weights ? P.weights + (size_t)b * P.C : nullptr;
+  for (u32 t = 0; t < P.T; ++t)
+#pragma unroll
+    for (int h = 0; h < CH; ++h)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[(size_t)t * P.D + h * 32 * VEC + ln * VEC + k] = 0.f;
+  const int32_t my_target = ln < P.T ? P.tslots[ln] : 0;
+  u32 cnt = 0;                                  // lane t: kept columns of target t
+  for (u32 c0 = 0; c0 < P.C; c0 += 32) {
+    const u32 c = c0 + ln;
+    const bool in = c < P.C;
+    const int32_t sl = in ? srow[c] : 0;
+    // which target (if any) is this column's slot?  every lane's slot is compared with lane t's target
+    int tix = -1;
+    for (u32 t = 0; t < P.T; ++t) {
+      const int32_t tg = __shfl_sync(0xFFFFFFFFu, my_target, (int)t);
+      const u32 bt = __ballot_sync(0xFFFFFFFFu, in && sl == tg);
+      if (in && sl == tg) tix = (int)t;
+      if (ln == t) cnt += (u32)__popc(bt);
+    }
+    int64_t id = 0; float w = 1.f;
+    bool hit = tix >= 0;
+    if (hit) { id = irow[c]; if (wrow) w = wrow[c]; }
+    if (hit && (id < 0 || id >= P.V)) { if (err) atomicOr(err, 8u); hit = false; }     // (tf.gather would raise: flagged, skipped)
+    u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+    while (m) {
+      int src[RIN]; float wv[RIN]; int tt[RIN]; float ev[RIN][CH][VEC];
+#pragma unroll
+      for (int r = 0; r < RIN; ++r) { src[r] = m ? __ffs(m) - 1 : -1; if (m) m &= m - 1; }
+#pragma unroll
+      for (int r = 0; r < RIN; ++r) {
+        const int sl_ = src[r] < 0 ? 0 : src[r];
+        const int64_t rid = __shfl_sync(0xFFFFFFFFu, id, sl_);
+        wv[r] = __shfl_sync(0xFFFFFFFFu, w, sl_);
+        tt[r] = __shfl_sync(0xFFFFFFFFu, tix, sl_);
+        if (src[r] >= 0) {
+          const float* e = P.table + (size_t)rid * P.D + (size_t)ln * VEC;
+#pragma unroll
+          for (int h = 0; h < CH; ++h) {
+            if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(e + h * 32 * VEC); ev[r][h][0] = q.x; ev[r][h][1 % VEC] = q.y; ev[r][h][2 % VEC] = q.z; ev[r][h][3 % VEC] = q.w; }
+            else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2*>(e + h * 32 * VEC); ev[r][h][0] = q.x; ev[r][h][1 % VEC] = q.y; }
+            else ev[r][h][0] = e[h * 32 * VEC];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RIN; ++r) {
+        if (src[r] >= 0) {
+          float* a = acc + (size_t)tt[r] * P.D + ln * VEC;
+#pragma unroll
+          for (int h = 0; h < CH; ++h)
+#pragma unroll
+            for (int k = 0; k < VEC; ++k)
+              a[h * 32 * VEC + k] = __fadd_rn(a[h * 32 * VEC + k], wrow ? __fmul_rn(ev[r][h][k], wv[r]) : ev[r][h][k]);
+        }
+      }
+    }
+  }
+  for (u32 t = 0; t < P.T; ++t) {
+    const u32 ct = __shfl_sync(0xFFFFFFFFu, cnt, (int)t);
+    float* o = out + ((size_t)b * P.T + t) * P.D + (size_t)ln * VEC;
+    const float* a = acc + (size_t)t * P.D + ln * VEC;
+#pragma unroll
+    for (int h = 0; h < CH; ++h) {
+      float v[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { v[k] = a[h * 32 * VEC + k]; if (P.mean && ct > 1) v[k] = __fdiv_rn(v[k], (float)ct); }
+      if (VEC == 4) *reinterpret_cast<float4*>(o + h * 32 * VEC) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+      else if (VEC == 2) *reinterpret_cast<float2*>(o + h * 32 * VEC) = make_float2(v[0], v[1 % VEC]);
+      else o[h * 32 * VEC] = v[0];
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256) k_pool_bwd(PoolParams P, const float* __restrict__ d_out, float* __restrict__ d_table,
                                                   float* __restrict__ d_weights) {
@@ -205,6 +293,19 @@ extern "C" int rn_segment_pool_fwd(const rn_pool_args* a, float* out, uint32_t* 
   if (check_align(a->table) == RN_OK && check_align(out) == RN_OK) {
     const u64 rgrid = ((u64)P.B * 32 + 255) / 256;
     if (rgrid <= 0x7FFFFFFFull) {
+      // all target slots in one pass when their accumulators fit the warps' shared memory
+      const size_t acc_bytes = (size_t)8 * P.T * P.D * sizeof(float);
+      if (P.T <= 32 && acc_bytes <= 48 * 1024) {
+        bool done = true;
+        switch (P.D) {
+          case 32:  k_pool_fwd_rows_all<1, 1, 8><<<(unsigned)rgrid, 256, acc_bytes, st>>>(P, out, err_flag); break;
+          case 64:  k_pool_fwd_rows_all<2, 1, 8><<<(unsigned)rgrid, 256, acc_bytes, st>>>(P, out, err_flag); break;
+          case 128: k_pool_fwd_rows_all<4, 1, 4><<<(unsigned)rgrid, 256, acc_bytes, st>>>(P, out, err_flag); break;
+          case 256: k_pool_fwd_rows_all<4, 2, 4><<<(unsigned)rgrid, 256, acc_bytes, st>>>(P, out, err_flag); break;
+          default: done = false;
+        }
+        if (done) return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+      }
       bool done = true;
       switch (P.D) {
         case 32:  k_pool_fwd_rows<1, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, out, err_flag); break;

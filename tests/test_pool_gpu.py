@@ -43,7 +43,8 @@ def test_reference_known_answers():
 
 
 @pytest.mark.parametrize("b,c,t,d,v", [(64, 12, 3, 2, 50), (500, 40, 8, 16, 1000), (4096, 64, 16, 64, 20000), (300, 7, 5, 33, 97),
-                                       (700, 70, 6, 32, 900), (600, 33, 4, 128, 500), (257, 20, 3, 256, 300)])
+                                       (700, 70, 6, 32, 900), (600, 33, 4, 128, 500), (257, 20, 3, 256, 300),
+                                       (200, 90, 40, 64, 500)])       # (T > 32: the per-target warp kernel)
 @pytest.mark.parametrize("method", ["sum", "mean"])
 @pytest.mark.parametrize("weighted", [False, True])
 def test_pool_matches_oracle(b, c, t, d, v, method, weighted):
