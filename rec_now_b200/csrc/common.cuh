@@ -392,6 +392,8 @@ struct GraphCall {
   bool capturing() const { return mode == 2; }
   bool updating() const { return mode == 1; }
 };
+// Calls enqueued from now on by this thread use the cached graphs of `lane` (0 = the default); see GraphSlot.
+void set_graph_lane(int lane);
 // The two events recorded by the timed graphs of this thread (created on first use; nullptr on failure).
 cudaEvent_t* timed_events();
 

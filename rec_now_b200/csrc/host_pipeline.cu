@@ -17,6 +17,10 @@ struct Slot {
   float* outs_host = nullptr;          // pinned staging of the three scalars: [loss f32][n_pair f32][n_pair i64]
   float* loss = nullptr; float* n_pair_f32 = nullptr; int64_t* n_pair = nullptr;      // where the caller wants them
   cudaEvent_t in_done = nullptr, cmp_done = nullptr, out_done = nullptr;
+  // the slot's own compute stream: the launches of consecutive batches are processed side by side, so the first kernel of
+  // batch k+1 is ready to start the moment the last kernel of batch k leaves the SMs (on one stream the ~7 us between two
+  // graph launches were idle GPU time); each stream has its own instance of the library's cached graphs (set_graph_lane)
+  cudaStream_t s_cmp = nullptr;
   bool busy = false;
 };
 
@@ -43,6 +47,7 @@ extern "C" int rn_host_pairwise_destroy(rn_host_pairwise* p) {
       if (s.in_done) cudaEventDestroy(s.in_done);
       if (s.cmp_done) cudaEventDestroy(s.cmp_done);
       if (s.out_done) cudaEventDestroy(s.out_done);
+      if (s.s_cmp) cudaStreamDestroy(s.s_cmp);
     }
     delete[] p->slots;
   }
@@ -83,6 +88,7 @@ extern "C" int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, 
     ok = ok && cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.cmp_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&s.s_cmp, cudaStreamNonBlocking) == cudaSuccess;
   }
   if (!ok) { cudaGetLastError(); rn_host_pairwise_destroy(p); return RN_ERR_LAUNCH; }
   *out = p;
@@ -123,7 +129,9 @@ extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_ar
   if (h->row_ok) h2d(p->o_ok, h->row_ok, B);
   ok = ok && cudaEventRecord(s.in_done, p->s_in) == cudaSuccess;
   // ---- kernels
-  ok = ok && cudaStreamWaitEvent(p->s_cmp, s.in_done, 0) == cudaSuccess;
+  static const bool one_stream = []() { const char* v = getenv("RN_HOST_ONE_STREAM"); return v && *v == '1'; }();
+  cudaStream_t cmp = one_stream ? p->s_cmp : s.s_cmp;
+  ok = ok && cudaStreamWaitEvent(cmp, s.in_done, 0) == cudaSuccess;
   if (!ok) { cudaGetLastError(); return RN_ERR_LAUNCH; }
   rn_pairwise_args a = *h;
   a.keys = reinterpret_cast<const int64_t*>(d + p->o_keys);
@@ -137,9 +145,11 @@ extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_ar
   a.dlogits = reinterpret_cast<float*>(d + p->o_dl);
   a.row_pairs = h->row_pairs ? reinterpret_cast<int64_t*>(d + p->o_rp) : nullptr;
   a.scratch_persistent = 1; a.scratch_rows = p->B_max;     // (one layout for every batch size this object accepts)
-  rc = rn_pairwise_fwd_bwd(&a, d + p->o_scr, p->scratch_bytes, p->s_cmp);
+  rn::set_graph_lane(one_stream ? 0 : q + 1);
+  rc = rn_pairwise_fwd_bwd(&a, d + p->o_scr, p->scratch_bytes, cmp);
+  rn::set_graph_lane(0);
   if (rc) return rc;
-  ok = ok && cudaEventRecord(s.cmp_done, p->s_cmp) == cudaSuccess;
+  ok = ok && cudaEventRecord(s.cmp_done, cmp) == cudaSuccess;
   // ---- copy-out
   ok = ok && cudaStreamWaitEvent(p->s_out, s.cmp_done, 0) == cudaSuccess;
   auto d2h = [&](void* dst, size_t off, size_t bytes) {

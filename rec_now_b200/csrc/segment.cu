@@ -54,8 +54,12 @@ __global__ void __launch_bounds__(256) k_init(uint4* zero, size_t nzero16, uint4
 // the stream: they set the parameters of the three kernel nodes of a cached, instantiated CUDA graph, which the
 // caller then launches once (smaller inter-kernel gaps, one driver call instead of three).
 // (f[0] == nullptr: a call without k_init -- the counting path on a persistent arena -- is a graph of two kernel nodes)
-struct GraphSlot { int dev; const void* f[3]; int nf; bool timed; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
-static thread_local GraphSlot tl_slots[48];
+// (lane: an executable graph runs one launch at a time -- a caller that keeps several calls in flight on different streams,
+// as the host-buffer front end does with its slots, gives every stream a lane of its own and so an executable of its own)
+struct GraphSlot { int dev; int lane; const void* f[3]; int nf; bool timed; cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[3]; };
+static thread_local int tl_lane = 0;
+void set_graph_lane(int lane) { tl_lane = lane; }
+static thread_local GraphSlot tl_slots[96];
 static thread_local int tl_nslots = 0;
 static thread_local GraphSlot* tl_update = nullptr;      // slot whose nodes receive the launches of this thread
 static thread_local int tl_next = 0;
@@ -123,7 +127,7 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (nf == 2) fl[2] = nullptr;
   for (int i = 0; i < tl_nslots; ++i) {
     GraphSlot& g = tl_slots[i];
-    if (g.dev == dev && g.nf == nf && g.f[0] == fl[0] && g.f[1] == fl[1] && g.f[2] == fl[2] && g.timed == timed) {
+    if (g.dev == dev && g.lane == tl_lane && g.nf == nf && g.f[0] == fl[0] && g.f[1] == fl[1] && g.f[2] == fl[2] && g.timed == timed) {
       slot = &g; tl_update = slot; tl_next = 0; mode = 1;
       return;
     }
@@ -132,7 +136,7 @@ GraphCall::GraphCall(const void* f_init, const void* f_seg, const void* f_pair, 
   if (!tl_cap_stream && cudaStreamCreateWithFlags(&tl_cap_stream, cudaStreamNonBlocking) != cudaSuccess) { tl_graph_broken = true; return; }
   if (cudaStreamBeginCapture(tl_cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { tl_graph_broken = true; cudaGetLastError(); return; }
   slot = &tl_slots[tl_nslots];
-  slot->dev = dev; slot->f[0] = fl[0]; slot->f[1] = fl[1]; slot->f[2] = fl[2]; slot->nf = nf; slot->timed = timed;
+  slot->dev = dev; slot->lane = tl_lane; slot->f[0] = fl[0]; slot->f[1] = fl[1]; slot->f[2] = fl[2]; slot->nf = nf; slot->timed = timed;
   run_stream = tl_cap_stream; tl_capturing = true; tl_capture_timed = timed; mode = 2;
 }
 

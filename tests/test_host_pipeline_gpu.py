@@ -100,3 +100,35 @@ def test_bound_buffers_are_read_at_submit():
         s.copy_(torch.from_numpy(rng.standard_normal(B).astype(np.float32)))       # the loader refills its buffer
         y.copy_(torch.from_numpy(rng.integers(0, 2, B).astype(np.float32)))
     hp.close()
+
+
+def test_soak_slots_on_their_own_streams():
+    """Every slot enqueues on its own compute stream with its own instance of the cached graph, so the cooperative kernels
+    of consecutive batches are in the launch queues at the same time.  4000 batches, three in flight: every result must
+    be the first one's (exact pair count, loss and gradient up to the jitter of the float atomics), no device error."""
+    from rec_now_b200.host import HostPairwise
+    d = G.cfg3(3, b=30000, n_groups=1500)
+    B = d["s"].size
+    hin = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("g", "s", "y", "w")}
+    depth = 3
+    hp = HostPairwise(B, depth=depth)
+    outs = [dict(loss=torch.empty(1).pin_memory(), n_pair_f32=torch.empty(1).pin_memory(),
+                 n_pair=torch.empty(1, dtype=torch.int64).pin_memory(), dlogits=torch.empty(B).pin_memory())
+            for _ in range(depth)]
+    bound = [hp.bind(hin["g"], hin["s"], hin["y"], rw_pos=hin["w"], label_func="diff", power=-0.5, **o) for o in outs]
+    ref = S.pairwise(d["s"], d["y"], d["g"], S.PairSpec(label_func="diff", rw_pos=d["w"], power=-0.5))
+    pending, seen = [], 0
+    for k in range(4000):
+        pending.append((bound[k % depth].submit(), k % depth))
+        if len(pending) == depth:
+            t, q = pending.pop(0)
+            hp.wait(t)
+            assert int(outs[q]["n_pair"]) == ref["n_pair"], f"batch {seen}"
+            assert abs(float(outs[q]["loss"]) - ref["loss"]) <= 1e-5 * abs(ref["loss"]), f"batch {seen}"
+            if seen % 500 == 0:
+                check_pairwise(_as_out(outs[q]), ref, ctx=f"soak batch {seen}")
+            seen += 1
+    for t, q in pending:
+        hp.wait(t)
+        assert int(outs[q]["n_pair"]) == ref["n_pair"]
+    hp.close()
