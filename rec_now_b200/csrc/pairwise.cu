@@ -901,7 +901,17 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           if (cb > zb || (cb == zb && (cj > zj || (cj == zj && ce >= ze)))) { st_done = true; return false; }
           const u32 jn = jn_[cb], jend = (jn & 0xFFFFu) + (jn >> 16);
           if (cj >= jend) {                       // (also skips virtual blocks without tiles)
-            ++cb; cj = cb < nvb ? (jn_[cb] & 0xFFFFu) : 0u; ce = 0;
+            // the next virtual block that has tiles, 32 candidates per look: a piece can hold a long run of empty blocks
+            // (rows of pairless small groups cost nothing on the cost line), and walking them one dependent load at a
+            // time made single warps the last to reach the barrier
+            u32 nb = cb + 1u;
+            while (nb < nvb && nb <= zb) {
+              const u32 idx = nb + ln;
+              const u32 m = __ballot_sync(0xFFFFFFFFu, idx >= nvb || (jn_[idx] >> 16) != 0u);
+              if (m) { nb += (u32)__ffs(m) - 1u; break; }
+              nb += 32u;
+            }
+            cb = nb; cj = cb < nvb ? (jn_[cb] & 0xFFFFu) : 0u; ce = 0;
             continue;
           }
           sg.b = cb >> 1; sg.jb0 = cj; sg.ea = ce;
