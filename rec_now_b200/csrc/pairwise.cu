@@ -328,6 +328,11 @@ struct HeadsTail {
       __syncthreads();
       total = sm_toff[my_tiles];
     }
+    constexpr u32 kWideBlocks = 128, kWideCap = 48, kWideWords = 4 + 2 * kLevels;
+    u32* sm_qn = smem + 100;                 // queue of very long groups (behind sm_toff): count, entries
+    u32* sm_q = smem + 128;
+    if (tid == 0) *sm_qn = 0;
+    __syncthreads();
     const u32 nrounds = flat ? (total + kSegThreads - 1) / kSegThreads : my_tiles;
     for (u32 rd = 0; rd < nrounds; ++rd) {
       // (flat: round rd handles items [rd * 512, +512) of the concatenated lists; else round rd = tile rd, lists <= 512 long)
@@ -389,7 +394,21 @@ struct HeadsTail {
           b0 = g.base / kIB; nblk = (g.base + g.tot - 1u) / kIB - b0 + 1u;
           for (u32 b = b0; b < b0 + min(nblk, 3u); ++b) block_range(b, b0, g);
         }
-        u32 big = __ballot_sync(0xFFFFFFFFu, nblk > 3u);
+        // Very long groups (the head of a Zipf batch; in the global mode tens of thousands of rows) go to a queue the
+        // whole CTA works off after the round: their creators' first rows all sit in the batch's first tile, so one
+        // warp of one CTA used to write the ranges of all of them, one after the other, with the grid waiting
+        bool queued = false;
+        if (act && nblk > kWideBlocks) {
+          const u32 qi = atomicAdd(sm_qn, 1u);
+          if (qi < kWideCap) {
+            u32* e = sm_q + qi * kWideWords;
+            e[0] = g.base; e[1] = g.tot; e[2] = b0; e[3] = nblk;
+#pragma unroll
+            for (int q = 0; q < kLevels; ++q) { e[4 + q] = g.ls[q]; e[4 + kLevels + q] = g.co[q]; }
+            queued = true;
+          }
+        }
+        u32 big = __ballot_sync(0xFFFFFFFFu, nblk > 3u && !queued);
         while (big) {
           const int src = __ffs(big) - 1; big &= big - 1;
           Geo h;
@@ -416,6 +435,23 @@ struct HeadsTail {
           }
         }
       }
+      // the queued long groups: every thread of the CTA takes I-blocks of each
+      __syncthreads();
+      {
+        const u32 nq = min(*sm_qn, kWideCap);
+        for (u32 qi = 0; qi < nq; ++qi) {
+          const u32* e = sm_q + qi * kWideWords;
+          Geo h;
+          h.base = e[0]; h.tot = e[1];
+          const u32 gb0 = e[2], gnb = e[3];
+#pragma unroll
+          for (int q = 0; q < kLevels; ++q) { h.ls[q] = e[4 + q]; h.co[q] = e[4 + kLevels + q]; }
+          for (u32 b = gb0 + 3u + tid; b < gb0 + gnb; b += kSegThreads) block_range(b, gb0, h);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) *sm_qn = 0;
+      __syncthreads();
     }
     if (!dyn) {
       npsum = warp_sum(npsum);
