@@ -143,6 +143,9 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     dev = s.device
     rwp, rwn = _f32(rw_pos), _f32(rw_neg)
     ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
+    for name, t in (("labels", y), ("rw_pos", rwp), ("rw_neg", rwn), ("row_ok", ok)):
+        if t is not None and t.numel() != b:        # (a shorter column would be read out of bounds on the device)
+            raise ValueError(f"{name} holds {t.numel()} elements, logits {b}")
     out = torch.empty(4, dtype=torch.float32, device=dev)          # loss, n_pair_f32, n_pair (int64 in [2:4])
     dlogits = torch.empty(b, dtype=torch.float32, device=dev)
     row_pairs = torch.empty(b, dtype=torch.int64, device=dev) if want_row_pairs else None
@@ -411,6 +414,9 @@ def listwise_fwd_bwd(keys, labels, logits, row_ok=None, list_w=None, pos_neg_th=
     dev = s.device
     ok = None if row_ok is None else row_ok.reshape(-1).to(torch.uint8).contiguous()
     lw = _f32(list_w)
+    for name, t in (("labels", y), ("keys", keys), ("row_ok", ok)):
+        if t is not None and t.numel() != b:        # (a shorter column would be read out of bounds on the device)
+            raise ValueError(f"{name} holds {t.numel()} elements, logits {b}")
     out = torch.empty(4, dtype=torch.float32, device=dev)           # loss f32, n_valid i32, n_group i32
     dlogits = torch.empty(b, dtype=torch.float32, device=dev)
     list_loss = torch.empty(b, dtype=torch.float32, device=dev) if (want_list_loss or not do_reduce) else None

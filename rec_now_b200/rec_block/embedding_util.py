@@ -34,12 +34,23 @@ class TableLookup:
         return torch.nn.functional.embedding(ids.long(), self.table)
 
 
+_target_cache: dict = {}
+
+
 def _targets(target_slots, device) -> torch.Tensor:
+    """The target slots as an int32 device tensor; cached per (slots, device) -- building it is a synchronous
+    host-to-device copy, a quarter of the pooling kernel's own time."""
     if not isinstance(target_slots, list):
         target_slots = list(target_slots)
-    if len(set(target_slots)) != len(target_slots):
-        raise ValueError("target_slots must be distinct (the reference's StaticHashTable rejects duplicate keys)")
-    return torch.tensor(target_slots, dtype=torch.int32, device=device)
+    key = (tuple(target_slots), str(device))
+    t = _target_cache.get(key)
+    if t is None:
+        if len(set(target_slots)) != len(target_slots):
+            raise ValueError("target_slots must be distinct (the reference's StaticHashTable rejects duplicate keys)")
+        if len(_target_cache) > 256:
+            _target_cache.clear()
+        t = _target_cache[key] = torch.tensor(target_slots, dtype=torch.int32, device=device)
+    return t
 
 
 def sparse_batch_segment_ids_of_targets(slots, target_slots):
@@ -63,19 +74,31 @@ def _pool_args(slots, ids, weights, tgt, table, mean) -> _lib.PoolArgs:
                          target_slots=tgt.data_ptr(), table=table.data_ptr(), V=table.shape[0])
 
 
+_err_flags: dict = {}
+
+
+def out_of_range_ids_seen(device=None) -> bool:
+    """True if any pooling call on `device` met an id outside [0, V) (such ids contribute nothing; tf.gather would have
+    raised).  Reads one word back (synchronises)."""
+    idx = torch.cuda.current_device() if device is None else torch.device(device).index
+    f = _err_flags.get(idx)
+    return bool(f is not None and int(f.item()) != 0)
+
+
 class _SegmentPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table, weights, slots, ids, tgt, mean):
         b = slots.shape[0]
         out = torch.empty((b, tgt.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
-        err = torch.zeros(1, dtype=torch.int32, device=table.device)
+        err = _err_flags.get(table.device.index)       # (one flag word per device, set by any call that saw an id outside the table)
+        if err is None:
+            err = _err_flags[table.device.index] = torch.zeros(1, dtype=torch.int32, device=table.device)
         a = _pool_args(slots, ids, weights, tgt, table, mean)
         with _on_device(table.device):
             _lib.check(_lib.lib().rn_segment_pool_fwd(C.byref(a), out.data_ptr(), err.data_ptr(), _stream(table.device)),
                        "rn_segment_pool_fwd")
         ctx.save_for_backward(table, weights if weights is not None else torch.empty(0, device=table.device), slots, ids, tgt)
         ctx.mean, ctx.has_w = mean, weights is not None
-        ctx.err = err
         return out
 
     @staticmethod
