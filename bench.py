@@ -395,6 +395,24 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
                                      "tolerance": 1e-5,
                                      "ok": bool(hn == ref["n_pair"] and abs(float(out["loss"].item()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
                                                 and (gerr <= 1e-5 * ref["grad_abs"] + 1e-12).all())}}
+    # the rarer kernel variants on cfg3's batch (score- / weight-dependent pair sets: general tiles, counts from the kernel)
+    for vname, vkw, skw in (("wrong_order_cfg3", dict(only_wrong=True), dict(only_wrong=True)),
+                            ("rw_neg_cfg3", dict(rw_neg=w), dict(rw_neg=d["w"]))):
+        step = lambda: ops.pairwise_fwd_bwd(s, y, keys, rw_pos=w, label_func="diff", power=-0.5, **vkw)
+        t = time_device(step, steps, 5, flush)
+        out = step()
+        spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=d["w"], **skw)
+        ref = S.pairwise(d["s"], d["y"], d["g"], spec)
+        gerr = np.abs(out["dlogits"].cpu().numpy().astype(np.float64) - ref["grad"])
+        vn = int(out["n_pair"].item())
+        recs[vname] = {"workload": f"cfg3's batch with {'only_use_wrong_order_pair' if 'only_wrong' in vkw else 'a negative-side weight column'}"
+                                   " (k_pair variant with general tiles and kernel-side pair counts)",
+                       "rows": s.numel(), "n_pair": vn, **t, "pairs_per_s": vn / (t["single_call_us"] * 1e-6),
+                       "parity": {"oracle": "oracle/seg_ref.py (float64)", "n_pair_exact": vn == ref["n_pair"],
+                                  "loss_rel": abs(float(out["loss"].item()) - ref["loss"]) / max(abs(ref["loss"]), 1e-30),
+                                  "tolerance": 1e-5,
+                                  "ok": bool(vn == ref["n_pair"] and abs(float(out["loss"].item()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+                                             and (gerr <= 1e-5 * ref["grad_abs"] + 1e-12).all())}}
     # segment pooling of slot embeddings: HBM-bound gather + segment sum, one kernel
     from oracle import pool_ref as PR
     from rec_now_b200.rec_block import embedding_util as EU

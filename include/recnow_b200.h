@@ -89,7 +89,9 @@ typedef struct rn_pairwise_args {
   int32_t part_rank;
   int32_t part_count;
   /* outputs */
-  float* loss;             /* [1]  sum_P w*l / (float(n)+1e-10)   (or the plain sum if !reduce_mean) */
+  float* loss;             /* [1]  sum_P w*l / (float(n)+1e-10)   (or the plain sum if !reduce_mean); NaN if the call failed
+                            *      on the device (a grid barrier timed out, the group table overflowed: the arena was
+                            *      not clean) -- rn_last_device_error then tells which */
   float* n_pair_f32;       /* [1]  float32(n) as PW:276 returns it */
   int64_t* n_pair;         /* [1]  exact n */
   float* dlogits;          /* [B]  d loss / d logits */

@@ -1198,6 +1198,8 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const double tot = lsum_all * P.loss_unit;
       float lossv = (float)(tot / (double)denom);
       if (P.focal_w != 0.f) lossv += P.focal_w * (float)(*reinterpret_cast<volatile double*>(&ctl->acc_d[3]) / (double)B);
+      // a device-side failure (grid barrier timed out, hash table full: the arena was not clean) must not look like a result
+      if (*reinterpret_cast<volatile u32*>(&ctl->err)) lossv = __int_as_float(0x7FC00000);
       *P.loss = lossv;
       *P.n_pair_f32 = (float)n;                  // PW:276
       *P.n_pair = (int64_t)n;
@@ -1310,7 +1312,8 @@ __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& 
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->ts[23] = globaltimer();
     const double tot = *reinterpret_cast<volatile double*>(&ctl->loss_sum) * P.loss_unit;
-    const float lossv = (float)(tot / (double)denom);
+    float lossv = (float)(tot / (double)denom);
+    if (*reinterpret_cast<volatile u32*>(&ctl->err)) lossv = __int_as_float(0x7FC00000);      // (see k_pair: a failed call returns NaN)
     *P.loss = lossv;
     *P.n_pair_f32 = (float)n;                  // PW:276
     *P.n_pair = (int64_t)n;

@@ -164,3 +164,31 @@ def test_non_persistent_arena_still_takes_the_radix_path():
     res = dict(loss=outv[0], n_pair_f32=outv[1], n_pair=outv[2:4].view(torch.int64)[0], dlogits=dl)
     check_pairwise(res, S.pairwise(d["s"], d["y"], d["g"]), ctx="non-persistent")
     assert ops.last_segmentation_path(scratch) == 2
+
+
+def test_device_side_failure_returns_nan_not_a_result():
+    """A call whose control block carries a device-side error flag (a grid barrier that timed out, a full group table --
+    here planted) must not look like a result: loss = NaN and rn_last_device_error != 0; the call after it is clean."""
+    import ctypes as C
+    from rec_now_b200 import _lib, ops
+    lib = _lib.lib()
+    d = G.cfg1(3, b=5000, n_groups=200)
+    b = d["s"].size
+    nbytes = lib.rn_pairwise_scratch_bytes(b, 1)
+    scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    ts, ty, tk = dev(d["s"]), dev(d["y"]), dev(d["g"])
+    outv = torch.empty(4, dtype=torch.float32, device="cuda")
+    dl = torch.empty(b, dtype=torch.float32, device="cuda")
+    a = _lib.PairwiseArgs(B=b, K=1, label_func=0, keys=tk.data_ptr(), logits=ts.data_ptr(), labels=ty.data_ptr(),
+                          factor=1.0, power=0.0, only_wrong=0, reduce_mean=1, part_rank=0, part_count=1,
+                          loss=outv.data_ptr(), n_pair_f32=outv.data_ptr() + 4, n_pair=outv.data_ptr() + 8,
+                          dlogits=dl.data_ptr(), scratch_persistent=1)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    scratch[48:52].view(torch.int32).fill_(1)               # Ctl::err (the 13th word of the control block)
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, st) == 0
+    assert torch.isnan(outv[0]).item()
+    assert ops.device_error(scratch) != 0
+    assert lib.rn_pairwise_fwd_bwd(C.byref(a), scratch.data_ptr(), nbytes, st) == 0      # (the report is filed, the flag reset)
+    res = dict(loss=outv[0], n_pair_f32=outv[1], n_pair=outv[2:4].view(torch.int64)[0], dlogits=dl)
+    check_pairwise(res, S.pairwise(d["s"], d["y"], d["g"]), ctx="after a failed call")
+    assert ops.device_error(scratch) == 0
