@@ -77,11 +77,16 @@ __device__ __forceinline__ float small_pair(const float x, const float c, const 
   return (xs >= 0.f ? e : 1.0f) * mufu_rcp(t1p);                            // sigma(-x)
 }
 
+// SIMPLE: the default call (no weights of any kind, no wrong-order filter, logistic loss) -- a second instantiation whose
+// pair walks carry none of the option tests (the kernel is bound by the issue slots of one SM).
+template <bool SIMPLE>
 __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
   extern __shared__ __align__(16) unsigned char small_raw[];
   SmallSmem& S = *reinterpret_cast<SmallSmem*>(small_raw);
   const u32 tid = threadIdx.x, ln = tid & 31u, w = tid >> 5, B = A.B;
-  const bool HASW = A.mode & M_HASW, DIFF = A.mode & M_DIFF, RWN = A.mode & M_RWN, WRONG = A.mode & M_WRONG;
+  const bool HASW = !SIMPLE && (A.mode & M_HASW), DIFF = !SIMPLE && (A.mode & M_DIFF), RWN = !SIMPLE && (A.mode & M_RWN),
+             WRONG = !SIMPLE && (A.mode & M_WRONG);
+  const int hinge = SIMPLE ? 0 : A.hinge;
   const bool in = tid < B;
   auto stamp_s = [&](int i) {                                                     // (phase stamps, as the general path's)
     if (tid == 0) A.ctl->ts[i] = globaltimer();
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
   u32 row = 0, grp = kSmallRows;
   uint4 ext = make_uint4(0, 0, 0, 0);
   if (in_p) { si = S.ss[tid]; wp = S.swp[tid]; row = S.srow[tid]; grp = S.sgrp[tid]; ext = S.sext[tid]; }
-  const bool wp_test = A.rw_pos != nullptr && !RWN;                       // PW:193 C = W > 0 with a positive-side factor only
+  const bool wp_test = !SIMPLE && A.rw_pos != nullptr && !RWN;                       // PW:193 C = W > 0 with a positive-side factor only
   const float c = A.c;
   // Work per position: negatives [a, l) as the positive side, positives [le, ge) as the negative side.  Most positions
   // have none (binary labels: the 25 % positives hold all the negative ranges), so the positions that have work are
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
           }
           if (WRONG) valid = valid && (x < 0.f);                          // PW:200-202
           float lo2 = 0.f;
-          const float d = small_pair<true>(x, c, A.hinge, A.margin, lo2) * wv;
+          const float d = small_pair<true>(x, c, hinge, A.margin, lo2) * wv;
           const float l = wv * lo2;
           li += valid ? l : 0.f; gi += valid ? d : 0.f; cnt += valid ? 1u : 0u;
         }
@@ -304,7 +309,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
           }
           if (WRONG) valid = valid && (x < 0.f);
           float unused;
-          const float d = small_pair<false>(x, c, A.hinge, A.margin, unused) * wv;
+          const float d = small_pair<false>(x, c, hinge, A.margin, unused) * wv;
           gn += valid ? d : 0.f;
         }
       }
@@ -371,7 +376,8 @@ bool small_pairwise(const rn_pairwise_args* a, void* scratch, cudaStream_t st, i
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { *rc = RN_ERR_LAUNCH; return true; }
   if (!attr_set[dev]) {
-    if (cudaFuncSetAttribute((const void*)k_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)) != cudaSuccess) {
+    if (cudaFuncSetAttribute((const void*)k_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)) != cudaSuccess ||
+        cudaFuncSetAttribute((const void*)k_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmallSmem)) != cudaSuccess) {
       cudaGetLastError(); *rc = RN_ERR_LAUNCH; return true;
     }
     attr_set[dev] = true;
@@ -389,7 +395,8 @@ bool small_pairwise(const rn_pairwise_args* a, void* scratch, cudaStream_t st, i
     const char* dv = getenv("RN_SMALL_DEBUG");
     if (dv && *dv && atoi(dv)) A.dbg = at<u64>(scratch, make_layout(a->scratch_rows ? a->scratch_rows : a->B, 1, a->B).gstat);
   }
-  k_small<<<1, kSmallThreads, sizeof(SmallSmem), st>>>(A);
+  if (mode == 0 && !hinge && !a->rw_pos) k_small<true><<<1, kSmallThreads, sizeof(SmallSmem), st>>>(A);
+  else k_small<false><<<1, kSmallThreads, sizeof(SmallSmem), st>>>(A);
   *rc = cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
   return true;
 }
