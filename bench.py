@@ -427,6 +427,14 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
     step = lambda: EU.segment_pool(table, slots_t, targets, ids_t, w_t)
     t = time_device(step, steps, 5, flush)
     out = step()
+    # forward + backward (gradient into the table: vector reductions; includes zeroing the 256 MiB gradient buffer)
+    table_g = table.clone().requires_grad_(True)
+    g_out = torch.randn_like(out)
+
+    def step_fb():
+        table_g.grad = None
+        EU.segment_pool(table_g, slots_t, targets, ids_t, w_t).backward(g_out)
+    t_fb = time_device(step_fb, max(10, steps // 4), 3, flush)
     kept = int(np.isin(slots_h, targets).sum())
     bytes_alg = kept * pd * 4 + pb * pt * pd * 4 + pb * pc * 16          # table rows in, pooled rows out, slots + ids + weights
     nchk = 256
@@ -436,6 +444,7 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
     recs["segment_pool"] = {"workload": f"embedding_using_sparse_batch_segment_ids: B={pb} rows x {pc} columns, {pt} target slots of 16, "
                                         f"D={pd}, table {pv} x {pd} f32 (256 MiB), weights, method sum",
                             "rows": pb, "kept_ids": kept, **t,
+                            "fwd_bwd_single_call_us": t_fb["single_call_us"], "fwd_bwd_streamed_us": t_fb["streamed_us"],
                             "hbm_roofline": {"bound": "hbm", "algorithmic_bytes": bytes_alg, "peak_gbs": hbm_gbs,
                                              "achieved_gbs_single_call": bytes_alg / (t["single_call_us"] * 1e-6) / 1e9,
                                              "frac_single_call": bytes_alg / (t["single_call_us"] * 1e-6) / 1e9 / hbm_gbs,

@@ -266,6 +266,93 @@ __global__ void __launch_bounds__(256) k_pool_bwd(PoolParams P, const float* __r
   }
 }
 
+// Vector reductions (sm_90+: REDG.E.ADD.F32x2 / x4): one instruction adds a lane's 8 / 16 contiguous bytes, so a warp
+// covers whole sectors of a table row with one atomic operation each.
+__device__ __forceinline__ void red_add_v2(float* a, float x, float y) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" :: "l"(a), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* a, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// Warp-per-row backward (same walk as k_pool_fwd_rows_all): for every kept column the warp reads the segment's slice of
+// d out (one contiguous row), scales it by the column's weight (and 1 / count for the mean) and adds it to the id's row
+// of d table with vector reductions -- eight full sectors per row instead of one scalar atomic per element; d weights is
+// a warp-reduced dot product stored by lane 0 (one warp owns a (row, column): no atomic).  T <= 32.
+template <int VEC, int CH>
+__global__ void __launch_bounds__(256) k_pool_bwd_rows(PoolParams P, const float* __restrict__ d_out, float* __restrict__ d_table,
+                                                       float* __restrict__ d_weights) {
+  const u32 ln = threadIdx.x & 31u;
+  const u64 b = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= P.B) return;
+  const int32_t* srow = P.slots + (size_t)b * P.C;
+  const int64_t* irow = P.ids + (size_t)b * P.C;
+  const float* wrow = P.weights ? P.weights + (size_t)b * P.C : nullptr;
+  const int32_t my_target = ln < P.T ? P.tslots[ln] : 0;
+  u32 cnt = 0;                                  // lane t: kept columns of target t (mean only)
+  if (P.mean) {
+    for (u32 c0 = 0; c0 < P.C; c0 += 32) {
+      const u32 c = c0 + ln;
+      const int32_t sl = c < P.C ? srow[c] : 0;
+      for (u32 t = 0; t < P.T; ++t) {
+        const int32_t tg = __shfl_sync(0xFFFFFFFFu, my_target, (int)t);
+        const u32 bt = __ballot_sync(0xFFFFFFFFu, c < P.C && sl == tg);
+        if (ln == t) cnt += (u32)__popc(bt);
+      }
+    }
+  }
+  for (u32 c0 = 0; c0 < P.C; c0 += 32) {
+    const u32 c = c0 + ln;
+    const bool in = c < P.C;
+    const int32_t sl = in ? srow[c] : 0;
+    int tix = -1;
+    for (u32 t = 0; t < P.T; ++t) {
+      const int32_t tg = __shfl_sync(0xFFFFFFFFu, my_target, (int)t);
+      if (in && sl == tg) tix = (int)t;
+    }
+    int64_t id = 0; float w = 1.f;
+    bool hit = tix >= 0;
+    if (hit) { id = irow[c]; if (wrow) w = wrow[c]; }
+    if (hit && (id < 0 || id >= P.V)) hit = false;
+    u32 m = __ballot_sync(0xFFFFFFFFu, hit);
+    float dw_mine = 0.f;                        // d weights of this lane's column (filled when its turn comes)
+    while (m) {
+      const int src = __ffs(m) - 1; m &= m - 1;
+      const int64_t rid = __shfl_sync(0xFFFFFFFFu, id, src);
+      const float wv = __shfl_sync(0xFFFFFFFFu, w, src);
+      const int tt = __shfl_sync(0xFFFFFFFFu, tix, src);
+      float scale = wv;
+      if (P.mean) { const u32 ct = __shfl_sync(0xFFFFFFFFu, cnt, tt); if (ct > 1) scale = wv / (float)ct; }
+      const float* go = d_out + ((size_t)b * P.T + (u32)tt) * P.D + (size_t)ln * VEC;
+      float* dt = d_table ? d_table + (size_t)rid * P.D + (size_t)ln * VEC : nullptr;
+      const float* e = P.table + (size_t)rid * P.D + (size_t)ln * VEC;
+      float dot = 0.f;
+#pragma unroll
+      for (int h = 0; h < CH; ++h) {
+        float g[VEC];
+        if (VEC == 4) { const float4 q = *reinterpret_cast<const float4*>(go + h * 32 * VEC); g[0] = q.x; g[1 % VEC] = q.y; g[2 % VEC] = q.z; g[3 % VEC] = q.w; }
+        else if (VEC == 2) { const float2 q = *reinterpret_cast<const float2*>(go + h * 32 * VEC); g[0] = q.x; g[1 % VEC] = q.y; }
+        else g[0] = go[h * 32 * VEC];
+        if (dt) {
+          if (VEC == 4) red_add_v4(dt + h * 32 * VEC, g[0] * scale, g[1 % VEC] * scale, g[2 % VEC] * scale, g[3 % VEC] * scale);
+          else if (VEC == 2) red_add_v2(dt + h * 32 * VEC, g[0] * scale, g[1 % VEC] * scale);
+          else atomicAdd(dt + h * 32 * VEC, g[0] * scale);
+        }
+        if (d_weights) {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) dot = fmaf(e[h * 32 * VEC + k], g[k], dot);
+        }
+      }
+      if (d_weights) {
+        dot = warp_sum(dot);
+        if (P.mean) { const u32 ct = __shfl_sync(0xFFFFFFFFu, cnt, tt); if (ct > 1) dot /= (float)ct; }
+        if ((int)ln == src) dw_mine = dot;
+      }
+    }
+    if (d_weights && hit) d_weights[(size_t)b * P.C + c] += dw_mine;       // (this warp is the only writer of the row's columns)
+  }
+}
+
 static int pool_params(const rn_pool_args* a, PoolParams& P) {
   if (!a || a->B <= 0 || a->C <= 0 || a->T <= 0 || a->D <= 0 || a->V <= 0) return RN_ERR_ARG;
   if (a->B > 0x7FFFFFFFll || a->C > 0x7FFFFFFFll) return RN_ERR_ARG;
@@ -334,6 +421,20 @@ extern "C" int rn_segment_pool_bwd(const rn_pool_args* a, const float* d_out, fl
   const u64 grid = (threads + 255) / 256;
   if (grid > 0x7FFFFFFFull) return RN_ERR_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (vec && P.T <= 32) {
+    const u64 rgrid = ((u64)P.B * 32 + 255) / 256;
+    if (rgrid <= 0x7FFFFFFFull) {
+      bool done = true;
+      switch (P.D) {
+        case 32:  k_pool_bwd_rows<1, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, d_out, d_table, d_weights); break;
+        case 64:  k_pool_bwd_rows<2, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, d_out, d_table, d_weights); break;
+        case 128: k_pool_bwd_rows<4, 1><<<(unsigned)rgrid, 256, 0, st>>>(P, d_out, d_table, d_weights); break;
+        case 256: k_pool_bwd_rows<4, 2><<<(unsigned)rgrid, 256, 0, st>>>(P, d_out, d_table, d_weights); break;
+        default: done = false;
+      }
+      if (done) return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
+    }
+  }
   if (vec) k_pool_bwd<4><<<(unsigned)grid, 256, 0, st>>>(P, d_out, d_table, d_weights);
   else k_pool_bwd<1><<<(unsigned)grid, 256, 0, st>>>(P, d_out, d_table, d_weights);
   return cudaGetLastError() == cudaSuccess ? RN_OK : RN_ERR_LAUNCH;
