@@ -317,6 +317,33 @@ __device__ __forceinline__ void clean_records_grid(GRec* rec, u32 rec2_off, cons
 // a second walk that adds the warp's offset.  a[n] receives the total (sc: 34 words).  All threads must call it.
 __device__ __forceinline__ void block_excl_scan(u32* a, u32 n, u32* sc) {
   const u32 ln = lane_id(), w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (n <= 4u * blockDim.x && (n & 3u) == 0u) {
+    // up to four elements per thread: one 16-byte load, the four sums in registers, ONE shuffle scan per warp and one over
+    // the warps' totals (the walk below pays a dependent shuffle scan per 32 elements of a warp's segment)
+    const u32 i4 = 4u * threadIdx.x;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i4 < n) v = *reinterpret_cast<const uint4*>(a + i4);
+    const u32 tsum = v.x + v.y + v.z + v.w;
+    u32 inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const u32 x = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (ln >= (u32)o) inc += x; }
+    if (ln == 31) sc[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const u32 x = ln < nw ? sc[ln] : 0u;
+      u32 xi = x;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const u32 y = __shfl_up_sync(0xFFFFFFFFu, xi, o); if (ln >= (u32)o) xi += y; }
+      sc[ln] = xi - x;
+      if (ln == 31) sc[32] = xi;
+    }
+    __syncthreads();
+    const u32 base = sc[w] + inc - tsum;
+    if (i4 < n) *reinterpret_cast<uint4*>(a + i4) = make_uint4(base, base + v.x, base + v.x + v.y, base + v.x + v.y + v.z);
+    if (threadIdx.x == 0) a[n] = sc[32];
+    __syncthreads();
+    return;
+  }
   const u32 seg = ((n + nw - 1) / nw + 31u) & ~31u;
   const u32 s0 = min(w * seg, n), s1 = min(s0 + seg, n);
   u32 carry = 0;
