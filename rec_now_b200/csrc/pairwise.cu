@@ -222,8 +222,11 @@ struct HeadsTail {
     // of another rank's rows counts into the REMOTE half of the groups' second records
     const bool glob = S.rm.Bl != 0;
     GRec2* rec2 = S.rec2;
+    bool bad;
     u32 k_slot = 0, k_meta = 0; float k_s = 0.f, k_y = 0.f, k_wp = 1.f, k_wn = 1.f;
-    bool bad = false;
+    // (one tile per CTA: the thread that created a record keeps it for the offsets phase -- no list to read back)
+    u32 k_cslot = 0; bool k_created = false, k_trash = false;
+    bad = false;
     // ---- count --------------------------------------------------------------------------------------------------
     for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
       const u32 i = t * kGTile + tid;
@@ -279,6 +282,7 @@ struct HeadsTail {
       const bool isrep = ok && rep == tid;
       if (isrep) { slot = grec_insert(rec, S.capmask, h, key, i, created, &ctl->err); sm_gslot[tid] = slot; }
       if (created) S.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = slot;
+      if (single) { k_created = created; k_cslot = slot; }
       __syncthreads();
       // reserve the tile's ranks inside every (group, level): one atomicAdd each, all in flight together
       if (isrep) {
@@ -293,7 +297,7 @@ struct HeadsTail {
       }
       if (tid == 0 && sm_misc[1]) {
         // rows that cannot pair (row_ok = 0, NaN label): one group of one level behind the table
-        if (atomicCAS(&rec[trash].rep1, 0u, 1u) == 0u) S.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = trash;
+        if (atomicCAS(&rec[trash].rep1, 0u, 1u) == 0u) { S.glist[(size_t)t * kGTile + atomicAdd(&sm_misc[0], 1u)] = trash; k_trash = true; }
         sm_misc[2] = atomicAdd(&rec[trash].cnt[0], sm_misc[1]);
       }
       __syncthreads();
@@ -319,7 +323,8 @@ struct HeadsTail {
     const u32 my_tiles = blockIdx.x < ntile ? (ntile - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
     const bool flat = my_tiles <= 64u;
     u32 total = 0;
-    if (flat) {
+    const bool trash_round = single && __syncthreads_or(k_trash);       // (this CTA created the record of the rows that cannot pair)
+    if (flat && !single) {
       if (tid == 0) {
         u32 acc = 0;
         for (u32 q = 0; q < my_tiles; ++q) { sm_toff[q] = acc; acc += S.gcount[blockIdx.x + q * gridDim.x]; }
@@ -333,11 +338,14 @@ struct HeadsTail {
     u32* sm_q = smem + 128;
     if (tid == 0) *sm_qn = 0;
     __syncthreads();
-    const u32 nrounds = flat ? (total + kSegThreads - 1) / kSegThreads : my_tiles;
+    const u32 nrounds = single ? (trash_round ? 2u : 1u) : flat ? (total + kSegThreads - 1) / kSegThreads : my_tiles;
     for (u32 rd = 0; rd < nrounds; ++rd) {
-      // (flat: round rd handles items [rd * 512, +512) of the concatenated lists; else round rd = tile rd, lists <= 512 long)
+      // (single: round 0 = every thread's own created record, round 1 = the record of the unpairable rows;
+      //  flat: round rd handles items [rd * 512, +512) of the concatenated lists; else round rd = tile rd, lists <= 512 long)
       u32 t = 0, k = 0; bool act = false;
-      if (flat) {
+      if (single) {
+        act = rd == 0 ? k_created : (tid == 0 && k_trash);
+      } else if (flat) {
         const u32 item = rd * kSegThreads + tid;
         if (item < total) {
           u32 q = 0;
@@ -354,7 +362,7 @@ struct HeadsTail {
 #pragma unroll
         for (int q = 0; q < kLevels; ++q) cl[q] = 0;
         if (act) {
-          slot = S.glist[(size_t)t * kGTile + k];
+          slot = single ? (rd == 0 ? k_cslot : trash) : S.glist[(size_t)t * kGTile + k];
           u32 cr[kLevels];
           if (glob && slot <= S.capmask) {
             const uint4 a0 = *reinterpret_cast<const uint4*>(rec2[slot].cl), a1 = *reinterpret_cast<const uint4*>(rec2[slot].cl + 4);
