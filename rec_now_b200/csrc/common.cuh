@@ -399,7 +399,8 @@ struct GatherArgs { const uint4* src[8]; uint4* dst; u32 n16; u32 world; };
 // Optionally (labels != nullptr) the same launch OR-reduces the label bits of the pairable rows into per-CTA partials
 // (Layout::labpart), which lets k_seg build the sort keys in its first phase; returns the grid size in *ncta.
 cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels = nullptr,
-                     const uint8_t* row_ok = nullptr, int* ncta = nullptr, const GatherArgs* gather = nullptr);
+                     const uint8_t* row_ok = nullptr, int* ncta = nullptr, const GatherArgs* gather = nullptr,
+                     bool gather_only = false);
 int device_sm_count();
 // Cooperative launch of `kernel` with `grid` CTAs of `threads` threads (grid must not exceed the co-resident limit).
 cudaError_t launch_coop(const void* kernel, int grid, int threads, void** args, cudaStream_t st, size_t smem = 0);

@@ -182,9 +182,10 @@ cudaError_t GraphCall::finish(bool ok) {
 }
 
 cudaError_t seg_init(const Layout& L, void* scratch, cudaStream_t st, const float* labels, const uint8_t* row_ok, int* ncta,
-                     const GatherArgs* gather) {
+                     const GatherArgs* gather, bool gather_only) {
   char* base = static_cast<char*>(scratch);
-  const size_t nz = (L.zero_end - L.zero_begin) / 16, no = (L.ones_end - L.ones_begin) / 16;
+  // (gather_only: the counting path on a persistent arena needs nothing initialised -- the launch is only the peer gather)
+  const size_t nz = gather_only ? 0 : (L.zero_end - L.zero_begin) / 16, no = gather_only ? 0 : (L.ones_end - L.ones_begin) / 16;
   GatherArgs G{};
   if (gather) G = *gather;
   int grid = (int)((nz + no + (size_t)G.world * G.n16 + 255) / 256);

@@ -509,7 +509,8 @@ cudaError_t seg_run(const Layout& L, void* scratch, const SegInputs& in, const T
   // (counting path: no initialisation kernel -- except in the global mode, whose first kernel is also the peer gather)
   if (!fast || in.gather.world)
     e = merged ? seg_init(L, scratch, st, in.labels, in.row_ok, &npart)
-               : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr);
+               : seg_init(L, scratch, st, nullptr, nullptr, nullptr, in.gather.world ? &in.gather : nullptr,
+                          fast && in.gather.world != 0);
   if (e != cudaSuccess) return e;
   SegParams S = make_seg_params(L, scratch, in);
   if (merged) { S.merged = 1; S.npart = npart; S.gbits = seg_merged_gbits(L); }
