@@ -564,6 +564,20 @@ def ours(args):
     pair_ms_plain, out = time_pair_kernel(0)
     n_pair = int(out["n_pair"].item())
     err = ops.device_error(out["_scratch"]) if world == 1 else 0
+    # ... and by the kernels' own %globaltimer stamps (CTA 0: first instruction behind the dependency wait -> last store of
+    # the final pass): the kernel without its launch latency, cold L2 as above.  Supplementary: the roofline uses the events.
+    pair_stamp_us = seg_stamp_us = None
+    if world == 1:
+        ts = (C.c_uint64 * 24)()
+        dp, ds = [], []
+        for k in range(20):
+            flush.fill_(k & 0xFF)
+            o = step()
+            lib.rn_debug_timestamps(o["_scratch"].data_ptr(), ts, 24, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+            if ts[23] > ts[20] > ts[0] > 0:
+                dp.append((ts[23] - ts[20]) / 1e3); ds.append((ts[19] - ts[0]) / 1e3 if ts[19] > ts[0] else float("nan"))
+        if dp:
+            pair_stamp_us, seg_stamp_us = float(np.median(dp)), float(np.nanmedian(ds))
 
     # ---- parity gate of the benchmarked workload (outside every timed region) ---------------------------
     spec_kw = dict(power=-0.5, label_func="diff")
@@ -822,6 +836,9 @@ def ours(args):
                          "peak_source": "measured in this run (rn_bench_mufu ex2/lg2/rcp chains)",
                          "nominal_peak": NOMINAL_MUFU_PER_S / 1e9, "frac_of_nominal": achieved / NOMINAL_MUFU_PER_S,
                          "kernel_ms": pair_ms, "kernel_share_of_step": pair_ms / (t_ms / K),
+                         "kernel_us_by_device_stamps": pair_stamp_us, "k_seg_us_by_device_stamps": seg_stamp_us,
+                         "frac_by_device_stamps": (MUFU_PER_PAIR * pairs_per_launch / (pair_stamp_us * 1e-6) / mufu_peak
+                                                   if pair_stamp_us else None),
                          "kernel_timing": "CUDA event-record nodes around the k_pair node of the step's CUDA graph (the "
                                           "default launch path), L2 flushed before every step",
                          "kernel_ms_plain_launches": pair_ms_plain,
