@@ -165,7 +165,10 @@ typedef struct rn_listwise_args {
    * list_loss the call is ONE kernel without a sort (per-list statistics accumulated on hash records, gradient
    * written in row order).  rn_listwise_dense needs the sorted form: call it after a non-persistent call only. */
   int32_t scratch_persistent;
-  int32_t reserved0;
+  /* 1 / temperature of the softmax (0 = 1): the loss is taken on logits * inv_temperature, dlogits is the gradient with
+   * respect to the UNSCALED logits.  Not in the reference's signature (a user divides the logits before the call);
+   * here it saves that elementwise pass.  rn_listwise_dense returns the member logits unscaled. */
+  float inv_temperature;
 } rn_listwise_args;
 
 int rn_version(void);

@@ -85,7 +85,7 @@ class ListwiseArgs(C.Structure):
         ("pos_neg_th", C.c_float), ("do_reduce", C.c_int32),
         ("loss", C.c_void_p), ("list_loss", C.c_void_p), ("n_valid", C.c_void_p),
         ("n_group", C.c_void_p), ("dlogits", C.c_void_p),
-        ("scratch_persistent", C.c_int32), ("reserved0", C.c_int32),
+        ("scratch_persistent", C.c_int32), ("inv_temperature", C.c_float),
     ]
 
 

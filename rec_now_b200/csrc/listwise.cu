@@ -13,6 +13,7 @@ namespace rn {
 struct LwParams {
   u32 B; int gbits;
   const float* list_w; float th; int do_reduce;
+  float inv_t;                  // 1 / temperature: the softmax runs on logits * inv_t, the gradient is scaled back
   float* loss; float* list_loss; int32_t* n_valid; int32_t* n_group; float* dlogits;
 };
 
@@ -45,11 +46,11 @@ struct ListwiseTail {
       const u32 h = __ffs(heads) - 1; heads &= heads - 1;
       const u32 a = blk * 32 + h, e = gend[a];
       float m = -INFINITY;
-      for (u32 q = a + ln; q < e; q += 32) m = fmaxf(m, ss[q]);
+      for (u32 q = a + ln; q < e; q += 32) m = fmaxf(m, ss[q] * P.inv_t);
       m = warp_maxf(m);
       float z = 0.f, sumy = 0.f; int hp = 0, hn = 0;
       for (u32 q = a + ln; q < e; q += 32) {
-        const float s = ss[q], y = sy[q];
+        const float s = ss[q] * P.inv_t, y = sy[q];
         z += expf(s - m); sumy += y;
         hp |= (y > P.th); hn |= ((y - P.th) < 0.f);                // LW:135-136
       }
@@ -58,7 +59,7 @@ struct ListwiseTail {
       const float lse = logf(z);
       float dot = 0.f;
       if (valid)
-        for (u32 q = a + ln; q < e; q += 32) dot += (sy[q] / sumy) * (lse - (ss[q] - m));   // LW:144, LW:167
+        for (u32 q = a + ln; q < e; q += 32) dot += (sy[q] / sumy) * (lse - (ss[q] * P.inv_t - m));   // LW:144, LW:167
       dot = warp_sum(dot);
       if (ln == 0) {
         rec[(size_t)R_MAX * P.B + a] = m; rec[(size_t)R_LSE * P.B + a] = lse; rec[(size_t)R_SY * P.B + a] = sumy;
@@ -150,7 +151,7 @@ struct ListwiseTail {
         float wr = 1.f;
         if (P.list_w) wr = P.list_w[__float_as_uint(rec[(size_t)R_RANK * B + a])];
         if (P.do_reduce) wr /= (float)V;
-        g = wr * (expf(ss[p] - m - lse) - sy[p] / sumy);               // xent backprop: softmax - labels
+        g = P.inv_t * wr * (expf(ss[p] * P.inv_t - m - lse) - sy[p] / sumy);               // xent backprop: softmax - labels
       }
       P.dlogits[bounds.perm[p]] = g;
     }
@@ -187,7 +188,7 @@ __device__ __forceinline__ float dec_label(u32 e) {     // inverse of enc_label
 struct LwCountArgs {
   u32 B; u32 capmask;
   const int64_t* keys; const uint8_t* row_ok; const float* labels; const float* logits;
-  float th;
+  float th; float inv_t;
   float* loss; int32_t* n_valid; int32_t* n_group; float* dlogits;
   GRec* rec; u32 *glist, *gcount, *rslot; Ctl* ctl;
 };
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_lw_count(LwCountArgs A) {
     const u32 i = t * kGTile + tid;
     const bool in = i < B;
     const u64 key = in ? (u64)A.keys[i] : 0ull;
-    const float y = in ? A.labels[i] : 0.f, s = in ? A.logits[i] : 0.f;
+    const float y = in ? A.labels[i] : 0.f, s = in ? A.logits[i] * A.inv_t : 0.f;
     const bool ok = in && (A.row_ok ? A.row_ok[i] != 0 : true);       // (0: the id was NaN / inf -- a singleton list, never valid)
     sm_tab[tid] = kEmpty; sm_tab[tid + kGTile] = kEmpty;
     sm_max[tid] = 0u; sm_sumy[tid] = 0.f; sm_flags[tid] = 0u;
@@ -281,7 +282,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_lw_count(LwCountArgs A) {
   for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
     const u32 i = t * kGTile + tid;
     if (single) { if (i < B) k_e = accumulate(k_slot, k_s, k_y); }
-    else if (i < B) accumulate(A.rslot[i], A.logits[i], A.labels[i]);
+    else if (i < B) accumulate(A.rslot[i], A.logits[i] * A.inv_t, A.labels[i]);
     const u32 ncr = A.gcount[t];
     for (u32 k = tid; k < ncr; k += kSegThreads) {
       ++nlist;
@@ -308,7 +309,7 @@ __global__ void __launch_bounds__(kSegThreads, 1) k_lw_count(LwCountArgs A) {
   double lsum = 0.0;
   for (u32 t = blockIdx.x; t < ntile; t += gridDim.x) {
     const u32 i = t * kGTile + tid;
-    if (i < B) A.dlogits[i] = single ? grad(k_slot, k_s, k_y, k_e, true) : grad(A.rslot[i], A.logits[i], A.labels[i], 0.f, false);
+    if (i < B) A.dlogits[i] = A.inv_t * (single ? grad(k_slot, k_s, k_y, k_e, true) : grad(A.rslot[i], A.logits[i] * A.inv_t, A.labels[i], 0.f, false));
     const u32 ncr = A.gcount[t];
     for (u32 k = tid; k < ncr; k += kSegThreads) {
       const LRec r = rec[A.glist[(size_t)t * kGTile + k]];
@@ -389,6 +390,7 @@ static int validate_listwise(const rn_listwise_args* a) {
   if (!a->keys || !a->labels || !a->logits || !a->n_valid || !a->n_group || !a->dlogits) return RN_ERR_ARG;
   if (a->do_reduce && !a->loss) return RN_ERR_ARG;
   if (!(a->pos_neg_th >= 0.f)) return RN_ERR_UNSUPPORTED;   // th < 0 also fires on the dense zero padding
+  if (a->inv_temperature < 0.f || a->inv_temperature != a->inv_temperature) return RN_ERR_ARG;
   const void* ptrs[] = {a->keys, a->labels, a->logits, a->row_ok, a->list_w, a->list_loss, a->dlogits};
   for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
   return RN_OK;
@@ -402,10 +404,11 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(scratch);
+  const float inv_t = a->inv_temperature == 0.f ? 1.0f : a->inv_temperature;       // (0 = a zero-initialised struct: no temperature)
   static const char* lwc = getenv("RN_LW_COUNT");
   if (a->scratch_persistent && a->do_reduce && !a->list_w && !a->list_loss && !(lwc && *lwc == '0')) {
     // counting form: one cooperative kernel, no sort, no scatter (the ranks of the valid lists are not needed)
-    LwCountArgs A{(u32)a->B, L.cap - 1, a->keys, a->row_ok, a->labels, a->logits, a->pos_neg_th, a->loss, a->n_valid,
+    LwCountArgs A{(u32)a->B, L.cap - 1, a->keys, a->row_ok, a->labels, a->logits, a->pos_neg_th, inv_t, a->loss, a->n_valid,
                   a->n_group, a->dlogits, at<GRec>(base, L.rec), at<u32>(base, L.glist), at<u32>(base, L.gcount),
                   at<u32>(base, L.slot), at<Ctl>(base, L.ctl)};
     void* args[] = {&A};
@@ -420,7 +423,7 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
   float* sy = at<float>(base, L.sy);
   float* rec = at<float>(base, L.gstat);
   GatherCols gc{{a->logits, a->labels, nullptr, nullptr}, {ss, sy, nullptr, nullptr}};
-  LwParams P{(u32)a->B, L.gbits, a->list_w, a->pos_neg_th, a->do_reduce, a->loss, a->list_loss, a->n_valid,
+  LwParams P{(u32)a->B, L.gbits, a->list_w, a->pos_neg_th, a->do_reduce, inv_t, a->loss, a->list_loss, a->n_valid,
              a->n_group, a->dlogits};
   ListwiseTail T{BoundsTail{astart, gend, perm, gc}, P, ss, sy, rec, at<u32>(base, L.blk)};
   if (seg_run(L, scratch, in, T, st) != cudaSuccess) return RN_ERR_LAUNCH;

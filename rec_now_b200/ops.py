@@ -401,7 +401,7 @@ _lw_scratch_bytes: dict = {}
 
 
 def listwise_fwd_bwd(keys, labels, logits, row_ok=None, list_w=None, pos_neg_th=0.5, do_reduce=True,
-                     want_list_loss=False, sorted_form=False):
+                     want_list_loss=False, sorted_form=False, temperature=1.0):
     """rn_listwise_fwd_bwd.  keys: canonical int64 [B].  Returns dict of device tensors (+ the scratch arena
     and args needed by listwise_dense).  sorted_form=True asks for the sorted (radix) form of the call, whose arena
     listwise_dense can read; otherwise a reduced loss without per-list weights / outputs runs as ONE sort-free kernel
@@ -433,6 +433,7 @@ def listwise_fwd_bwd(keys, labels, logits, row_ok=None, list_w=None, pos_neg_th=
     po = out.data_ptr()
     a.B = b; a.keys = keys.data_ptr(); a.row_ok = _ptr(ok); a.labels = y.data_ptr(); a.logits = s.data_ptr()
     a.list_w = _ptr(lw); a.pos_neg_th = pos_neg_th; a.do_reduce = 1 if do_reduce else 0
+    a.inv_temperature = 1.0 / float(temperature)
     a.loss = po; a.n_valid = po + 4; a.n_group = po + 8
     a.list_loss = _ptr(list_loss); a.dlogits = dlogits.data_ptr(); a.scratch_persistent = 1 if counting else 0
     with _on_device(dev):

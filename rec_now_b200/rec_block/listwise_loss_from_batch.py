@@ -59,12 +59,12 @@ class _ListwiseBatch:
         self._fwd = {}
         self._dense = None
 
-    def fwd(self, weights=None, do_reduce=True, sorted_form=False):
-        key = (None if weights is None else weights.data_ptr(), bool(do_reduce), bool(sorted_form))
+    def fwd(self, weights=None, do_reduce=True, sorted_form=False, temperature=1.0):
+        key = (None if weights is None else weights.data_ptr(), bool(do_reduce), bool(sorted_form), float(temperature))
         if key not in self._fwd:
             self._fwd[key] = ops.listwise_fwd_bwd(self.keys[0], self.labels_in, self.logits_in, row_ok=self.row_ok,
                                                   list_w=weights, pos_neg_th=self.th, do_reduce=do_reduce,
-                                                  sorted_form=sorted_form)
+                                                  sorted_form=sorted_form, temperature=temperature)
         return self._fwd[key]
 
     def n_valid(self) -> int:
@@ -139,8 +139,8 @@ def to_listwise_sample(group_ids, labels, logits, do_mask_logits=True, value_of_
 
 class _FusedListwiseLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, logits, batch, weights, do_reduce):
-        out = batch.fwd(weights, do_reduce)
+    def forward(ctx, logits, batch, weights, do_reduce, temperature=1.0):
+        out = batch.fwd(weights, do_reduce, temperature=temperature)
         ctx.in_shape, ctx.in_dtype, ctx.do_reduce = logits.shape, logits.dtype, do_reduce
         if do_reduce:
             ctx.save_for_backward(out["dlogits"])
@@ -154,11 +154,11 @@ class _FusedListwiseLoss(torch.autograd.Function):
     def backward(ctx, g):
         (dlogits,) = ctx.saved_tensors
         if ctx.do_reduce:
-            return (g * dlogits).reshape(ctx.in_shape).to(ctx.in_dtype), None, None, None
+            return (g * dlogits).reshape(ctx.in_shape).to(ctx.in_dtype), None, None, None, None
         # per-list upstream gradients: scale each member's gradient by its list's g (via the dense mask)
         dm = ctx.batch.dense()[0]
         per_row = (dm.to(g.dtype) * g.reshape(-1, 1)).sum(0)
-        return (per_row * dlogits).reshape(ctx.in_shape).to(ctx.in_dtype), None, None, None
+        return (per_row * dlogits).reshape(ctx.in_shape).to(ctx.in_dtype), None, None, None, None
 
 
 def listwise_loss_via_softmax_cross_entropy_with_logits(labels_for_softmax,
@@ -188,3 +188,16 @@ def listwise_loss_via_softmax_cross_entropy_with_logits(labels_for_softmax,
         listwise_loss = torch.mean(listwise_loss)                                     # LW:171 (empty -> NaN)
         listwise_loss = nan_to_zero(listwise_loss)                                    # LW:172
     return listwise_loss
+
+
+def listwise_loss_from_batch(group_ids, labels, logits, weights=None, do_reduce=True, pos_neg_th=0.5, temperature=1.0):
+    """``listwise_loss_via_softmax_cross_entropy_with_logits(*to_listwise_sample(group_ids, labels, logits)[1:], weights,
+    do_reduce)`` (LW:89-173) as ONE call that never builds the (V, B) tensors, with an optional softmax temperature
+    (the loss is taken on ``logits / temperature``; the gradient reaches the unscaled logits).  Returns
+    ``(loss, n_valid_lists)`` -- n_valid_lists as a device tensor (no synchronisation)."""
+    if not temperature > 0:
+        raise ValueError("temperature must be positive")
+    batch = _ListwiseBatch(group_ids, labels, logits, True, -1E9, pos_neg_th)
+    w = None if weights is None else _f32(weights).reshape(-1).contiguous()
+    loss = _FusedListwiseLoss.apply(batch.logits_in, batch, w, bool(do_reduce), float(temperature))
+    return loss, batch.fwd(w, bool(do_reduce), temperature=float(temperature))["n_valid"]

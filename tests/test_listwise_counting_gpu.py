@@ -130,3 +130,31 @@ def test_mild_masked_logit_takes_the_dense_formula():
     assert np.abs(lg.grad.cpu().numpy() - dref["grad"]).max() < 1e-6
     dref9 = D.listwise_full(g, y, s)
     assert abs(float(dref9["loss"]) - float(dref["loss"])) > 1e-4       # (the two really differ)
+
+
+@pytest.mark.parametrize("temperature", [0.5, 2.0])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_listwise_temperature(temperature, weighted):
+    """SURVEY 8f N2 (listwise variants): a softmax temperature inside the fused call = the oracle on logits / T, with the
+    gradient scaled back to the unscaled logits; both kernels (the sort-free one and, with per-list weights, the sorted
+    form)."""
+    import torch
+    from oracle import generators as G
+    from oracle import seg_ref as S
+    from rec_now_b200.rec_block import listwise_loss_from_batch as LW
+    d = G.cfg4(3, b=20000, cap=128)
+    ref = S.listwise(d["g"], d["y"], (d["s"] / np.float32(temperature)).astype(np.float32))
+    w = None
+    if weighted:
+        rng = np.random.default_rng(1)
+        wv = rng.uniform(0.5, 1.5, ref["n_valid"]).astype(np.float32)
+        ref = S.listwise(d["g"], d["y"], (d["s"] / np.float32(temperature)).astype(np.float32), weights=wv)
+        w = torch.tensor(wv, device="cuda")
+    lg = torch.tensor(d["s"], device="cuda", requires_grad=True)
+    loss, nv = LW.listwise_loss_from_batch(torch.tensor(d["g"], device="cuda"), torch.tensor(d["y"], device="cuda"), lg,
+                                           weights=w, temperature=temperature)
+    loss.backward()
+    assert int(nv.item()) == ref["n_valid"]
+    assert abs(loss.item() - ref["loss"]) <= 2e-5 * abs(ref["loss"])
+    want = ref["grad"] / temperature
+    assert np.abs(lg.grad.cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
