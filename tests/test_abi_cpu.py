@@ -153,3 +153,35 @@ def test_pair_kernel_spills_stay_small():
     assert (3, 0) in seen, "k_pair<M_HASW|M_DIFF> not found in the build log"
     assert seen[(3, 0)] <= 128, f"k_pair<3> spills {seen[(3, 0)]} bytes of stores"
     assert max(seen.values()) <= 400, seen
+
+
+def test_ctypes_structs_mirror_the_header(tmp_path):
+    """The ctypes mirrors in rec_now_b200/_lib.py against the C compiler's view of include/recnow_b200.h: size of every
+    argument struct and the offset of its last field (a field added on one side only shifts one of them)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from rec_now_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "recnow_b200.h"\n'
+        'int main(void) {\n'
+        '  printf("%zu %zu\\n", sizeof(rn_pairwise_args), offsetof(rn_pairwise_args, margin));\n'
+        '  printf("%zu %zu\\n", sizeof(rn_listwise_args), offsetof(rn_listwise_args, inv_temperature));\n'
+        '  printf("%zu %zu\\n", sizeof(rn_global_args), offsetof(rn_global_args, step));\n'
+        '  printf("%zu %zu\\n", sizeof(rn_gauc_args), offsetof(rn_gauc_args, concordant2));\n'
+        '  printf("%zu %zu\\n", sizeof(rn_pool_args), offsetof(rn_pool_args, V));\n'
+        '  return 0;\n}\n')
+    exe = str(tmp_path / "abi")
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [tuple(int(x) for x in line.split()) for line in subprocess.run([exe], capture_output=True, text=True).stdout.split("\n") if line]
+    want = [(C.sizeof(_lib.PairwiseArgs), _lib.PairwiseArgs.margin.offset),
+            (C.sizeof(_lib.ListwiseArgs), _lib.ListwiseArgs.inv_temperature.offset),
+            (C.sizeof(_lib.GlobalArgs), _lib.GlobalArgs.step.offset),
+            (C.sizeof(_lib.GaucArgs), _lib.GaucArgs.concordant2.offset),
+            (C.sizeof(_lib.PoolArgs), _lib.PoolArgs.V.offset)]
+    assert got == want, (got, want)
