@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RN_VERSION 103 /* 0.1.3: pair_loss / margin (hinge), RN_LABEL_GAIN2, small-batch kernel, segment pooling */
+#define RN_VERSION 104 /* 0.1.4: RN_LABEL_LUT / weight_lut (label-level weight table) */
 
 enum {
   RN_OK = 0,
@@ -60,10 +60,16 @@ enum {
  * Optional per-sample factors rw_pos (row/positive side) and rw_neg (column/negative side) multiply W;
  * whenever any weight is present the reference's rule C = (W > 0) applies (a non-positive or NaN factor
  * removes the pairs it touches).  Anything else goes through rn_pair_indices_* + the caller's own code. */
-enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2 };
+enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2, RN_LABEL_LUT = 3 };
 /*   GAIN2: W = (2^y_i - 2^y_j)*[y_i > y_j]   (NDCG-style exponential gains, the usual RankNet / LambdaRank gain; the
  *          sorted label column then holds 2^y.  Labels whose gains coincide in float32 although y_i > y_j keep their pair
  *          with weight 0 -- integer labels never do.)
+ *   LUT:   W = weight_lut[l_i][l_j]*[y_i > y_j] with the label LEVEL l = y + 1 of integer labels -1 .. 6 (binary clicks, graded
+ *          relevance): ANY label-only label_pair_to_weight_func evaluated once on the 8 x 8 grid of levels (SURVEY 8b
+ *          weight_lut, hard part 5).  The table's entries with l_i > l_j must be finite and > 0, so
+ *          that the pair set stays [y_i > y_j] (C = W > 0, PW:193) and the counts stay position arithmetic; the other
+ *          entries are ignored.  A label outside the menu or a bad entry fails the call on the device: loss = NaN,
+ *          rn_last_device_error bit 8.
  * pairloss_func menu (pairwise_loss_from_batch.py:229, 274; the reference ships bpr_loss_func only, :96-127):
  *   LOGISTIC: l = softplus(-x), x = (s_i - s_j)*factor            (bpr_loss_func)
  *   HINGE:    l = max(0, margin - x)                               (margin ranking loss; d l / d x = -[margin - x > 0]) */
@@ -143,6 +149,9 @@ typedef struct rn_pairwise_args {
    * weights, counts, occurrence weights, 1/n -- is shared.  HINGE: not with deterministic. */
   int32_t pair_loss;
   float margin;
+  /* RN_LABEL_LUT: float32[8][8] in DEVICE memory, weight_lut[l_i * 8 + l_j] = W of a positive row at label level l_i and a
+   * negative row at level l_j (level = label + 1).  NULL otherwise.  Single GPU, not with deterministic. */
+  const float* weight_lut;
 } rn_pairwise_args;
 
 typedef struct rn_listwise_args {

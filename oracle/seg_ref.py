@@ -15,6 +15,9 @@ The fused weight menu mirrored here (and in include/recnow_b200.h):
     label_func "step" with row weights:  W = [y_i > y_j] [* rw_pos_i] [* rw_neg_j], C = W > 0
     label_func "gain2": W = (2^y_i - 2^y_j) * [y_i > y_j] [* rw ...]   (exponential gains; float32 exp2 as the product)
 i.e. what a reference user writes as label_pair_to_weight_func(Y, Yt, sample_weight=w).
+    label_func "callable": W = weight_func(Y_i, Y_j) [* rw ...], C = W > 0 -- ANY label_pair_to_weight_func of the two label
+                        matrices (PW:192-193), evaluated block by block in float32; the truth for the level-table path
+                        (RN_LABEL_LUT) of the product.
 """
 from __future__ import annotations
 
@@ -32,7 +35,8 @@ class PairSpec:
     reduce_mean: bool = True            # bpr_loss_func reduce_mean       PW:125-126
     only_wrong: bool = False            # only_use_wrong_order_pair       PW:197-203
     power: float = 0.0                  # click_occurance_power           PW:282-291
-    label_func: str = "step"            # "step" | "diff"
+    label_func: str = "step"            # "step" | "diff" | "gain2" | "callable"
+    weight_func: Optional[object] = None  # label_func "callable": f(label_matrix, label_matrix_transpose) -> weights   PW:192
     rw_pos: Optional[np.ndarray] = None  # per-sample weight applied on the positive (row) side
     rw_neg: Optional[np.ndarray] = None  # per-sample weight applied on the negative (column) side
     # pairloss_func menu beyond bpr_loss_func (the reference only ships the hook, PW:229, 274):
@@ -101,7 +105,7 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         ok = ok & np.asarray(mask, bool).reshape(-1)                         # PW:154-172
     rwp = None if spec.rw_pos is None else np.asarray(spec.rw_pos, F32).reshape(-1)
     rwn = None if spec.rw_neg is None else np.asarray(spec.rw_neg, F32).reshape(-1)
-    has_w = spec.label_func in ("diff", "gain2") or rwp is not None or rwn is not None
+    has_w = spec.label_func in ("diff", "gain2", "callable") or rwp is not None or rwn is not None
     g32 = np.exp2(y32).astype(F32) if spec.label_func == "gain2" else y32
     segs = _group_members(keys, ok)
 
@@ -123,6 +127,9 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         else:
             if spec.label_func in ("diff", "gain2"):
                 w = ((g32[mi][:, None] - g32[m][None, :]).astype(F32) * gt.astype(F32)).astype(F32)
+            elif spec.label_func == "callable":
+                yim, yjm = np.broadcast_arrays(yi, yj)
+                w = np.asarray(spec.weight_func(yim, yjm), F32)               # PW:192 (no label condition of its own)
             else:
                 w = gt.astype(F32)
             if rwp is not None:

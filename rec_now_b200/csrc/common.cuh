@@ -3,9 +3,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <nvtx3/nvToolsExt.h>
 #include "../../include/recnow_b200.h"
 
 namespace rn {
+
+// NVTX range around a C-ABI entry point (header-only NVTX 3: a pointer test when no tool is attached), so that a
+// profiler can filter on the call (`ncu --nvtx --nvtx-include "rn_pairwise_fwd_bwd/"`) and a timeline names it.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define RN_NVTX_RANGE(name) ::rn::NvtxRange rn_nvtx_range_(name)
 
 typedef unsigned int u32;
 typedef unsigned long long u64;

@@ -92,6 +92,7 @@ extern "C" size_t rn_global_gather_bytes(int64_t B_loc, int32_t K, int32_t world
 }
 
 extern "C" int rn_global_pairwise_fwd_bwd(const rn_global_args* g, void* scratch, size_t scratch_bytes, void* stream) {
+  RN_NVTX_RANGE("rn_global_pairwise_fwd_bwd");
   if (!g || g->world < 1 || g->world > 8 || g->rank < 0 || g->rank >= g->world || !g->gather_buf || g->step < 0) return RN_ERR_ARG;
   const rn_pairwise_args& l = g->local;
   if (l.B <= 0 || (l.B & 15) || l.K <= 0 || l.K > 8) return RN_ERR_ARG;

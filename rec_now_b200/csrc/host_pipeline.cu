@@ -96,6 +96,7 @@ extern "C" int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, 
 }
 
 extern "C" int rn_host_pairwise_wait(rn_host_pairwise* p, int32_t ticket) {
+  RN_NVTX_RANGE("rn_host_pairwise_wait");
   if (!p || ticket < 0 || ticket >= p->depth) return RN_ERR_ARG;
   Slot& s = p->slots[ticket];
   if (!s.busy) return RN_OK;
@@ -106,6 +107,7 @@ extern "C" int rn_host_pairwise_wait(rn_host_pairwise* p, int32_t ticket) {
 }
 
 extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_args* h, int32_t* ticket) {
+  RN_NVTX_RANGE("rn_host_pairwise_submit");
   if (!p || !h || !ticket) return RN_ERR_ARG;
   if (h->B <= 0 || h->B > p->B_max || h->K != p->K) return RN_ERR_ARG;
   if (!h->keys || !h->logits || !h->labels || !h->loss || !h->n_pair_f32 || !h->n_pair || !h->dlogits) return RN_ERR_ARG;

@@ -397,6 +397,7 @@ static int validate_listwise(const rn_listwise_args* a) {
 }
 
 extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, size_t scratch_bytes, void* stream) {
+  RN_NVTX_RANGE("rn_listwise_fwd_bwd");
   int rc = validate_listwise(a);
   if (rc) return rc;
   if (!scratch || check_align(scratch)) return scratch ? RN_ERR_ALIGN : RN_ERR_ARG;
@@ -433,6 +434,7 @@ extern "C" int rn_listwise_fwd_bwd(const rn_listwise_args* a, void* scratch, siz
 extern "C" int rn_listwise_dense(const rn_listwise_args* a, void* scratch, size_t scratch_bytes, int64_t V,
                                  uint8_t* dense_mask, float* dense_labels, float* dense_logits,
                                  int32_t do_mask_logits, float value_of_masked_logit, void* stream) {
+  RN_NVTX_RANGE("rn_listwise_dense");
   if (!a || a->B <= 0 || V < 0 || !scratch) return RN_ERR_ARG;
   const Layout L = make_layout(a->B, 1);
   if (scratch_bytes < L.total) return RN_ERR_SCRATCH;

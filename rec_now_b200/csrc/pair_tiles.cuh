@@ -7,7 +7,15 @@
 
 namespace rn {
 
-enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8 };
+enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8, M_LUT = 64 };      // (16, 32: dispatch-only bits of pairwise.cu)
+
+// Label part of a pair weight under M_DIFF: the difference of the (transformed) labels, or -- M_LUT, RN_LABEL_LUT -- the
+// entry of the 8 x 8 level table (shared memory; the sorted label column then holds the label LEVEL 0 .. 7 as a float).
+template <bool LUT>
+__device__ __forceinline__ float label_weight(const float* lut, const float yi, const float yj) {
+  if (LUT) return lut[(int)yi * 8 + (int)yj];
+  return yi - yj;
+}
 
 // General (masked) 32x32 tile for one positive row per lane, rotation steps [t0, t1) (multiples of 4; the whole tile is
 // [0, 32)).  Lane l meets negative l ^ t at step t, so disjoint step ranges score disjoint pair sets: a tile can be
@@ -18,8 +26,8 @@ template <int MODE, bool FULL, bool HINGE = false>
 __device__ __forceinline__ void tile_general(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
                                              const u32 pjm, const float sjm, const float yjm, const float wnjm,
                                              const float c, const int t0, const int t1, float& li, float& gi, u32& cnt,
-                                             float& accj, const float margin = 0.f) {
-  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
+                                             float& accj, const float margin = 0.f, const float* lut = nullptr) {
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG, LUT = MODE & M_LUT;
   float gi_t = 0.f, li_t = 0.f;
 #pragma unroll 2
   for (int tb = t0; tb < t1; tb += 4) {
@@ -47,7 +55,7 @@ __device__ __forceinline__ void tile_general(const float si, const float yi, con
       float wv = 1.f;
       if (HASW) {
         wv = wpi;
-        if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = (yi - yj) * wpi; }
+        if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = label_weight<LUT>(lut, yi, yj) * wpi; }
         if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
         d *= wv;
       }
@@ -211,8 +219,9 @@ __device__ __forceinline__ void tile_prod(const float E0, const float E1, const 
 template <int MODE, bool FULL>
 __device__ __forceinline__ void tile_general_prod(const float Ei, const float yi, const float wpi, const u32 lo, const u32 hi,
                                                   const u32 pjm, const float Fm, const float yjm, const float wnjm,
-                                                  const int t0, const int t1, float& li, float& gi, u32& cnt, float& accj) {
-  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
+                                                  const int t0, const int t1, float& li, float& gi, u32& cnt, float& accj,
+                                                  const float* lut = nullptr) {
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, LUT = MODE & M_LUT;
   float gi_t = 0.f, li_t = 0.f;
 #pragma unroll 2
   for (int tb = t0; tb < t1; tb += 4) {
@@ -228,7 +237,7 @@ __device__ __forceinline__ void tile_general_prod(const float Ei, const float yi
       float wv = 1.f;
       if (HASW) {
         wv = wpi;
-        if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = (yi - yj) * wpi; }
+        if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = label_weight<LUT>(lut, yi, yj) * wpi; }
         if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
         d *= wv;
       }

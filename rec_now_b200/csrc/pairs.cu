@@ -146,6 +146,7 @@ static PiParams pi_params(const rn_pairwise_args* a, int label_cond) {
 
 extern "C" int rn_pair_indices_count(const rn_pairwise_args* a, int32_t label_cond, void* scratch, size_t scratch_bytes,
                                      int64_t* n_pairs_host, void* stream) {
+  RN_NVTX_RANGE("rn_pair_indices_count");
   Layout L;
   int rc = pi_common(a, scratch, scratch_bytes, L);
   if (rc) return rc;
@@ -175,6 +176,7 @@ extern "C" int rn_pair_indices_count(const rn_pairwise_args* a, int32_t label_co
 
 extern "C" int rn_pair_indices_fill(const rn_pairwise_args* a, int32_t label_cond, void* scratch, size_t scratch_bytes,
                                     int32_t* pos_idx, int32_t* neg_idx, float* w, int64_t capacity, void* stream) {
+  RN_NVTX_RANGE("rn_pair_indices_fill");
   Layout L;
   int rc = pi_common(a, scratch, scratch_bytes, L);
   if (rc) return rc;
@@ -205,6 +207,7 @@ extern "C" size_t rn_occurrence_scratch_bytes(int64_t N) {
 
 extern "C" int rn_occurrence_power_weight(const int64_t* ids, int64_t N, float power, float* out, void* scratch,
                                           size_t scratch_bytes, void* stream) {
+  RN_NVTX_RANGE("rn_occurrence_power_weight");
   if (!ids || !out || N <= 0 || N > (1ll << 28) || !scratch) return RN_ERR_ARG;
   if (check_align(ids) || check_align(out) || check_align(scratch)) return RN_ERR_ALIGN;
   u32 cap; size_t o_table, o_count, o_slot, total;

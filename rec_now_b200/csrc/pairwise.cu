@@ -44,7 +44,8 @@ struct PairParams {
   float focal_w, focal_alpha, focal_gamma; int focal_stop;      // fused focal term (rn_pairwise_args.focal_*); focal_w = 0: off
   float margin;          // hinge pair loss (rn_pairwise_args.pair_loss = RN_LOSS_HINGE): max(0, margin - x); c_log2 is then the plain factor
   double loss_unit;      // unit of the accumulated pair losses: ln 2 (logistic, log2 units) or 1 (hinge)
-  int gain2;             // label_func RN_LABEL_GAIN2: the sorted label column holds 2^y (W = 2^y_i - 2^y_j)
+  int gain2;             // what the sorted label column holds: 0 the label; 1 (RN_LABEL_GAIN2) 2^y (W = 2^y_i - 2^y_j);
+                         // 2 (RN_LABEL_LUT) the label LEVEL 0 .. 7 (W = weight_lut[l_i][l_j])
   int part_rank, part_count; int ascending;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
   RowMap rm; u32 out_chunk;       // blocked input rows; floats per output chunk (0 = dlogits[B]), see rn_pairwise_args
@@ -120,7 +121,7 @@ struct HeadsTail {
     aj[pos] = make_uint2(a, n);
     // (a NaN label pairs with nothing, but its row shares I-blocks with rows that do: under label-gain weights the tile
     // multiplies a zero row weight by (y_i - y_ref), and 0 * NaN would poison the block's sums)
-    ss[pos] = s; sy[pos] = (y != y) ? 0.f : (P.gain2 ? exp2f(y) : y);
+    ss[pos] = s; sy[pos] = (y != y) ? 0.f : (P.gain2 == 2 ? (float)li : (P.gain2 ? exp2f(y) : y));      // (counting path: every label is on the level menu)
     if (P.rw_pos) swp[pos] = wp;
     if (P.rw_neg) swn[pos] = wn;
     gacc[pos] = 0.f; perm[pos] = i; sgrp[pos] = slot;
@@ -541,7 +542,16 @@ struct HeadsTail {
         if (P.rw_neg) wn = P.rw_neg[ro];
         aj[p] = make_uint2(a, n);
         ss[p] = P.logits[ro];
-        { const float yv = P.labels[ro]; sy[p] = (yv != yv) ? 0.f : (P.gain2 ? exp2f(yv) : yv); }     // (NaN labels pair with nothing; see scatter_row)
+        {
+          const float yv = P.labels[ro];
+          float yc = (yv != yv) ? 0.f : (P.gain2 == 1 ? exp2f(yv) : yv);      // (NaN labels pair with nothing; see scatter_row)
+          if (P.gain2 == 2 && yv == yv) {                                      // RN_LABEL_LUT: the level; off the menu = a failed call
+            int lv;
+            if (!label_level(yv, lv)) { lv = 0; if (!S.row_ok || S.row_ok[row]) atomicOr(&ctl->err, 8u); }      // (not with blocked rows)
+            yc = (float)lv;
+          }
+          sy[p] = yc;
+        }
         if (P.rw_pos) swp[p] = wp;
         if (P.rw_neg) swn[p] = wn;
         gacc[p] = 0.f; perm[p] = row;
@@ -652,6 +662,7 @@ struct KpArgs {
   u32 cost_switch;           // fixed cost of a virtual block (row loads, flush of the row accumulators), same unit
   u32 cost_straddle, cost_levels;   // extra cost of a block that holds a label-level boundary; boundaries per range (see vcost)
   float *gacc, *lossrow; u32* cnt; const u32* perm; Ctl* ctl;
+  const float* lut;          // RN_LABEL_LUT: the caller's 8 x 8 level weight table (copied to shared memory by every CTA)
   const u32* sgrp;           // per sorted row: index of its (primary) group's pair total -- cprim[] or, counting path, rec[]
   u64* cprim;
   // counting path (group_count.cuh): the call ran without k_init; the records its count phase created are listed per
@@ -718,7 +729,8 @@ __device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u3
 // A block whose negatives span several label levels of ONE group (label-gain weights): every row covers a level of the
 // block entirely or not at all, so the block is the sum of one product-form pass per level, each with the other levels'
 // negatives switched off (F = 0).  Up to three levels (a general tile costs about four fast ones); false = not taken.
-__device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const u32 lo0, const u32 lo1, const u32 hi0,
+template <bool LUT>
+__device__ __forceinline__ bool runs_tile(const float* lut, const bool in0, const bool in1, const u32 lo0, const u32 lo1, const u32 hi0,
                                           const u32 hi1, const float si0, const float si1, const float yi0, const float yi1,
                                           const float wp0, const float wp1, const u32 pjm, const float sjm, const float yjm,
                                           const bool jin, const u32 smin, const u32 j0, const float c, const int ts,
@@ -742,8 +754,8 @@ __device__ __forceinline__ bool runs_tile(const bool in0, const bool in1, const 
     const float yv = __shfl_sync(0xFFFFFFFFu, yjm, lead);
     const u32 runm = __ballot_sync(0xFFFFFFFFu, jin && yjm == yv) | (1u << lead);
     const u32 rs = j0 + (u32)(__ffs(runm) - 1), re = j0 + 32u - (u32)__clz(runm);
-    const float wv0 = (in0 && lo0 <= rs && re <= hi0) ? wp0 * (yi0 - yv) : 0.f;
-    const float wv1 = (in1 && lo1 <= rs && re <= hi1) ? wp1 * (yi1 - yv) : 0.f;
+    const float wv0 = (in0 && lo0 <= rs && re <= hi0) ? wp0 * label_weight<LUT>(lut, yi0, yv) : 0.f;
+    const float wv1 = (in1 && lo1 <= rs && re <= hi1) ? wp1 * label_weight<LUT>(lut, yi1, yv) : 0.f;
     tile_prod<true>(E0, E1, wv0, wv1, ((runm >> ln) & 1u) ? Fm : 0.f, li0, li1, gi0, gi1, accj, ts, te);
     rem &= ~runm;
   }
@@ -773,12 +785,28 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   __shared__ double red_d[kPairWarps];
   __shared__ u32 s_scan[kPairWarps + 2];
   __shared__ u32 s_bnd[6 * kPairWarps];
-  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG;
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG, LUT = MODE & M_LUT;
   constexpr bool DYN = RWN || WRONG;
   Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
   const u32 B = P.B;
+  // RN_LABEL_LUT: the level weight table in shared memory.  Only entries with l_i > l_j are ever a kept pair's weight;
+  // they must be finite and > 0 (else the pair set would not be [y_i > y_j]: the call fails, loss = NaN), the others are
+  // zeroed (a row without overlap multiplies its zero weight with whatever entry its level addresses).
+  __shared__ float s_lut[LUT ? 64 : 1];
+  bool lut_bad = false;
+  if (LUT) {
+    if (threadIdx.x < 64) {
+      float v = A.lut[threadIdx.x];
+      if ((threadIdx.x >> 3) > (threadIdx.x & 7u)) {
+        if (!(v > 0.f) || v > 3.0e38f) { v = 0.f; lut_bad = true; }
+      } else v = 0.f;
+      s_lut[threadIdx.x] = v;
+    }
+    __syncthreads();
+  }
   grid_dep_wait();
+  if (LUT && lut_bad) atomicOr(&ctl->err, 8u);            // (the control block is the previous kernel's until here)
   stamp(ctl, 20);
   if (threadIdx.x == 0) s_cnt = 0;
   const bool own_list = A.nib <= kMaxNibS;
@@ -1042,7 +1070,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         TR_ADD(tr_pre);
         if (fast) {
           float wv0 = in0 ? wp0 : 0.f, wv1 = in1 ? wp1 : 0.f;
-          if (DIFF) { wv0 *= (yi0 - yref); wv1 *= (yi1 - yref); }
+          if (DIFF) { wv0 *= label_weight<LUT>(s_lut, yi0, yref); wv1 *= label_weight<LUT>(s_lut, yi1, yref); }
           const float sje = jin ? sjm : -3.0e38f;
           if (HINGE) {
             if (part) tile_hinge<true>(si0, si1, wv0, wv1, sje, c, P.margin, li0, li1, gi0, gi1, accj, ts, te);
@@ -1065,7 +1093,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           }
           }
         } else if (!HINGE && any_in && DIFF && !RWN && !WRONG && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
-                   runs_tile(in0, in1, lo0, lo1, hi0, hi1, si0, si1, yi0, yi1, wp0, wp1, pjm, sjm, yjm, jin, smin, j0, c, ts, te,
+                   runs_tile<LUT>(s_lut, in0, in1, lo0, lo1, hi0, hi1, si0, si1, yi0, yi1, wp0, wp1, pjm, sjm, yjm, jin, smin, j0, c, ts, te,
                              li0, li1, gi0, gi1, accj)) {
           // (scored as up to three product-form passes, one per label level of the negatives)
         } else if (any_in) {
@@ -1084,21 +1112,21 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           }
           if (gprod) {
             if (any0) {
-              if (full0) tile_general_prod<MODE, true>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj);
-              else       tile_general_prod<MODE, false>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj);
+              if (full0) tile_general_prod<MODE, true>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut);
+              else       tile_general_prod<MODE, false>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut);
             }
             if (any1) {
-              if (full1) tile_general_prod<MODE, true>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj);
-              else       tile_general_prod<MODE, false>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj);
+              if (full1) tile_general_prod<MODE, true>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut);
+              else       tile_general_prod<MODE, false>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut);
             }
           } else {
           if (any0) {
-            if (full0) tile_general<MODE, true, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin);
-            else       tile_general<MODE, false, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin);
+            if (full0) tile_general<MODE, true, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut);
+            else       tile_general<MODE, false, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut);
           }
           if (any1) {
-            if (full1) tile_general<MODE, true, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin);
-            else       tile_general<MODE, false, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin);
+            if (full1) tile_general<MODE, true, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut);
+            else       tile_general<MODE, false, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut);
           }
           }
         }
@@ -1414,6 +1442,8 @@ static const void* pair_func(int mode) {
     RN_CASE(M_HASW | M_RWN) RN_CASE(M_HASW | M_RWN | M_WRONG)
     RN_CASE(M_HASW | M_DIFF | M_RWN) RN_CASE(M_HASW | M_DIFF | M_RWN | M_WRONG)
 #undef RN_CASE
+    case M_HINGE | M_HASW | M_DIFF | M_LUT: return (const void*)k_pair<M_HASW | M_DIFF | M_LUT, false, true>;
+    case M_HASW | M_DIFF | M_LUT: return (const void*)k_pair<M_HASW | M_DIFF | M_LUT>;
     case M_DET: return (const void*)k_pair<0, true>;
     case M_DET | M_HASW: return (const void*)k_pair<M_HASW, true>;
     case M_DET | M_HASW | M_DIFF: return (const void*)k_pair<M_HASW | M_DIFF, true>;
@@ -1437,6 +1467,8 @@ static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A,
     RN_CASE(M_HASW | M_RWN) RN_CASE(M_HASW | M_RWN | M_WRONG)
     RN_CASE(M_HASW | M_DIFF | M_RWN) RN_CASE(M_HASW | M_DIFF | M_RWN | M_WRONG)
 #undef RN_CASE
+    case M_HINGE | M_HASW | M_DIFF | M_LUT: return launch_pair<M_HASW | M_DIFF | M_LUT, false, true>(P, A, st);
+    case M_HASW | M_DIFF | M_LUT: return launch_pair<M_HASW | M_DIFF | M_LUT>(P, A, st);
     case M_DET: return launch_pair<0, true>(P, A, st);
     case M_DET | M_HASW: return launch_pair<M_HASW, true>(P, A, st);
     case M_DET | M_HASW | M_DIFF: return launch_pair<M_HASW | M_DIFF, true>(P, A, st);
@@ -1521,7 +1553,14 @@ extern "C" int rn_pairwise_launch_count(int64_t B, int32_t K) {
 static int validate_pairwise(const rn_pairwise_args* a, bool split = false) {
   if (!a || a->B <= 0 || a->B > (1ll << 28) || a->K <= 0 || a->K > 8) return RN_ERR_ARG;
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
-  if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF && a->label_func != RN_LABEL_GAIN2) return RN_ERR_UNSUPPORTED;
+  if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF && a->label_func != RN_LABEL_GAIN2 &&
+      a->label_func != RN_LABEL_LUT) return RN_ERR_UNSUPPORTED;
+  if ((a->label_func == RN_LABEL_LUT) != (a->weight_lut != nullptr)) return RN_ERR_ARG;
+  if (a->label_func == RN_LABEL_LUT) {
+    // the level table rides on the label-gain tiles of the one-GPU call; the score- / weight-dependent pair sets, the
+    // deterministic instantiation and the blocked rows of the global mode have no table variant
+    if (a->only_wrong || a->rw_neg || a->deterministic || a->block_rows || a->part_count != 1 || split) return RN_ERR_UNSUPPORTED;
+  }
   if (a->pair_loss != RN_LOSS_LOGISTIC && a->pair_loss != RN_LOSS_HINGE) return RN_ERR_UNSUPPORTED;
   if (a->pair_loss == RN_LOSS_HINGE && !(a->margin >= 0.f)) return RN_ERR_ARG;
   if (a->part_count < 1 || a->part_rank < 0 || a->part_rank >= a->part_count) return RN_ERR_ARG;
@@ -1537,12 +1576,13 @@ static int validate_pairwise(const rn_pairwise_args* a, bool split = false) {
       for (int64_t r = 0; r < world; ++r) if (!a->peer_blocks[r] || check_align(a->peer_blocks[r])) return RN_ERR_ARG;
     }
   } else if (a->out_chunk || a->gather_dst) return RN_ERR_ARG;
-  const void* ptrs[] = {a->keys, a->logits, a->labels, a->row_ok, a->rw_pos, a->rw_neg, a->dlogits, a->row_pairs};
+  const void* ptrs[] = {a->keys, a->logits, a->labels, a->row_ok, a->rw_pos, a->rw_neg, a->dlogits, a->row_pairs, a->weight_lut};
   for (const void* p : ptrs) if (p && check_align(p)) return RN_ERR_ALIGN;
   return RN_OK;
 }
 
 extern "C" int rn_pairwise_fwd_bwd(const rn_pairwise_args* a, void* scratch, size_t scratch_bytes, void* stream) {
+  RN_NVTX_RANGE("rn_pairwise_fwd_bwd");
   return rn::pairwise_call(a, scratch, scratch_bytes, stream, nullptr, 0);
 }
 
@@ -1570,7 +1610,8 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
   const bool hinge = a->pair_loss == RN_LOSS_HINGE;
   if (det && hinge) return RN_ERR_UNSUPPORTED;
-  if (!split && !(g_prof.on && g_prof.n < g_prof.cap)) {
+  const bool lut = a->label_func == RN_LABEL_LUT;
+  if (!split && !lut && !(g_prof.on && g_prof.n < g_prof.cap)) {       // (the level table: the general kernels at any size)
     // batches of up to 1024 rows: one launch of one CTA, everything in shared memory (small.cu)
     int smode = 0;
     const bool sdiff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
@@ -1591,7 +1632,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;
   P.c_log2 = hinge ? a->factor : a->factor * 1.4426950408889634f;
   P.margin = a->margin; P.loss_unit = hinge ? 1.0 : 0.6931471805599453;
-  P.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : 0;
+  P.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : (lut ? 2 : 0);
   static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
   P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;
@@ -1637,7 +1678,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   A.cost_straddle = kCostUnit * (u32)(cost_straddle < 0 ? 0 : (cost_straddle > 64 ? 64 : cost_straddle));
   A.cost_levels = (u32)(cost_levels < 0 ? 0 : (cost_levels > 64 ? 64 : cost_levels));
   A.gacc = H.gacc; A.lossrow = H.lossrow; A.cnt = H.cnt; A.perm = H.perm; A.ctl = at<Ctl>(base, L.ctl);
-  A.sgrp = H.sgrp; A.cprim = H.cprim;
+  A.sgrp = H.sgrp; A.cprim = H.cprim; A.lut = a->weight_lut;
   A.fast = fast ? 1 : 0; A.rec2_off = (fast && a->block_rows) ? (u32)((L.rec2 - L.rec) / sizeof(GRec)) : 0u; A.rec = at<GRec>(base, L.rec); A.glist = at<u32>(base, L.glist); A.gcount = at<u32>(base, L.gcount);
   A.ngt = (u32)((a->B + kGTile - 1) / kGTile); A.blk_w = H.blk;
   A.dbgbuf = at<u64>(base, L.gstat);
@@ -1648,9 +1689,10 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
     A.xsum = at<u32>(base, L.misc);
   }
   int mode = 0;
-  const bool diff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
+  const bool diff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2 || lut;
   if (diff || a->rw_pos || a->rw_neg) mode |= M_HASW;
   if (diff) mode |= M_DIFF;
+  if (lut) mode |= M_LUT;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
   if (det) mode |= M_DET;
@@ -1724,6 +1766,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
 extern "C" size_t rn_gauc_scratch_bytes(int64_t B, int32_t K) { return rn_pairwise_scratch_bytes(B, K); }
 
 extern "C" int rn_gauc(const rn_gauc_args* g, void* scratch, size_t scratch_bytes, void* stream) {
+  RN_NVTX_RANGE("rn_gauc");
   if (!g || g->B <= 0 || g->B > (1ll << 28) || g->K <= 0 || g->K > 8) return RN_ERR_ARG;
   if (!g->keys || !g->scores || !g->labels || !g->gauc || !g->n_valid_groups) return RN_ERR_ARG;
   const void* ptrs[] = {g->keys, g->scores, g->labels, g->row_ok};

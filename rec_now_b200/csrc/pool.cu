@@ -367,6 +367,7 @@ static int pool_params(const rn_pool_args* a, PoolParams& P) {
 using namespace rn;
 
 extern "C" int rn_segment_pool_fwd(const rn_pool_args* a, float* out, uint32_t* err_flag, void* stream) {
+  RN_NVTX_RANGE("rn_segment_pool_fwd");
   PoolParams P;
   int rc = pool_params(a, P);
   if (rc) return rc;
@@ -410,6 +411,7 @@ extern "C" int rn_segment_pool_fwd(const rn_pool_args* a, float* out, uint32_t* 
 }
 
 extern "C" int rn_segment_pool_bwd(const rn_pool_args* a, const float* d_out, float* d_table, float* d_weights, void* stream) {
+  RN_NVTX_RANGE("rn_segment_pool_bwd");
   PoolParams P;
   int rc = pool_params(a, P);
   if (rc) return rc;

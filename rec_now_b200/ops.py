@@ -124,16 +124,18 @@ class _PairCall:
 
 import threading
 
-_LABEL_FUNCS = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF, "gain2": _lib.RN_LABEL_GAIN2}
+_LABEL_FUNCS = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF, "gain2": _lib.RN_LABEL_GAIN2, "lut": _lib.RN_LABEL_LUT}
 _tls = threading.local()             # (ctypes releases the GIL during the call: the argument struct is per thread)
 _pair_scratch_bytes: dict = {}
 
 
 def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None, label_func="step",
                      factor=1.0, power=0.0, only_wrong=False, reduce_mean=True, part=(0, 1),
-                     want_row_pairs=False, deterministic=False, focal=None, pair_loss="logistic", margin=1.0):
+                     want_row_pairs=False, deterministic=False, focal=None, pair_loss="logistic", margin=1.0,
+                     weight_lut=None):
     """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors.
-    label_func: "step" | "diff" | "gain2"; pair_loss: "logistic" (bpr_loss_func) | "hinge" (max(0, margin - x))."""
+    label_func: "step" | "diff" | "gain2" | "lut" (weight_lut: float32 [8, 8] on the device, W by label level = label + 1 of
+    integer labels -1 .. 6); pair_loss: "logistic" (bpr_loss_func) | "hinge" (max(0, margin - x))."""
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()
@@ -162,6 +164,13 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
     a.B = b; a.K = kk; a.label_func = _LABEL_FUNCS[label_func]
     a.pair_loss = _lib.RN_LOSS_HINGE if pair_loss == "hinge" else _lib.RN_LOSS_LOGISTIC
     a.margin = margin
+    if label_func == "lut":
+        if weight_lut is None or weight_lut.numel() != 64 or weight_lut.device != dev:
+            raise ValueError("label_func 'lut' needs weight_lut: 64 float32 on the logits' device")
+        weight_lut = _f32(weight_lut)
+        a.weight_lut = weight_lut.data_ptr()
+    else:
+        a.weight_lut = None
     a.keys = keys.data_ptr(); a.logits = s.data_ptr(); a.labels = y.data_ptr()
     a.row_ok = _ptr(ok); a.rw_pos = _ptr(rwp); a.rw_neg = _ptr(rwn)
     a.factor = factor; a.power = power; a.only_wrong = 1 if only_wrong else 0; a.reduce_mean = 1 if reduce_mean else 0

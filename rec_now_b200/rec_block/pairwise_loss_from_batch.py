@@ -121,23 +121,59 @@ class FusedPairWeight:
     (label_matrix, label_matrix_transpose, **kwargs) -> weights, so the same object works with the reference.
     """
 
-    def __init__(self, label_func: str = "step", pos_kw: Optional[str] = None, neg_kw: Optional[str] = None):
-        if label_func not in ("step", "diff", "gain2"):
-            raise ValueError("label_func must be 'step', 'diff' or 'gain2'")
+    #: label levels of the table form: integer labels -1 .. 6 (binary clicks, graded relevance), level = label + 1
+    LEVEL_LABELS = tuple(float(v) for v in range(-1, 7))
+
+    def __init__(self, label_func: str = "step", pos_kw: Optional[str] = None, neg_kw: Optional[str] = None, table=None):
+        if label_func not in ("step", "diff", "gain2", "lut"):
+            raise ValueError("label_func must be 'step', 'diff', 'gain2' or 'lut'")
         self.label_func, self.pos_kw, self.neg_kw = label_func, pos_kw, neg_kw
+        self.table = None
+        self._table_dev: dict = {}
+        if label_func == "lut":
+            # W[i,j] = table[level(y_i)][level(y_j)] * [y_i > y_j]: ANY label-only weight function, evaluated once on the
+            # 8 x 8 grid of label levels (rn_pairwise_args.weight_lut).  Entries with level_i > level_j must be finite
+            # and > 0 (so that C = W > 0 is exactly y_i > y_j, PW:193); the others are not used.
+            t = torch.as_tensor(table, dtype=torch.float32).detach().cpu().reshape(8, 8).clone()
+            lower = torch.tril(torch.ones(8, 8, dtype=torch.bool), -1)
+            if not bool((torch.isfinite(t[lower]) & (t[lower] > 0)).all()):
+                raise ValueError("table entries with level_i > level_j must be finite and > 0")
+            self.table = torch.where(lower, t, torch.zeros(()))
+            if neg_kw is not None:
+                raise ValueError("the table form has no negative-side weights")
+
+    @classmethod
+    def from_callable(cls, f, pos_kw: Optional[str] = None, **kwargs):
+        """The table form of a label-only ``label_pair_to_weight_func`` ``f`` (evaluated on the label levels -1 .. 6)."""
+        y = torch.tensor(cls.LEVEL_LABELS, dtype=torch.float32)
+        return cls("lut", pos_kw=pos_kw, table=f(y.reshape(-1, 1).expand(8, 8), y.reshape(1, -1).expand(8, 8), **kwargs))
+
+    def table_on(self, device) -> torch.Tensor:
+        t = self._table_dev.get(device)
+        if t is None:
+            t = self._table_dev[device] = self.table.to(device).contiguous()
+        return t
 
     def __call__(self, label_matrix, label_matrix_transpose, **kwargs):
         gt = (label_matrix > label_matrix_transpose).to(torch.float32)
-        if self.label_func == "diff":
+        if self.label_func == "lut":
+            # (a label off the level menu has no table entry: weight 0, the pair is dropped)
+            def level(y):
+                on = (y == torch.round(y)) & (y >= -1) & (y <= 6)
+                return torch.where(on, y + 1, torch.zeros_like(y)).long(), on
+            (li, oi), (lj, oj) = level(label_matrix), level(label_matrix_transpose)
+            w = self.table.to(label_matrix.device)[li, lj] * gt * (oi & oj).to(torch.float32)
+        elif self.label_func == "diff":
             w = (label_matrix - label_matrix_transpose) * gt
         elif self.label_func == "gain2":
             w = (torch.exp2(label_matrix) - torch.exp2(label_matrix_transpose)) * gt
         else:
             w = gt
+        # ((B, B) label matrices as the reference passes them; pair vectors on this module's general path)
         if self.pos_kw is not None:
-            w = w * kwargs[self.pos_kw].reshape(-1, 1)
+            w = w * (kwargs[self.pos_kw].reshape(-1, 1) if w.dim() == 2 else kwargs[self.pos_kw].reshape(w.shape))
         if self.neg_kw is not None:
-            w = w * kwargs[self.neg_kw].reshape(1, -1)
+            w = w * (kwargs[self.neg_kw].reshape(1, -1) if w.dim() == 2 else kwargs[self.neg_kw].reshape(w.shape))
         return w
 
 
@@ -148,11 +184,11 @@ label_gain_times_sample_weight = FusedPairWeight("diff", pos_kw="sample_weight")
 class _FusedPairwiseLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor, reduce_mean,
-                only_wrong, power, hinge_margin=None):
+                only_wrong, power, hinge_margin=None, weight_lut=None):
         out = ops.pairwise_fwd_bwd(outputs, labels, keys, row_ok=row_ok, rw_pos=rw_pos, rw_neg=rw_neg,
                                    label_func=label_func, factor=factor, power=power, only_wrong=only_wrong,
                                    reduce_mean=reduce_mean, pair_loss="logistic" if hinge_margin is None else "hinge",
-                                   margin=1.0 if hinge_margin is None else hinge_margin)
+                                   margin=1.0 if hinge_margin is None else hinge_margin, weight_lut=weight_lut)
         ctx.save_for_backward(out["dlogits"])
         ctx.out_shape, ctx.out_dtype = outputs.shape, outputs.dtype
         n_pair = out["n_pair_f32"]
@@ -167,7 +203,7 @@ class _FusedPairwiseLoss(torch.autograd.Function):
             g = g.reshape(ctx.out_shape)
         if g.dtype != ctx.out_dtype:
             g = g.to(ctx.out_dtype)
-        return (g,) + (None,) * 11
+        return (g,) + (None,) * 12
 
 
 def _match_bpr(pairloss_func) -> Optional[tuple]:
@@ -232,12 +268,53 @@ def _classify_weight_func(f, kwargs: dict, device) -> Optional["FusedPairWeight"
                 if ok:
                     res = FusedPairWeight(name)
                     break
+            if res is None:
+                res = _table_of_weight_func(f, kwargs, device)
     except Exception:
         res = None
     if len(_probe_cache) > 256:
         _probe_cache.clear()
     _probe_cache[key] = (f, res)
     return res
+
+
+def _table_of_weight_func(f, kwargs: dict, device) -> Optional["FusedPairWeight"]:
+    """Level-table form (FusedPairWeight 'lut') of a label-only callable that is none of the closed forms: ``f`` evaluated on
+    the 8 x 8 grid of the label levels -1 .. 6.  Taken only if the pair set it implies is exactly ``y_i > y_j`` (entries
+    with level_i > level_j finite and > 0, all others not > 0: PW:193) and if ``f`` is elementwise in its two arguments --
+    checked on a shuffled (N, N) arrangement and on 1-D pair vectors against the table."""
+    lev = torch.tensor(FusedPairWeight.LEVEL_LABELS, dtype=torch.float32, device=device)
+    t = f(lev.reshape(-1, 1).expand(8, 8).contiguous(), lev.reshape(1, -1).expand(8, 8).contiguous(), **kwargs)
+    if not isinstance(t, torch.Tensor) or t.shape != (8, 8):
+        return None
+    t = t.to(torch.float32)
+    lower = torch.tril(torch.ones(8, 8, dtype=torch.bool, device=device), -1)
+    if not bool((torch.isfinite(t[lower]) & (t[lower] > 0)).all()) or bool((t[~lower] > 0).any()):
+        return None
+    g = torch.Generator(device="cpu").manual_seed(20240607)
+    idx = torch.randint(0, 8, (48,), generator=g).to(device)
+    v = lev[idx]
+    n = v.numel()
+    w2 = f(v.reshape(-1, 1).expand(n, n).contiguous(), v.reshape(1, -1).expand(n, n).contiguous(), **kwargs)
+    ia, ib = torch.randint(0, 8, (257,), generator=g).to(device), torch.randint(0, 8, (257,), generator=g).to(device)
+    w1 = f(lev[ia], lev[ib], **kwargs)
+    for w, want in ((w2, t[idx.reshape(-1, 1), idx.reshape(1, -1)]), (w1, t[ia, ib])):
+        if not isinstance(w, torch.Tensor) or w.shape != want.shape:
+            return None
+        w = w.to(torch.float32)
+        keep = want > 0
+        if not (torch.equal(w > 0, keep) and torch.equal(w[keep], want[keep])):
+            return None
+    return FusedPairWeight("lut", table=t)
+
+
+def _labels_on_level_menu(labels: torch.Tensor, row_ok: Optional[torch.Tensor]) -> bool:
+    """True if every label that can take part in a pair is an integer in -1 .. 6 (one device reduction + one read-back)."""
+    y = labels.reshape(-1).to(torch.float32)
+    fine = ((y == torch.round(y)) & (y >= -1.0) & (y <= 6.0)) | torch.isnan(y)
+    if row_ok is not None:
+        fine = fine | ~row_ok.reshape(-1).bool()
+    return bool(fine.all())
 
 
 def _classify_pairloss_func(f, device) -> Optional[tuple]:
@@ -305,6 +382,7 @@ def pairwise_loss(outputs, labels, groups,
     b = outputs.numel()
     mask_t = None if mask is None else _as_cuda(mask).reshape(-1).to(torch.bool)
     keys, row_ok = ops.canon_keys(group_list, mask_t)
+    users_weight_func = label_pair_to_weight_func
     if label_pair_to_weight_func is not None and not isinstance(label_pair_to_weight_func, FusedPairWeight):
         # a label-only callable that computes one of the fused forms (e.g. the reference's test lambda, TPW:51-53)
         recognised = _classify_weight_func(label_pair_to_weight_func, kwargs, outputs.device)
@@ -324,16 +402,28 @@ def pairwise_loss(outputs, labels, groups,
     if bpr is None and callable(pairloss_func):
         bpr = _classify_pairloss_func(pairloss_func, outputs.device)      # e.g. a wrapper around bpr_loss_func (TPW:38-39)
     power = float(click_occurance_power)
+    weight_lut = None
+    menu_w = label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight)
+    if fused_w is not None and fused_w.label_func == "lut":
+        # the level table: fused when the labels are on its menu (checked on the device: one read-back) and the pair set
+        # does not depend on the scores; otherwise the table object is just another callable of the general path
+        if bpr is not None and not only_use_wrong_order_pair and _labels_on_level_menu(labels, row_ok):
+            weight_lut = fused_w.table_on(outputs.device)
+        else:
+            menu_w = False
+            label_pair_to_weight_func = users_weight_func          # (the caller's own function, where the table stood in for one)
+            rw_pos = None
 
-    if bpr is not None and (label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight)):
+    if bpr is not None and menu_w:
         factor, reduce_mean, hinge_margin = bpr
         loss, n_pair = _FusedPairwiseLoss.apply(outputs, labels, keys, row_ok, rw_pos, rw_neg, label_func, factor,
-                                                reduce_mean, bool(only_use_wrong_order_pair), power, hinge_margin)
+                                                reduce_mean, bool(only_use_wrong_order_pair), power, hinge_margin,
+                                                weight_lut)
         return (loss, n_pair) if return_num_pair else loss
 
     # ---- general path: materialised pairs + the caller's callables ------------------------------------
     flat_out = outputs.reshape(-1)
-    if label_pair_to_weight_func is None or isinstance(label_pair_to_weight_func, FusedPairWeight):
+    if menu_w:
         want_w = isinstance(label_pair_to_weight_func, FusedPairWeight)
         pos, neg, w = ops.pair_indices(outputs, labels, keys, row_ok=row_ok, rw_pos=rw_pos, rw_neg=rw_neg,
                                        label_func=label_func, only_wrong=only_use_wrong_order_pair,

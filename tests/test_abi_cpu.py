@@ -33,7 +33,7 @@ def test_exports_match_header(lib):
 
 
 def test_version_and_errors(lib):
-    assert lib.rn_version() == 103
+    assert lib.rn_version() == 104
     assert lib.rn_strerror(0) == b"ok"
     for code in range(1, 8):
         assert lib.rn_strerror(code) not in (b"ok", b"unknown error")
@@ -133,7 +133,7 @@ def test_header_is_plain_c_and_example_links(lib, tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "librecnow_b200 version 103" in r.stdout
+    assert "librecnow_b200 version 104" in r.stdout
 
 
 def test_pair_kernel_spills_stay_small():

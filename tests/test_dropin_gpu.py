@@ -180,13 +180,18 @@ def test_reference_test_callables_take_the_fused_path(monkeypatch):
     a = PW.pairwise_loss(s, y, gg, pairwise_loss_func, label_pair_to_weight_func=gain_weights)
     bb = PW.pairwise_loss(s, y, gg, label_pair_to_weight_func=PW.FusedPairWeight("diff"))
     assert calls["n"] == 0 and abs(a.item() - bb.item()) <= 2e-6 * abs(bb.item())
-    # not one of the fused forms: squared label gain -> materialised pairs, still the right value
+    # not one of the closed forms: squared label gain.  Labels on the level menu -> the level table, still fused
+    # (tests/test_weight_lut_gpu.py); labels off the menu -> materialised pairs; the right value both ways
     sq = lambda lm, lmt: ((lm - lmt) ** 2) * (lm > lmt).to(torch.float32)
-    c = PW.pairwise_loss(s, y, gg, label_pair_to_weight_func=sq)
-    assert calls["n"] == 1
+    sq_np = lambda lm, lmt: ((lm - lmt) ** 2) * (lm > lmt).astype(np.float32)
     from oracle import dense_ref as D
-    ref = D.pairwise_loss(s.cpu().numpy(), y.cpu().numpy(), gg.cpu().numpy(),
-                          label_pair_to_weight_func=lambda lm, lmt: ((lm - lmt) ** 2) * (lm > lmt).astype(np.float32))
+    c = PW.pairwise_loss(s, y, gg, label_pair_to_weight_func=sq)
+    assert calls["n"] == 0
+    ref = D.pairwise_loss(s.cpu().numpy(), y.cpu().numpy(), gg.cpu().numpy(), label_pair_to_weight_func=sq_np)
+    assert abs(c.item() - float(ref)) <= 1e-4 * abs(float(ref))
+    c = PW.pairwise_loss(s, y * 0.5, gg, label_pair_to_weight_func=sq)
+    assert calls["n"] == 1
+    ref = D.pairwise_loss(s.cpu().numpy(), (y * 0.5).cpu().numpy(), gg.cpu().numpy(), label_pair_to_weight_func=sq_np)
     assert abs(c.item() - float(ref)) <= 1e-4 * abs(float(ref))
     # the recognition can be switched off
     monkeypatch.setenv("RN_PROBE_CALLABLES", "0")

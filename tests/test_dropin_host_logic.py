@@ -51,6 +51,38 @@ def test_fused_pair_weight_is_a_reference_style_callable():
         PW.FusedPairWeight("cube")
 
 
+def test_level_table_form_of_label_only_weight_functions():
+    """VERDICT r1 item 7 / SURVEY 8b weight_lut: ANY label-only label_pair_to_weight_func whose pair set is y_i > y_j has a
+    level-table form (evaluated once on the label levels -1 .. 6); functions with another pair set, functions that are not
+    elementwise and bad tables have none."""
+    sq = lambda a, b: ((a - b) ** 2 + 0.5 * a + 1.0) * (a > b).float()
+    f = PW._table_of_weight_func(sq, {}, "cpu")
+    assert f is not None and f.label_func == "lut"
+    lev = torch.tensor(PW.FusedPairWeight.LEVEL_LABELS)
+    want = sq(lev.reshape(-1, 1).expand(8, 8), lev.reshape(1, -1).expand(8, 8))
+    assert torch.equal(f.table, want)
+    # the table object is a reference-style callable: (B, B) label matrices and pair vectors, labels off the menu -> 0
+    y = torch.tensor([0.0, 1.0, 2.0, 5.0, 7.0, 0.5, -1.0])
+    ym, ymt = y.reshape(-1, 1).expand(-1, 7), y.reshape(1, -1).expand(7, -1)
+    on = ((y == y.round()) & (y <= 6)).float()
+    assert torch.equal(f(ym, ymt), sq(ym, ymt) * on.reshape(-1, 1) * on.reshape(1, -1))
+    assert torch.equal(f(y[[3, 2, 1]], y[[0, 6, 2]]), sq(y[[3, 2, 1]], y[[0, 6, 2]]))
+    w = torch.arange(1.0, 8.0)
+    g = PW.FusedPairWeight.from_callable(sq, pos_kw="sw")
+    assert torch.equal(g(ym, ymt, sw=w), f(ym, ymt) * w.reshape(-1, 1))
+    # pair set is not y_i > y_j: symmetric weights, weights with holes, negative gains
+    assert PW._table_of_weight_func(lambda a, b: (a - b).abs(), {}, "cpu") is None
+    assert PW._table_of_weight_func(lambda a, b: (a - b - 1.0) * (a > b).float(), {}, "cpu") is None
+    assert PW._table_of_weight_func(lambda a, b: (b - a) * (a > b).float(), {}, "cpu") is None
+    # not elementwise in the labels (depends on the position)
+    pos_dep = lambda a, b: (a > b).float() * (1.0 + torch.arange(a.numel(), dtype=torch.float32).reshape(a.shape))
+    assert PW._table_of_weight_func(pos_dep, {}, "cpu") is None
+    with pytest.raises(ValueError):
+        PW.FusedPairWeight("lut", table=torch.zeros(8, 8))
+    with pytest.raises(ValueError):
+        PW.FusedPairWeight("lut", table=torch.ones(8, 8), neg_kw="w")
+
+
 def test_no_cpu_fallback_anywhere():
     from rec_now_b200.rec_block import embedding_util as EU
     from rec_now_b200.rec_block import listwise_loss_from_batch as LW
