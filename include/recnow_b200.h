@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define RN_VERSION 104 /* 0.1.4: RN_LABEL_LUT / weight_lut (label-level weight table) */
+#define RN_VERSION 104 /* 0.1.4: RN_LABEL_LUT / weight_lut (label-level weight table), RN_LABEL_LAMBDA */
 
 enum {
   RN_OK = 0,
@@ -60,7 +60,7 @@ enum {
  * Optional per-sample factors rw_pos (row/positive side) and rw_neg (column/negative side) multiply W;
  * whenever any weight is present the reference's rule C = (W > 0) applies (a non-positive or NaN factor
  * removes the pairs it touches).  Anything else goes through rn_pair_indices_* + the caller's own code. */
-enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2, RN_LABEL_LUT = 3 };
+enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2, RN_LABEL_LUT = 3, RN_LABEL_LAMBDA = 4 };
 /*   GAIN2: W = (2^y_i - 2^y_j)*[y_i > y_j]   (NDCG-style exponential gains, the usual RankNet / LambdaRank gain; the
  *          sorted label column then holds 2^y.  Labels whose gains coincide in float32 although y_i > y_j keep their pair
  *          with weight 0 -- integer labels never do.)
@@ -70,6 +70,13 @@ enum { RN_LABEL_STEP = 0, RN_LABEL_DIFF = 1, RN_LABEL_GAIN2 = 2, RN_LABEL_LUT = 
  *          that the pair set stays [y_i > y_j] (C = W > 0, PW:193) and the counts stay position arithmetic; the other
  *          entries are ignored.  A label outside the menu or a bad entry fails the call on the device: loss = NaN,
  *          rn_last_device_error bit 8.
+ *   LAMBDA: LambdaRank, W = |delta NDCG_ij| = (2^y_i - 2^y_j) * |D(r_i) - D(r_j)| / IDCG_g * [y_i > y_j]: D(r) = 1 / log2(1 + r),
+ *          r_i the 1-based rank of row i by score among the rows of its group that can pair (descending, ties by row
+ *          index), IDCG_g the DCG of the group's labels in descending order with gains 2^y - 1 (a group whose ideal DCG
+ *          is not positive gets weight 0).  Not expressible as a label_pair_to_weight_func of the reference (it needs the
+ *          scores): an extension on the same pair set, counts and normalisation; like every weight it is a constant
+ *          of the step (PW:270).  rw_pos multiplies it.  Logistic loss, one GPU, not with only_wrong / rw_neg /
+ *          deterministic / the focal term.
  * pairloss_func menu (pairwise_loss_from_batch.py:229, 274; the reference ships bpr_loss_func only, :96-127):
  *   LOGISTIC: l = softplus(-x), x = (s_i - s_j)*factor            (bpr_loss_func)
  *   HINGE:    l = max(0, margin - x)                               (margin ranking loss; d l / d x = -[margin - x > 0]) */

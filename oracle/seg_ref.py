@@ -18,6 +18,11 @@ i.e. what a reference user writes as label_pair_to_weight_func(Y, Yt, sample_wei
     label_func "callable": W = weight_func(Y_i, Y_j) [* rw ...], C = W > 0 -- ANY label_pair_to_weight_func of the two label
                         matrices (PW:192-193), evaluated block by block in float32; the truth for the level-table path
                         (RN_LABEL_LUT) of the product.
+    label_func "lambda": LambdaRank, W = (2^y_i - 2^y_j) * |D(r_i) - D(r_j)| / IDCG_g [* rw_pos_i] on the pair set y_i > y_j
+                        (defined in include/recnow_b200.h -- the reference ships only the hook): D(r) =
+                        1 / log2(1 + r) rounded to float32, r = 1-based rank by score inside the group among the rows that
+                        can pair (descending, ties by row index), IDCG_g = DCG of the group's labels in descending
+                        order with gains 2^y - 1 (float64); IDCG_g <= 0 gives weight 0.
 """
 from __future__ import annotations
 
@@ -35,7 +40,7 @@ class PairSpec:
     reduce_mean: bool = True            # bpr_loss_func reduce_mean       PW:125-126
     only_wrong: bool = False            # only_use_wrong_order_pair       PW:197-203
     power: float = 0.0                  # click_occurance_power           PW:282-291
-    label_func: str = "step"            # "step" | "diff" | "gain2" | "callable"
+    label_func: str = "step"            # "step" | "diff" | "gain2" | "callable" | "lambda"
     weight_func: Optional[object] = None  # label_func "callable": f(label_matrix, label_matrix_transpose) -> weights   PW:192
     rw_pos: Optional[np.ndarray] = None  # per-sample weight applied on the positive (row) side
     rw_neg: Optional[np.ndarray] = None  # per-sample weight applied on the negative (column) side
@@ -105,9 +110,23 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         ok = ok & np.asarray(mask, bool).reshape(-1)                         # PW:154-172
     rwp = None if spec.rw_pos is None else np.asarray(spec.rw_pos, F32).reshape(-1)
     rwn = None if spec.rw_neg is None else np.asarray(spec.rw_neg, F32).reshape(-1)
-    has_w = spec.label_func in ("diff", "gain2", "callable") or rwp is not None or rwn is not None
-    g32 = np.exp2(y32).astype(F32) if spec.label_func == "gain2" else y32
+    has_w = spec.label_func in ("diff", "gain2", "callable", "lambda") or rwp is not None or rwn is not None
+    g32 = np.exp2(y32).astype(F32) if spec.label_func in ("gain2", "lambda") else y32
     segs = _group_members(keys, ok)
+    disc32 = np.zeros(b, F32)            # "lambda": rank discount of every row, 1 / IDCG of its group
+    inv_idcg32 = np.zeros(b, F32)
+    if spec.label_func == "lambda":
+        for m in segs:
+            mm = m[~np.isnan(y32[m])]                                        # (a NaN label pairs with nothing: not ranked)
+            if mm.size == 0:
+                continue
+            order = np.lexsort((mm, -s32[mm].astype(np.float64)))            # score descending, ties by row index
+            rank = np.empty(mm.size, np.float64)
+            rank[order] = np.arange(1, mm.size + 1)
+            disc32[mm] = (1.0 / np.log2(1.0 + rank)).astype(F32)
+            gains = np.sort(g32[mm].astype(np.float64) - 1.0)[::-1]
+            idcg = float((gains / np.log2(1.0 + np.arange(1, mm.size + 1))).sum())
+            inv_idcg32[mm] = F32(1.0 / idcg) if idcg > 0.0 else F32(0.0)
 
     row_pairs = np.zeros(b, np.int64)
     # pass 1: exact counts (needed for c_h before any weight can be formed, PW:288-289)
@@ -125,7 +144,7 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
         if not has_w:
             cond, w = gt, None                                               # PW:188-190
         else:
-            if spec.label_func in ("diff", "gain2"):
+            if spec.label_func in ("diff", "gain2", "lambda"):
                 w = ((g32[mi][:, None] - g32[m][None, :]).astype(F32) * gt.astype(F32)).astype(F32)
             elif spec.label_func == "callable":
                 yim, yjm = np.broadcast_arrays(yi, yj)
@@ -137,6 +156,11 @@ def pairwise(outputs, labels, groups, spec: PairSpec = PairSpec(), mask=None,
             if rwn is not None:
                 w = (w * rwn[m][None, :]).astype(F32)
             cond = w > 0                                                     # PW:193
+            if spec.label_func == "lambda":
+                # (the pair set is y_i > y_j -- the label gain times the row weight, tested above, decides it; the rank
+                # part of the weight only scales the pairs)
+                w = (w * inv_idcg32[mi][:, None]).astype(F32)
+                w = (w * np.abs(disc32[mi][:, None] - disc32[m][None, :]).astype(F32)).astype(F32)
         cond = cond & (mi[:, None] != m[None, :])                            # PW:36 (identity removed)
         if spec.only_wrong:
             cond = cond & (s32[mi][:, None] < s32[m][None, :])               # PW:200-202

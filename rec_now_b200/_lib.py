@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RN_LIB_PATH") or os.path.join(HERE, "librecnow_b200.so")
 
 RN_OK = 0
-RN_LABEL_STEP, RN_LABEL_DIFF, RN_LABEL_GAIN2, RN_LABEL_LUT = 0, 1, 2, 3
+RN_LABEL_STEP, RN_LABEL_DIFF, RN_LABEL_GAIN2, RN_LABEL_LUT, RN_LABEL_LAMBDA = 0, 1, 2, 3, 4
 RN_LOSS_LOGISTIC, RN_LOSS_HINGE = 0, 1
 ERR_NAMES = {1: "RN_ERR_ARG", 2: "RN_ERR_ALIGN", 3: "RN_ERR_SCRATCH", 4: "RN_ERR_LAUNCH",
              5: "RN_ERR_UNSUPPORTED", 6: "RN_ERR_NO_DEVICE", 7: "RN_ERR_INTERNAL"}

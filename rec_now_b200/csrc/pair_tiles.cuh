@@ -7,7 +7,10 @@
 
 namespace rn {
 
-enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8, M_LUT = 64 };      // (16, 32: dispatch-only bits of pairwise.cu)
+enum { M_HASW = 1, M_DIFF = 2, M_RWN = 4, M_WRONG = 8, M_LUT = 64, M_LAMBDA = 128 };      // (16, 32: dispatch-only bits of pairwise.cu)
+// M_LAMBDA (RN_LABEL_LAMBDA, with M_DIFF on the 2^y label column): the pair weight also carries |D_i - D_j|, the difference
+// of the rows' rank discounts (the negatives' discounts travel in the negative-side weight column, the row's own in `di`);
+// every tile is a general tile then -- the weight changes from pair to pair.
 
 // Label part of a pair weight under M_DIFF: the difference of the (transformed) labels, or -- M_LUT, RN_LABEL_LUT -- the
 // entry of the 8 x 8 level table (shared memory; the sorted label column then holds the label LEVEL 0 .. 7 as a float).
@@ -26,8 +29,10 @@ template <int MODE, bool FULL, bool HINGE = false>
 __device__ __forceinline__ void tile_general(const float si, const float yi, const float wpi, const u32 lo, const u32 hi,
                                              const u32 pjm, const float sjm, const float yjm, const float wnjm,
                                              const float c, const int t0, const int t1, float& li, float& gi, u32& cnt,
-                                             float& accj, const float margin = 0.f, const float* lut = nullptr) {
+                                             float& accj, const float margin = 0.f, const float* lut = nullptr,
+                                             const float di = 0.f) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG, LUT = MODE & M_LUT;
+  constexpr bool LAMBDA = MODE & M_LAMBDA;
   float gi_t = 0.f, li_t = 0.f;
 #pragma unroll 2
   for (int tb = t0; tb < t1; tb += 4) {
@@ -56,6 +61,7 @@ __device__ __forceinline__ void tile_general(const float si, const float yi, con
       if (HASW) {
         wv = wpi;
         if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = label_weight<LUT>(lut, yi, yj) * wpi; }
+        if (LAMBDA) { const float dj = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv *= fabsf(di - dj); }
         if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
         d *= wv;
       }
@@ -220,8 +226,9 @@ template <int MODE, bool FULL>
 __device__ __forceinline__ void tile_general_prod(const float Ei, const float yi, const float wpi, const u32 lo, const u32 hi,
                                                   const u32 pjm, const float Fm, const float yjm, const float wnjm,
                                                   const int t0, const int t1, float& li, float& gi, u32& cnt, float& accj,
-                                                  const float* lut = nullptr) {
+                                                  const float* lut = nullptr, const float di = 0.f) {
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, LUT = MODE & M_LUT;
+  constexpr bool LAMBDA = MODE & M_LAMBDA;
   float gi_t = 0.f, li_t = 0.f;
 #pragma unroll 2
   for (int tb = t0; tb < t1; tb += 4) {
@@ -238,6 +245,7 @@ __device__ __forceinline__ void tile_general_prod(const float Ei, const float yi
       if (HASW) {
         wv = wpi;
         if (DIFF) { const float yj = __shfl_xor_sync(0xFFFFFFFFu, yjm, t); wv = label_weight<LUT>(lut, yi, yj) * wpi; }
+        if (LAMBDA) { const float dj = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv *= fabsf(di - dj); }
         if (RWN) { const float wn = __shfl_xor_sync(0xFFFFFFFFu, wnjm, t); wv = wv * wn; valid = valid && (wv > 0.f); }
         d *= wv;
       }

@@ -706,6 +706,7 @@ __device__ __forceinline__ void clean_records(const KpArgs& A, u32 t0, u32 tstep
 // Positive-side rows of an I-block (two per lane) and the first J block of a segment: loaded one segment ahead.
 struct UnitRows {
   uint2 an0, an1; float si0, si1, yi0, yi1, wp0, wp1; float sjm, yjm, wnjm;
+  float di0, di1;          // M_LAMBDA: the rows' rank discounts
 };
 
 // One piece of work of a warp: I-block b x J-blocks [jb0, jb1); of the first J-block only the rotation-step eighths
@@ -714,16 +715,17 @@ struct Seg { u32 b, jb0, jb1, ea, eb; };
 
 template <int MODE>
 __device__ __forceinline__ void load_unit_rows(const KpArgs& A, u32 B, u32 b, u32 jb0, u32 ln, UnitRows& r) {
-  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN;
+  constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, LAMBDA = MODE & M_LAMBDA;
   const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
   r.an0 = make_uint2(0, 0); r.an1 = make_uint2(0, 0);
-  r.si0 = r.si1 = r.yi0 = r.yi1 = 0.f; r.wp0 = r.wp1 = 1.f;
+  r.si0 = r.si1 = r.yi0 = r.yi1 = 0.f; r.wp0 = r.wp1 = 1.f; r.di0 = r.di1 = 0.f;
+  if (LAMBDA) { if (pi0 < B) r.di0 = A.swn[pi0]; if (pi1 < B) r.di1 = A.swn[pi1]; }
   if (pi0 < B) { r.an0 = A.aj[pi0]; r.si0 = A.ss[pi0]; if (DIFF) r.yi0 = A.sy[pi0]; if (HASW && A.swp) r.wp0 = A.swp[pi0]; }
   if (pi1 < B) { r.an1 = A.aj[pi1]; r.si1 = A.ss[pi1]; if (DIFF) r.yi1 = A.sy[pi1]; if (HASW && A.swp) r.wp1 = A.swp[pi1]; }
   const u32 pjm = jb0 * 32 + ln;
   r.sjm = pjm < B ? A.ss[pjm] : 0.f; r.yjm = 0.f; r.wnjm = 1.f;
   if (DIFF) r.yjm = pjm < B ? A.sy[pjm] : 0.f;
-  if (RWN) r.wnjm = pjm < B ? A.swn[pjm] : 0.f;
+  if (RWN || LAMBDA) r.wnjm = pjm < B ? A.swn[pjm] : 0.f;
 }
 
 // A block whose negatives span several label levels of ONE group (label-gain weights): every row covers a level of the
@@ -765,6 +767,65 @@ __device__ __forceinline__ bool runs_tile(const float* lut, const bool in0, cons
 __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& A, const u64* cprim, u32 cstride, u32 nvb,
                                              u32& epoch2, u64* red_u, double* red_d);
 
+// ---- LambdaRank weights (RN_LABEL_LAMBDA) -----------------------------------------------------------------
+// W_ij = |delta NDCG_ij| = (2^y_i - 2^y_j) * |D(r_i) - D(r_j)| / IDCG_g for y_i > y_j, with D(r) = 1 / log2(1 + r), r_i the
+// 1-based rank of row i among the rows of its group by score (descending; ties by original row) and IDCG_g the DCG of
+// the group's labels in descending order (gain 2^y - 1).  The weights are constants of the step (PW:270 stops the gradient
+// through every weight).  This pre-pass of the pair kernel works the per-row parts out on the sorted columns:
+//   0  zero the per-group accumulators (indexed by the group's first sorted position)
+//   1  rows per group (one atomic per group and warp)
+//   2  one warp per row: its rank by a scan of the group's scores (coalesced; consecutive rows go to consecutive warps of
+//      the grid, so the rows of a big group are spread over all SMs), its discount D(r) -> the negative-side weight column;
+//      its term of the ideal DCG -- the labels ascend along the sorted positions, so the row's ideal rank is its distance
+//      from the group's end -- added in double precision
+//   3  row weight = rw_pos (or 1) / IDCG -> the positive-side weight column
+// Discounts are rounded to float32 from double precision (|D_i - D_j| of neighbouring ranks of a long group cancels
+// six digits: the oracle rounds the same way).  Groups of one label level (and the rows that cannot pair) are skipped.
+constexpr u32 kLambdaBarriers = 4;
+static __device__ __noinline__ void lambda_prepare(const PairParams& P, const KpArgs& A) {
+  Ctl* ctl = A.ctl;
+  const u32 B = P.B, ln = lane_id();
+  const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+  u32* gsz = A.cnt;                                     // (the dynamic modes' pair counters: free here)
+  double* idcg = reinterpret_cast<double*>(A.g64);      // (the deterministic mode's accumulators: free here)
+  float* sd = const_cast<float*>(A.swn);
+  float* swp = const_cast<float*>(A.swp);
+  u32 epoch = 0;
+  for (u32 p = gtid; p < B; p += gthreads) { gsz[p] = 0u; idcg[p] = 0.0; }
+  grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
+  for (u32 p0 = 0; p0 < B; p0 += gthreads) {
+    const u32 p = p0 + gtid;
+    const u32 a = p < B ? A.aj[p].x : kEmpty;
+    const u32 m = __match_any_sync(0xFFFFFFFFu, a);
+    if (a != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(gsz + a, (u32)__popc(m));
+  }
+  grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
+  for (u32 p = gtid >> 5; p < B; p += gthreads >> 5) {
+    const u32 a = A.aj[p].x, sz = gsz[a];
+    if (A.aj[a + sz - 1u].y == 0u) { if (ln == 0) sd[p] = 0.f; continue; }      // one label level: the group has no pairs
+    const float sp = A.ss[p];
+    const u32 rp = A.perm[p];
+    u32 c = 0;
+    for (u32 q = a + ln; q < a + sz; q += 32u) {
+      const float sq = A.ss[q];
+      if (sq > sp) ++c;
+      else if (sq == sp && A.perm[q] < rp) ++c;
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);              // rows ranked above this one: r = c + 1
+    if (ln == 0) {
+      sd[p] = (float)(1.0 / log2(2.0 + (double)c));
+      const double gain = (double)A.sy[p] - 1.0;        // (the label column holds 2^y)
+      if (gain != 0.0) atomicAdd(idcg + a, gain / log2(1.0 + (double)(a + sz - p)));
+    }
+  }
+  grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
+  for (u32 p = gtid; p < B; p += gthreads) {
+    const double t = idcg[A.aj[p].x];
+    swp[p] = t > 0.0 ? (P.rw_pos ? swp[p] : 1.0f) * (float)(1.0 / t) : 0.f;
+  }
+  grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
+}
+
 // DET: deterministic mode (fixed-point gradient accumulators, ordered loss partials) -- a separate instantiation, so that
 // the default kernel carries none of it through the pair loop.
 // HINGE: the pair loss is the hinge max(0, margin - x) (tile_hinge / tile_general<.., HINGE>) instead of the logistic loss.
@@ -786,6 +847,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   __shared__ u32 s_scan[kPairWarps + 2];
   __shared__ u32 s_bnd[6 * kPairWarps];
   constexpr bool HASW = MODE & M_HASW, DIFF = MODE & M_DIFF, RWN = MODE & M_RWN, WRONG = MODE & M_WRONG, LUT = MODE & M_LUT;
+  constexpr bool LAMBDA = MODE & M_LAMBDA;
   constexpr bool DYN = RWN || WRONG;
   Ctl* ctl = A.ctl;
   const u32 ln = lane_id();
@@ -807,6 +869,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
   }
   grid_dep_wait();
   if (LUT && lut_bad) atomicOr(&ctl->err, 8u);            // (the control block is the previous kernel's until here)
+  if (LAMBDA) lambda_prepare(P, A);                       // rank discounts and 1 / IDCG of every row (kLambdaBarriers grid barriers)
   stamp(ctl, 20);
   if (threadIdx.x == 0) s_cnt = 0;
   const bool own_list = A.nib <= kMaxNibS;
@@ -1021,6 +1084,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
       const u32 pi0 = b * kIB + ln, pi1 = pi0 + 32;
       const uint2 an0 = R.an0, an1 = R.an1;
       const float si0 = R.si0, si1 = R.si1, yi0 = R.yi0, yi1 = R.yi1, wp0 = R.wp0, wp1 = R.wp1;
+      const float di0 = R.di0, di1 = R.di1;
       const u32 lo0 = an0.x, hi0 = an0.x + an0.y, lo1 = an1.x, hi1 = an1.x + an1.y;
       float li0 = 0.f, li1 = 0.f, gi0 = 0.f, gi1 = 0.f; u32 cnt0 = 0, cnt1 = 0;
       u32 pjm = jb0 * 32 + ln;
@@ -1035,7 +1099,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         const bool more = (jb + 1 < jb1) && pjn < B;
         float sjn = more ? A.ss[pjn] : 0.f, yjn = 0.f, wnjn = 1.f;
         if (DIFF) yjn = more ? A.sy[pjn] : 0.f;
-        if (RWN) wnjn = more ? A.swn[pjn] : 0.f;
+        if (RWN || LAMBDA) wnjn = more ? A.swn[pjn] : 0.f;
         float accj = 0.f;
         const u32 j0 = jb * 32;
         const int ts = (jb == jb0) ? 4 * (int)sg.ea : 0, te = (jb + 1 == jb1) ? 4 * (int)sg.eb : 32;   // rotation steps
@@ -1059,7 +1123,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
         }
         const bool any_in = smin != 0xFFFFFFFFu;
         const bool jin = pjm >= smin && pjm < emax;                  // this lane's negative is inside the overlap
-        bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG;
+        bool fast = any_in && smin == smax && emin == emax && !RWN && !WRONG && !LAMBDA;
         float yref = 0.f;
         if (DIFF && fast) {
           yref = __shfl_sync(0xFFFFFFFFu, yjm, smin - j0);
@@ -1092,7 +1156,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
             else      tile_fast<true>(si0, si1, wv0, wv1, sje, c, li0, li1, gi0, gi1, accj);
           }
           }
-        } else if (!HINGE && any_in && DIFF && !RWN && !WRONG && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
+        } else if (!HINGE && any_in && DIFF && !RWN && !WRONG && !LAMBDA && use_prod && !(P.debug & 32) &&      // (debug bit 32: without the level passes)
                    runs_tile<LUT>(s_lut, in0, in1, lo0, lo1, hi0, hi1, si0, si1, yi0, yi1, wp0, wp1, pjm, sjm, yjm, jin, smin, j0, c, ts, te,
                              li0, li1, gi0, gi1, accj)) {
           // (scored as up to three product-form passes, one per label level of the negatives)
@@ -1112,21 +1176,21 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
           }
           if (gprod) {
             if (any0) {
-              if (full0) tile_general_prod<MODE, true>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut);
-              else       tile_general_prod<MODE, false>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut);
+              if (full0) tile_general_prod<MODE, true>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut, di0);
+              else       tile_general_prod<MODE, false>(Eg0, yi0, wp0, lo0, hi0, pjm, Fg, yjm, wnjm, ts, te, li0, gi0, cnt0, accj, s_lut, di0);
             }
             if (any1) {
-              if (full1) tile_general_prod<MODE, true>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut);
-              else       tile_general_prod<MODE, false>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut);
+              if (full1) tile_general_prod<MODE, true>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut, di1);
+              else       tile_general_prod<MODE, false>(Eg1, yi1, wp1, lo1, hi1, pjm, Fg, yjm, wnjm, ts, te, li1, gi1, cnt1, accj, s_lut, di1);
             }
           } else {
           if (any0) {
-            if (full0) tile_general<MODE, true, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut);
-            else       tile_general<MODE, false, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut);
+            if (full0) tile_general<MODE, true, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut, di0);
+            else       tile_general<MODE, false, HINGE>(si0, yi0, wp0, lo0, hi0, pjm, sjm, yjm, wnjm, c, ts, te, li0, gi0, cnt0, accj, P.margin, s_lut, di0);
           }
           if (any1) {
-            if (full1) tile_general<MODE, true, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut);
-            else       tile_general<MODE, false, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut);
+            if (full1) tile_general<MODE, true, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut, di1);
+            else       tile_general<MODE, false, HINGE>(si1, yi1, wp1, lo1, hi1, pjm, sjm, yjm, wnjm, c, ts, te, li1, gi1, cnt1, accj, P.margin, s_lut, di1);
           }
           }
         }
@@ -1195,7 +1259,7 @@ __global__ void __launch_bounds__(kPairThreads) k_pair(PairParams P, KpArgs A) {
     }
   }
   const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
-  u32 epoch2 = 0;
+  u32 epoch2 = LAMBDA ? kLambdaBarriers * gridDim.x : 0u;        // (lambda_prepare's barriers came first)
   if (!DYN) {
     // ---- this CTA's share of sum w * loss, then (after the grid barrier) un-permute and scale the gradient ----
     lsum = warp_sum(lsum);
@@ -1444,6 +1508,7 @@ static const void* pair_func(int mode) {
 #undef RN_CASE
     case M_HINGE | M_HASW | M_DIFF | M_LUT: return (const void*)k_pair<M_HASW | M_DIFF | M_LUT, false, true>;
     case M_HASW | M_DIFF | M_LUT: return (const void*)k_pair<M_HASW | M_DIFF | M_LUT>;
+    case M_HASW | M_DIFF | M_LAMBDA: return (const void*)k_pair<M_HASW | M_DIFF | M_LAMBDA>;
     case M_DET: return (const void*)k_pair<0, true>;
     case M_DET | M_HASW: return (const void*)k_pair<M_HASW, true>;
     case M_DET | M_HASW | M_DIFF: return (const void*)k_pair<M_HASW | M_DIFF, true>;
@@ -1469,6 +1534,7 @@ static cudaError_t dispatch_pair(int mode, const PairParams& P, const KpArgs& A,
 #undef RN_CASE
     case M_HINGE | M_HASW | M_DIFF | M_LUT: return launch_pair<M_HASW | M_DIFF | M_LUT, false, true>(P, A, st);
     case M_HASW | M_DIFF | M_LUT: return launch_pair<M_HASW | M_DIFF | M_LUT>(P, A, st);
+    case M_HASW | M_DIFF | M_LAMBDA: return launch_pair<M_HASW | M_DIFF | M_LAMBDA>(P, A, st);
     case M_DET: return launch_pair<0, true>(P, A, st);
     case M_DET | M_HASW: return launch_pair<M_HASW, true>(P, A, st);
     case M_DET | M_HASW | M_DIFF: return launch_pair<M_HASW | M_DIFF, true>(P, A, st);
@@ -1554,12 +1620,18 @@ static int validate_pairwise(const rn_pairwise_args* a, bool split = false) {
   if (!a || a->B <= 0 || a->B > (1ll << 28) || a->K <= 0 || a->K > 8) return RN_ERR_ARG;
   if (!a->keys || !a->logits || !a->labels || !a->loss || !a->n_pair_f32 || !a->n_pair || !a->dlogits) return RN_ERR_ARG;
   if (a->label_func != RN_LABEL_STEP && a->label_func != RN_LABEL_DIFF && a->label_func != RN_LABEL_GAIN2 &&
-      a->label_func != RN_LABEL_LUT) return RN_ERR_UNSUPPORTED;
+      a->label_func != RN_LABEL_LUT && a->label_func != RN_LABEL_LAMBDA) return RN_ERR_UNSUPPORTED;
   if ((a->label_func == RN_LABEL_LUT) != (a->weight_lut != nullptr)) return RN_ERR_ARG;
   if (a->label_func == RN_LABEL_LUT) {
     // the level table rides on the label-gain tiles of the one-GPU call; the score- / weight-dependent pair sets, the
     // deterministic instantiation and the blocked rows of the global mode have no table variant
     if (a->only_wrong || a->rw_neg || a->deterministic || a->block_rows || a->part_count != 1 || split) return RN_ERR_UNSUPPORTED;
+  }
+  if (a->label_func == RN_LABEL_LAMBDA) {
+    // per-pair weights from the rows' score ranks: general tiles of the logistic loss on one GPU (the pre-pass lives in
+    // the pair kernel; the negative-side weight column carries the rank discounts)
+    if (a->only_wrong || a->rw_neg || a->deterministic || a->block_rows || a->part_count != 1 || split ||
+        a->pair_loss != RN_LOSS_LOGISTIC || a->focal_weight != 0.f) return RN_ERR_UNSUPPORTED;
   }
   if (a->pair_loss != RN_LOSS_LOGISTIC && a->pair_loss != RN_LOSS_HINGE) return RN_ERR_UNSUPPORTED;
   if (a->pair_loss == RN_LOSS_HINGE && !(a->margin >= 0.f)) return RN_ERR_ARG;
@@ -1610,8 +1682,8 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   if (det && (dyn || a->block_rows || a->part_count > 1)) return RN_ERR_UNSUPPORTED;
   const bool hinge = a->pair_loss == RN_LOSS_HINGE;
   if (det && hinge) return RN_ERR_UNSUPPORTED;
-  const bool lut = a->label_func == RN_LABEL_LUT;
-  if (!split && !lut && !(g_prof.on && g_prof.n < g_prof.cap)) {       // (the level table: the general kernels at any size)
+  const bool lut = a->label_func == RN_LABEL_LUT, lambda = a->label_func == RN_LABEL_LAMBDA;
+  if (!split && !lut && !lambda && !(g_prof.on && g_prof.n < g_prof.cap)) {       // (the level table: the general kernels at any size)
     // batches of up to 1024 rows: one launch of one CTA, everything in shared memory (small.cu)
     int smode = 0;
     const bool sdiff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
@@ -1632,7 +1704,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   P.factor = a->factor; P.power = a->power; P.reduce_mean = a->reduce_mean; P.dyn_count = dyn ? 1 : 0;
   P.c_log2 = hinge ? a->factor : a->factor * 1.4426950408889634f;
   P.margin = a->margin; P.loss_unit = hinge ? 1.0 : 0.6931471805599453;
-  P.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : (lut ? 2 : 0);
+  P.gain2 = (a->label_func == RN_LABEL_GAIN2 || lambda) ? 1 : (lut ? 2 : 0);
   static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
   P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;
@@ -1667,7 +1739,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   in.allow_merged = allow_merged && a->part_count == 1 && !fast && !det;      // ranks of the global mode need identical ids; so does a deterministic call (table slots depend on insertion order)
   if (in.allow_merged && a->K == 1 && !P.rm.Bl) { P.gbits = seg_merged_gbits(L); H.P.gbits = P.gbits; }
   KpArgs A{};
-  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = a->rw_pos ? H.swp : nullptr; A.swn = H.swn;
+  A.aj = H.aj; A.ss = H.ss; A.sy = H.sy; A.swp = (a->rw_pos || lambda) ? H.swp : nullptr; A.swn = H.swn;
   A.units = H.units; A.blk = H.blk; A.nib = L.nib; A.target_units = H.target_units;
   static const int cost_gen = tune_int("RN_PAIR_COST_GEN", 17);
   A.cost_gen = kCostUnit * (u32)(cost_gen < 1 ? 1 : (cost_gen > 64 ? 64 : cost_gen));            // (knobs are in eighths of a fast tile)
@@ -1689,10 +1761,11 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
     A.xsum = at<u32>(base, L.misc);
   }
   int mode = 0;
-  const bool diff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2 || lut;
+  const bool diff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2 || lut || lambda;
   if (diff || a->rw_pos || a->rw_neg) mode |= M_HASW;
   if (diff) mode |= M_DIFF;
   if (lut) mode |= M_LUT;
+  if (lambda) mode |= M_LAMBDA;
   if (a->rw_neg) mode |= M_RWN;
   if (a->only_wrong) mode |= M_WRONG;
   if (det) mode |= M_DET;

@@ -124,7 +124,8 @@ class _PairCall:
 
 import threading
 
-_LABEL_FUNCS = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF, "gain2": _lib.RN_LABEL_GAIN2, "lut": _lib.RN_LABEL_LUT}
+_LABEL_FUNCS = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF, "gain2": _lib.RN_LABEL_GAIN2, "lut": _lib.RN_LABEL_LUT,
+                "lambda": _lib.RN_LABEL_LAMBDA}
 _tls = threading.local()             # (ctypes releases the GIL during the call: the argument struct is per thread)
 _pair_scratch_bytes: dict = {}
 
@@ -135,7 +136,7 @@ def pairwise_fwd_bwd(logits, labels, keys, row_ok=None, rw_pos=None, rw_neg=None
                      weight_lut=None):
     """rn_pairwise_fwd_bwd.  keys: int64 [K,B] (canonical).  Returns dict of device tensors.
     label_func: "step" | "diff" | "gain2" | "lut" (weight_lut: float32 [8, 8] on the device, W by label level = label + 1 of
-    integer labels -1 .. 6); pair_loss: "logistic" (bpr_loss_func) | "hinge" (max(0, margin - x))."""
+    integer labels -1 .. 6) | "lambda" (LambdaRank |delta NDCG| weights from the rows' score ranks); pair_loss: "logistic" (bpr_loss_func) | "hinge" (max(0, margin - x))."""
     _need_cuda(logits, labels, keys, row_ok, rw_pos, rw_neg)
     s, y = _f32(logits), _f32(labels)
     b = s.numel()

@@ -117,7 +117,10 @@ class FusedPairWeight:
     """A ``label_pair_to_weight_func`` the fused kernel understands.
 
     ``W[i,j] = phi(y_i, y_j) * kwargs[pos_kw][i] * kwargs[neg_kw][j]`` with ``phi`` = ``[y_i > y_j]`` ("step"),
-    ``(y_i - y_j) * [y_i > y_j]`` ("diff") or ``(2^y_i - 2^y_j) * [y_i > y_j]`` ("gain2": NDCG-style exponential gains).  It is also a plain callable with the reference's contract
+    ``(y_i - y_j) * [y_i > y_j]`` ("diff") or ``(2^y_i - 2^y_j) * [y_i > y_j]`` ("gain2": NDCG-style exponential gains);
+    "lut": a table over the label levels (any label-only function, see ``from_callable``); "lambda": LambdaRank,
+    ``phi = (2^y_i - 2^y_j) * |D(r_i) - D(r_j)| / IDCG_group * [y_i > y_j]`` with the rows' score ranks inside their group
+    (include/recnow_b200.h RN_LABEL_LAMBDA; fused path only -- the reference's callable contract has no access to the scores).  It is also a plain callable with the reference's contract
     (label_matrix, label_matrix_transpose, **kwargs) -> weights, so the same object works with the reference.
     """
 
@@ -125,8 +128,10 @@ class FusedPairWeight:
     LEVEL_LABELS = tuple(float(v) for v in range(-1, 7))
 
     def __init__(self, label_func: str = "step", pos_kw: Optional[str] = None, neg_kw: Optional[str] = None, table=None):
-        if label_func not in ("step", "diff", "gain2", "lut"):
-            raise ValueError("label_func must be 'step', 'diff', 'gain2' or 'lut'")
+        if label_func not in ("step", "diff", "gain2", "lut", "lambda"):
+            raise ValueError("label_func must be 'step', 'diff', 'gain2', 'lut' or 'lambda'")
+        if label_func == "lambda" and neg_kw is not None:
+            raise ValueError("LambdaRank weights take no negative-side weights")
         self.label_func, self.pos_kw, self.neg_kw = label_func, pos_kw, neg_kw
         self.table = None
         self._table_dev: dict = {}
@@ -155,6 +160,9 @@ class FusedPairWeight:
         return t
 
     def __call__(self, label_matrix, label_matrix_transpose, **kwargs):
+        if self.label_func == "lambda":
+            # |delta NDCG| needs the scores' ranks inside the groups: not a function of the label matrices
+            raise NotImplementedError("LambdaRank weights exist on the fused path of pairwise_loss only")
         gt = (label_matrix > label_matrix_transpose).to(torch.float32)
         if self.label_func == "lut":
             # (a label off the level menu has no table entry: weight 0, the pair is dropped)
@@ -413,6 +421,10 @@ def pairwise_loss(outputs, labels, groups,
             menu_w = False
             label_pair_to_weight_func = users_weight_func          # (the caller's own function, where the table stood in for one)
             rw_pos = None
+
+    if fused_w is not None and fused_w.label_func == "lambda" and (
+            bpr is None or bpr[2] is not None or only_use_wrong_order_pair):
+        raise ValueError("LambdaRank weights need the logistic pair loss (bpr_loss_func) and the label-ordered pair set")
 
     if bpr is not None and menu_w:
         factor, reduce_mean, hinge_margin = bpr

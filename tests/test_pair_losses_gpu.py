@@ -11,7 +11,7 @@ import torch
 from oracle import dense_ref as D
 from oracle import generators as G
 from oracle import seg_ref as S
-from tests.util import check_pairwise, run_pairwise
+from tests.util import check_pairwise, dev, run_pairwise
 
 pytestmark = pytest.mark.gpu
 
@@ -101,3 +101,64 @@ def test_dropin_hinge_and_gain2():
         assert calls["n"] == 0                                # nothing was materialised
     finally:
         ops.pair_indices = real
+
+
+# ---- LambdaRank |delta NDCG| weights (RN_LABEL_LAMBDA) ----------------------------------------------------
+@pytest.mark.parametrize("b,ng,rw", [(400, 6, False), (7000, 50, True), (1000, 1, False)])
+def test_lambdarank_weights_match_oracle(b, ng, rw):
+    """Loss, gradient and exact counts of the LambdaRank-weighted logistic pair loss against the float64 oracle (ranks by
+    score inside the group, ties by row; discounts rounded to float32 as the product rounds them)."""
+    rng = np.random.default_rng(b + ng)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    s = rng.standard_normal(b).astype(np.float32)
+    s[rng.integers(0, b, b // 10)] = 0.25                              # tied scores: ranks by row index
+    y = rng.integers(0, 5, b).astype(np.float32)
+    spec = S.PairSpec(label_func="lambda", rw_pos=rng.uniform(0.5, 1.5, b).astype(np.float32) if rw else None,
+                      power=-0.5 if rw else 0.0)
+    out = run_pairwise(s, y, g, spec)
+    check_pairwise(out, S.pairwise(s, y, g, spec), ctx=f"lambda B={b}")
+
+
+def test_lambdarank_cfg3_full_size_and_mask():
+    """cfg3's batch (B = 65 536, groups of up to ~7 500 rows: neighbouring ranks of a long group differ in the sixth digit
+    of their discounts) on the counting segmentation; then a masked batch with NaN labels on two key columns (radix)."""
+    from oracle import generators as G
+    c = G.cfg3()
+    spec = S.PairSpec(label_func="lambda", rw_pos=c["w"], power=-0.5)
+    out = run_pairwise(c["s"], c["y"], c["g_f32"], spec)
+    check_pairwise(out, S.pairwise(c["s"], c["y"], c["g_f32"], spec), ctx="lambda cfg3")
+    rng = np.random.default_rng(11)
+    b = 9000
+    g1, g2 = rng.integers(0, 25, b).astype(np.float32), rng.integers(0, 3, b).astype(np.float32)
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(0, 4, b).astype(np.float32)
+    y[rng.random(b) < 0.02] = np.nan
+    mask = rng.random(b) < 0.85
+    spec = S.PairSpec(label_func="lambda", factor=2.0, reduce_mean=False)
+    out = run_pairwise(s, y, [g1, g2], spec, mask=mask)
+    check_pairwise(out, S.pairwise(s, y, [g1, g2], spec, mask=mask), ctx="lambda K=2 masked")
+
+
+def test_lambdarank_dropin_and_menu():
+    from rec_now_b200 import ops
+    from rec_now_b200.rec_block import pairwise_loss_from_batch as PW
+    rng = np.random.default_rng(12)
+    b = 3000
+    g = rng.integers(0, 30, b).astype(np.float32)
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(0, 5, b).astype(np.float32)
+    ts = torch.tensor(s, device="cuda", requires_grad=True)
+    loss = PW.pairwise_loss(ts, dev(y), dev(g), label_pair_to_weight_func=PW.FusedPairWeight("lambda"))
+    loss.backward()
+    ref = S.pairwise(s, y, g, S.PairSpec(label_func="lambda"))
+    assert abs(float(loss.detach()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
+    err = np.abs(ts.grad.cpu().numpy().astype(np.float64) - ref["grad"])
+    assert (err <= 1e-5 * ref["grad_abs"] + 1e-12).all()
+    with pytest.raises(ValueError):
+        PW.pairwise_loss(dev(s), dev(y), dev(g), PW.hinge_loss_func, label_pair_to_weight_func=PW.FusedPairWeight("lambda"))
+    with pytest.raises(ValueError):
+        PW.pairwise_loss(dev(s), dev(y), dev(g), only_use_wrong_order_pair=True,
+                         label_pair_to_weight_func=PW.FusedPairWeight("lambda"))
+    keys, _ = ops.canon_keys([dev(g)])
+    with pytest.raises(Exception):
+        ops.pairwise_fwd_bwd(dev(s), dev(y), keys, label_func="lambda", pair_loss="hinge")
