@@ -395,21 +395,38 @@ def other_configs(lib, dev, flush, mufu_peak, hbm_gbs, steps, with_cpu):
                                      "tolerance": 1e-5,
                                      "ok": bool(hn == ref["n_pair"] and abs(float(out["loss"].item()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
                                                 and (gerr <= 1e-5 * ref["grad_abs"] + 1e-12).all())}}
-    # the rarer kernel variants on cfg3's batch (score- / weight-dependent pair sets: general tiles, counts from the kernel)
-    for vname, vkw, skw in (("wrong_order_cfg3", dict(only_wrong=True), dict(only_wrong=True)),
-                            ("rw_neg_cfg3", dict(rw_neg=w), dict(rw_neg=d["w"]))):
-        step = lambda: ops.pairwise_fwd_bwd(s, y, keys, rw_pos=w, label_func="diff", power=-0.5, **vkw)
+    # the rarer kernel variants on cfg3's batch: score- / weight-dependent pair sets (general tiles, counts from the kernel),
+    # the level weight table (any label-only weight function: the label-gain tiles with a lookup) and LambdaRank weights
+    # (rank pre-pass inside the pair kernel, general tiles)
+    def lut_fn(a, b):
+        return (((a - b) ** 2 + 0.5 * a + 1.0) * (a > b)).astype(np.float32)
+    lev = np.arange(-1, 7, dtype=np.float32)
+    lut_t = torch.tensor(lut_fn(np.broadcast_to(lev[:, None], (8, 8)), np.broadcast_to(lev[None, :], (8, 8))), device=dev)
+    variants = (
+        ("wrong_order_cfg3", dict(label_func="diff", only_wrong=True), dict(label_func="diff", only_wrong=True),
+         "only_use_wrong_order_pair (k_pair variant with general tiles and kernel-side pair counts)"),
+        ("rw_neg_cfg3", dict(label_func="diff", rw_neg=w), dict(label_func="diff", rw_neg=d["w"]),
+         "a negative-side weight column (k_pair variant with general tiles and kernel-side pair counts)"),
+        ("weight_lut_cfg3", dict(label_func="lut", weight_lut=lut_t), dict(label_func="callable", weight_func=lut_fn),
+         "a label-only weight function that is none of the closed forms, W = ((y_i - y_j)^2 + y_i / 2 + 1) [y_i > y_j], as the "
+         "8 x 8 level table RN_LABEL_LUT (fast tiles with a table lookup)"),
+        ("lambdarank_cfg3", dict(label_func="lambda"), dict(label_func="lambda"),
+         "LambdaRank |delta NDCG| pair weights RN_LABEL_LAMBDA (score ranks inside the groups worked out by a pre-pass of "
+         "the pair kernel, general tiles)"),
+    )
+    for vname, vkw, skw, what in variants:
+        step = lambda: ops.pairwise_fwd_bwd(s, y, keys, rw_pos=w, power=-0.5, **vkw)
         t = time_device(step, steps, 5, flush)
         out = step()
-        spec = S.PairSpec(power=-0.5, label_func="diff", rw_pos=d["w"], **skw)
+        spec = S.PairSpec(power=-0.5, rw_pos=d["w"], **skw)
         ref = S.pairwise(d["s"], d["y"], d["g"], spec)
         gerr = np.abs(out["dlogits"].cpu().numpy().astype(np.float64) - ref["grad"])
         vn = int(out["n_pair"].item())
-        recs[vname] = {"workload": f"cfg3's batch with {'only_use_wrong_order_pair' if 'only_wrong' in vkw else 'a negative-side weight column'}"
-                                   " (k_pair variant with general tiles and kernel-side pair counts)",
+        recs[vname] = {"workload": f"cfg3's batch with {what}",
                        "rows": s.numel(), "n_pair": vn, **t, "pairs_per_s": vn / (t["single_call_us"] * 1e-6),
                        "parity": {"oracle": "oracle/seg_ref.py (float64)", "n_pair_exact": vn == ref["n_pair"],
                                   "loss_rel": abs(float(out["loss"].item()) - ref["loss"]) / max(abs(ref["loss"]), 1e-30),
+                                  "grad_max_abs_err_over_A": float((gerr / np.maximum(ref["grad_abs"], 1e-30))[ref["grad_abs"] > 0].max()),
                                   "tolerance": 1e-5,
                                   "ok": bool(vn == ref["n_pair"] and abs(float(out["loss"].item()) - ref["loss"]) <= 1e-5 * abs(ref["loss"])
                                              and (gerr <= 1e-5 * ref["grad_abs"] + 1e-12).all())}}

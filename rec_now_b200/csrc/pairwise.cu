@@ -44,6 +44,7 @@ struct PairParams {
   float focal_w, focal_alpha, focal_gamma; int focal_stop;      // fused focal term (rn_pairwise_args.focal_*); focal_w = 0: off
   float margin;          // hinge pair loss (rn_pairwise_args.pair_loss = RN_LOSS_HINGE): max(0, margin - x); c_log2 is then the plain factor
   double loss_unit;      // unit of the accumulated pair losses: ln 2 (logistic, log2 units) or 1 (hinge)
+  int lambda;            // RN_LABEL_LAMBDA: the scatter zeroes the pre-pass's per-group accumulators (cnt, g64)
   int gain2;             // what the sorted label column holds: 0 the label; 1 (RN_LABEL_GAIN2) 2^y (W = 2^y_i - 2^y_j);
                          // 2 (RN_LABEL_LUT) the label LEVEL 0 .. 7 (W = weight_lut[l_i][l_j])
   int part_rank, part_count; int ascending;
@@ -128,6 +129,7 @@ struct HeadsTail {
     lossrow[pos] = P.dyn_count ? 0.f : wocc;                 // (non-dynamic: the row's occurrence weight, read by k_pair)
     if (P.dyn_count) cnt[pos] = 0;
     else if (P.row_pairs) P.row_pairs[i] = (int64_t)n;
+    if (P.lambda) { cnt[pos] = 0; g64[pos] = 0ull; }         // (the LambdaRank pre-pass's per-group accumulators)
   }
 
   // J ranges of the I-blocks a group touches, from its geometry alone (offsets phase: base, level starts `pre`, level
@@ -557,6 +559,7 @@ struct HeadsTail {
         gacc[p] = 0.f; perm[p] = row;
         lossrow[p] = 0.f;
         if (P.dyn_count) cnt[p] = 0;
+        if (P.lambda) { cnt[p] = 0; g64[p] = 0ull; }           // (see scatter_row)
         if (P.det) {
           // bound of one pair weight, for the scale of the fixed-point accumulators: max |w_i| and max |y| over the rows
           g64[p] = 0ull;
@@ -772,16 +775,16 @@ __device__ __forceinline__ void dyn_finalize(const PairParams& P, const KpArgs& 
 // 1-based rank of row i among the rows of its group by score (descending; ties by original row) and IDCG_g the DCG of
 // the group's labels in descending order (gain 2^y - 1).  The weights are constants of the step (PW:270 stops the gradient
 // through every weight).  This pre-pass of the pair kernel works the per-row parts out on the sorted columns:
-//   0  zero the per-group accumulators (indexed by the group's first sorted position)
-//   1  rows per group (one atomic per group and warp)
-//   2  one warp per row: its rank by a scan of the group's scores (coalesced; consecutive rows go to consecutive warps of
-//      the grid, so the rows of a big group are spread over all SMs), its discount D(r) -> the negative-side weight column;
-//      its term of the ideal DCG -- the labels ascend along the sorted positions, so the row's ideal rank is its distance
-//      from the group's end -- added in double precision
+//   1  rows per group (one atomic per group and warp; the per-group accumulators, indexed by the group's first sorted
+//      position, were zeroed by the segmentation kernel's scatter)
+//   2  one warp per row: its rank by a scan of the group's scores (coalesced; rows are dealt to the CTAs round-robin, so
+//      the rows of a big group are spread evenly over all SMs), its discount D(r) -> the negative-side weight column;
+//      then one thread per row: its term of the ideal DCG -- the labels ascend along the sorted positions, so the row's
+//      ideal rank is its distance from the group's end -- summed in double precision
 //   3  row weight = rw_pos (or 1) / IDCG -> the positive-side weight column
 // Discounts are rounded to float32 from double precision (|D_i - D_j| of neighbouring ranks of a long group cancels
 // six digits: the oracle rounds the same way).  Groups of one label level (and the rows that cannot pair) are skipped.
-constexpr u32 kLambdaBarriers = 4;
+constexpr u32 kLambdaBarriers = 3;
 static __device__ __noinline__ void lambda_prepare(const PairParams& P, const KpArgs& A) {
   Ctl* ctl = A.ctl;
   const u32 B = P.B, ln = lane_id();
@@ -791,8 +794,6 @@ static __device__ __noinline__ void lambda_prepare(const PairParams& P, const Kp
   float* sd = const_cast<float*>(A.swn);
   float* swp = const_cast<float*>(A.swp);
   u32 epoch = 0;
-  for (u32 p = gtid; p < B; p += gthreads) { gsz[p] = 0u; idcg[p] = 0.0; }
-  grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
   for (u32 p0 = 0; p0 < B; p0 += gthreads) {
     const u32 p = p0 + gtid;
     const u32 a = p < B ? A.aj[p].x : kEmpty;
@@ -800,28 +801,67 @@ static __device__ __noinline__ void lambda_prepare(const PairParams& P, const Kp
     if (a != kEmpty && ln == (u32)(__ffs(m) - 1)) atomicAdd(gsz + a, (u32)__popc(m));
   }
   grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
-  for (u32 p = gtid >> 5; p < B; p += gthreads >> 5) {
+  stamp(ctl, 13);
+  u32* sdu = reinterpret_cast<u32*>(sd);                // (the rank count first; the discount is worked out row-parallel in step 3)
+  // (row p -> CTA p % grid: every CTA takes the same share of every big group's rows -- whole 32-row windows per CTA left
+  // some SMs with two windows of the biggest group and others with one; a CTA's warps still scan the same few groups)
+  for (u32 p = blockIdx.x + gridDim.x * (threadIdx.x >> 5); p < B; p += gridDim.x * (blockDim.x >> 5)) {
     const u32 a = A.aj[p].x, sz = gsz[a];
-    if (A.aj[a + sz - 1u].y == 0u) { if (ln == 0) sd[p] = 0.f; continue; }      // one label level: the group has no pairs
+    if (A.aj[a + sz - 1u].y == 0u) { if (ln == 0) sdu[p] = 0xFFFFFFFFu; continue; }      // one label level: the group has no pairs
     const float sp = A.ss[p];
-    const u32 rp = A.perm[p];
-    u32 c = 0;
-    for (u32 q = a + ln; q < a + sz; q += 32u) {
-      const float sq = A.ss[q];
-      if (sq > sp) ++c;
-      else if (sq == sp && A.perm[q] < rp) ++c;
+    // Rows ranked above this one = scores greater + tied scores of earlier rows.  The scan is bound by its instruction
+    // count (L1 serves 94 % of its loads): whole rounds of 256 positions run without bounds tests, eight loads in flight,
+    // two compares and two predicated adds per load; the tie-break by row index is a second scan taken only when a tie
+    // exists (the first version -- bounds test, compare and tie branch per element -- took 17 instructions per load).
+    u32 c = 0, e = 0;
+    const u32 end = a + sz;
+    u32 base = a;
+    for (; base + 256u <= end; base += 256u) {
+      const float* ps = A.ss + base + ln;
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ps[32 * k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c += v[k] > sp ? 1u : 0u; e += v[k] == sp ? 1u : 0u; }
     }
-    c = __reduce_add_sync(0xFFFFFFFFu, c);              // rows ranked above this one: r = c + 1
-    if (ln == 0) {
-      sd[p] = (float)(1.0 / log2(2.0 + (double)c));
-      const double gain = (double)A.sy[p] - 1.0;        // (the label column holds 2^y)
-      if (gain != 0.0) atomicAdd(idcg + a, gain / log2(1.0 + (double)(a + sz - p)));
+    for (u32 q = base + ln; q < end; q += 32u) { const float v = A.ss[q]; c += v > sp ? 1u : 0u; e += v == sp ? 1u : 0u; }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    e = __reduce_add_sync(0xFFFFFFFFu, e);
+    if (e > 1u) {                                       // (the row itself is one of the ties)
+      const u32 rp = A.perm[p];
+      u32 t = 0;
+      for (u32 q = a + ln; q < end; q += 32u) t += (A.ss[q] == sp && A.perm[q] < rp) ? 1u : 0u;
+      c += __reduce_add_sync(0xFFFFFFFFu, t);
     }
+    if (ln == 0) sdu[p] = c;                            // r = c + 1
+  }
+  stamp(ctl, 14);
+  // (the ideal DCG: one thread per row; consecutive lanes hold consecutive rows of a group -- a segmented warp sum, then
+  // one atomic per group and warp instead of 7 000 on the accumulator of a big group)
+  for (u32 p0 = 0; p0 < B; p0 += gthreads) {
+    const u32 p = p0 + gtid;
+    u32 a = kEmpty; double t = 0.0;
+    if (p < B) {
+      a = A.aj[p].x;
+      const u32 sz = gsz[a];
+      if (A.aj[a + sz - 1u].y != 0u) t = ((double)A.sy[p] - 1.0) / log2(1.0 + (double)(a + sz - p));      // (the label column holds 2^y)
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tv = __shfl_down_sync(0xFFFFFFFFu, t, o);
+      const u32 av = __shfl_down_sync(0xFFFFFFFFu, a, o);
+      if (ln + (u32)o < 32u && av == a) t += tv;
+    }
+    const u32 ap = __shfl_up_sync(0xFFFFFFFFu, a, 1);
+    if (a != kEmpty && (ln == 0 || ap != a) && t != 0.0) atomicAdd(idcg + a, t);
   }
   grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
+  stamp(ctl, 15);
   for (u32 p = gtid; p < B; p += gthreads) {
     const double t = idcg[A.aj[p].x];
     swp[p] = t > 0.0 ? (P.rw_pos ? swp[p] : 1.0f) * (float)(1.0 / t) : 0.f;
+    const u32 c = sdu[p];
+    sd[p] = c == 0xFFFFFFFFu ? 0.f : (float)(1.0 / log2(2.0 + (double)c));      // D(r) = 1 / log2(1 + r), r = c + 1
   }
   grid_sync(&ctl->bar2_cnt, epoch, &ctl->err);
 }
@@ -1705,6 +1745,7 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   P.c_log2 = hinge ? a->factor : a->factor * 1.4426950408889634f;
   P.margin = a->margin; P.loss_unit = hinge ? 1.0 : 0.6931471805599453;
   P.gain2 = (a->label_func == RN_LABEL_GAIN2 || lambda) ? 1 : (lut ? 2 : 0);
+  P.lambda = lambda ? 1 : 0;
   static const int pair_debug = tune_int("RN_PAIR_DEBUG", 0);
   P.debug = pair_debug;
   P.part_rank = a->part_rank; P.part_count = a->part_count;

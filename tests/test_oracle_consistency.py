@@ -135,3 +135,46 @@ def test_hinge_and_gain2_dense_vs_segmented(seed, b, ng, margin, label_func, pow
                 l0 = r["loss"]
                 f1 = (lp - l0) / float(np.float32(sp[i]) - s[i]); f2 = (l0 - lm) / float(s[i] - np.float32(sm[i]))
                 assert min(f1, f2) - 0.05 <= r["grad"][i] <= max(f1, f2) + 0.05
+
+
+@settings(max_examples=20, deadline=None)
+@given(seed=st.integers(0, 10_000), b=st.integers(2, 90), ng=st.integers(1, 9), wrong=st.booleans(),
+       power=st.sampled_from([0.0, -0.5, 1.0]))
+def test_callable_weight_func_dense_vs_segmented(seed, b, ng, wrong, power):
+    """The segmented oracle with an arbitrary label_pair_to_weight_func plugged in (label_func "callable": the truth for
+    the level-table path RN_LABEL_LUT) against the op-for-op dense pipeline running the same callable (PW:192-193)."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(-1, 7, b).astype(np.float32)
+    f = lambda a, c: (((a - c) ** 2 + 0.5 * a + 1.0) * (a > c)).astype(np.float32)
+    dense, n = D.pairwise_loss(s, y, g, only_use_wrong_order_pair=wrong, return_num_pair=True,
+                               click_occurance_power=power, label_pair_to_weight_func=f)
+    seg = S.pairwise(s, y, g, S.PairSpec(label_func="callable", weight_func=f, only_wrong=wrong, power=power))
+    assert seg["n_pair"] == int(n)
+    assert abs(seg["loss"] - float(dense)) <= 2e-5 * max(abs(float(dense)), 1e-6)
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st.integers(0, 10_000), b=st.integers(2, 60), ng=st.integers(1, 5))
+def test_lambdarank_weights_are_the_swap_delta_ndcg(seed, b, ng):
+    """The oracle's LambdaRank weight of a pair is |NDCG(ranking) - NDCG(ranking with rows i and j swapped)| of its group
+    (gains 2^y - 1, discounts 1 / log2(1 + rank), ranks by score descending with ties by row index) -- the definition
+    include/recnow_b200.h gives for RN_LABEL_LAMBDA, restated here by brute force."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, ng, b).astype(np.float32)
+    s = np.round(rng.standard_normal(b), 1).astype(np.float32)              # (rounded: tied scores occur)
+    y = rng.integers(0, 5, b).astype(np.float32)
+    res = S.pairwise(s, y, g, S.PairSpec(label_func="lambda"), want_pairs=True)
+    for i, j, w in zip(res["pos_idx"], res["neg_idx"], res["w"]):
+        m = np.flatnonzero(g == g[i])
+        order = np.lexsort((m, -s[m].astype(np.float64)))
+        rank = np.empty(m.size)
+        rank[order] = np.arange(1, m.size + 1)
+        gain = 2.0 ** y[m].astype(np.float64) - 1.0
+        idcg = (np.sort(gain)[::-1] / np.log2(1.0 + np.arange(1, m.size + 1))).sum()
+        ii, jj = int(np.flatnonzero(m == i)[0]), int(np.flatnonzero(m == j)[0])
+        swapped = rank.copy()
+        swapped[ii], swapped[jj] = rank[jj], rank[ii]
+        want = abs((gain / np.log2(1.0 + swapped)).sum() - (gain / np.log2(1.0 + rank)).sum()) / idcg
+        assert abs(w - want) <= 2e-5 * want + 1e-9, (w, want)
