@@ -21,14 +21,14 @@ if not os.path.exists(_SO):
 _ops = tf.load_op_library(_SO)
 
 SMALL_POSIVITE_FLOAT = 1.0E-10      # (sic) PW:13
-RN_LABEL_STEP, RN_LABEL_DIFF = 0, 1
+RN_LABEL_STEP, RN_LABEL_DIFF, RN_LABEL_LUT = 0, 1, 3
 
 
 @tf.RegisterGradient("RecNowPairwiseLoss")
 def _pairwise_grad(op, g_loss, g_n, g_ni, g_dlogits):
     # d loss / d logits was computed by the forward kernel; labels, keys, masks and weights get no gradient
     # (PW:264, PW:270).  Second-order terms through dlogits are not provided.
-    return [g_loss * op.outputs[3], None, None, None, None, None]
+    return [g_loss * op.outputs[3], None, None, None, None, None, None]
 
 
 @tf.RegisterGradient("RecNowListwiseLoss")
@@ -76,15 +76,27 @@ def bpr_loss_func(outputs_pos, outputs_neg, weights=None, factor=1.0, reduce_mea
 
 class FusedPairWeight:
     """label_pair_to_weight_func the fused kernel understands: phi(y_i, y_j) * kwargs[pos_kw][i] * kwargs[neg_kw][j],
-    phi = [y_i > y_j] ("step") or (y_i - y_j)[y_i > y_j] ("diff").  Also a plain callable with the reference's
-    contract, so the same object works with the reference implementation."""
+    phi = [y_i > y_j] ("step"), (y_i - y_j)[y_i > y_j] ("diff") or table[y_i + 1][y_j + 1][y_i > y_j] ("lut": any
+    label-only weight function as an 8 x 8 table over the label levels -1 .. 6, see from_callable).  Also a plain callable
+    with the reference's contract, so the same object works with the reference implementation."""
 
-    def __init__(self, label_func="step", pos_kw=None, neg_kw=None):
+    def __init__(self, label_func="step", pos_kw=None, neg_kw=None, table=None):
         self.label_func, self.pos_kw, self.neg_kw = label_func, pos_kw, neg_kw
+        self.table = None if table is None else tf.reshape(tf.cast(table, tf.float32), [8, 8])
+
+    @classmethod
+    def from_callable(cls, f, pos_kw=None, **kwargs):
+        lev = tf.range(-1.0, 7.0, dtype=tf.float32)
+        return cls("lut", pos_kw=pos_kw, table=f(tf.tile(lev[:, None], [1, 8]), tf.tile(lev[None, :], [8, 1]), **kwargs))
 
     def __call__(self, label_matrix, label_matrix_transpose, **kwargs):
         gt = tf.cast(label_matrix > label_matrix_transpose, tf.float32)
-        w = (label_matrix - label_matrix_transpose) * gt if self.label_func == "diff" else gt
+        if self.label_func == "lut":
+            li = tf.clip_by_value(tf.cast(label_matrix + 1.0, tf.int32), 0, 7)
+            lj = tf.clip_by_value(tf.cast(label_matrix_transpose + 1.0, tf.int32), 0, 7)
+            w = tf.gather_nd(self.table, tf.stack([li, lj], axis=-1)) * gt
+        else:
+            w = (label_matrix - label_matrix_transpose) * gt if self.label_func == "diff" else gt
         if self.pos_kw is not None:
             w = w * tf.reshape(kwargs[self.pos_kw], [-1, 1])
         if self.neg_kw is not None:
@@ -113,10 +125,16 @@ def pairwise_loss(outputs, labels, groups, pairloss_func=bpr_loss_func, only_use
     wp = _empty(tf.float32) if fw is None or fw.pos_kw is None else tf.reshape(tf.cast(kwargs[fw.pos_kw], tf.float32), [-1])
     wn = _empty(tf.float32) if fw is None or fw.neg_kw is None else tf.reshape(tf.cast(kwargs[fw.neg_kw], tf.float32), [-1])
     lf = RN_LABEL_DIFF if (fw is not None and fw.label_func == "diff") else RN_LABEL_STEP
+    lut = _empty(tf.float32)
+    if fw is not None and fw.label_func == "lut" and not only_use_wrong_order_pair:
+        lf, lut = RN_LABEL_LUT, tf.reshape(fw.table, [-1])       # (labels off the menu -1 .. 6 fail the op: loss = NaN)
+    elif fw is not None and fw.label_func == "lut":
+        label_pair_to_weight_func, fw = fw, None                 # general path: the table object as a plain callable
+        wp = _empty(tf.float32)
     bpr = _match_bpr(pairloss_func)
     if bpr is not None and (label_pair_to_weight_func is None or fw is not None):
         loss, n, _, _ = _ops.rec_now_pairwise_loss(logits=s, labels=y, group_keys=keys, row_ok=ok, rw_pos=wp, rw_neg=wn,
-                                                   label_func=lf, factor=bpr[0], power=float(click_occurance_power),
+                                                   weight_lut=lut, label_func=lf, factor=bpr[0], power=float(click_occurance_power),
                                                    only_wrong=bool(only_use_wrong_order_pair), reduce_mean=bpr[1])
         return (loss, n) if return_num_pair else loss
     # general path: materialised pairs (row-major order, PW:217) + the caller's callables

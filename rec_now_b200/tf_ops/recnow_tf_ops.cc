@@ -89,6 +89,7 @@ REGISTER_KERNEL_BUILDER(Name("RecNowCanonKeys").Device(tf::DEVICE_GPU).TypeConst
 REGISTER_OP("RecNowPairwiseLoss")
     .Input("logits: float").Input("labels: float").Input("group_keys: int64")      // keys: [K, B]
     .Input("row_ok: uint8").Input("rw_pos: float").Input("rw_neg: float")          // empty tensor = absent
+    .Input("weight_lut: float")                                                    // [8, 8] level table (label_func = RN_LABEL_LUT) or empty
     .Attr("label_func: int = 0").Attr("factor: float = 1.0").Attr("power: float = 0.0")
     .Attr("only_wrong: bool = false").Attr("reduce_mean: bool = true")
     .Output("loss: float").Output("n_pair: float").Output("n_pair_i64: int64").Output("dlogits: float")
@@ -134,6 +135,12 @@ class RecNowPairwiseLossOp : public OpKernel {
   void Compute(OpKernelContext* ctx) override {
     rn_pairwise_args a;
     OP_REQUIRES_OK(ctx, FillPairArgs(ctx, at_, &a));
+    {
+      // SURVEY 8b weight_lut: any label-only label_pair_to_weight_func as a table over the label levels (recnow_b200.h)
+      const Tensor& lut = ctx->input(6);
+      OP_REQUIRES(ctx, lut.NumElements() == 0 || lut.NumElements() == 64, InvalidArgument("weight_lut must be empty or hold 8 x 8 floats"));
+      a.weight_lut = OptPtr<float>(lut);
+    }
     Tensor *loss = nullptr, *n = nullptr, *ni = nullptr, *d = nullptr, scratch;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({}), &loss));
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({}), &n));
