@@ -244,8 +244,8 @@ int rn_global_pairwise_fwd_bwd(const rn_global_args* args, void* scratch, size_t
 
 /* ---- pairwise, HOST buffers ------------------------------------------------------------------------------
  * Front end for callers whose tensors live in host memory (a CPU-placed TF2 op, a data loader): the same call as
- * rn_pairwise_fwd_bwd, but EVERY pointer of rn_pairwise_args is a HOST pointer (pinned memory, or the copies are
- * synchronous).  The object owns `depth` slots of device memory (input columns, outputs, scratch arena), a copy-in, a
+ * rn_pairwise_fwd_bwd, but EVERY pointer of rn_pairwise_args (weight_lut included) is a HOST pointer (pinned memory, or
+ * the copies are synchronous).  The object owns `depth` slots of device memory (input columns, outputs, scratch arena), a copy-in, a
  * compute and a copy-out stream; it allocates at create time only.  submit enqueues copy-in -> kernels -> copy-out of
  * one batch and returns a ticket without waiting (it blocks only while all `depth` slots are in flight); wait returns
  * when that batch's loss, n_pair_f32, n_pair, dlogits (and row_pairs) are in the host buffers given to submit.  With
@@ -254,6 +254,13 @@ int rn_global_pairwise_fwd_bwd(const rn_global_args* args, void* scratch, size_t
 typedef struct rn_host_pairwise rn_host_pairwise;
 int rn_host_pairwise_create(int64_t B_max, int32_t K, int32_t depth, rn_host_pairwise** out);
 int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_args* host_args, int32_t* ticket);
+/* Opt-in (environment RN_HOST_STEP_GRAPH, read at create: 1 = always, 2 = once the object has found its eager submits host
+ * bound, i.e. their mean host time above RN_HOST_STEP_GRAPH_US = 25): a slot that is handed the SAME host_args (the same
+ * pinned buffers, sizes and options: a loader refilling its staging buffers) a second time captures its step -- copy-in,
+ * kernels, copy-out -- as one CUDA graph and launches that from then on: three driver calls per step instead of fourteen.
+ * Off by default: on a quiet host the pipeline is device bound and the eager path measured faster.
+ * The buffers must stay page-locked at those addresses while the object lives.  Number of submits that went out that way: */
+int64_t rn_host_pairwise_graph_steps(const rn_host_pairwise* p);
 int rn_host_pairwise_wait(rn_host_pairwise* p, int32_t ticket);
 int rn_host_pairwise_destroy(rn_host_pairwise* p);
 

@@ -30,6 +30,7 @@ EXPORTS = [
     "rn_debug_graph_launches", "rn_debug_arena_offset", "rn_pack_row_block", "rn_reduce_peer_chunks",
     "rn_global_buffer_bytes", "rn_global_gather_bytes", "rn_global_pairwise_fwd_bwd",
     "rn_host_pairwise_create", "rn_host_pairwise_submit", "rn_host_pairwise_wait", "rn_host_pairwise_destroy",
+    "rn_host_pairwise_graph_steps",
     "rn_segment_pool_fwd", "rn_segment_pool_bwd",
 ]
 
@@ -146,6 +147,9 @@ def lib() -> C.CDLL:
     L.rn_host_pairwise_submit.argtypes = [vp, C.POINTER(PairwiseArgs), C.POINTER(i32)]
     L.rn_host_pairwise_wait.argtypes = [vp, i32]
     L.rn_host_pairwise_destroy.argtypes = [vp]
+    if hasattr(L, "rn_host_pairwise_graph_steps"):
+        L.rn_host_pairwise_graph_steps.restype = i64
+        L.rn_host_pairwise_graph_steps.argtypes = [vp]
     if hasattr(L, "rn_segment_pool_fwd"):       # (absent only from older builds loaded through RN_LIB_PATH for A/B timing)
         L.rn_segment_pool_fwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp]
         L.rn_segment_pool_bwd.argtypes = [C.POINTER(PoolArgs), vp, vp, vp, vp]

@@ -8,11 +8,18 @@
 
 namespace rn {
 
-// NVTX range around a C-ABI entry point (header-only NVTX 3: a pointer test when no tool is attached), so that a
-// profiler can filter on the call (`ncu --nvtx --nvtx-include "rn_pairwise_fwd_bwd/"`) and a timeline names it.
+// NVTX range around a C-ABI entry point, so that a profiler can filter on the call (`ncu --nvtx --nvtx-include
+// "rn_pairwise_fwd_bwd/"`) and a timeline names it.  Opt-in (RN_NVTX=1, read once): with the ranges always on, every
+// push / pop pair cost 4-9 us of host time on the GPU boxes of this project (the NVTX 3 globals are shared with the
+// framework's copy, whose callbacks are not free) -- the host-buffer front end went from 46 to 76 us per step.
+inline bool nvtx_enabled() {
+  static const bool on = []() { const char* v = getenv("RN_NVTX"); return v && *v && *v != '0'; }();
+  return on;
+}
 struct NvtxRange {
-  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-  ~NvtxRange() { nvtxRangePop(); }
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_enabled()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
   NvtxRange(const NvtxRange&) = delete;
   NvtxRange& operator=(const NvtxRange&) = delete;
 };

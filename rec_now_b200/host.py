@@ -66,22 +66,25 @@ class HostPairwise:
 
     def submit(self, keys, logits, labels, *, loss, n_pair_f32, n_pair, dlogits, rw_pos=None, rw_neg=None, row_ok=None,
                row_pairs=None, label_func: str = "step", factor: float = 1.0, power: float = 0.0,
-               only_wrong: bool = False, reduce_mean: bool = True) -> int:
+               only_wrong: bool = False, reduce_mean: bool = True, weight_lut=None) -> int:
         """Enqueue one batch; returns the ticket to pass to :meth:`wait`.  ``keys`` is int64 ``[K, B]``; the outputs
         ``loss`` (f32[1]), ``n_pair_f32`` (f32[1]), ``n_pair`` (i64[1]), ``dlogits`` (f32[B]) are filled by wait."""
         return self.bind(keys, logits, labels, loss=loss, n_pair_f32=n_pair_f32, n_pair=n_pair, dlogits=dlogits,
                          rw_pos=rw_pos, rw_neg=rw_neg, row_ok=row_ok, row_pairs=row_pairs, label_func=label_func,
-                         factor=factor, power=power, only_wrong=only_wrong, reduce_mean=reduce_mean).submit()
+                         factor=factor, power=power, only_wrong=only_wrong, reduce_mean=reduce_mean,
+                         weight_lut=weight_lut).submit()
 
     def bind(self, keys, logits, labels, *, loss, n_pair_f32, n_pair, dlogits, rw_pos=None, rw_neg=None, row_ok=None,
              row_pairs=None, label_func: str = "step", factor: float = 1.0, power: float = 0.0,
-             only_wrong: bool = False, reduce_mean: bool = True) -> "BoundBatch":
+             only_wrong: bool = False, reduce_mean: bool = True, weight_lut=None) -> "BoundBatch":
         """Validate a set of host buffers once and return a :class:`BoundBatch` whose ``submit()`` enqueues whatever
         they hold at that moment -- for loaders that refill the same staging buffers every step."""
         B = int(logits.numel() if hasattr(logits, "numel") else logits.size)
         a = _lib.PairwiseArgs()
         a.B, a.K = B, self.K
-        a.label_func = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF}[label_func]
+        a.label_func = {"step": _lib.RN_LABEL_STEP, "diff": _lib.RN_LABEL_DIFF, "gain2": _lib.RN_LABEL_GAIN2,
+                        "lut": _lib.RN_LABEL_LUT, "lambda": _lib.RN_LABEL_LAMBDA}[label_func]
+        a.weight_lut = _ptr(weight_lut, np.float32, 64)        # (label_func "lut": the 8 x 8 level table, a host buffer too)
         a.keys = _ptr(keys, np.int64, self.K * B)
         a.logits, a.labels = _ptr(logits, np.float32, B), _ptr(labels, np.float32, B)
         a.row_ok, a.rw_pos, a.rw_neg = _ptr(row_ok, np.uint8, B), _ptr(rw_pos, np.float32, B), _ptr(rw_neg, np.float32, B)
@@ -91,11 +94,17 @@ class HostPairwise:
         a.loss, a.n_pair_f32 = _ptr(loss, np.float32, 1), _ptr(n_pair_f32, np.float32, 1)
         a.n_pair, a.dlogits = _ptr(n_pair, np.int64, 1), _ptr(dlogits, np.float32, B)
         a.row_pairs = _ptr(row_pairs, np.int64, B)
-        return BoundBatch(self, a, (keys, logits, labels, rw_pos, rw_neg, row_ok, loss, n_pair_f32, n_pair, dlogits, row_pairs))
+        return BoundBatch(self, a, (keys, logits, labels, rw_pos, rw_neg, row_ok, loss, n_pair_f32, n_pair, dlogits, row_pairs,
+                                    weight_lut))
 
     def wait(self, ticket: int) -> None:
         _lib.check(_lib.lib().rn_host_pairwise_wait(self._h, ticket), "rn_host_pairwise_wait")
         self._keep[ticket] = None
+
+    def graph_steps(self) -> int:
+        """Submits that went out as one launch of a slot's whole-step CUDA graph (same pinned buffers as the slot's previous
+        submit: see rn_host_pairwise_graph_steps)."""
+        return int(_lib.lib().rn_host_pairwise_graph_steps(self._h))
 
     def close(self) -> None:
         if self._h:

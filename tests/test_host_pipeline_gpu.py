@@ -71,6 +71,30 @@ def test_matches_device_path_cfg3():
     assert np.abs(o["dlogits"].numpy() - gd).max() <= 1e-6 * np.abs(gd).max()
 
 
+def test_level_table_and_lambdarank_through_host_buffers():
+    """RN_LABEL_LUT with the table in HOST memory (it is copied in with the batch's columns) and RN_LABEL_LAMBDA through the
+    host front end, against the oracle with the callable itself."""
+    from rec_now_b200.host import HostPairwise
+    rng = np.random.default_rng(21)
+    B = 12000
+    g = rng.integers(0, 90, B).astype(np.int64)
+    s = rng.standard_normal(B).astype(np.float32)
+    y = rng.integers(0, 5, B).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, B).astype(np.float32)
+    f = lambda a, b: (((a - b) ** 2 + 0.5 * a + 1.0) * (a > b)).astype(np.float32)
+    lev = np.arange(-1, 7, dtype=np.float32)
+    table = np.ascontiguousarray(f(np.broadcast_to(lev[:, None], (8, 8)), np.broadcast_to(lev[None, :], (8, 8))))
+    hp = HostPairwise(B, depth=2)
+    o1, o2 = _outs(B, False), _outs(B, False)
+    t1 = hp.submit(g, s, y, rw_pos=w, label_func="lut", weight_lut=table, power=-0.5, **o1)
+    t2 = hp.submit(g, s, y, rw_pos=w, label_func="lambda", **o2)
+    hp.wait(t1); hp.wait(t2)
+    hp.close()
+    check_pairwise(_as_out(o1), S.pairwise(s, y, g, S.PairSpec(label_func="callable", weight_func=f, rw_pos=w, power=-0.5)),
+                   ctx="host lut")
+    check_pairwise(_as_out(o2), S.pairwise(s, y, g, S.PairSpec(label_func="lambda", rw_pos=w)), ctx="host lambda")
+
+
 def test_argument_errors():
     from rec_now_b200 import _lib
     from rec_now_b200.host import HostPairwise
@@ -83,9 +107,12 @@ def test_argument_errors():
     hp.close()
 
 
-def test_bound_buffers_are_read_at_submit():
-    """bind() validates the staging buffers once; every submit() copies what they hold at that moment."""
+@pytest.mark.parametrize("step_graph", ["1", "0"])
+def test_bound_buffers_are_read_at_submit(monkeypatch, step_graph):
+    """bind() validates the staging buffers once; every submit() copies what they hold at that moment -- on the eager path
+    and when the slots launch their whole-step graphs (RN_HOST_STEP_GRAPH, read when the object is created)."""
     from rec_now_b200.host import HostPairwise
+    monkeypatch.setenv("RN_HOST_STEP_GRAPH", step_graph)
     B = 5000
     rng = np.random.default_rng(7)
     g = torch.from_numpy(rng.integers(0, 50, B).astype(np.int64)).pin_memory()
@@ -94,19 +121,32 @@ def test_bound_buffers_are_read_at_submit():
     o = _outs(B, True)
     hp = HostPairwise(B)
     batch = hp.bind(g, s, y, **o)
-    for rep in range(3):
+    for rep in range(7):
         hp.wait(batch.submit())
         check_pairwise(_as_out(o), S.pairwise(s.numpy(), y.numpy(), g.numpy()), ctx=f"bound rep {rep}")
         s.copy_(torch.from_numpy(rng.standard_normal(B).astype(np.float32)))       # the loader refills its buffer
         y.copy_(torch.from_numpy(rng.integers(0, 2, B).astype(np.float32)))
+    # two slots, the same pinned buffers every step: from its second submit on a slot launches its whole-step graph
+    # (copy-in, kernels, copy-out as one launch) -- submits 2 .. 6 here
+    want = 5 if step_graph == "1" else 0
+    assert hp.graph_steps() == want, hp.graph_steps()
+    # pageable buffers stay on the eager path
+    o2 = _outs(B, False)
+    b2 = hp.bind(g.numpy().copy(), s.numpy().copy(), y.numpy().copy(), **o2)
+    for rep in range(4):
+        hp.wait(b2.submit())
+    check_pairwise(_as_out(o2), S.pairwise(s.numpy(), y.numpy(), g.numpy()), ctx="pageable")
+    assert hp.graph_steps() == want
     hp.close()
 
 
-def test_soak_slots_on_their_own_streams():
+@pytest.mark.parametrize("step_graph", ["0", "1"])
+def test_soak_slots_on_their_own_streams(monkeypatch, step_graph):
     """Every slot enqueues on its own compute stream with its own instance of the cached graph, so the cooperative kernels
     of consecutive batches are in the launch queues at the same time.  4000 batches, three in flight: every result must
     be the first one's (exact pair count, loss and gradient up to the jitter of the float atomics), no device error."""
     from rec_now_b200.host import HostPairwise
+    monkeypatch.setenv("RN_HOST_STEP_GRAPH", step_graph)          # (eager submits / whole-step graphs from each slot's second submit on)
     d = G.cfg3(3, b=30000, n_groups=1500)
     B = d["s"].size
     hin = {k: torch.from_numpy(np.ascontiguousarray(d[k])).pin_memory() for k in ("g", "s", "y", "w")}
@@ -131,4 +171,5 @@ def test_soak_slots_on_their_own_streams():
     for t, q in pending:
         hp.wait(t)
         assert int(outs[q]["n_pair"]) == ref["n_pair"]
+    assert hp.graph_steps() == (4000 - depth if step_graph == "1" else 0)
     hp.close()
