@@ -122,6 +122,43 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index: int):
+    """Run this process on the CPUs of the NUMA node its GPU hangs off (what `numactl --cpunodebind` / NCCL's affinity do for
+    a production job): page-locked host buffers are then allocated next to the GPU's PCIe root.  Host-side e2e figures
+    of this bench were bimodal across boxes (46 vs 76 us per step with the same device-timed step) before this.  Returns a
+    record for the JSON line and the previous affinity (restored in front of the CPU-baseline legs, which use every core
+    the process may use)."""
+    rec = {"gpu_numa_node": None, "bound": False}
+    before = None
+    try:
+        before = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        sysid = f"{int(dom, 16):04x}:{rest.lower()}"
+        node = int(open(f"/sys/bus/pci/devices/{sysid}/numa_node").read())
+        rec["gpu_numa_node"] = node
+        cpu_now = os.sched_getcpu() if hasattr(os, "sched_getcpu") else -1
+        rec["cpu_at_start"] = cpu_now
+        if node < 0:
+            return rec, before
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        rec["cpu_at_start_on_gpu_node"] = cpu_now in cpus
+        target = cpus & before
+        if target:
+            os.sched_setaffinity(0, target)
+            rec["bound"] = True
+            rec["cpus"] = len(target)
+    except Exception as e:          # (no sysfs / NVML: run as started)
+        rec["note"] = f"{type(e).__name__}: {e}"[:120]
+    return rec, before
+
+
 def make_workload(world: int):
     from oracle import generators as G        # generators only (pure numpy); nothing of the oracle is timed here
     d = G.cfg3(0) if world == 1 else G.cfg5(world, 0)
@@ -488,6 +525,7 @@ def ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world != max(1, args.gpus):
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    numa_rec, affinity_before = bind_to_gpu_numa(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -891,7 +929,16 @@ def ours(args):
             "step_breakdown_us": {"step": t_ms / K * 1e3, "k_pair": pair_ms * 1e3, "non_pair": (t_ms / K - pair_ms) * 1e3,
                                   "step_sfu_roofline_frac": MUFU_PER_PAIR * pairs_per_launch / (t_ms / K * 1e-3) / mufu_peak},
             "clocks": clocks, "device_error": err,
+            "host_placement": numa_rec,
         }
+        if affinity_before:
+            # the CPU legs below use every core the process may use: the affinity goes back on EVERY thread of the process
+            # (worker threads created meanwhile inherited the narrow mask)
+            for tid in [0] + [int(t) for t in os.listdir("/proc/self/task")]:
+                try:
+                    os.sched_setaffinity(tid, affinity_before)
+                except OSError:
+                    pass
         if world == 1 and not args.no_cpu:
             r = run_cpu_dense(d, steps=3, warmup=1, budget_s=25.0)
             line["cpu_baseline"] = {
