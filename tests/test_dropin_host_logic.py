@@ -83,6 +83,18 @@ def test_level_table_form_of_label_only_weight_functions():
         PW.FusedPairWeight("lut", table=torch.ones(8, 8), neg_kw="w")
 
 
+def test_lambdarank_weight_object():
+    """FusedPairWeight("lambda") selects LambdaRank weights on the fused path; it is not a function of the label matrices
+    (|delta NDCG| needs the scores' ranks), so calling it the reference's way says so instead of returning something."""
+    f = PW.FusedPairWeight("lambda", pos_kw="sample_weight")
+    assert f.label_func == "lambda" and f.pos_kw == "sample_weight"
+    y = torch.tensor([0.0, 1.0, 2.0])
+    with pytest.raises(NotImplementedError):
+        f(y.reshape(-1, 1).expand(3, 3), y.reshape(1, -1).expand(3, 3))
+    with pytest.raises(ValueError):
+        PW.FusedPairWeight("lambda", neg_kw="w")
+
+
 def test_no_cpu_fallback_anywhere():
     from rec_now_b200.rec_block import embedding_util as EU
     from rec_now_b200.rec_block import listwise_loss_from_batch as LW
