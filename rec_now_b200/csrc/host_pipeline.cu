@@ -173,11 +173,10 @@ extern "C" int rn_host_pairwise_submit(rn_host_pairwise* p, const rn_pairwise_ar
       s.busy = true; *ticket = q; p->next = (q + 1) % p->depth; ++p->graph_steps;
       return RN_OK;
     }
-    if (same_as_last && !s.seen_pageable && !(
-            pinned(h->keys) && pinned(h->logits) && pinned(h->labels) && pinned(h->rw_pos) && pinned(h->rw_neg) &&
-            pinned(h->row_ok) && pinned(h->weight_lut) && pinned(h->dlogits) && pinned(h->row_pairs))) s.seen_pageable = true;
-    if (same_as_last && !s.seen_pageable && pinned(h->keys) && pinned(h->logits) && pinned(h->labels) && pinned(h->rw_pos) && pinned(h->rw_neg) &&
-        pinned(h->row_ok) && pinned(h->weight_lut) && pinned(h->dlogits) && pinned(h->row_pairs)) {
+    if (same_as_last && !s.seen_pageable)
+      s.seen_pageable = !(pinned(h->keys) && pinned(h->logits) && pinned(h->labels) && pinned(h->rw_pos) && pinned(h->rw_neg) &&
+                          pinned(h->row_ok) && pinned(h->weight_lut) && pinned(h->dlogits) && pinned(h->row_pairs));
+    if (same_as_last && !s.seen_pageable) {
       // second submit of the same buffers: capture this step on the slot's stream, instantiate, launch
       if (s.exec) { cudaGraphExecDestroy(s.exec); s.exec = nullptr; }
       if (s.graph) { cudaGraphDestroy(s.graph); s.graph = nullptr; }
