@@ -1723,10 +1723,10 @@ int rn::pairwise_call(const rn_pairwise_args* a, void* scratch, size_t scratch_b
   const bool hinge = a->pair_loss == RN_LOSS_HINGE;
   if (det && hinge) return RN_ERR_UNSUPPORTED;
   const bool lut = a->label_func == RN_LABEL_LUT, lambda = a->label_func == RN_LABEL_LAMBDA;
-  if (!split && !lut && !lambda && !(g_prof.on && g_prof.n < g_prof.cap)) {       // (the level table: the general kernels at any size)
+  if (!split && !lambda && !(g_prof.on && g_prof.n < g_prof.cap)) {       // (LambdaRank weights: the general kernels at any size)
     // batches of up to 1024 rows: one launch of one CTA, everything in shared memory (small.cu)
     int smode = 0;
-    const bool sdiff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2;
+    const bool sdiff = a->label_func == RN_LABEL_DIFF || a->label_func == RN_LABEL_GAIN2 || lut;
     if (sdiff || a->rw_pos || a->rw_neg) smode |= M_HASW;
     if (sdiff) smode |= M_DIFF;
     if (a->rw_neg) smode |= M_RWN;

@@ -34,6 +34,7 @@ struct SmallArgs {
   float focal_w, focal_alpha, focal_gamma; int focal_stop;
   float* loss; float* n_pair_f32; int64_t* n_pair; float* dlogits; int64_t* row_pairs;
   Ctl* ctl; int persistent;
+  const float* lut;                // gain2 == 2 (RN_LABEL_LUT): the 8 x 8 level weight table, W = lut[l_i][l_j] for l_i > l_j
   u64* dbg;                        // RN_SMALL_DEBUG: per-warp phase stamps [phase][32] (developer aid), else nullptr
 };
 
@@ -54,6 +55,7 @@ struct SmallSmem {
   float r_li[kSmallRows], r_gi[kSmallRows], r_gn[kSmallRows]; u32 r_cnt[kSmallRows];   // per position: results of the walks
   double red_d[2][32]; u32 red_u[32]; u32 scan[34];
   double tot_d[2]; u32 tot_u; u32 bad; u32 trash;
+  float lut[64]; u32 lutbad;       // RN_LABEL_LUT: the level weight table (entries with l_i <= l_j zeroed); an entry was not usable
 };
 
 __device__ __forceinline__ u32 small_lower_bound(const u64* a, u32 n, u64 key) {   // first idx with a[idx] >= key
@@ -103,11 +105,21 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
   *reinterpret_cast<uint4*>(&S.u.cnt[tid][0]) = make_uint4(0, 0, 0, 0);
   *reinterpret_cast<uint4*>(&S.u.cnt[tid][4]) = make_uint4(0, 0, 0, 0);
   S.gc[tid] = 0;
-  if (tid == 0) { S.gc[kSmallRows] = 0; S.bad = 0; S.trash = 0; }
+  if (tid == 0) { S.gc[kSmallRows] = 0; S.bad = 0; S.trash = 0; S.lutbad = 0; }
+  // RN_LABEL_LUT: the table, checked as in k_pair (entries with l_i > l_j finite and > 0, the others zeroed)
+  const bool lutmode = !SIMPLE && A.gain2 == 2;
+  bool lut_entry_bad = false;
+  if (lutmode && tid < 64) {
+    float v = A.lut[tid];
+    if ((tid >> 3) > (tid & 7u)) { if (!(v > 0.f) || v > 3.0e38f) { v = 0.f; lut_entry_bad = true; } }
+    else v = 0.f;
+    S.lut[tid] = v;
+  }
   double fsum = 0.0;
   if (A.focal_w != 0.f && in) fsum = (double)focal_row(s_row, y_row, A.focal_alpha, A.focal_gamma, A.focal_stop).x;
-  const float yv_row = (y_row != y_row) ? 0.f : (A.gain2 ? exp2f(y_row) : y_row);          // the label the weights see
+  float yv_row = (y_row != y_row) ? 0.f : (A.gain2 == 1 ? exp2f(y_row) : y_row);          // the label the weights see
   __syncthreads();
+  if (lut_entry_bad) S.lutbad = 1;
   // ---- group: the first thread to claim a key's cell represents it --------------------------------------------------
   u32 rep = kSmallRows;                            // rows that cannot pair: one group behind all others
   int lev = 0;
@@ -126,6 +138,9 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
     }
     if (!label_level(y_row, lev)) { S.bad = 1; lev = 0; }
   }
+  if (lutmode) yv_row = (float)lev;                // (the weights see the label LEVEL; a label off the menu fails the call below)
+  // label part of a pair weight under M_DIFF (as label_weight of pair_tiles.cuh)
+  auto lw = [&](const float yi, const float yj) -> float { return lutmode ? S.lut[(int)yi * 8 + (int)yj] : yi - yj; };
   // rank inside (group, level): the counting sort's only atomic
   u32 rank = 0;
   if (ok) rank = atomicAdd(&S.u.cnt[rep][lev], 1u);
@@ -266,7 +281,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
           float wv = 1.f;
           if (HASW) {
             wv = w_p;
-            if (DIFF) wv = (y_p - S.sy[qq]) * w_p;
+            if (DIFF) wv = lw(y_p, S.sy[qq]) * w_p;
             if (RWN) { wv *= S.swn[qq]; valid = valid && wv > 0.f; }      // PW:193
           }
           if (WRONG) valid = valid && (x < 0.f);                          // PW:200-202
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
           float wv = 1.f;
           if (HASW) {
             wv = wq;
-            if (DIFF) wv = (S.sy[qq] - y_p) * wq;
+            if (DIFF) wv = lw(S.sy[qq], y_p) * wq;
             if (RWN) { wv *= wn_p; valid = valid && wv > 0.f; }
           }
           if (WRONG) valid = valid && (x < 0.f);
@@ -357,11 +372,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_small(SmallArgs A) {
   if (tid == 0) {
     float lossv = (float)(S.tot_d[0] * A.loss_unit / (double)denom);
     if (A.focal_w != 0.f) lossv += A.focal_w * (float)(S.tot_d[1] / (double)B);
+    // RN_LABEL_LUT: a label without a level or an unusable table entry fails the call (as in k_pair: never a plausible number)
+    const u32 lut_err = (lutmode && (S.bad || S.lutbad)) ? 8u : 0u;
+    if (lut_err) lossv = __int_as_float(0x7FC00000);
     *A.loss = lossv;
     *A.n_pair_f32 = (float)n;                    // PW:276
     *A.n_pair = (int64_t)n;
     // report for rn_last_device_error / the path query (3 = this kernel); the working fields stay as they are (clean)
-    A.ctl->rep_err = 0; A.ctl->rep_path = 3; A.ctl->ts[23] = globaltimer();
+    A.ctl->rep_err = lut_err; A.ctl->rep_path = 3; A.ctl->ts[23] = globaltimer();
     if (!A.persistent) { A.ctl->err = 0; A.ctl->path = 0; }
   }
 }
@@ -387,7 +405,8 @@ bool small_pairwise(const rn_pairwise_args* a, void* scratch, cudaStream_t st, i
   A.keys = a->keys; A.logits = a->logits; A.labels = a->labels; A.rw_pos = a->rw_pos; A.rw_neg = a->rw_neg; A.row_ok = a->row_ok;
   A.c = hinge ? a->factor : a->factor * 1.4426950408889634f;
   A.factor = a->factor; A.power = a->power; A.margin = a->margin; A.loss_unit = hinge ? 1.0 : 0.6931471805599453;
-  A.reduce_mean = a->reduce_mean; A.hinge = hinge ? 1 : 0; A.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : 0;
+  A.reduce_mean = a->reduce_mean; A.hinge = hinge ? 1 : 0;
+  A.gain2 = a->label_func == RN_LABEL_GAIN2 ? 1 : (a->label_func == RN_LABEL_LUT ? 2 : 0); A.lut = a->weight_lut;
   A.focal_w = a->focal_weight; A.focal_alpha = a->focal_alpha; A.focal_gamma = a->focal_gamma; A.focal_stop = a->focal_stop_weight_gradient;
   A.loss = a->loss; A.n_pair_f32 = a->n_pair_f32; A.n_pair = a->n_pair; A.dlogits = a->dlogits; A.row_pairs = a->row_pairs;
   A.ctl = static_cast<Ctl*>(scratch); A.persistent = a->scratch_persistent;

@@ -52,6 +52,34 @@ def test_table_matches_oracle(b, ng):
     y = rng.integers(-1, 7, b).astype(np.float32)                  # all eight levels
     out = run_lut(s, y, g, table_of())
     check_pairwise(out, S.pairwise(s, y, g, oracle_spec()), ctx=f"lut B={b}")
+    from rec_now_b200 import ops
+    assert ops.last_segmentation_path(out["_scratch"]) == (3 if b <= 1024 else 1)      # (the one-CTA kernel takes the table too)
+
+
+def test_table_small_batch_kernel_options_and_errors():
+    """The one-CTA kernel of batches up to 1024 rows with the level table: row weights, occurrence power, hinge, mask; a label
+    off the menu or an unusable table entry fails the call there as well."""
+    from rec_now_b200 import ops
+    rng = np.random.default_rng(31)
+    b = 900
+    g = rng.integers(0, 12, b).astype(np.float32)
+    s = rng.standard_normal(b).astype(np.float32)
+    y = rng.integers(0, 5, b).astype(np.float32)
+    w = rng.uniform(0.5, 1.5, b).astype(np.float32)
+    mask = rng.random(b) < 0.9
+    for kw in (dict(rw_pos=w, power=-0.5), dict(pair_loss="hinge", margin=0.5, factor=2.0, reduce_mean=False)):
+        spec = oracle_spec(**kw)
+        out = run_lut(s, y, g, table_of(), spec, mask=mask)
+        check_pairwise(out, S.pairwise(s, y, g, spec, mask=mask), ctx=f"small lut {sorted(kw)}")
+        assert ops.last_segmentation_path(out["_scratch"]) == 3
+    y_off = y.copy(); y_off[5] = 2.5
+    out = run_lut(s, y_off, g, table_of())
+    assert np.isnan(float(out["loss"])) and ops.device_error(out["_scratch"]) & 8
+    bad = table_of().copy(); bad[4, 2] = -1.0
+    out = run_lut(s, y, g, bad)
+    assert np.isnan(float(out["loss"])) and ops.device_error(out["_scratch"]) & 8
+    out = run_lut(s, y, g, table_of())
+    check_pairwise(out, S.pairwise(s, y, g, oracle_spec()), ctx="small lut after failed calls")
 
 
 def test_table_cfg3_full_size_with_row_weights_and_power():
